@@ -1,0 +1,392 @@
+"""FlacArray: FLAC-compressed N-d array, drop-in for /root/reference/src/flacarray/array.py:19-884.
+
+Same constructor keywords, properties, slicing semantics (`__getitem__`, array.py:279-449), `to_array`
+(keep mask / stream_slice / keep_indices, array.py:518-584), `from_array` (array.py:586-637) and byte
+bookkeeping (`stream_starts`, `stream_nbytes`, global offsets via an all-gather of byte counts,
+mpi.py:156-187).  Compression and decompression run on the GPU.
+
+Documented differences: properties that raise AttributeError in the reference (Q3:
+`global_process_nbytes`, `nstreams`, `global_nstreams`, `global_stream_nbytes`) return the intended
+values; an all-integer key returns the selected sample instead of a zero (Q4).  `to_array` keeps the
+reference behaviour of forwarding `stream_slice.start/.stop` unnormalised (Q5).
+"""
+import copy
+
+import numpy as np
+
+from .compress import array_compress
+from .decompress import array_decompress_slice
+from .libflacarray import is_torch
+from .mpi import global_array_properties, global_bytes
+from .utils import log
+
+
+def _nbytes_of(compressed):
+    if is_torch(compressed):
+        return int(compressed.numel())
+    return int(compressed.nbytes)
+
+
+class FlacArray:
+    """FLAC compressed array representation (see the reference class docstring, array.py:20-77)."""
+
+    def __init__(
+        self,
+        other,
+        shape=None,
+        global_shape=None,
+        compressed=None,
+        dtype=None,
+        stream_starts=None,
+        stream_nbytes=None,
+        stream_offsets=None,
+        stream_gains=None,
+        mpi_comm=None,
+        mpi_dist=None,
+    ):
+        if other is not None:
+            self._shape = copy.deepcopy(other._shape)
+            self._global_shape = copy.deepcopy(other._global_shape)
+            self._compressed = other._compressed.clone() if is_torch(other._compressed) else copy.deepcopy(other._compressed)
+            self._dtype = np.dtype(other._dtype)
+            self._stream_starts = copy.deepcopy(other._stream_starts)
+            self._stream_nbytes = copy.deepcopy(other._stream_nbytes)
+            self._stream_offsets = copy.deepcopy(other._stream_offsets)
+            self._stream_gains = copy.deepcopy(other._stream_gains)
+            self._mpi_dist = copy.deepcopy(other._mpi_dist)
+            self._mpi_comm = other._mpi_comm
+        else:
+            self._shape = tuple(shape)
+            self._global_shape = tuple(global_shape)
+            self._compressed = compressed
+            self._dtype = np.dtype(dtype)
+            self._stream_starts = stream_starts
+            self._stream_nbytes = stream_nbytes
+            self._stream_offsets = stream_offsets
+            self._stream_gains = stream_gains
+            self._mpi_comm = mpi_comm
+            self._mpi_dist = mpi_dist
+        self._init_params()
+
+    def _init_params(self):
+        if len(self._shape) == 1:
+            self._flatten_single = True
+            self._local_shape = (1, self._shape[0])
+        else:
+            self._flatten_single = False
+            self._local_shape = self._shape
+        self._local_nbytes = _nbytes_of(self._compressed)
+        (
+            self._global_nbytes,
+            self._global_proc_nbytes,
+            self._global_stream_starts,
+        ) = global_bytes(self._local_nbytes, self._stream_starts, self._mpi_comm)
+        self._leading_shape = self._local_shape[:-1]
+        self._global_leading_shape = self._global_shape[:-1]
+        self._stream_size = self._local_shape[-1]
+        self._local_nstreams = int(np.prod(self._leading_shape))
+        self._global_nstreams = int(np.prod(self._global_leading_shape))
+        self._typestr = self._dtype_str(self._dtype)
+        self._is_int64 = self._dtype == np.dtype(np.int64) or self._dtype == np.dtype(np.float64)
+
+    @staticmethod
+    def _dtype_str(dt):
+        for name in ("float64", "float32", "int64", "int32"):
+            if dt == np.dtype(name):
+                return name
+        raise RuntimeError(f"Unsupported dtype '{dt}'")
+
+    # ---- shapes ----
+    @property
+    def shape(self):
+        """The shape of the local, uncompressed array."""
+        return self._shape
+
+    @property
+    def global_shape(self):
+        """The global shape of array across any communicator."""
+        return self._global_shape
+
+    @property
+    def leading_shape(self):
+        return self._leading_shape
+
+    @property
+    def global_leading_shape(self):
+        return self._global_leading_shape
+
+    @property
+    def stream_size(self):
+        """The uncompressed length of each stream."""
+        return self._stream_size
+
+    # ---- compressed data ----
+    @property
+    def nbytes(self):
+        """Compressed bytes on the local process."""
+        return self._local_nbytes
+
+    @property
+    def global_nbytes(self):
+        return self._global_nbytes
+
+    @property
+    def global_process_nbytes(self):
+        return self._global_proc_nbytes
+
+    @property
+    def nstreams(self):
+        return self._local_nstreams
+
+    @property
+    def global_nstreams(self):
+        return self._global_nstreams
+
+    @property
+    def compressed(self):
+        """The concatenated raw bytes of all streams on the local process."""
+        return self._compressed
+
+    @property
+    def stream_starts(self):
+        return self._stream_starts
+
+    @property
+    def stream_nbytes(self):
+        return self._stream_nbytes
+
+    @property
+    def global_stream_starts(self):
+        return self._global_stream_starts
+
+    @property
+    def global_stream_nbytes(self):
+        return self._stream_nbytes
+
+    @property
+    def stream_offsets(self):
+        return self._stream_offsets
+
+    @property
+    def stream_gains(self):
+        return self._stream_gains
+
+    @property
+    def mpi_comm(self):
+        return self._mpi_comm
+
+    @property
+    def mpi_dist(self):
+        return self._mpi_dist
+
+    @property
+    def dtype(self):
+        return self._dtype
+
+    @property
+    def typestr(self):
+        return self._typestr
+
+    # ---- __getitem__ helpers (array.py:279-407) ----
+    def _slice_nelem(self, slc, dim):
+        start, stop, step = slc.indices(dim)
+        nslc = (stop - start) // step
+        return max(nslc, 0)
+
+    def _keep_view(self, key):
+        if len(key) != len(self._leading_shape):
+            msg = f"keep_view {key} does not match leading "
+            msg += f"dimensions {len(self._leading_shape)}"
+            raise ValueError(msg)
+        view = np.zeros(self._leading_shape, dtype=bool)
+        view[key] = True
+        return view
+
+    def _get_full_key(self, key):
+        ndim = len(self._local_shape)
+        full_key = list()
+        if self._flatten_single:
+            if isinstance(key, tuple):
+                if len(key) != 1:
+                    msg = f"Slice key {key} is not valid for single, "
+                    msg += "flattened stream."
+                    raise ValueError(msg)
+                full_key = [0, key[0]]
+            else:
+                full_key = [0, key]
+        else:
+            if isinstance(key, tuple):
+                full_key.extend(key)
+            else:
+                full_key.append(key)
+        if len(full_key) > ndim:
+            raise ValueError(f"Invalid slice key {key}, too many dimensions")
+        full_key.extend([slice(None) for _ in range(ndim - len(full_key))])
+        return full_key
+
+    def _get_leading_axes(self, full_key):
+        leading_shape = list()
+        keep_slice = list()
+        if self._flatten_single:
+            keep_slice = [0]
+        else:
+            for axis, axkey in enumerate(full_key[:-1]):
+                if not isinstance(axkey, (int, np.integer)):
+                    leading_shape.append(self._slice_nelem(axkey, self._local_shape[axis]))
+                else:
+                    if axkey < 0 or axkey >= self._local_shape[axis]:
+                        leading_shape.append(0)
+                keep_slice.append(axkey)
+        leading_shape = tuple(leading_shape)
+        keep_slice = tuple(keep_slice)
+        keep = None if len(keep_slice) == 0 else self._keep_view(keep_slice)
+        return leading_shape, keep
+
+    def _get_sample_axis(self, full_key):
+        sample_key = full_key[-1]
+        if sample_key is None:
+            return (0, self._stream_size, (self._stream_size,))
+        if isinstance(sample_key, slice):
+            start, stop, step = sample_key.indices(self._stream_size)
+            if step != 1:
+                raise ValueError("Only stride==1 supported on stream slices")
+            if stop - start <= 0:
+                return (0, 0, (0,))
+            return (start, stop, (stop - start,))
+        elif isinstance(sample_key, (int, np.integer)):
+            return (sample_key, sample_key + 1, ())
+        raise ValueError("Stream dimension supports contiguous slices or single indices.")
+
+    def __getitem__(self, raw_key):
+        """Decompress a slice of data on the fly (array.py:409-449)."""
+        key = self._get_full_key(raw_key)
+        leading_shape, keep = self._get_leading_axes(key)
+        first, last, sample_shape = self._get_sample_axis(key)
+        full_shape = leading_shape + sample_shape
+        n_total = 1 if len(full_shape) == 0 else int(np.prod(full_shape))
+        if n_total == 0:
+            return np.zeros(full_shape, dtype=self._dtype)
+        if len(full_shape) == 0 and (first < 0 or first >= self._stream_size):
+            return np.zeros(full_shape, dtype=self._dtype)
+        arr, _ = array_decompress_slice(
+            self._compressed,
+            self._stream_size,
+            self._stream_starts,
+            self._stream_nbytes,
+            stream_offsets=self._stream_offsets,
+            stream_gains=self._stream_gains,
+            keep=keep,
+            first_stream_sample=first,
+            last_stream_sample=last,
+            is_int64=self._is_int64,
+        )
+        return arr.reshape(full_shape)
+
+    def __delitem__(self, key):
+        raise RuntimeError("Cannot delete individual streams")
+
+    def __setitem__(self, key, value):
+        raise RuntimeError("Cannot modify individual byte streams")
+
+    def __repr__(self):
+        mpistr = ""
+        if self._mpi_comm is not None:
+            rank = self._mpi_comm.rank
+            mpistr = f" | Rank {rank:04d} "
+            mpistr += f"{self._mpi_dist[rank][0]}-"
+            mpistr += f"{self._mpi_dist[rank][1] - 1} |"
+        rep = f"<FlacArray{mpistr} {self._typestr} "
+        rep += f"shape={self._shape} bytes={self._local_nbytes}>"
+        return rep
+
+    def __eq__(self, other):
+        """array.py:469-516: shapes, dtype, starts and compressed BYTES equal; offsets/gains allclose."""
+        def host(x):
+            return x.cpu().numpy() if is_torch(x) else x
+
+        if self._shape != other._shape:
+            log.debug(f"other shape {other._shape} != {self._shape}")
+            return False
+        if self._dtype != other._dtype:
+            log.debug(f"other dtype {other._dtype} != {self._dtype}")
+            return False
+        if self._global_shape != other._global_shape:
+            log.debug(f"other global_shape {other._global_shape} != {self._global_shape}")
+            return False
+        if not np.array_equal(host(self._stream_starts), host(other._stream_starts)):
+            log.debug("other starts != starts")
+            return False
+        if not np.array_equal(host(self._compressed), host(other._compressed)):
+            log.debug("other compressed != compressed")
+            return False
+        for a, b, nm in ((self._stream_offsets, other._stream_offsets, "offsets"),
+                         (self._stream_gains, other._stream_gains, "gains")):
+            if (a is None) != (b is None):
+                log.debug(f"stream_{nm}: one is None")
+                return False
+            if a is not None and not np.allclose(host(a), host(b)):
+                log.debug(f"other stream_{nm} != stream_{nm}")
+                return False
+        return True
+
+    def to_array(self, keep=None, stream_slice=None, keep_indices=False, use_threads=False):
+        """Decompress local data into an array (array.py:518-584)."""
+        first_samp = None
+        last_samp = None
+        if stream_slice is not None:
+            if stream_slice.step is not None and stream_slice.step != 1:
+                raise RuntimeError("Only stream slices with a step size of 1 are supported")
+            first_samp = stream_slice.start
+            last_samp = stream_slice.stop
+        arr, indices = array_decompress_slice(
+            self._compressed,
+            self._stream_size,
+            self._stream_starts,
+            self._stream_nbytes,
+            stream_offsets=self._stream_offsets,
+            stream_gains=self._stream_gains,
+            keep=keep,
+            first_stream_sample=first_samp,
+            last_stream_sample=last_samp,
+            is_int64=self._is_int64,
+            use_threads=use_threads,
+            no_flatten=(not self._flatten_single),
+        )
+        if keep is not None and keep_indices:
+            return (arr, indices)
+        return arr
+
+    @classmethod
+    def from_array(cls, arr, level=5, quanta=None, precision=None, mpi_comm=None, use_threads=False):
+        """Construct a FlacArray from an array (array.py:586-637).
+
+        `arr` may be a numpy array or a CUDA torch tensor; in the latter case the compressed bytes stay
+        on the device.  With `mpi_comm` the array is this rank's block of the leading axis.
+        """
+        global_props = global_array_properties(tuple(arr.shape), mpi_comm=mpi_comm)
+        global_shape = global_props["shape"]
+        mpi_dist = global_props["dist"]
+        compressed, starts, nbytes, offsets, gains = array_compress(
+            arr, level=level, quanta=quanta, precision=precision, use_threads=use_threads
+        )
+        if is_torch(starts):
+            starts = starts.cpu().numpy()
+            nbytes = nbytes.cpu().numpy()
+            if offsets is not None:
+                offsets = offsets.cpu().numpy()
+                gains = gains.cpu().numpy()
+        from .libflacarray import np_dtype
+
+        return FlacArray(
+            None,
+            shape=tuple(arr.shape),
+            global_shape=global_shape,
+            compressed=compressed,
+            dtype=np_dtype(arr),
+            stream_starts=starts,
+            stream_nbytes=nbytes,
+            stream_offsets=offsets,
+            stream_gains=gains,
+            mpi_comm=mpi_comm,
+            mpi_dist=mpi_dist,
+        )

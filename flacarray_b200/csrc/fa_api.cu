@@ -1,0 +1,756 @@
+// fa_api.cu -- CUDA kernels (sm_100a) and the C ABI of libflacarray_b200.so.
+//
+// See include/flacarray_b200.h for the contract.  This translation unit is the whole product
+// library: kernels are thin __global__ wrappers around the bodies in fa_encode.h / fa_decode.h /
+// fa_quant.h.  No CPU fallback exists: without a CUDA device every entry point fails with
+// FAB_ERROR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/flacarray_b200.h"
+#include "fa_decode.h"
+#include "fa_encode.h"
+#include "fa_quant.h"
+
+using namespace fa;
+
+// =================================================================================================
+// Kernels
+// =================================================================================================
+
+__global__ void __launch_bounds__(kEncThreads, 2) k_encode(const EncParams P) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    encode_frame_cta(P, smem);
+}
+
+__global__ void k_enc_finalize(const long long* __restrict__ starts, const long long* __restrict__ ends,
+                               long long* __restrict__ nbytes, int64_t n, long long* __restrict__ total) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) nbytes[i] = ends[i] - starts[i];
+    if (i == n - 1 && total) *total = ends[i];
+}
+
+// ---- float -> int: per-stream min/max (utils.c:182-193 / :267-278), chunked over the stream ------
+constexpr int kMmThreads = 256;
+constexpr int kMmChunk = 32768;  // elements per CTA
+
+template <typename T>
+__global__ void __launch_bounds__(kMmThreads) k_minmax(const T* __restrict__ data, int64_t stream_size, int nchunk,
+                                                       T* __restrict__ pmin, T* __restrict__ pmax, int* __restrict__ err) {
+    const int64_t s = blockIdx.y;
+    const int c = blockIdx.x;
+    const int64_t lo = (int64_t)c * kMmChunk;
+    const int64_t hi = lo + kMmChunk < stream_size ? lo + kMmChunk : stream_size;
+    const T* p = data + s * stream_size;
+    T mn = p[lo], mx = p[lo];
+    bool nan = false;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += kMmThreads) {
+        T v = p[i];
+        nan |= (v != v);
+        mn = v < mn ? v : mn;
+        mx = v > mx ? v : mx;
+    }
+    __shared__ T smn[kMmThreads / 32], smx[kMmThreads / 32];
+    for (int m = 16; m >= 1; m >>= 1) {
+        T a = __shfl_xor_sync(0xffffffffu, mn, m), b = __shfl_xor_sync(0xffffffffu, mx, m);
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+    }
+    if (__syncthreads_or(nan) && threadIdx.x == 0) atomicOr(err, FAB_ERROR_NAN);
+    if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kMmThreads / 32; ++w) {
+            mn = smn[w] < mn ? smn[w] : mn;
+            mx = smx[w] > mx ? smx[w] : mx;
+        }
+        pmin[s * nchunk + c] = mn;
+        pmax[s * nchunk + c] = mx;
+    }
+}
+
+template <typename T>
+__global__ void k_quant_params(const T* __restrict__ pmin, const T* __restrict__ pmax, int nchunk, int64_t n_stream,
+                               const T* __restrict__ quanta, T* __restrict__ offsets, T* __restrict__ gains) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_stream) return;
+    T mn = pmin[s * nchunk], mx = pmax[s * nchunk];
+    for (int c = 1; c < nchunk; ++c) {
+        T a = pmin[s * nchunk + c], b = pmax[s * nchunk + c];
+        mn = a < mn ? a : mn;
+        mx = b > mx ? b : mx;
+    }
+    if constexpr (sizeof(T) == 4) quant_params_f32(mn, mx, quanta != nullptr, quanta ? quanta[s] : 0.f, &offsets[s], &gains[s]);
+    else quant_params_f64(mn, mx, quanta != nullptr, quanta ? quanta[s] : 0., &offsets[s], &gains[s]);
+}
+
+template <typename T, typename I>
+__global__ void __launch_bounds__(256) k_quantise(const T* __restrict__ data, int64_t stream_size, int64_t per_cta,
+                                                  const T* __restrict__ offsets, const T* __restrict__ gains,
+                                                  I* __restrict__ out) {
+    const int64_t s = blockIdx.y;
+    const T off = offsets[s], gain = gains[s];
+    const int64_t lo = (int64_t)blockIdx.x * per_cta;
+    const int64_t hi = lo + per_cta < stream_size ? lo + per_cta : stream_size;
+    const T* p = data + s * stream_size;
+    I* o = out + s * stream_size;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += 256) {
+        if constexpr (sizeof(T) == 4) o[i] = quant_f32(p[i], off, gain);
+        else o[i] = quant_f64(p[i], off, gain);
+    }
+}
+
+// int -> float (utils.c:330-368).  `in` and `out` may alias (same element size).
+template <typename I, typename T>
+__global__ void __launch_bounds__(256) k_restore(const I* in, int64_t n_per_stream, int64_t per_cta,
+                                                 const T* __restrict__ offsets, const T* __restrict__ gains, T* out) {
+    const int64_t s = blockIdx.y;
+    const T off = offsets[s];
+    T coeff;
+    if constexpr (sizeof(T) == 4) coeff = restore_coeff_f32(gains[s]);
+    else coeff = restore_coeff_f64(gains[s]);
+    const int64_t lo = (int64_t)blockIdx.x * per_cta;
+    const int64_t hi = lo + per_cta < n_per_stream ? lo + per_cta : n_per_stream;
+    const I* p = in + s * n_per_stream;
+    T* o = out + s * n_per_stream;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += 256) {
+        I v = p[i];
+        if constexpr (sizeof(T) == 4) o[i] = restore_f32(v, off, coeff);
+        else o[i] = restore_f64(v, off, coeff);
+    }
+}
+
+// ---- decode stages ---------------------------------------------------------------------------------
+__global__ void k_dec_meta(const DecParams P) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < P.n_sel) meta_body(P, k);
+}
+
+constexpr int kSyncThreads = 256;
+constexpr int kSyncBytesPerThread = 64;
+
+__global__ void __launch_bounds__(kSyncThreads) k_dec_sync(const DecParams P) {
+    const int64_t k = blockIdx.y;
+    if (P.stream_flag[k] != 0 || P.meta[k].table_off >= 0) return;
+    const int64_t p0 = ((int64_t)blockIdx.x * kSyncThreads + threadIdx.x) * kSyncBytesPerThread;
+    const int64_t nb = P.nbytes[k];
+    if (p0 >= nb) return;
+    const uint8_t* buf = P.bytes + P.starts[k];
+    int64_t p1 = p0 + kSyncBytesPerThread < nb - 1 ? p0 + kSyncBytesPerThread : nb - 1;
+    uint32_t prev = buf[p0];
+    for (int64_t p = p0; p < p1; ++p) {
+        uint32_t cur = buf[p + 1];
+        if (prev == 0xFF && cur == 0xF8) sync_body(P, k, p);
+        prev = cur;
+    }
+}
+
+constexpr int kDecThreads = 128;
+
+__global__ void __launch_bounds__(kDecThreads) k_dec_frames(const DecParams P, int64_t nwin) {
+    // one thread per (stream, frame index inside the sample window)
+    int64_t idx = (int64_t)blockIdx.x * kDecThreads + threadIdx.x;
+    int64_t k = idx / nwin;
+    if (k >= P.n_sel) return;
+    if (P.stream_flag[k] != 0) return;
+    int bs = P.meta[k].blocksize;
+    int64_t j0 = P.first / bs, j1 = (P.first + P.n_decode - 1) / bs;
+    if (j1 - j0 + 1 > nwin) {  // blocksize differs from the host's hint: leave the stream to the walker
+        if (idx % nwin == 0) atomicOr(&P.stream_flag[k], 1);
+        return;
+    }
+    int64_t j = j0 + idx % nwin;
+    if (j > j1) return;
+    frame_body(P, k, j);
+}
+
+__global__ void k_dec_walker(const DecParams P) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < P.n_sel) walker_body(P, k);
+}
+
+__global__ void k_max_i64(const long long* __restrict__ v, int64_t n, long long* __restrict__ out) {
+    long long m = 0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) m = v[i] > m ? v[i] : m;
+    __shared__ long long sm[256];
+    sm[threadIdx.x] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < blockDim.x; ++i) m = sm[i] > m ? sm[i] : m;
+        *out = m;
+    }
+}
+
+// =================================================================================================
+// Context
+// =================================================================================================
+struct fab_ctx {
+    int device = -1;
+    CrcTables* d_crc = nullptr;
+    float* d_window[2] = {nullptr, nullptr};  // [0] 1152, [1] 4096
+    int* d_err = nullptr;
+    int* h_err = nullptr;  // pinned
+    unsigned char* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    int64_t launches = 0;
+    std::string last_error = "";
+    bool smem_configured = false;
+};
+
+#define FAB_CUDA(ctx, call)                                                                   \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            if (ctx) (ctx)->last_error = std::string(#call) + ": " + cudaGetErrorString(e_);  \
+            return FAB_ERROR_CUDA;                                                            \
+        }                                                                                     \
+    } while (0)
+
+static int ctx_scratch(fab_ctx* ctx, size_t bytes, unsigned char** out) {
+    if (bytes > ctx->scratch_bytes) {
+        if (ctx->scratch) {
+            FAB_CUDA(ctx, cudaDeviceSynchronize());
+            cudaFree(ctx->scratch);
+            ctx->scratch = nullptr;
+            ctx->scratch_bytes = 0;
+        }
+        size_t want = bytes + (bytes >> 2) + (1 << 20);
+        cudaError_t e = cudaMalloc((void**)&ctx->scratch, want);
+        if (e != cudaSuccess) {
+            ctx->last_error = std::string("cudaMalloc(scratch): ") + cudaGetErrorString(e);
+            cudaGetLastError();
+            return ERROR_ALLOC | FAB_ERROR_CUDA;
+        }
+        ctx->scratch_bytes = want;
+    }
+    *out = ctx->scratch;
+    return 0;
+}
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+extern "C" int fab_create(fab_ctx** out) {
+    *out = nullptr;
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { cudaGetLastError(); return FAB_ERROR_CUDA; }
+    fab_ctx* ctx = new fab_ctx();
+    ctx->device = dev;
+    CrcTables* h = new CrcTables();
+    crc_tables_init(h);
+    std::vector<float> w0(1152), w1(4096);
+    make_tukey_window(w0.data(), 1152);
+    make_tukey_window(w1.data(), 4096);
+    bool ok = cudaMalloc((void**)&ctx->d_crc, sizeof(CrcTables)) == cudaSuccess &&
+              cudaMemcpy(ctx->d_crc, h, sizeof(CrcTables), cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMalloc((void**)&ctx->d_window[0], 1152 * 4) == cudaSuccess &&
+              cudaMemcpy(ctx->d_window[0], w0.data(), 1152 * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMalloc((void**)&ctx->d_window[1], 4096 * 4) == cudaSuccess &&
+              cudaMemcpy(ctx->d_window[1], w1.data(), 4096 * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMalloc((void**)&ctx->d_err, 4) == cudaSuccess && cudaMemset(ctx->d_err, 0, 4) == cudaSuccess &&
+              cudaMallocHost((void**)&ctx->h_err, 4) == cudaSuccess;
+    delete h;
+    if (!ok) {
+        cudaGetLastError();
+        fab_destroy(ctx);
+        return FAB_ERROR_CUDA;
+    }
+    *out = ctx;
+    return 0;
+}
+
+extern "C" void fab_destroy(fab_ctx* ctx) {
+    if (!ctx) return;
+    if (ctx->d_crc) cudaFree(ctx->d_crc);
+    if (ctx->d_window[0]) cudaFree(ctx->d_window[0]);
+    if (ctx->d_window[1]) cudaFree(ctx->d_window[1]);
+    if (ctx->d_err) cudaFree(ctx->d_err);
+    if (ctx->h_err) cudaFreeHost(ctx->h_err);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    delete ctx;
+}
+
+extern "C" const char* fab_last_error(const fab_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "no context"; }
+extern "C" int64_t fab_launch_count(const fab_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int fab_finish(fab_ctx* ctx, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    FAB_CUDA(ctx, cudaMemcpyAsync(ctx->h_err, ctx->d_err, 4, cudaMemcpyDeviceToHost, st));
+    FAB_CUDA(ctx, cudaMemsetAsync(ctx->d_err, 0, 4, st));
+    FAB_CUDA(ctx, cudaStreamSynchronize(st));
+    FAB_CUDA(ctx, cudaGetLastError());
+    return *ctx->h_err;
+}
+
+// =================================================================================================
+// Encode
+// =================================================================================================
+static int dtype_channels(int dtype) { return (dtype == FAB_I64 || dtype == FAB_F64) ? 2 : 1; }
+
+extern "C" int64_t fab_encode_bound(int64_t n_stream, int64_t stream_size, int dtype, uint32_t level) {
+    if (level > 8 || n_stream <= 0 || stream_size <= 0) return 0;
+    LevelPreset lp = level_preset((int)level);
+    int nch = dtype_channels(dtype);
+    int64_t nf = (stream_size + lp.blocksize - 1) / lp.blocksize;
+    return n_stream * (stream_header_bytes((int)nf) + nf * (16 + 2 + (int64_t)nch * (lp.blocksize * 4 + 8)));
+}
+
+template <typename T>
+static int launch_quant_params(fab_ctx* ctx, const T* d_in, int64_t n_stream, int64_t stream_size, const T* d_quanta,
+                               T* d_off, T* d_gain, cudaStream_t st) {
+    int nchunk = (int)((stream_size + kMmChunk - 1) / kMmChunk);
+    unsigned char* scr;
+    size_t need = 2 * align256((size_t)n_stream * nchunk * sizeof(T));
+    int rc = ctx_scratch(ctx, need, &scr);
+    if (rc) return rc;
+    T* pmin = (T*)scr;
+    T* pmax = (T*)(scr + align256((size_t)n_stream * nchunk * sizeof(T)));
+    // gridDim.y is limited to 65535: loop over slabs of streams
+    for (int64_t s0 = 0; s0 < n_stream; s0 += 65535) {
+        int64_t ns = std::min<int64_t>(65535, n_stream - s0);
+        dim3 grid((unsigned)nchunk, (unsigned)ns);
+        k_minmax<T><<<grid, kMmThreads, 0, st>>>(d_in + s0 * stream_size, stream_size, nchunk, pmin + s0 * nchunk,
+                                                 pmax + s0 * nchunk, ctx->d_err);
+        ctx->launches++;
+    }
+    k_quant_params<T><<<(unsigned)((n_stream + 127) / 128), 128, 0, st>>>(pmin, pmax, nchunk, n_stream, d_quanta, d_off, d_gain);
+    ctx->launches++;
+    FAB_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n_stream, int64_t stream_size,
+                          uint32_t level, const void* d_quanta, void* d_offsets, void* d_gains, unsigned char* d_out,
+                          int64_t out_capacity, int64_t* d_starts, int64_t* d_nbytes, int64_t* d_total, void* stream) {
+    if (!ctx) return FAB_ERROR_CUDA;
+    // argument checks: compress.c:143-152
+    if (level > 8) return ERROR_INVALID_LEVEL;
+    if (n_stream == 0) return ERROR_ZERO_NSTREAM;
+    if (stream_size == 0) return ERROR_ZERO_STREAMSIZE;
+    if (dtype < 0 || dtype > 3) return ERROR_CONVERT_TYPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    LevelPreset lp = level_preset((int)level);
+    const int nch = dtype_channels(dtype);
+    const int64_t nf = (stream_size + lp.blocksize - 1) / lp.blocksize;
+    if (n_stream * nf > 0x7fffffffLL) return ERROR_ALLOC;  // ticket counter is 32 bit
+
+    // scratch: [min/max partials of the quantise pre-pass] | desc | ends | ticket.  Sized once up front
+    // so that the pre-pass (queued first on the same stream) and the encoder never share bytes.
+    size_t pre = 0;
+    if (dtype >= FAB_F32) {
+        int nchunk = (int)((stream_size + kMmChunk - 1) / kMmChunk);
+        pre = 2 * align256((size_t)n_stream * nchunk * (dtype == FAB_F32 ? 4 : 8));
+    }
+    size_t desc_b = align256((size_t)(n_stream * nf) * 8), ends_b = align256((size_t)n_stream * 8);
+    unsigned char* scr;
+    int rc = ctx_scratch(ctx, pre + desc_b + ends_b + 256, &scr);
+    if (rc) return rc;
+
+    if (dtype == FAB_F32) {
+        rc = launch_quant_params<float>(ctx, (const float*)d_data, n_stream, stream_size, (const float*)d_quanta,
+                                        (float*)d_offsets, (float*)d_gains, st);
+        if (rc) return rc;
+    } else if (dtype == FAB_F64) {
+        rc = launch_quant_params<double>(ctx, (const double*)d_data, n_stream, stream_size, (const double*)d_quanta,
+                                         (double*)d_offsets, (double*)d_gains, st);
+        if (rc) return rc;
+    }
+    unsigned long long* desc = (unsigned long long*)(scr + pre);
+    long long* ends = (long long*)(scr + pre + desc_b);
+    uint32_t* ticket = (uint32_t*)(scr + pre + desc_b + ends_b);
+    FAB_CUDA(ctx, cudaMemsetAsync(desc, 0, desc_b + ends_b + 256, st));
+    FAB_CUDA(ctx, cudaMemsetAsync(d_starts, 0xFF, (size_t)n_stream * 8, st));
+
+    EncParams P;
+    P.data = d_data; P.dtype = dtype; P.offsets = d_offsets; P.gains = d_gains;
+    P.n_stream = n_stream; P.stream_size = stream_size; P.nch = nch;
+    P.blocksize = lp.blocksize; P.nframes = (int)nf;
+    P.max_lpc_order = lp.max_lpc_order; P.max_porder = lp.max_porder;
+    P.qlp_precision = lp.blocksize <= 384 ? 13 : (lp.blocksize <= 1152 ? 14 : 15);
+    P.window = ctx->d_window[lp.blocksize == 1152 ? 0 : 1];
+    P.crc = ctx->d_crc;
+    P.out = d_out; P.out_capacity = out_capacity;
+    P.starts = (long long*)d_starts; P.ends = ends; P.desc = desc; P.ticket = ticket; P.err = ctx->d_err;
+    P.hdr_bytes = stream_header_bytes((int)nf);
+
+    size_t smem = enc_smem_bytes(nch);
+    if (!ctx->smem_configured) {
+        FAB_CUDA(ctx, cudaFuncSetAttribute(k_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_smem_bytes(2)));
+        ctx->smem_configured = true;
+    }
+    k_encode<<<(unsigned)(n_stream * nf), kEncThreads, smem, st>>>(P);
+    ctx->launches++;
+    k_enc_finalize<<<(unsigned)((n_stream + 255) / 256), 256, 0, st>>>((const long long*)d_starts, ends, (long long*)d_nbytes,
+                                                                     n_stream, (long long*)d_total);
+    ctx->launches++;
+    FAB_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
+// =================================================================================================
+// Decode
+// =================================================================================================
+extern "C" int fab_decode(fab_ctx* ctx, const unsigned char* d_bytes, const int64_t* d_starts, const int64_t* d_nbytes,
+                          int64_t n_stream, int64_t stream_size, int is_int64, int64_t first_sample, int64_t last_sample,
+                          void* d_out, const void* d_offsets, const void* d_gains, int64_t max_nbytes,
+                          int blocksize_hint, void* stream) {
+    if (!ctx) return FAB_ERROR_CUDA;
+    if (n_stream <= 0) return ERROR_ZERO_NSTREAM;
+    if (stream_size <= 0) return ERROR_ZERO_STREAMSIZE;
+    // decompress.c:207-222
+    int64_t first_decode = 0, n_decode = stream_size;
+    if (first_sample >= 0 && last_sample >= 0) {
+        if (last_sample > stream_size) return ERROR_DECODE_SAMPLE_RANGE;
+        if (first_sample > stream_size - 1) return ERROR_DECODE_SAMPLE_RANGE;
+        if (first_sample >= last_sample) return ERROR_DECODE_SAMPLE_RANGE;
+        first_decode = first_sample;
+        n_decode = last_sample - first_sample;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nch = is_int64 ? 2 : 1;
+    int bsh = blocksize_hint > 0 ? blocksize_hint : 4096;
+    if (bsh < 16) bsh = 16;
+    int64_t cap64 = (stream_size + bsh - 1) / bsh;
+    if (cap64 > (1 << 26)) return ERROR_ALLOC;
+    const int nframes_cap = (int)cap64;
+
+    size_t meta_b = align256((size_t)n_stream * sizeof(StreamMeta));
+    size_t fo_b = align256((size_t)n_stream * (size_t)(nframes_cap + 1) * 8);
+    size_t flag_b = align256((size_t)n_stream * 4);
+    unsigned char* scr;
+    int rc = ctx_scratch(ctx, meta_b + fo_b + flag_b + 256, &scr);
+    if (rc) return rc;
+
+    if (max_nbytes <= 0) {
+        long long* d_max = (long long*)(scr + meta_b + fo_b + flag_b);
+        k_max_i64<<<1, 256, 0, st>>>((const long long*)d_nbytes, n_stream, d_max);
+        ctx->launches++;
+        long long h = 0;
+        FAB_CUDA(ctx, cudaMemcpyAsync(&h, d_max, 8, cudaMemcpyDeviceToHost, st));
+        FAB_CUDA(ctx, cudaStreamSynchronize(st));
+        max_nbytes = h;
+    }
+
+    DecParams P;
+    P.bytes = d_bytes; P.starts = (const long long*)d_starts; P.nbytes = (const long long*)d_nbytes;
+    P.n_sel = n_stream; P.stream_size = stream_size; P.nch = nch;
+    P.first = first_decode; P.n_decode = n_decode; P.data = (int32_t*)d_out; P.crc = ctx->d_crc;
+    P.meta = (StreamMeta*)scr; P.frame_off = (long long*)(scr + meta_b); P.nframes_cap = nframes_cap;
+    P.stream_flag = (int*)(scr + meta_b + fo_b); P.err = ctx->d_err; P.verify_crc16 = 0;
+
+    k_dec_meta<<<(unsigned)((n_stream + 127) / 128), 128, 0, st>>>(P);
+    ctx->launches++;
+    {
+        int64_t per_cta = (int64_t)kSyncThreads * kSyncBytesPerThread;
+        int64_t gx = (max_nbytes + per_cta - 1) / per_cta;
+        for (int64_t s0 = 0; s0 < n_stream; s0 += 65535) {
+            int64_t ns = std::min<int64_t>(65535, n_stream - s0);
+            DecParams Q = P;
+            Q.starts += s0; Q.nbytes += s0; Q.meta += s0; Q.frame_off += s0 * (int64_t)(nframes_cap + 1); Q.stream_flag += s0;
+            Q.n_sel = ns;
+            dim3 grid((unsigned)gx, (unsigned)ns);
+            k_dec_sync<<<grid, kSyncThreads, 0, st>>>(Q);
+            ctx->launches++;
+        }
+    }
+    {
+        // frames overlapping the window, for the hinted blocksize (streams with another blocksize that
+        // need more frames than the table holds were flagged for the walker by k_dec_meta)
+        int64_t nwin = (first_decode + n_decode - 1) / bsh - first_decode / bsh + 1;
+        int64_t total = n_stream * nwin;
+        k_dec_frames<<<(unsigned)((total + kDecThreads - 1) / kDecThreads), kDecThreads, 0, st>>>(P, nwin);
+        ctx->launches++;
+    }
+    k_dec_walker<<<(unsigned)((n_stream + 31) / 32), 32, 0, st>>>(P);
+    ctx->launches++;
+
+    if (d_offsets && d_gains) {
+        int64_t per_cta = 256 * 16;
+        int64_t gx = (n_decode + per_cta - 1) / per_cta;
+        for (int64_t s0 = 0; s0 < n_stream; s0 += 65535) {
+            int64_t ns = std::min<int64_t>(65535, n_stream - s0);
+            dim3 grid((unsigned)gx, (unsigned)ns);
+            if (is_int64)
+                k_restore<long long, double><<<grid, 256, 0, st>>>((const long long*)d_out + s0 * n_decode, n_decode, per_cta,
+                                                                   (const double*)d_offsets + s0, (const double*)d_gains + s0,
+                                                                   (double*)d_out + s0 * n_decode);
+            else
+                k_restore<int32_t, float><<<grid, 256, 0, st>>>((const int32_t*)d_out + s0 * n_decode, n_decode, per_cta,
+                                                                (const float*)d_offsets + s0, (const float*)d_gains + s0,
+                                                                (float*)d_out + s0 * n_decode);
+            ctx->launches++;
+        }
+    }
+    FAB_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
+// =================================================================================================
+// Converters
+// =================================================================================================
+extern "C" int fab_float_to_int(fab_ctx* ctx, const void* d_input, int dtype, int64_t n_stream, int64_t stream_size,
+                                const void* d_quanta, void* d_output, void* d_offsets, void* d_gains, void* stream) {
+    if (!ctx) return FAB_ERROR_CUDA;
+    if (n_stream <= 0) return ERROR_ZERO_NSTREAM;
+    if (stream_size <= 0) return ERROR_ZERO_STREAMSIZE;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t per_cta = 256 * 16;
+    int64_t gx = (stream_size + per_cta - 1) / per_cta;
+    if (dtype == FAB_F32) {
+        int rc = launch_quant_params<float>(ctx, (const float*)d_input, n_stream, stream_size, (const float*)d_quanta,
+                                            (float*)d_offsets, (float*)d_gains, st);
+        if (rc) return rc;
+        for (int64_t s0 = 0; s0 < n_stream; s0 += 65535) {
+            dim3 grid((unsigned)gx, (unsigned)std::min<int64_t>(65535, n_stream - s0));
+            k_quantise<float, int32_t><<<grid, 256, 0, st>>>((const float*)d_input + s0 * stream_size, stream_size, per_cta,
+                                                             (const float*)d_offsets + s0, (const float*)d_gains + s0,
+                                                             (int32_t*)d_output + s0 * stream_size);
+            ctx->launches++;
+        }
+    } else if (dtype == FAB_F64) {
+        int rc = launch_quant_params<double>(ctx, (const double*)d_input, n_stream, stream_size, (const double*)d_quanta,
+                                             (double*)d_offsets, (double*)d_gains, st);
+        if (rc) return rc;
+        for (int64_t s0 = 0; s0 < n_stream; s0 += 65535) {
+            dim3 grid((unsigned)gx, (unsigned)std::min<int64_t>(65535, n_stream - s0));
+            k_quantise<double, long long><<<grid, 256, 0, st>>>((const double*)d_input + s0 * stream_size, stream_size, per_cta,
+                                                                (const double*)d_offsets + s0, (const double*)d_gains + s0,
+                                                                (long long*)d_output + s0 * stream_size);
+            ctx->launches++;
+        }
+    } else {
+        return ERROR_CONVERT_TYPE;
+    }
+    FAB_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int fab_int_to_float(fab_ctx* ctx, const void* d_input, int dtype, int64_t n_stream, int64_t stream_size,
+                                const void* d_offsets, const void* d_gains, void* d_output, void* stream) {
+    if (!ctx) return FAB_ERROR_CUDA;
+    if (n_stream <= 0) return ERROR_ZERO_NSTREAM;
+    if (stream_size <= 0) return ERROR_ZERO_STREAMSIZE;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t per_cta = 256 * 16;
+    int64_t gx = (stream_size + per_cta - 1) / per_cta;
+    for (int64_t s0 = 0; s0 < n_stream; s0 += 65535) {
+        dim3 grid((unsigned)gx, (unsigned)std::min<int64_t>(65535, n_stream - s0));
+        if (dtype == FAB_I32)
+            k_restore<int32_t, float><<<grid, 256, 0, st>>>((const int32_t*)d_input + s0 * stream_size, stream_size, per_cta,
+                                                            (const float*)d_offsets + s0, (const float*)d_gains + s0,
+                                                            (float*)d_output + s0 * stream_size);
+        else if (dtype == FAB_I64)
+            k_restore<long long, double><<<grid, 256, 0, st>>>((const long long*)d_input + s0 * stream_size, stream_size, per_cta,
+                                                               (const double*)d_offsets + s0, (const double*)d_gains + s0,
+                                                               (double*)d_output + s0 * stream_size);
+        else
+            return ERROR_CONVERT_TYPE;
+        ctx->launches++;
+    }
+    FAB_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
+// =================================================================================================
+// Reference-compatible host-buffer entry points (flacarray.h:209-311)
+// =================================================================================================
+namespace {
+std::mutex g_mu;
+fab_ctx* g_ctx = nullptr;
+
+fab_ctx* default_ctx() {
+    if (!g_ctx) {
+        if (fab_create(&g_ctx) != 0) g_ctx = nullptr;
+    }
+    return g_ctx;
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    bool alloc(size_t n) { return cudaMalloc(&p, n ? n : 1) == cudaSuccess; }
+};
+
+int host_encode(const void* data, int dtype, int64_t n_stream, int64_t stream_size, uint32_t level, int64_t* n_bytes,
+                int64_t* starts, unsigned char** bytes) {
+    if (level > 8) return ERROR_INVALID_LEVEL;
+    if (n_stream == 0) return ERROR_ZERO_NSTREAM;
+    if (stream_size == 0) return ERROR_ZERO_STREAMSIZE;
+    *n_bytes = 0;
+    *bytes = nullptr;
+    std::lock_guard<std::mutex> lock(g_mu);
+    fab_ctx* ctx = default_ctx();
+    if (!ctx) return FAB_ERROR_CUDA;
+    size_t in_b = (size_t)n_stream * stream_size * (dtype == FAB_I64 ? 8 : 4);
+    int64_t bound = fab_encode_bound(n_stream, stream_size, dtype, level);
+    DevBuf d_in, d_out, d_aux;
+    if (!d_in.alloc(in_b) || !d_out.alloc((size_t)bound) || !d_aux.alloc((size_t)n_stream * 16 + 64)) {
+        cudaGetLastError();
+        return ERROR_ALLOC | FAB_ERROR_CUDA;
+    }
+    int64_t* d_starts = (int64_t*)d_aux.p;
+    int64_t* d_nb = d_starts + n_stream;
+    int64_t* d_total = d_nb + n_stream;
+    if (cudaMemcpy(d_in.p, data, in_b, cudaMemcpyHostToDevice) != cudaSuccess) return FAB_ERROR_CUDA;
+    int rc = fab_encode(ctx, d_in.p, dtype, n_stream, stream_size, level, nullptr, nullptr, nullptr,
+                        (unsigned char*)d_out.p, bound, d_starts, d_nb, d_total, nullptr);
+    if (rc) return rc;
+    rc = fab_finish(ctx, nullptr);
+    if (rc) return rc;
+    int64_t total = 0;
+    if (cudaMemcpy(&total, d_total, 8, cudaMemcpyDeviceToHost) != cudaSuccess) return FAB_ERROR_CUDA;
+    if (cudaMemcpy(starts, d_starts, (size_t)n_stream * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return FAB_ERROR_CUDA;
+    unsigned char* hb = (unsigned char*)malloc((size_t)total);
+    if (!hb) return ERROR_ALLOC;
+    if (cudaMemcpy(hb, d_out.p, (size_t)total, cudaMemcpyDeviceToHost) != cudaSuccess) { free(hb); return FAB_ERROR_CUDA; }
+    *n_bytes = total;
+    *bytes = hb;
+    return ERROR_NONE;
+}
+
+int host_decode(const unsigned char* bytes, const int64_t* starts, const int64_t* nbytes, int64_t n_stream,
+                int64_t stream_size, int is_int64, int64_t first, int64_t last, void* data) {
+    if (n_stream <= 0) return ERROR_ZERO_NSTREAM;
+    int64_t n_decode = stream_size;
+    if (first >= 0 && last >= 0) {
+        if (last > stream_size || first > stream_size - 1 || first >= last) return ERROR_DECODE_SAMPLE_RANGE;
+        n_decode = last - first;
+    }
+    std::lock_guard<std::mutex> lock(g_mu);
+    fab_ctx* ctx = default_ctx();
+    if (!ctx) return FAB_ERROR_CUDA;
+    // the selected windows may be scattered (keep mask): upload the covering byte range only
+    int64_t lo = INT64_MAX, hi = 0, mx = 0;
+    for (int64_t i = 0; i < n_stream; ++i) {
+        lo = std::min(lo, starts[i]);
+        hi = std::max(hi, starts[i] + nbytes[i]);
+        mx = std::max(mx, nbytes[i]);
+    }
+    std::vector<int64_t> rel((size_t)n_stream);
+    for (int64_t i = 0; i < n_stream; ++i) rel[(size_t)i] = starts[i] - lo;
+    size_t out_b = (size_t)n_stream * n_decode * (is_int64 ? 8 : 4);
+    DevBuf d_b, d_aux, d_o;
+    if (!d_b.alloc((size_t)(hi - lo)) || !d_aux.alloc((size_t)n_stream * 16) || !d_o.alloc(out_b)) {
+        cudaGetLastError();
+        return ERROR_ALLOC | FAB_ERROR_CUDA;
+    }
+    int64_t* d_starts = (int64_t*)d_aux.p;
+    int64_t* d_nb = d_starts + n_stream;
+    if (cudaMemcpy(d_b.p, bytes + lo, (size_t)(hi - lo), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(d_starts, rel.data(), (size_t)n_stream * 8, cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(d_nb, nbytes, (size_t)n_stream * 8, cudaMemcpyHostToDevice) != cudaSuccess)
+        return FAB_ERROR_CUDA;
+    int bs_hint = 0;
+    if (nbytes[0] >= 12 && memcmp(bytes + starts[0], "fLaC", 4) == 0) bs_hint = (bytes[starts[0] + 8] << 8) | bytes[starts[0] + 9];
+    int rc = fab_decode(ctx, (const unsigned char*)d_b.p, d_starts, d_nb, n_stream, stream_size, is_int64, first, last,
+                        d_o.p, nullptr, nullptr, mx, bs_hint, nullptr);
+    if (rc) return rc;
+    rc = fab_finish(ctx, nullptr);
+    if (rc) return rc;
+    if (cudaMemcpy(data, d_o.p, out_b, cudaMemcpyDeviceToHost) != cudaSuccess) return FAB_ERROR_CUDA;
+    return ERROR_NONE;
+}
+
+template <typename T, typename I>
+int host_float_to_int(const T* input, int64_t n_stream, int64_t stream_size, const T* quanta, I* output, T* offsets,
+                      T* gains) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    fab_ctx* ctx = default_ctx();
+    if (!ctx) return FAB_ERROR_CUDA;
+    size_t n = (size_t)n_stream * stream_size;
+    DevBuf d_in, d_out, d_aux;
+    if (!d_in.alloc(n * sizeof(T)) || !d_out.alloc(n * sizeof(I)) || !d_aux.alloc((size_t)n_stream * 3 * sizeof(T))) {
+        cudaGetLastError();
+        return ERROR_ALLOC | FAB_ERROR_CUDA;
+    }
+    T* d_off = (T*)d_aux.p;
+    T* d_gain = d_off + n_stream;
+    T* d_q = d_gain + n_stream;
+    if (cudaMemcpy(d_in.p, input, n * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return FAB_ERROR_CUDA;
+    if (quanta && cudaMemcpy(d_q, quanta, (size_t)n_stream * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return FAB_ERROR_CUDA;
+    int rc = fab_float_to_int(ctx, d_in.p, sizeof(T) == 4 ? FAB_F32 : FAB_F64, n_stream, stream_size, quanta ? d_q : nullptr,
+                              d_out.p, d_off, d_gain, nullptr);
+    if (rc) return rc;
+    rc = fab_finish(ctx, nullptr);
+    rc &= ~FAB_ERROR_NAN;  // the reference's C function does not look for NaNs (utils.py:268 does, before calling)
+    if (rc) return rc;
+    if (cudaMemcpy(output, d_out.p, n * sizeof(I), cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(offsets, d_off, (size_t)n_stream * sizeof(T), cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(gains, d_gain, (size_t)n_stream * sizeof(T), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return FAB_ERROR_CUDA;
+    return ERROR_NONE;
+}
+
+template <typename I, typename T>
+void host_int_to_float(const I* input, int64_t n_stream, int64_t stream_size, const T* offsets, const T* gains, T* output) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    fab_ctx* ctx = default_ctx();
+    size_t n = (size_t)n_stream * stream_size;
+    DevBuf d_in, d_out, d_aux;
+    if (!ctx || !d_in.alloc(n * sizeof(I)) || !d_out.alloc(n * sizeof(T)) || !d_aux.alloc((size_t)n_stream * 2 * sizeof(T))) {
+        fprintf(stderr, "flacarray_b200: int_to_float failed: no CUDA device or out of memory\n");
+        abort();  // the reference signature returns void: fail loudly rather than return garbage
+    }
+    T* d_off = (T*)d_aux.p;
+    T* d_gain = d_off + n_stream;
+    cudaMemcpy(d_in.p, input, n * sizeof(I), cudaMemcpyHostToDevice);
+    cudaMemcpy(d_off, offsets, (size_t)n_stream * sizeof(T), cudaMemcpyHostToDevice);
+    cudaMemcpy(d_gain, gains, (size_t)n_stream * sizeof(T), cudaMemcpyHostToDevice);
+    int rc = fab_int_to_float(ctx, d_in.p, sizeof(I) == 4 ? FAB_I32 : FAB_I64, n_stream, stream_size, d_off, d_gain, d_out.p, nullptr);
+    if (!rc) rc = fab_finish(ctx, nullptr);
+    if (rc || cudaMemcpy(output, d_out.p, n * sizeof(T), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        fprintf(stderr, "flacarray_b200: int_to_float failed (code %d): %s\n", rc, fab_last_error(ctx));
+        abort();
+    }
+}
+}  // namespace
+
+extern "C" {
+int encode_i32(int32_t* const data, int64_t n_stream, int64_t stream_size, uint32_t level, int64_t* n_bytes,
+               int64_t* starts, unsigned char** bytes) {
+    return host_encode(data, FAB_I32, n_stream, stream_size, level, n_bytes, starts, bytes);
+}
+int encode_i32_threaded(int32_t* const data, int64_t n_stream, int64_t stream_size, uint32_t level, int64_t* n_bytes,
+                        int64_t* starts, unsigned char** bytes) {
+    return host_encode(data, FAB_I32, n_stream, stream_size, level, n_bytes, starts, bytes);
+}
+int encode_i64(int64_t* const data, int64_t n_stream, int64_t stream_size, uint32_t level, int64_t* n_bytes,
+               int64_t* starts, unsigned char** bytes) {
+    return host_encode(data, FAB_I64, n_stream, stream_size, level, n_bytes, starts, bytes);
+}
+int encode_i64_threaded(int64_t* const data, int64_t n_stream, int64_t stream_size, uint32_t level, int64_t* n_bytes,
+                        int64_t* starts, unsigned char** bytes) {
+    return host_encode(data, FAB_I64, n_stream, stream_size, level, n_bytes, starts, bytes);
+}
+int decode_i32(unsigned char* const bytes, int64_t* const starts, int64_t* const nbytes, int64_t n_stream,
+               int64_t stream_size, int64_t first_sample, int64_t last_sample, int32_t* data, bool) {
+    return host_decode(bytes, starts, nbytes, n_stream, stream_size, 0, first_sample, last_sample, data);
+}
+int decode_i64(unsigned char* const bytes, int64_t* const starts, int64_t* const nbytes, int64_t n_stream,
+               int64_t stream_size, int64_t first_sample, int64_t last_sample, int64_t* data, bool) {
+    return host_decode(bytes, starts, nbytes, n_stream, stream_size, 1, first_sample, last_sample, data);
+}
+int float32_to_int32(float const* input, int64_t n_stream, int64_t stream_size, float const* quanta, int32_t* output,
+                     float* offsets, float* gains) {
+    return host_float_to_int<float, int32_t>(input, n_stream, stream_size, quanta, output, offsets, gains);
+}
+int float64_to_int64(double const* input, int64_t n_stream, int64_t stream_size, double const* quanta, int64_t* output,
+                     double* offsets, double* gains) {
+    return host_float_to_int<double, long long>(input, n_stream, stream_size, quanta, (long long*)output, offsets, gains);
+}
+void int64_to_float64(int64_t const* input, int64_t n_stream, int64_t stream_size, double const* offsets,
+                      double const* gains, double* output) {
+    host_int_to_float<long long, double>((const long long*)input, n_stream, stream_size, offsets, gains, output);
+}
+void int32_to_float32(int32_t const* input, int64_t n_stream, int64_t stream_size, float const* offsets,
+                      float const* gains, float* output) {
+    host_int_to_float<int32_t, float>(input, n_stream, stream_size, offsets, gains, output);
+}
+}

@@ -1,0 +1,199 @@
+// fa_simt.h -- thin SIMT vocabulary used by every kernel body in this directory.
+//
+// Compiled by nvcc (sm_100a) every name below maps 1:1 onto a CUDA intrinsic.  Compiled by a
+// plain host C++ compiler (tests/hostsim only -- NEVER part of the shipped library) the same names
+// are backed by an OS-thread-per-CUDA-thread emulator so that the block-cooperative kernel bodies
+// can be unit-tested in the GPU-less build container before GPU minutes are spent.  The emulator
+// is test infrastructure: libflacarray_b200.so contains only the CUDA instantiation and there is
+// no CPU fallback in the product.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+// ------------------------------------------------------------------------------------------------
+// CUDA instantiation
+// ------------------------------------------------------------------------------------------------
+#define FA_D __device__ __forceinline__
+#define FA_DNOINL __device__ __noinline__
+#define FA_SHARED_BASE(name) extern __shared__ __align__(16) unsigned char name[]
+#define FA_RESTRICT __restrict__
+
+namespace fa {
+FA_D int tid() { return (int)threadIdx.x; }
+FA_D int nthreads() { return (int)blockDim.x; }
+FA_D int lane() { return (int)(threadIdx.x & 31); }
+FA_D int warp() { return (int)(threadIdx.x >> 5); }
+FA_D void sync() { __syncthreads(); }
+FA_D void syncwarp() { __syncwarp(); }
+FA_D uint32_t shfl(uint32_t v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+FA_D uint32_t shfl_xor(uint32_t v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+FA_D uint32_t shfl_up(uint32_t v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+FA_D uint32_t shfl_down(uint32_t v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+FA_D uint32_t ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+FA_D int clz32(uint32_t v) { return __clz((int)v); }
+FA_D int clz64(uint64_t v) { return __clzll((long long)v); }
+FA_D int ctz32(uint32_t v) { return __ffs((int)v) - 1; }
+FA_D int popc32(uint32_t v) { return __popc(v); }
+FA_D uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+FA_D uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_l(lo, hi, s); }
+FA_D void atom_or_shared(uint32_t* p, uint32_t v) { atomicOr(p, v); }
+FA_D void atom_add_shared64(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }
+FA_D void atom_or_shared_u32(uint32_t* p, uint32_t v) { atomicOr(p, v); }
+FA_D uint32_t atom_add_global(uint32_t* p, uint32_t v) { return atomicAdd(p, v); }
+FA_D void atom_or_global(int* p, int v) { atomicOr(p, v); }
+FA_D long long atom_cas_global64(long long* p, long long cmp, long long v) {
+    return (long long)atomicCAS((unsigned long long*)p, (unsigned long long)cmp, (unsigned long long)v);
+}
+FA_D int atom_cas_global32(int* p, int cmp, int v) { return atomicCAS(p, cmp, v); }
+FA_D void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+FA_D unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+FA_D void spin_pause() { __nanosleep(20); }
+FA_D uint32_t ldg32(const uint32_t* p) { return __ldg(p); }
+// float ops with the rounding and (non-)contraction spelled out
+FA_D float fadd(float a, float b) { return __fadd_rn(a, b); }
+FA_D float fsub(float a, float b) { return __fsub_rn(a, b); }
+FA_D float fmul(float a, float b) { return __fmul_rn(a, b); }
+FA_D float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+FA_D double dadd(double a, double b) { return __dadd_rn(a, b); }
+FA_D double dsub(double a, double b) { return __dsub_rn(a, b); }
+FA_D double dmul(double a, double b) { return __dmul_rn(a, b); }
+FA_D double ddiv(double a, double b) { return __ddiv_rn(a, b); }
+FA_D double dfma(double a, double b, double c) { return __fma_rn(a, b, c); }
+}  // namespace fa
+
+#else
+// ------------------------------------------------------------------------------------------------
+// Host emulation (tests/hostsim only)
+// ------------------------------------------------------------------------------------------------
+#include <atomic>
+#include <barrier>
+#include <cmath>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#define FA_D inline
+#define FA_DNOINL inline
+#define FA_RESTRICT __restrict__
+
+namespace fasim {
+struct Block {
+    int nthreads;
+    std::barrier<> bar;
+    std::vector<std::unique_ptr<std::barrier<>>> wbar;
+    std::vector<uint64_t> xchg;  // one slot per thread
+    std::vector<unsigned char> smem;
+    explicit Block(int n, size_t smem_bytes) : nthreads(n), bar(n), xchg((size_t)n), smem(smem_bytes + 16) {
+        for (int w = 0; w < (n + 31) / 32; ++w) {
+            int cnt = (w + 1) * 32 <= n ? 32 : n - w * 32;
+            wbar.emplace_back(new std::barrier<>(cnt));
+        }
+    }
+};
+struct ThreadCtx {
+    Block* blk = nullptr;
+    int tid = 0;
+    int bid = 0;
+};
+extern thread_local ThreadCtx tls;
+
+// Run `body(block_index)` for every block sequentially; each block = nthreads OS threads.
+template <class F>
+void launch(int nblocks, int nthreads, size_t smem_bytes, F body) {
+    for (int b = 0; b < nblocks; ++b) {
+        Block blk(nthreads, smem_bytes);
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; ++t) {
+            th.emplace_back([&, t] {
+                tls.blk = &blk;
+                tls.tid = t;
+                tls.bid = b;
+                body(b);
+            });
+        }
+        for (auto& x : th) x.join();
+    }
+}
+inline unsigned char* smem() {
+    uintptr_t p = (uintptr_t)tls.blk->smem.data();
+    return (unsigned char*)((p + 15) & ~(uintptr_t)15);
+}
+}  // namespace fasim
+
+#define FA_SHARED_BASE(name) unsigned char* name = fasim::smem()
+
+namespace fa {
+inline int tid() { return fasim::tls.tid; }
+inline int nthreads() { return fasim::tls.blk->nthreads; }
+inline int lane() { return fasim::tls.tid & 31; }
+inline int warp() { return fasim::tls.tid >> 5; }
+inline void sync() { fasim::tls.blk->bar.arrive_and_wait(); }
+inline void syncwarp() { fasim::tls.blk->wbar[(size_t)warp()]->arrive_and_wait(); }
+inline uint64_t xchg_(uint64_t v, int src_lane) {
+    auto* b = fasim::tls.blk;
+    int base = fasim::tls.tid & ~31;
+    b->xchg[(size_t)fasim::tls.tid] = v;
+    syncwarp();
+    int s = base + (src_lane & 31);
+    uint64_t r = s < b->nthreads ? b->xchg[(size_t)s] : v;
+    syncwarp();
+    return r;
+}
+inline uint32_t shfl(uint32_t v, int src) { return (uint32_t)xchg_(v, src); }
+inline uint32_t shfl_xor(uint32_t v, int m) { return (uint32_t)xchg_(v, lane() ^ m); }
+inline uint32_t shfl_up(uint32_t v, int d) { return lane() - d >= 0 ? (uint32_t)xchg_(v, lane() - d) : ((void)xchg_(v, lane()), v); }
+inline uint32_t shfl_down(uint32_t v, int d) { return lane() + d < 32 ? (uint32_t)xchg_(v, lane() + d) : ((void)xchg_(v, lane()), v); }
+inline uint32_t ballot(bool p) {
+    uint32_t r = 0;
+    auto* b = fasim::tls.blk;
+    int base = fasim::tls.tid & ~31;
+    b->xchg[(size_t)fasim::tls.tid] = p ? 1u : 0u;
+    syncwarp();
+    for (int l = 0; l < 32 && base + l < b->nthreads; ++l) r |= (uint32_t)b->xchg[(size_t)(base + l)] << l;
+    syncwarp();
+    return r;
+}
+inline int clz32(uint32_t v) { return v ? __builtin_clz(v) : 32; }
+inline int clz64(uint64_t v) { return v ? __builtin_clzll(v) : 64; }
+inline int ctz32(uint32_t v) { return v ? __builtin_ctz(v) : -1; }
+inline int popc32(uint32_t v) { return __builtin_popcount(v); }
+inline uint32_t bswap32(uint32_t v) { return __builtin_bswap32(v); }
+inline uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t s) {
+    s &= 31;
+    return s ? (hi << s) | (lo >> (32 - s)) : hi;
+}
+inline void atom_or_shared(uint32_t* p, uint32_t v) { __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+inline void atom_add_shared64(unsigned long long* p, unsigned long long v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+inline uint32_t atom_add_global(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline void atom_or_global(int* p, int v) { __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+inline long long atom_cas_global64(long long* p, long long cmp, long long v) {
+    __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+    return cmp;
+}
+inline int atom_cas_global32(int* p, int cmp, int v) {
+    __atomic_compare_exchange_n(p, &cmp, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+    return cmp;
+}
+inline void st_release_u64(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
+inline unsigned long long ld_acquire_u64(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline void spin_pause() { std::this_thread::yield(); }
+inline uint32_t ldg32(const uint32_t* p) { return *p; }
+// host build is compiled with -ffp-contract=off so these are the IEEE single operations
+inline float fadd(float a, float b) { return a + b; }
+inline float fsub(float a, float b) { return a - b; }
+inline float fmul(float a, float b) { return a * b; }
+inline float fdiv(float a, float b) { return a / b; }
+inline double dadd(double a, double b) { return a + b; }
+inline double dsub(double a, double b) { return a - b; }
+inline double dmul(double a, double b) { return a * b; }
+inline double ddiv(double a, double b) { return a / b; }
+inline double dfma(double a, double b, double c) { return std::fma(a, b, c); }
+}  // namespace fa
+#endif

@@ -1,0 +1,162 @@
+// hostsim.cpp -- TEST HARNESS ONLY.  Compiles the kernel bodies of flacarray_b200/csrc for the host
+// with the OS-thread SIMT emulator of fa_simt.h so their logic can be unit-tested in the GPU-less
+// build container (bit packing, CRC, look-back bookkeeping, frame index, decode).  This file is never
+// linked into libflacarray_b200.so and the Python package never loads it: the product has no CPU path.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../flacarray_b200/csrc/fa_decode.h"
+#include "../../flacarray_b200/csrc/fa_encode.h"
+
+namespace fasim {
+thread_local ThreadCtx tls;
+}
+
+using namespace fa;
+
+static CrcTables g_crc;
+static bool g_crc_ready = false;
+static const CrcTables* crc() {
+    if (!g_crc_ready) { crc_tables_init(&g_crc); g_crc_ready = true; }
+    return &g_crc;
+}
+
+extern "C" {
+
+int64_t hs_encode_bound(int64_t n_stream, int64_t stream_size, int nch, int level) {
+    LevelPreset lp = level_preset(level);
+    int64_t nf = (stream_size + lp.blocksize - 1) / lp.blocksize;
+    return n_stream * (stream_header_bytes((int)nf) + nf * (16 + 2 + (int64_t)nch * (lp.blocksize * 4 + 8)));
+}
+
+// dtype: 0 i32, 1 i64, 2 f32, 3 f64.  quanta may be NULL (auto) for float input.
+int hs_encode(const void* data, int dtype, int64_t n_stream, int64_t stream_size, int level, const void* quanta,
+              uint8_t* out, int64_t cap, long long* starts, long long* nbytes, void* offsets, void* gains,
+              long long* total) {
+    LevelPreset lp = level_preset(level);
+    int nch = (dtype == kI64 || dtype == kF64) ? 2 : 1;
+    int nf = (int)((stream_size + lp.blocksize - 1) / lp.blocksize);
+    std::vector<float> window((size_t)lp.blocksize);
+    make_tukey_window(window.data(), lp.blocksize);
+    if (dtype == kF32) {
+        const float* d = (const float*)data;
+        for (int64_t s = 0; s < n_stream; ++s) {
+            float mn = d[s * stream_size], mx = mn;
+            for (int64_t i = 1; i < stream_size; ++i) { float v = d[s * stream_size + i]; if (v < mn) mn = v; if (v > mx) mx = v; }
+            quant_params_f32(mn, mx, quanta != nullptr, quanta ? ((const float*)quanta)[s] : 0.f, (float*)offsets + s, (float*)gains + s);
+        }
+    } else if (dtype == kF64) {
+        const double* d = (const double*)data;
+        for (int64_t s = 0; s < n_stream; ++s) {
+            double mn = d[s * stream_size], mx = mn;
+            for (int64_t i = 1; i < stream_size; ++i) { double v = d[s * stream_size + i]; if (v < mn) mn = v; if (v > mx) mx = v; }
+            quant_params_f64(mn, mx, quanta != nullptr, quanta ? ((const double*)quanta)[s] : 0., (double*)offsets + s, (double*)gains + s);
+        }
+    }
+    std::vector<long long> ends((size_t)n_stream, 0);
+    std::vector<unsigned long long> desc((size_t)(n_stream * nf), 0ull);
+    for (int64_t s = 0; s < n_stream; ++s) starts[s] = -1;
+    uint32_t ticket = 0;
+    int err = 0;
+    EncParams P;
+    P.data = data; P.dtype = dtype; P.offsets = offsets; P.gains = gains;
+    P.n_stream = n_stream; P.stream_size = stream_size; P.nch = nch;
+    P.blocksize = lp.blocksize; P.nframes = nf;
+    P.max_lpc_order = lp.max_lpc_order; P.max_porder = lp.max_porder;
+    P.qlp_precision = lp.blocksize <= 384 ? 13 : (lp.blocksize <= 1152 ? 14 : 15);
+    P.window = window.data(); P.crc = crc();
+    P.out = out; P.out_capacity = cap; P.starts = starts; P.ends = ends.data(); P.desc = desc.data();
+    P.ticket = &ticket; P.err = &err; P.hdr_bytes = stream_header_bytes(nf);
+    fasim::launch((int)(n_stream * nf), kEncThreads, enc_smem_bytes(nch), [&](int) {
+        encode_frame_cta(P, fasim::smem());
+    });
+    for (int64_t s = 0; s < n_stream; ++s) nbytes[s] = ends[s] - starts[s];
+    *total = n_stream ? ends[n_stream - 1] : 0;
+    return err;
+}
+
+// mode 0: parallel-path emulation (meta -> sync scan -> per-frame decode -> walker for flagged streams)
+// mode 1: walker only
+int hs_decode(const uint8_t* bytes, const long long* starts, const long long* nbytes, int64_t n_sel,
+              int64_t stream_size, int nch, int64_t first, int64_t last, int32_t* data, int mode, int* n_walked) {
+    int64_t n_decode = stream_size;
+    int64_t first_decode = 0;
+    if (first >= 0 && last >= 0) {
+        if (last > stream_size || first > stream_size - 1 || first >= last) return kErrDecodeSampleRange;
+        first_decode = first;
+        n_decode = last - first;
+    }
+    int nframes_cap = (int)((stream_size + 15) / 16) + 1;  // smallest legal blocksize is 16
+    if (nframes_cap > (1 << 22)) nframes_cap = 1 << 22;
+    std::vector<StreamMeta> meta((size_t)n_sel);
+    std::vector<long long> fo((size_t)n_sel * (size_t)(nframes_cap + 1), -1);
+    std::vector<int> flag((size_t)n_sel, 0);
+    int err = 0;
+    DecParams P;
+    P.bytes = bytes; P.starts = starts; P.nbytes = nbytes; P.n_sel = n_sel; P.stream_size = stream_size;
+    P.nch = nch; P.first = first_decode; P.n_decode = n_decode; P.data = data; P.crc = crc();
+    P.meta = meta.data(); P.frame_off = fo.data(); P.nframes_cap = nframes_cap; P.stream_flag = flag.data();
+    P.err = &err; P.verify_crc16 = 0;
+    fasim::launch(1, 1, 0, [&](int) {
+        for (int64_t k = 0; k < n_sel; ++k) meta_body(P, k);
+        if (mode == 1) for (int64_t k = 0; k < n_sel; ++k) if (flag[(size_t)k] == 0) flag[(size_t)k] = 1;
+        if (mode == 0) {
+            for (int64_t k = 0; k < n_sel; ++k)
+                for (int64_t p = 0; p < nbytes[k]; ++p) sync_body(P, k, p);
+            for (int64_t k = 0; k < n_sel; ++k) {
+                if (flag[(size_t)k]) continue;
+                int bs = meta[(size_t)k].blocksize;
+                int64_t j0 = first_decode / bs, j1 = (first_decode + n_decode - 1) / bs;
+                for (int64_t j = j0; j <= j1; ++j) frame_body(P, k, j);
+            }
+        }
+        int walked = 0;
+        for (int64_t k = 0; k < n_sel; ++k) { if (flag[(size_t)k] && flag[(size_t)k] != 4) walked++; walker_body(P, k); }
+        if (n_walked) *n_walked = walked;
+    });
+    return err;
+}
+
+int hs_float_to_int(const void* data, int is64, int64_t n_stream, int64_t stream_size, const void* quanta, void* out,
+                    void* offsets, void* gains) {
+    for (int64_t s = 0; s < n_stream; ++s) {
+        if (!is64) {
+            const float* d = (const float*)data + s * stream_size;
+            float mn = d[0], mx = d[0];
+            for (int64_t i = 1; i < stream_size; ++i) { if (d[i] < mn) mn = d[i]; if (d[i] > mx) mx = d[i]; }
+            float off, gain;
+            quant_params_f32(mn, mx, quanta != nullptr, quanta ? ((const float*)quanta)[s] : 0.f, &off, &gain);
+            ((float*)offsets)[s] = off; ((float*)gains)[s] = gain;
+            for (int64_t i = 0; i < stream_size; ++i) ((int32_t*)out)[s * stream_size + i] = quant_f32(d[i], off, gain);
+        } else {
+            const double* d = (const double*)data + s * stream_size;
+            double mn = d[0], mx = d[0];
+            for (int64_t i = 1; i < stream_size; ++i) { if (d[i] < mn) mn = d[i]; if (d[i] > mx) mx = d[i]; }
+            double off, gain;
+            quant_params_f64(mn, mx, quanta != nullptr, quanta ? ((const double*)quanta)[s] : 0., &off, &gain);
+            ((double*)offsets)[s] = off; ((double*)gains)[s] = gain;
+            for (int64_t i = 0; i < stream_size; ++i) ((long long*)out)[s * stream_size + i] = quant_f64(d[i], off, gain);
+        }
+    }
+    return 0;
+}
+
+void hs_int_to_float(const void* data, int is64, int64_t n_stream, int64_t stream_size, const void* offsets,
+                     const void* gains, void* out) {
+    for (int64_t s = 0; s < n_stream; ++s) {
+        if (!is64) {
+            float c = restore_coeff_f32(((const float*)gains)[s]);
+            for (int64_t i = 0; i < stream_size; ++i)
+                ((float*)out)[s * stream_size + i] = restore_f32(((const int32_t*)data)[s * stream_size + i], ((const float*)offsets)[s], c);
+        } else {
+            double c = restore_coeff_f64(((const double*)gains)[s]);
+            for (int64_t i = 0; i < stream_size; ++i)
+                ((double*)out)[s * stream_size + i] = restore_f64(((const long long*)data)[s * stream_size + i], ((const double*)offsets)[s], c);
+        }
+    }
+}
+
+uint32_t hs_crc16(const uint8_t* p, int64_t n) { return crc16_bytes(crc(), p, n); }
+}

@@ -1,0 +1,146 @@
+"""GPU ports of the reference's own tests (src/flacarray/tests/{bindings,utils,array}.py): round-trip
+identities, slice semantics, float tolerances, FlacArray slicing shapes and keep masks."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fa():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import __graft_entry__ as g
+
+    g.build()
+    import flacarray_b200
+
+    return flacarray_b200
+
+
+def test_wrappers_i32_i64(fa):
+    """reference tests/bindings.py:27-163"""
+    from flacarray_b200 import libflacarray as lf
+
+    rng = np.random.default_rng()
+    n_stream, stream_size = 3, 10000
+    for dt, enc, dec, ext in ((np.int32, lf.wrap_encode_i32_threaded, lf.wrap_decode_i32, [2147483647, -2147483647]),
+                              (np.int64, lf.wrap_encode_i64_threaded, lf.wrap_decode_i64,
+                               [2 ** 63 - 1, -(2 ** 63 - 1), 2 ** 32, -2 ** 32])):
+        ii = np.iinfo(dt)
+        data = rng.integers(ii.min, ii.max, (n_stream * stream_size), dtype=np.int64).astype(dt)
+        data[:len(ext)] = ext
+        comp, starts, nbytes = enc(data, n_stream, stream_size, 5)
+        out = dec(comp, starts, nbytes, n_stream, stream_size, -1, -1, True)
+        assert np.array_equal(out, data)
+        first, last = stream_size // 2 - 5, stream_size // 2 + 5
+        out = dec(comp, starts, nbytes, n_stream, stream_size, first, last, True)
+        assert np.array_equal(out.reshape(n_stream, -1), data.reshape(n_stream, -1)[:, first:last])
+
+
+def test_encode_decode_roundtrip(fa):
+    """reference tests/bindings.py:165-230"""
+    from flacarray_b200.demo import create_fake_data
+    from flacarray_b200.libflacarray import decode_flac, encode_flac
+
+    for shape in ((4, 3, 1000), (10000,)):
+        for dt in (np.int32, np.int64):
+            data, _ = create_fake_data(shape, sigma=None, dtype=dt)
+            comp, starts, nbytes = encode_flac(data, 5)
+            assert starts.shape == (shape[:-1] if len(shape) > 1 else (1,))
+            out = decode_flac(comp, starts, nbytes, shape[-1], is_int64=(dt == np.int64))
+            assert np.array_equal(out.reshape(data.shape), data)
+            first, last = shape[-1] // 2 - 5, shape[-1] // 2 + 5
+            out = decode_flac(comp, starts, nbytes, shape[-1], first_sample=first, last_sample=last, is_int64=(dt == np.int64))
+            assert np.array_equal(out.reshape(data.shape[:-1] + (10,)), data[..., first:last])
+
+
+def test_float_to_int_roundtrips(fa):
+    """reference tests/utils.py:22-108"""
+    from flacarray_b200.demo import create_fake_data
+
+    data, _ = create_fake_data((4, 3, 1000), sigma=1.0, dtype=np.float64)
+    for kw, tol in (({"quanta": 1e-16}, 1e-14), ({"quanta": 1e-5}, 1e-5), ({"precision": 5}, 1e-4),
+                    ({"precision": 5 * np.ones((4, 3), dtype=np.int32)}, 1e-4)):
+        idata, off, gain = fa.float_to_int(data, **kw)
+        assert idata.dtype == np.int64 and off.shape == (4, 3)
+        assert np.allclose(fa.int_to_float(idata, off, gain), data, rtol=0, atol=tol * 10)
+    d32 = data.astype(np.float32)
+    for kw, tol in (({"quanta": 1e-6}, 1e-5), ({"quanta": 1e-5}, 1e-5), ({"precision": 5}, 1e-4)):
+        idata, off, gain = fa.float_to_int(d32, **kw)
+        assert idata.dtype == np.int32
+        assert np.allclose(fa.int_to_float(idata, off, gain), d32, rtol=0, atol=max(tol, 1e-5) * 10)
+
+
+def test_helpers_all_dtypes(fa):
+    """reference tests/array.py:26-146"""
+    from flacarray_b200.demo import create_fake_data
+
+    for shape in ((4, 3, 1000), (10000,)):
+        first, last = shape[-1] // 2 - 5, shape[-1] // 2 + 5
+        for dt, kw, tol in ((np.int32, {}, 0), (np.int64, {}, 0), (np.float32, {"quanta": 1e-6}, 1e-5),
+                            (np.float64, {"quanta": 1e-7}, 1e-6)):
+            sig = None if np.dtype(dt).kind == "i" else 1.0
+            data, _ = create_fake_data(shape, sigma=sig, dtype=dt)
+            comp, starts, nbytes, off, gain = fa.array_compress(data, level=5, **kw)
+            is64 = np.dtype(dt).itemsize == 8
+            out = fa.array_decompress(comp, shape[-1], starts, nbytes, stream_offsets=off, stream_gains=gain, is_int64=is64)
+            assert out.shape == data.shape and out.dtype == np.dtype(dt)
+            assert np.allclose(out, data, rtol=0, atol=tol)
+            out = fa.array_decompress(comp, shape[-1], starts, nbytes, stream_offsets=off, stream_gains=gain,
+                                      first_stream_sample=first, last_stream_sample=last, is_int64=is64)
+            assert np.allclose(out, data[..., first:last], rtol=0, atol=tol)
+
+
+def test_flacarray_slicing_and_keep(fa):
+    """reference tests/array.py:148-232 (values are compared too, not only shapes)"""
+    from flacarray_b200.demo import create_fake_data
+
+    data, _ = create_fake_data((4, 3, 1000), sigma=1.0, dtype=np.float64)
+    far = fa.FlacArray.from_array(data, quanta=1e-16)
+    assert far.shape == data.shape and far.dtype == np.float64 and far.stream_size == 1000
+    assert far.nstreams == 12 and far.global_nbytes == far.nbytes == far.compressed.nbytes
+    assert np.allclose(far.to_array(), data, rtol=0, atol=1e-13)
+    assert np.allclose(far.to_array(stream_slice=slice(100, 200)), data[..., 100:200], rtol=0, atol=1e-13)
+    keys = [(slice(None),), (1,), (slice(1, 3), slice(None), slice(10, 20)), (1, 2, slice(None)),
+            (slice(None), 1, slice(-20, None)), (3, slice(0, 2), 500), (2, 1, 17), (slice(None), slice(None), 999),
+            (slice(0, 0),), (7,), (1, slice(None), slice(30, 30))]
+    for key in keys:
+        got = far[key]
+        try:
+            want = data[key]
+        except IndexError:
+            want = np.zeros(got.shape)
+        assert got.shape == want.shape, key
+        if want.size:
+            assert np.allclose(got, want, rtol=0, atol=1e-13), key
+    keep = np.zeros((4, 3), bool)
+    keep[1, 2] = keep[3, 0] = keep[0, 0] = True
+    arr, idx = far.to_array(keep=keep, stream_slice=slice(200, 300), keep_indices=True)
+    assert arr.shape == (3, 100) and idx == [(0, 0), (1, 2), (3, 0)]
+    for row, i in zip(arr, idx):
+        assert np.allclose(row, data[i][200:300], rtol=0, atol=1e-13)
+    one, _ = create_fake_data((5000,), sigma=1.0, dtype=np.float32)
+    f1 = fa.FlacArray.from_array(one, quanta=1e-6)
+    assert f1.to_array().shape == (5000,) and f1[10:20].shape == (10,) and f1.stream_starts.shape == (1,)
+    assert np.allclose(f1[10:20], one[10:20], rtol=0, atol=1e-5)
+    cp = fa.FlacArray(far)
+    assert cp == far and not (cp == f1)
+    with pytest.raises(RuntimeError):
+        far[0] = 1
+
+
+def test_quantization_error_bounds(fa):
+    """reference tests/array.py:234-283"""
+    rng = np.random.default_rng(7)
+    n = 10000
+    quanta = 1e-3
+    for dc in (0.0, 0.5, -0.5, 10.0, -10.0, -10.51, -10.4):
+        data = (rng.normal(0, 1, n) + dc).astype(np.float64)
+        far = fa.FlacArray.from_array(data, quanta=quanta)
+        assert np.max(np.abs(far.to_array() - data)) <= 0.5 * quanta * (1 + 1e-9)
+        pre = np.round(data / quanta) * quanta
+        far = fa.FlacArray.from_array(pre, quanta=quanta)
+        assert np.max(np.abs(far.to_array() - pre)) <= 2 * np.max(np.abs(pre)) * np.finfo(np.float64).eps + 1e-15

@@ -1,0 +1,285 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle and the
+committed golden vectors.  Bit-exact for every integer / byte quantity.
+
+Criteria of BASELINE.json:north_star:
+ (1) GPU decoder bit-exact on reference-format bytes (oracle-encoded, FFmpeg-encoded golden streams);
+ (2) GPU-encoded streams decode bit-exactly through the reference path's stand-ins (oracle decoder,
+     FFmpeg decoder);
+ (3) quantised integers bit-exact with the reference's conversion (golden vectors from utils.c);
+ (4) compressed size within 2 % of the oracle's libFLAC-procedure encoder at the same level.
+"""
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def fa():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import __graft_entry__ as g
+
+    g.build()
+    import flacarray_b200
+
+    return flacarray_b200
+
+
+def _walk(rng, shape, scale=1000):
+    return (np.cumsum(rng.integers(-scale, scale + 1, shape), axis=-1) + rng.integers(-50, 51, shape)).astype(np.int32)
+
+
+def _cases(rng):
+    walk = _walk(rng, (4, 10000))
+    full = rng.integers(-2 ** 31, 2 ** 31, (3, 10000), dtype=np.int64).astype(np.int32)
+    full[0, 0], full[0, 1] = -2 ** 31, 2 ** 31 - 1
+    return {
+        "walk": walk, "full": full, "const": np.full((2, 5000), -77, np.int32),
+        "wasted": (walk[:2] << 5).astype(np.int32), "tiny": rng.integers(-5, 6, (3, 7)).astype(np.int32),
+        "one": np.array([[42]], np.int32), "odd": rng.integers(-100, 100, (2, 1000)).astype(np.int32),
+        "smooth": (1e6 * np.sin(np.arange(3 * 8192) / 50.0)).astype(np.int32).reshape(3, -1),
+    }
+
+
+# ---- (3) quantisation ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["quant_f32", "quant_f64"])
+def test_quantise_matches_reference_golden(fa, golden_dir, name):
+    with np.load(os.path.join(golden_dir, name + ".npz")) as z:
+        g = {k: z[k] for k in z.files}
+    data = g["data"]
+    for key, q in (("0", g["quanta0"]), ("1", g["quanta1"]), ("_auto", None)):
+        ints, off, gain = fa.float_to_int(data, quanta=q)
+        assert np.array_equal(ints, g["ints" + key])
+        assert np.array_equal(off, g["off" + key]) and np.array_equal(gain, g["gain" + key])
+        assert np.array_equal(fa.int_to_float(ints, off, gain), g["restored" + key])
+    ints, off, gain = fa.float_to_int(g["const"], quanta=None)  # quirk Q8: constant stream, auto quanta
+    assert np.array_equal(ints, g["ints_const"]) and np.array_equal(gain, g["gain_const"])
+    assert np.array_equal(off, g["off_const"]) and np.array_equal(np.signbit(off), np.signbit(g["off_const"]))
+
+
+@pytest.mark.parametrize("dt,q", [(np.float32, 1e-5), (np.float64, 1e-12)])
+def test_quantise_matches_oracle_random(fa, oracle, dt, q):
+    rng = np.random.default_rng(31)
+    d = (rng.normal(0, 3, (7, 50001)) + rng.normal(0, 100, (7, 1))).astype(dt)
+    for quanta in (None, np.full(7, q, dt), (q * (1 + np.arange(7))).astype(dt)):
+        a = fa.float_to_int(d, quanta=quanta)
+        b = oracle.float_to_int(d, quanta)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+        assert np.array_equal(fa.int_to_float(*a), oracle.int_to_float(*b))
+    with pytest.raises(RuntimeError, match="NaNs"):
+        bad = d.copy(); bad[3, 77] = np.nan
+        fa.float_to_int(bad, quanta=q)
+
+
+# ---- (1) decoder on reference-format bytes ----------------------------------------------------------------
+def test_decode_golden_third_party_streams(fa, golden_dir):
+    from flacarray_b200.libflacarray import decode_flac
+
+    paths = sorted(glob.glob(os.path.join(golden_dir, "ffmpeg_*.npz")) + glob.glob(os.path.join(golden_dir, "handmade_*.npz")))
+    assert len(paths) >= 20
+    for p in paths:
+        with np.load(p) as z:
+            stream, samples = z["stream"], z["samples"]
+        n, nch = samples.shape
+        st = np.zeros(1, np.int64)
+        nb = np.array([stream.size], np.int64)
+        y = decode_flac(stream, st, nb, n, is_int64=(nch == 2))
+        want = samples.reshape(1, -1).view(np.int64) if nch == 2 else samples.reshape(1, -1)
+        assert np.array_equal(y, want), p
+        if n > 100:
+            y = decode_flac(stream, st, nb, n, first_sample=n // 2 - 7, last_sample=n // 2 + 9, is_int64=(nch == 2))
+            assert np.array_equal(y, want[:, n // 2 - 7:n // 2 + 9]), p
+
+
+@pytest.mark.parametrize("level", [0, 2, 3, 5, 8])
+def test_decode_oracle_encoded(fa, oracle, level):
+    rng = np.random.default_rng(32)
+    for name, x in _cases(rng).items():
+        c, s, n = oracle.encode(x, level)
+        y = fa.array_decompress(c, x.shape[1], s, n)
+        assert np.array_equal(y, x), name
+        if x.shape[1] > 20:
+            f, l = x.shape[1] // 2 - 5, x.shape[1] // 2 + 5
+            y = fa.array_decompress(c, x.shape[1], s, n, first_stream_sample=f, last_stream_sample=l)
+            assert np.array_equal(y, x[:, f:l]), name
+
+
+def test_decode_oracle_encoded_int64_all_stereo_modes(fa, oracle):
+    from flacarray_b200.libflacarray import decode_flac
+
+    rng = np.random.default_rng(33)
+    left = np.cumsum(rng.integers(-1000, 1001, 30000)).astype(np.int64)
+    pair = np.stack([left, left + rng.integers(-30, 31, 30000)], 1).astype(np.int32)
+    wide = rng.integers(-2 ** 31, 2 ** 31, (30000, 2), dtype=np.int64).astype(np.int32)
+    for x in (pair, wide):
+        for mode in (-1, 0, 1, 2, 3):
+            b = oracle.encode_stream(x, 5, mode)
+            y = decode_flac(b, np.zeros(1, np.int64), np.array([b.size], np.int64), x.shape[0], is_int64=True)
+            assert np.array_equal(y, x.reshape(1, -1).view(np.int64)), mode
+    a = rng.integers(-2 ** 63, 2 ** 63 - 1, (3, 10000), dtype=np.int64)
+    a[0, :4] = [-2 ** 63, 2 ** 63 - 1, 2 ** 32, -2 ** 32]
+    c, s, n = oracle.encode(a, 5)
+    assert np.array_equal(fa.array_decompress(c, 10000, s, n, is_int64=True), a)
+
+
+# ---- (2) + (4) encoder ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("level", [0, 2, 3, 5, 8])
+def test_encode_decodes_through_oracle_and_size(fa, oracle, level):
+    rng = np.random.default_rng(34)
+    for name, x in _cases(rng).items():
+        c, s, n, off, gain = fa.array_compress(x, level=level)
+        assert off is None and gain is None
+        assert c.dtype == np.uint8 and s.dtype == np.int64 and n.dtype == np.int64
+        assert s.shape == x.shape[:-1] and n.shape == x.shape[:-1]
+        fs, fn = s.reshape(-1), n.reshape(-1)
+        assert fs[0] == 0 and np.array_equal(np.cumsum(fn) - fn, fs) and fn.sum() == c.size  # compress.c:402-411
+        assert np.array_equal(oracle.decode(c, fs, fn, x.shape[1]), x), name
+        assert np.array_equal(fa.array_decompress(c, x.shape[1], s, n), x), name
+        oc, _, _ = oracle.encode(x, level)
+        if x.size >= 10000:
+            assert c.size <= 1.02 * oc.size, (name, level, c.size, oc.size)
+        c2, s2, n2, _, _ = fa.array_compress(x, level=level)   # deterministic bytes (FlacArray.__eq__ relies on it)
+        assert np.array_equal(c, c2) and np.array_equal(s, s2)
+
+
+def test_encode_int64_decodes_through_oracle(fa, oracle):
+    rng = np.random.default_rng(35)
+    a = rng.integers(-2 ** 63, 2 ** 63 - 1, (3, 10000), dtype=np.int64)
+    a[0, :4] = [-2 ** 63, 2 ** 63 - 1, 2 ** 32, -2 ** 32]                      # reference tests/bindings.py:106-109
+    b = (np.cumsum(rng.integers(-2 ** 20, 2 ** 20, (4, 50000)), axis=1) + 2 ** 40 * rng.integers(-4, 5, (4, 1))).astype(np.int64)
+    for x in (a, b):
+        c, s, n, _, _ = fa.array_compress(x)
+        assert np.array_equal(oracle.decode(c, s, n, x.shape[1], is_int64=True), x)
+        assert np.array_equal(fa.array_decompress(c, x.shape[1], s, n, is_int64=True), x)
+        f, l = x.shape[1] // 2 - 5, x.shape[1] // 2 + 5
+        assert np.array_equal(fa.array_decompress(c, x.shape[1], s, n, first_stream_sample=f, last_stream_sample=l,
+                                                  is_int64=True), x[:, f:l])
+        oc, _, _ = oracle.encode(x, 5)
+        assert c.size <= 1.02 * oc.size
+
+
+def test_encode_decodes_through_third_party_decoder(fa, oracle):
+    from oracle import ffmpeg_flac as ff
+
+    if not ff.available():
+        pytest.skip("bundled FFmpeg FLAC codec not loadable")
+    rng = np.random.default_rng(36)
+    x = _walk(rng, (2, 30000))
+    c, s, n, _, _ = fa.array_compress(x)
+    for i in range(2):
+        b = c[s[i]:s[i] + n[i]]
+        offs, _, _ = oracle.index_frames(b)
+        ends = list(offs[1:]) + [b.size]
+        z = ff.decode_frames([bytes(b[o:e]) for o, e in zip(offs, ends)], 1)
+        assert np.array_equal(z[:, 0], x[i])
+    a = (np.cumsum(rng.integers(-2 ** 20, 2 ** 20, (1, 30000)), axis=1) + 2 ** 40).astype(np.int64)
+    c, s, n, _, _ = fa.array_compress(a)
+    offs, _, _ = oracle.index_frames(c)
+    ends = list(offs[1:]) + [c.size]
+    z = ff.decode_frames([bytes(c[o:e]) for o, e in zip(offs, ends)], 2)
+    assert np.array_equal(np.ascontiguousarray(z).view(np.int64).reshape(1, -1), a)
+
+
+def test_float_fused_encode_matches_two_step(fa, oracle):
+    """array_compress on floats == reference sequence float_to_int -> encode_flac (compress.py:74-77)."""
+    rng = np.random.default_rng(37)
+    for dt, q in ((np.float32, 1e-4), (np.float64, 1e-9)):
+        d = (rng.normal(0, 1, (5, 30000)) + rng.normal(0, 5, (5, 1))).astype(dt)
+        c, s, n, off, gain = fa.array_compress(d, quanta=q)
+        oi, oo, og = oracle.float_to_int(d, np.full(5, q, dt))
+        assert np.array_equal(off, oo) and np.array_equal(gain, og)
+        is64 = dt == np.float64
+        assert np.array_equal(oracle.decode(c, s, n, 30000, is_int64=is64), oi)
+        back = fa.array_decompress(c, 30000, s, n, stream_offsets=off, stream_gains=gain, is_int64=is64)
+        assert back.dtype == dt and np.array_equal(back, oracle.int_to_float(oi, oo, og))
+        assert np.max(np.abs(back - d)) <= 0.5 * q * 1.0001 + 1e-7 * (dt == np.float32) * np.max(np.abs(d))
+
+
+# ---- C ABI called directly with host pointers (what the reference's Cython binding would link) ---------------
+def test_reference_signature_entry_points(fa, oracle):
+    from flacarray_b200 import _lib
+
+    L = C.CDLL(_lib.SO_PATH)
+    libc = C.CDLL(None)
+    rng = np.random.default_rng(38)
+    x = _walk(rng, (3, 20000))
+    starts = np.zeros(3, np.int64)
+    nb = C.c_int64(0)
+    buf = C.POINTER(C.c_ubyte)()
+    L.encode_i32_threaded.restype = C.c_int
+    rc = L.encode_i32_threaded(C.c_void_p(x.ctypes.data), C.c_int64(3), C.c_int64(20000), C.c_uint32(5), C.byref(nb),
+                               C.c_void_p(starts.ctypes.data), C.byref(buf))
+    assert rc == 0 and nb.value > 0 and starts[0] == 0
+    comp = np.ctypeslib.as_array(buf, shape=(nb.value,)).copy()
+    libc.free(buf)                                     # caller frees with free(): pyx:336-337
+    nbytes = np.empty(3, np.int64)
+    nbytes[:-1] = np.diff(starts); nbytes[-1] = nb.value - starts[-1]   # pyx:331-332
+    assert np.array_equal(oracle.decode(comp, starts, nbytes, 20000), x)
+    out = np.zeros((3, 100), np.int32)
+    L.decode_i32.restype = C.c_int
+    rc = L.decode_i32(C.c_void_p(comp.ctypes.data), C.c_void_p(starts.ctypes.data), C.c_void_p(nbytes.ctypes.data),
+                      C.c_int64(3), C.c_int64(20000), C.c_int64(10000), C.c_int64(10100), C.c_void_p(out.ctypes.data),
+                      C.c_bool(True))
+    assert rc == 0 and np.array_equal(out, x[:, 10000:10100])
+    # error codes: flacarray.h:20-40
+    assert L.encode_i32(C.c_void_p(x.ctypes.data), C.c_int64(3), C.c_int64(20000), C.c_uint32(9), C.byref(nb),
+                        C.c_void_p(starts.ctypes.data), C.byref(buf)) == 1 << 1
+    assert L.encode_i32(C.c_void_p(x.ctypes.data), C.c_int64(0), C.c_int64(20000), C.c_uint32(5), C.byref(nb),
+                        C.c_void_p(starts.ctypes.data), C.byref(buf)) == 1 << 2
+    assert L.encode_i32(C.c_void_p(x.ctypes.data), C.c_int64(3), C.c_int64(0), C.c_uint32(5), C.byref(nb),
+                        C.c_void_p(starts.ctypes.data), C.byref(buf)) == 1 << 3
+    assert L.decode_i32(C.c_void_p(comp.ctypes.data), C.c_void_p(starts.ctypes.data), C.c_void_p(nbytes.ctypes.data),
+                        C.c_int64(3), C.c_int64(20000), C.c_int64(10), C.c_int64(20001), C.c_void_p(out.ctypes.data),
+                        C.c_bool(False)) == 1 << 17
+    f = rng.normal(0, 1, (2, 5000)).astype(np.float32)
+    q = np.full(2, 1e-3, np.float32)
+    ints = np.zeros((2, 5000), np.int32); off = np.zeros(2, np.float32); gain = np.zeros(2, np.float32)
+    L.float32_to_int32.restype = C.c_int
+    assert L.float32_to_int32(C.c_void_p(f.ctypes.data), C.c_int64(2), C.c_int64(5000), C.c_void_p(q.ctypes.data),
+                              C.c_void_p(ints.ctypes.data), C.c_void_p(off.ctypes.data), C.c_void_p(gain.ctypes.data)) == 0
+    oi, oo, og = oracle.float_to_int(f, q)
+    assert np.array_equal(ints, oi) and np.array_equal(off, oo) and np.array_equal(gain, og)
+    back = np.zeros((2, 5000), np.float32)
+    L.int32_to_float32(C.c_void_p(ints.ctypes.data), C.c_int64(2), C.c_int64(5000), C.c_void_p(off.ctypes.data),
+                       C.c_void_p(gain.ctypes.data), C.c_void_p(back.ctypes.data))
+    assert np.array_equal(back, oracle.int_to_float(oi, oo, og))
+
+
+def test_corrupt_stream_is_an_error(fa, oracle):
+    rng = np.random.default_rng(39)
+    x = _walk(rng, (2, 20000))
+    c, s, n, _, _ = fa.array_compress(x)
+    bad = c.copy()
+    bad[s[1] + n[1] // 2] ^= 0x5A
+    with pytest.raises(RuntimeError, match="Decoding failed"):
+        fa.array_decompress(bad, 20000, s, n)
+    oc, os_, on = oracle.encode(x, 5)
+    bad = oc.copy()
+    bad[os_[1] + on[1] // 2] ^= 0x5A
+    with pytest.raises(RuntimeError, match="Decoding failed"):
+        fa.array_decompress(bad, 20000, os_, on)
+
+
+def test_device_resident_roundtrip(fa, oracle):
+    import torch
+
+    rng = np.random.default_rng(40)
+    x = _walk(rng, (8, 40000))
+    d = torch.from_numpy(x).cuda()
+    c, s, n, _, _ = fa.array_compress(d)
+    assert c.is_cuda and s.is_cuda
+    assert np.array_equal(oracle.decode(c.cpu().numpy(), s.cpu().numpy(), n.cpu().numpy(), 40000), x)
+    y = fa.array_decompress(c, 40000, s, n)
+    assert y.is_cuda and torch.equal(y, d)
+    f = torch.from_numpy(rng.normal(0, 1, (4, 40000)).astype(np.float32)).cuda()
+    far = fa.FlacArray.from_array(f, quanta=1e-4)
+    back = far.to_array()
+    assert back.is_cuda and float((back - f).abs().max()) <= 0.5e-4 * 1.001 + 1e-6

@@ -1,0 +1,114 @@
+"""Logic tests of the CUDA kernel bodies through the OS-thread SIMT emulator (tests/hostsim).
+
+These run the SAME source the GPU runs (flacarray_b200/csrc/*.h) on the CPU, purely as a unit-test
+harness for the GPU-less container; the oracle is the checker.  The emulator is not part of the product.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim"))
+
+
+@pytest.fixture(scope="module")
+def H():
+    import hostsim
+
+    hostsim.lib()
+    return hostsim
+
+
+def _cases(rng):
+    walk = (np.cumsum(rng.integers(-1000, 1001, (2, 9000)), axis=1) + rng.integers(-50, 51, (2, 9000))).astype(np.int32)
+    full = rng.integers(-2 ** 31, 2 ** 31, (1, 5000), dtype=np.int64).astype(np.int32)
+    full[0, 0], full[0, 1] = -2 ** 31, 2 ** 31 - 1
+    return {
+        "walk": walk, "full": full, "const": np.full((1, 5000), -77, np.int32),
+        "wasted": (walk[:1] << 5).astype(np.int32), "tiny": rng.integers(-5, 6, (2, 7)).astype(np.int32),
+        "one": np.array([[42]], np.int32), "odd": rng.integers(-100, 100, (1, 1000)).astype(np.int32),
+    }
+
+
+@pytest.mark.parametrize("level", [0, 5, 8])
+def test_encoder_body_roundtrips_through_oracle(H, oracle, level):
+    rng = np.random.default_rng(21)
+    for name, x in _cases(rng).items():
+        c, s, n, _, _ = H.encode(x, level)
+        assert s[0] == 0 and np.array_equal(np.cumsum(n) - n, s) and n.sum() == c.size
+        assert np.array_equal(oracle.decode(c, s, n, x.shape[1]), x), name
+        oc, _, _ = oracle.encode(x, level)
+        if x.size > 4000:
+            assert c.size <= 1.02 * oc.size, (name, c.size, oc.size)
+
+
+def test_decoder_bodies_on_own_and_foreign_streams(H, oracle):
+    rng = np.random.default_rng(22)
+    for name, x in _cases(rng).items():
+        c, s, n, _, _ = H.encode(x, 5)          # carries the frame-size table
+        oc, os_, on = oracle.encode(x, 5)       # foreign: needs the sync scan
+        for comp, st, nb in ((c, s, n), (oc, os_, on)):
+            y, walked = H.decode(comp, st, nb, x.shape[1])
+            assert np.array_equal(y, x) and walked == 0, name
+            y, walked = H.decode(comp, st, nb, x.shape[1], mode=1)  # sequential walker
+            assert np.array_equal(y, x) and walked == x.shape[0], name
+            if x.shape[1] > 20:
+                f, l = x.shape[1] // 2 - 5, x.shape[1] // 2 + 5
+                y, _ = H.decode(comp, st, nb, x.shape[1], f, l)
+                assert np.array_equal(y, x[:, f:l]), name
+
+
+def test_int64_bodies(H, oracle):
+    rng = np.random.default_rng(23)
+    a = rng.integers(-2 ** 63, 2 ** 63 - 1, (1, 5000), dtype=np.int64)
+    a[0, :4] = [-2 ** 63, 2 ** 63 - 1, 2 ** 32, -2 ** 32]
+    b = (np.cumsum(rng.integers(-2 ** 20, 2 ** 20, (1, 9000)), axis=1) + 2 ** 40 * 3).astype(np.int64)
+    for x in (a, b):
+        c, s, n, _, _ = H.encode(x, 5)
+        assert np.array_equal(oracle.decode(c, s, n, x.shape[1], is_int64=True), x)
+        oc, os_, on = oracle.encode(x, 5)  # stereo search: exercises side/mid decoding
+        for comp, st, nb in ((c, s, n), (oc, os_, on)):
+            y, walked = H.decode(comp, st, nb, x.shape[1], is_int64=True)
+            assert np.array_equal(y, x) and walked == 0
+
+
+def test_decoder_bodies_on_golden_third_party_streams(H, golden_dir):
+    import glob
+
+    paths = sorted(glob.glob(os.path.join(golden_dir, "ffmpeg_*.npz")) + glob.glob(os.path.join(golden_dir, "handmade_*.npz")))
+    for p in paths:
+        with np.load(p) as z:
+            stream, samples = z["stream"], z["samples"]
+        n, nch = samples.shape
+        st = np.zeros(1, np.int64)
+        nb = np.array([stream.size], np.int64)
+        y, walked = H.decode(stream, st, nb, n, is_int64=(nch == 2))
+        want = samples.reshape(1, -1).view(np.int64) if nch == 2 else samples.reshape(1, -1)
+        assert np.array_equal(y, want), p
+        assert walked == 0, p
+
+
+def test_float_bodies_match_reference_vectors(H, golden_dir):
+    import ctypes as C
+
+    L = H.lib()
+    for name, is64, fdt, idt in (("quant_f32", 0, np.float32, np.int32), ("quant_f64", 1, np.float64, np.int64)):
+        with np.load(os.path.join(golden_dir, name + ".npz")) as z:
+            g = {k: z[k] for k in z.files}
+        data = np.ascontiguousarray(g["data"])
+        ns, ss = data.shape
+        for key, q in (("0", g["quanta0"]), ("1", g["quanta1"]), ("_auto", None)):
+            out = np.zeros(data.shape, idt); off = np.zeros(ns, fdt); gain = np.zeros(ns, fdt)
+            qq = None if q is None else np.ascontiguousarray(q, fdt)
+            L.hs_float_to_int(data.ctypes.data, is64, ns, ss, None if qq is None else qq.ctypes.data, out.ctypes.data,
+                              off.ctypes.data, gain.ctypes.data)
+            assert np.array_equal(out, g["ints" + key]) and np.array_equal(off, g["off" + key]) and np.array_equal(gain, g["gain" + key])
+            rest = np.zeros(data.shape, fdt)
+            L.hs_int_to_float(out.ctypes.data, is64, ns, ss, off.ctypes.data, gain.ctypes.data, rest.ctypes.data)
+            assert np.array_equal(rest, g["restored" + key])
+        # fused quantise + encode of floats decodes to the reference's integers
+        c, s, n, off, gain = H.encode(data, 5, quanta=g["quanta0"])
+        from oracle import oracle as O
+        assert np.array_equal(O.decode(c, s, n, ss, is_int64=bool(is64)), g["ints0"])
+        assert np.array_equal(off, g["off0"]) and np.array_equal(gain, g["gain0"])
