@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py -- FLAC encode/decode throughput of the hot path on B200 (contract: see the task brief).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--streams S] [--samples L]
+
+Workload (BASELINE.json configs[1]): float32 detector timestreams (1000, 1M) quantised with
+quanta = 1e-4, full encode + decode.  One "step" = one encode pass + one decode pass over the batch
+(per GPU; `--gpus N` is weak scaling: every rank owns its own (1000, 1M) shard and the only collective
+is the all-gather of per-rank byte counts).
+
+value   = raw sample bytes that went through the codec per second, 2 * raw_bytes / (t_enc + t_dec),
+          whole job (all ranks), device-resident in/out, CUDA-event timed, max over ranks.
+e2e     = the same metric through the public Python API (FlacArray.from_array / to_array) with
+          pinned HOST buffers: H2D of the input and D2H of every result inside the timed region.
+roofline= dominant kernel (k_encode): algorithmic bytes (raw in + compressed out) per launch /
+          CUDA-event duration of that kernel (events recorded by the library on the launching stream).
+cpu_baseline = the CPU oracle port (restatement of the reference's OpenMP-over-streams loops) timed on
+          this box's host cores on a bounded sample of the same workload.
+`--impl reference` times that CPU implementation as the whole job (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEED = 123456789  # reference demo.py:12
+QUANTA = 1e-4
+METRIC = "encode+decode GB/s of raw samples (float32 TOD, quanta 1e-4, level 5)"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------
+# synthetic detector timestreams: the reference's demo model (demo.py:70-97)
+# ---------------------------------------------------------------------------------------------------
+def make_tod_numpy(n_stream, n_samp, seed):
+    rng = np.random.default_rng(seed)
+    dc = 5.0 * (rng.random((n_stream, 1)) - 0.5)
+    t = np.arange(n_samp)
+    minf = 5 / n_samp
+    wave = 2.0 * np.sin(2 * np.pi * 3 * minf * t) + 6.0 * np.sin(2 * np.pi * minf * t)
+    scale = rng.random((n_stream, 1))
+    out = np.empty((n_stream, n_samp), np.float32)
+    for i in range(n_stream):
+        out[i] = dc[i] + scale[i] * wave + rng.normal(0.0, 1.0, n_samp)
+    return out
+
+
+def make_tod_torch(n_stream, n_samp, seed, device):
+    import torch
+
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    dc = 5.0 * (torch.rand((n_stream, 1), generator=g, device=device) - 0.5)
+    scale = torch.rand((n_stream, 1), generator=g, device=device)
+    t = torch.arange(n_samp, device=device, dtype=torch.float64)
+    minf = 5.0 / n_samp
+    wave = (2.0 * torch.sin(2 * np.pi * 3 * minf * t) + 6.0 * torch.sin(2 * np.pi * minf * t)).to(torch.float32)
+    out = torch.empty((n_stream, n_samp), dtype=torch.float32, device=device)
+    chunk = max(1, (1 << 28) // n_samp)
+    for i in range(0, n_stream, chunk):
+        j = min(n_stream, i + chunk)
+        out[i:j] = torch.randn((j - i, n_samp), generator=g, device=device)
+        out[i:j] += dc[i:j] + scale[i:j] * wave
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md recipe)
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = sorted(sm)[len(sm) // 2:]  # upper half ~ samples under load
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port (kind "port"), OpenMP over streams like compress.c:315-392
+# ---------------------------------------------------------------------------------------------------
+def cpu_pipeline(sample, threads, level=5):
+    """float32 [n, L] -> seconds of (quantise, encode, decode, restore) with the reference's structure:
+    converters single-threaded (utils.c has no OpenMP), encode/decode OpenMP over streams."""
+    from oracle import oracle as O
+
+    os.environ["OMP_NUM_THREADS"] = str(threads)
+    q = np.full(sample.shape[0], QUANTA, np.float32)
+    t0 = time.perf_counter()
+    ints, off, gain = O.float_to_int(sample, q)
+    t1 = time.perf_counter()
+    comp, starts, nbytes = O.encode(ints, level, use_threads=True)
+    t2 = time.perf_counter()
+    back = O.decode(comp, starts, nbytes, sample.shape[1], use_threads=True)
+    t3 = time.perf_counter()
+    rest = O.int_to_float(back, off, gain)
+    t4 = time.perf_counter()
+    assert np.array_equal(back, ints) and rest.shape == sample.shape
+    return {"t_enc": t2 - t0, "t_dec": t4 - t2, "quant": t1 - t0, "encode": t2 - t1, "decode": t3 - t2,
+            "restore": t4 - t3, "ratio": comp.size / sample.nbytes}
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+
+    O.build()
+    cores = os.cpu_count() or 1
+    n_samp = args.samples
+    per_step = max(cores, min(args.streams, 2 * cores, 128))   # bounded sample of the (streams, samples) workload
+    sample = make_tod_numpy(per_step, n_samp, SEED)
+    raw = sample.nbytes
+    for _ in range(args.warmup):
+        cpu_pipeline(sample[: max(1, min(per_step, cores))], cores)
+    t_enc = t_dec = 0.0
+    ratio = 0.0
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = cpu_pipeline(sample, cores)
+        t_enc += r["t_enc"]; t_dec += r["t_dec"]; ratio = r["ratio"]
+    wall = time.perf_counter() - t_wall0
+    value = 2.0 * raw * args.steps / (t_enc + t_dec) / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32 (float32 in/out, double intermediates)", "data": "synthetic",
+        "config": {"workload": f"float32 TOD ({args.streams}, {n_samp}) quanta=1e-4 level 5, encode+decode",
+                   "sample_streams": per_step},
+        "encode_gbs": raw * args.steps / t_enc / 1e9, "decode_gbs": raw * args.steps / t_dec / 1e9, "ratio": ratio,
+        "cpu_baseline": {"value": value, "unit": "GB/s", "cores": cores, "kind": "port",
+                         "sample": f"{per_step} of {args.streams} streams x {n_samp} float32 samples per step; "
+                                   "oracle/flac_oracle.c (libFLAC absent here), OpenMP over streams, converters 1 thread"},
+        "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: flacarray_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import __graft_entry__ as ge
+
+    ge.build()
+    import flacarray_b200 as fa
+    from flacarray_b200 import _lib
+    from flacarray_b200 import libflacarray as lf
+    from flacarray_b200.mpi import TorchComm, global_bytes
+
+    n_stream, n_samp = args.streams, args.samples
+    data = make_tod_torch(n_stream, n_samp, SEED + rank, dev)
+    raw = data.numel() * 4
+    quanta = torch.full((n_stream,), QUANTA, dtype=torch.float32, device=dev)
+    ctx = _lib.context(dev)
+    comm = TorchComm() if world > 1 else None
+    flat = data.reshape(-1)
+
+    def step_device():
+        comp, starts, nbytes, off, gain = lf.encode_device(flat, n_stream, n_samp, 5, quanta)
+        local_nbytes = int(comp.numel())
+        if comm is not None:  # the only collective on the path: byte counts -> global offsets (mpi.py:177-187)
+            global_bytes(local_nbytes, starts, comm)
+        mx = int(nbytes.max().item())
+        out = lf.decode_device(comp, starts, nbytes, n_stream, n_samp, -1, -1, False, mx, 4096, off, gain)
+        return comp, out
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- parity guard on the exact bench input (cheap subset through the oracle) ----
+    comp, out = step_device()
+    ratio = comp.numel() / raw
+    if rank == 0:
+        from oracle import oracle as O
+
+        sub = data[:2].cpu().numpy()
+        oi, oo, og = O.float_to_int(sub, np.full(2, QUANTA, np.float32))
+        want = O.int_to_float(oi, oo, og)
+        got = out.reshape(n_stream, n_samp)[:2].cpu().numpy()
+        if not np.array_equal(got, want):
+            raise SystemExit("bench parity guard failed: GPU round trip differs from the oracle")
+    del comp, out
+
+    # ---- device-resident timed region (separate encode / decode timings inside one loop) ----
+    for _ in range(args.warmup):
+        step_device()
+    ctx.profile(True)
+    launches0 = ctx.launches()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        ev[k][0].record()
+        comp, starts, nbytes, off, gain = lf.encode_device(flat, n_stream, n_samp, 5, quanta)
+        if comm is not None:
+            global_bytes(int(comp.numel()), starts, comm)
+        ev[k][1].record()
+        mx = int(nbytes.max().item())
+        out = lf.decode_device(comp, starts, nbytes, n_stream, n_samp, -1, -1, False, mx, 4096, off, gain)
+        ev[k][2].record()
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    launches = ctx.launches() - launches0
+    t_enc = sum(e[0].elapsed_time(e[1]) for e in ev) / 1e3
+    t_dec = sum(e[1].elapsed_time(e[2]) for e in ev) / 1e3
+    enc_ms, enc_n = ctx.profile_ms(0)
+    dec_ms, dec_n = ctx.profile_ms(1)
+    ctx.profile(False)
+    comp_bytes = int(comp.numel())
+    del comp, out
+
+    tt = torch.tensor([t_enc, t_dec, wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    t_enc_m, t_dec_m, wall_m = [float(x) for x in tt.cpu()]
+    value = 2.0 * raw * world * args.steps / (t_enc_m + t_dec_m) / 1e9
+
+    # ---- e2e: public API with pinned host buffers, H2D + D2H inside the timed region ----
+    e2e_streams = min(n_stream, args.e2e_streams)
+    host = torch.empty((e2e_streams, n_samp), dtype=torch.float32, pin_memory=True)
+    host.copy_(data[:e2e_streams])
+    torch.cuda.synchronize()
+    host_np = host.numpy()
+    e2e_raw = host_np.nbytes
+    far = fa.FlacArray.from_array(host_np, quanta=QUANTA)   # warm-up (pinned pools, scratch)
+    far.to_array()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    h2d = d2h = 0
+    for _ in range(e2e_steps):
+        far = fa.FlacArray.from_array(host_np, quanta=QUANTA)
+        back = far.to_array()
+        h2d += e2e_raw + far.nbytes
+        d2h += far.nbytes + back.nbytes
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = 2.0 * e2e_raw * world * e2e_steps / float(te.item()) / 1e9
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        alg_enc = raw + comp_bytes            # raw in + compressed out, per launch
+        alg_dec = comp_bytes + raw
+        enc_gbs = alg_enc * enc_n / (enc_ms / 1e3) / 1e9 if enc_ms > 0 else None
+        dec_gbs = alg_dec * dec_n / (dec_ms / 1e3) / 1e9 if dec_ms > 0 else None
+        dominant = "k_encode" if (enc_ms / max(enc_n, 1)) >= (dec_ms / max(dec_n, 1)) else "k_dec_frames"
+        ach = enc_gbs if dominant == "k_encode" else dec_gbs
+        # CPU baseline beside it (bounded sample, all host cores)
+        cores = os.cpu_count() or 1
+        cpu = None
+        if not args.no_cpu_baseline:
+            from oracle import oracle as O
+
+            O.build()
+            ns = max(cores, min(n_stream, 2 * cores, 128))
+            sample = data[:ns].cpu().numpy()
+            r = cpu_pipeline(sample, cores)
+            cpu = {"value": 2.0 * sample.nbytes / (r["t_enc"] + r["t_dec"]) / 1e9, "unit": "GB/s", "cores": cores,
+                   "kind": "port",
+                   "sample": f"{ns} of {n_stream} streams x {n_samp} float32 samples, one pass; oracle/flac_oracle.c "
+                             "(libFLAC absent), OpenMP over streams, converters single-threaded like utils.c",
+                   "encode_gbs": sample.nbytes / r["t_enc"] / 1e9, "decode_gbs": sample.nbytes / r["t_dec"] / 1e9,
+                   "ratio": r["ratio"]}
+        line = {
+            "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * (t_enc_m + t_dec_m) / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32 (float32 in/out, double intermediates)", "data": "synthetic",
+            "config": {"workload": f"float32 TOD ({n_stream}, {n_samp}) per GPU, quanta=1e-4, level 5, encode+decode",
+                       "l2": "inputs (4 GB) larger than L2 (126 MB); no explicit flush",
+                       "parallelism": f"streams sharded over {world} GPU(s); all-gather of byte counts only"},
+            "encode_gbs": raw * world * args.steps / t_enc_m / 1e9, "decode_gbs": raw * world * args.steps / t_dec_m / 1e9,
+            "ratio": ratio, "wall_ms_per_step": 1e3 * wall_m / args.steps,
+            "roofline": {"bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_enc if dominant == "k_encode" else alg_dec,
+                         "ms_per_launch": (enc_ms / max(enc_n, 1)) if dominant == "k_encode" else (dec_ms / max(dec_n, 1))},
+            "roofline_encode": {"kernel": "k_encode", "achieved": enc_gbs, "frac": enc_gbs / peak if enc_gbs else None,
+                                "ms_per_launch": enc_ms / max(enc_n, 1)},
+            "roofline_decode": {"kernel": "k_dec_frames", "achieved": dec_gbs, "frac": dec_gbs / peak if dec_gbs else None,
+                                "ms_per_launch": dec_ms / max(dec_n, 1)},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d // e2e_steps,
+                    "d2h_bytes_per_step": d2h // e2e_steps, "streams": e2e_streams, "steps": e2e_steps},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=1000)
+    ap.add_argument("--samples", type=int, default=1000000)
+    ap.add_argument("--e2e-streams", type=int, default=1000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -90,6 +90,9 @@ def lib():
         L.fab_float_to_int.argtypes = [_vp, _vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp]
         L.fab_int_to_float.restype = _i32
         L.fab_int_to_float.argtypes = [_vp, _vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp]
+        L.fab_profile.argtypes = [_vp, _i32]
+        L.fab_profile_ms.restype = C.c_double
+        L.fab_profile_ms.argtypes = [_vp, _i32, C.POINTER(_i64)]
         L.fab_finish.restype = _i32
         L.fab_finish.argtypes = [_vp, _vp]
         _lib = L
@@ -101,7 +104,7 @@ EXPORTED = [
     "encode_i32", "encode_i32_threaded", "encode_i64", "encode_i64_threaded", "decode_i32", "decode_i64",
     "float32_to_int32", "float64_to_int64", "int64_to_float64", "int32_to_float32",
     "fab_create", "fab_destroy", "fab_last_error", "fab_launch_count", "fab_encode_bound", "fab_encode",
-    "fab_decode", "fab_float_to_int", "fab_int_to_float", "fab_finish",
+    "fab_decode", "fab_float_to_int", "fab_int_to_float", "fab_finish", "fab_profile", "fab_profile_ms",
 ]
 
 
@@ -127,6 +130,14 @@ class Context:
 
     def launches(self):
         return int(lib().fab_launch_count(self._h))
+
+    def profile(self, enable):
+        lib().fab_profile(self._h, 1 if enable else 0)
+
+    def profile_ms(self, which):
+        n = _i64(0)
+        ms = lib().fab_profile_ms(self._h, which, C.byref(n))
+        return float(ms), int(n.value)
 
     def __del__(self):
         try:

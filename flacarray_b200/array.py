@@ -239,7 +239,12 @@ class FlacArray:
                 keep_slice.append(axkey)
         leading_shape = tuple(leading_shape)
         keep_slice = tuple(keep_slice)
-        keep = None if len(keep_slice) == 0 else self._keep_view(keep_slice)
+        if len(keep_slice) == 0 or 0 in leading_shape:
+            # (an out-of-range integer index gives a zero-length result; the reference's _keep_view
+            # would raise IndexError here before reaching its own empty-array branch)
+            keep = None
+        else:
+            keep = self._keep_view(keep_slice)
         return leading_shape, keep
 
     def _get_sample_axis(self, full_key):

@@ -202,7 +202,38 @@ struct fab_ctx {
     int64_t launches = 0;
     std::string last_error = "";
     bool smem_configured = false;
+    // optional per-kernel timing (bench.py's roofline): CUDA events on the launching stream
+    bool prof = false;
+    struct Pending { cudaEvent_t a, b; int which; };
+    std::vector<Pending> pending;
+    double prof_ms[2] = {0.0, 0.0};
+    int64_t prof_n[2] = {0, 0};
 };
+
+static void prof_begin(fab_ctx* ctx, int which, cudaStream_t st) {
+    if (!ctx->prof) return;
+    fab_ctx::Pending p;
+    p.which = which;
+    if (cudaEventCreate(&p.a) != cudaSuccess || cudaEventCreate(&p.b) != cudaSuccess) return;
+    cudaEventRecord(p.a, st);
+    ctx->pending.push_back(p);
+}
+static void prof_end(fab_ctx* ctx, cudaStream_t st) {
+    if (!ctx->prof || ctx->pending.empty()) return;
+    cudaEventRecord(ctx->pending.back().b, st);
+}
+static void prof_collect(fab_ctx* ctx) {
+    for (auto& p : ctx->pending) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            ctx->prof_ms[p.which] += ms;
+            ctx->prof_n[p.which]++;
+        }
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    ctx->pending.clear();
+}
 
 #define FAB_CUDA(ctx, call)                                                                   \
     do {                                                                                      \
@@ -279,6 +310,20 @@ extern "C" void fab_destroy(fab_ctx* ctx) {
 
 extern "C" const char* fab_last_error(const fab_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "no context"; }
 extern "C" int64_t fab_launch_count(const fab_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" void fab_profile(fab_ctx* ctx, int enable) {
+    if (!ctx) return;
+    prof_collect(ctx);
+    ctx->prof = enable != 0;
+    ctx->prof_ms[0] = ctx->prof_ms[1] = 0.0;
+    ctx->prof_n[0] = ctx->prof_n[1] = 0;
+}
+extern "C" double fab_profile_ms(fab_ctx* ctx, int which, int64_t* count) {
+    if (!ctx || which < 0 || which > 1) return 0.0;
+    prof_collect(ctx);
+    if (count) *count = ctx->prof_n[which];
+    return ctx->prof_ms[which];
+}
 
 extern "C" int fab_finish(fab_ctx* ctx, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
@@ -385,7 +430,9 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
         FAB_CUDA(ctx, cudaFuncSetAttribute(k_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_smem_bytes(2)));
         ctx->smem_configured = true;
     }
+    prof_begin(ctx, 0, st);
     k_encode<<<(unsigned)(n_stream * nf), kEncThreads, smem, st>>>(P);
+    prof_end(ctx, st);
     ctx->launches++;
     k_enc_finalize<<<(unsigned)((n_stream + 255) / 256), 256, 0, st>>>((const long long*)d_starts, ends, (long long*)d_nbytes,
                                                                      n_stream, (long long*)d_total);
@@ -443,7 +490,7 @@ extern "C" int fab_decode(fab_ctx* ctx, const unsigned char* d_bytes, const int6
     P.n_sel = n_stream; P.stream_size = stream_size; P.nch = nch;
     P.first = first_decode; P.n_decode = n_decode; P.data = (int32_t*)d_out; P.crc = ctx->d_crc;
     P.meta = (StreamMeta*)scr; P.frame_off = (long long*)(scr + meta_b); P.nframes_cap = nframes_cap;
-    P.stream_flag = (int*)(scr + meta_b + fo_b); P.err = ctx->d_err; P.verify_crc16 = 0;
+    P.stream_flag = (int*)(scr + meta_b + fo_b); P.err = ctx->d_err; P.verify_crc16 = 1;
 
     k_dec_meta<<<(unsigned)((n_stream + 127) / 128), 128, 0, st>>>(P);
     ctx->launches++;
@@ -465,7 +512,9 @@ extern "C" int fab_decode(fab_ctx* ctx, const unsigned char* d_bytes, const int6
         // need more frames than the table holds were flagged for the walker by k_dec_meta)
         int64_t nwin = (first_decode + n_decode - 1) / bsh - first_decode / bsh + 1;
         int64_t total = n_stream * nwin;
+        prof_begin(ctx, 1, st);
         k_dec_frames<<<(unsigned)((total + kDecThreads - 1) / kDecThreads), kDecThreads, 0, st>>>(P, nwin);
+        prof_end(ctx, st);
         ctx->launches++;
     }
     k_dec_walker<<<(unsigned)((n_stream + 31) / 32), 32, 0, st>>>(P);

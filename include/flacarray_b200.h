@@ -141,6 +141,12 @@ int fab_float_to_int(fab_ctx* ctx, const void* d_input, int dtype, int64_t n_str
 int fab_int_to_float(fab_ctx* ctx, const void* d_input, int dtype, int64_t n_stream, int64_t stream_size,
                      const void* d_offsets, const void* d_gains, void* d_output, void* stream);
 
+/* Optional per-kernel timing for roofline reports: when enabled, CUDA events are recorded on the
+ * launching stream around the dominant kernel of fab_encode (which = 0) and fab_decode (which = 1).
+ * fab_profile_ms returns the accumulated milliseconds and (through *count) the number of launches. */
+void fab_profile(fab_ctx* ctx, int enable);
+double fab_profile_ms(fab_ctx* ctx, int which, int64_t* count);
+
 /* Synchronise `stream`, return (and clear) the device-side error mask accumulated since the last call. */
 int fab_finish(fab_ctx* ctx, void* stream);
 

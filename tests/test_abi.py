@@ -20,7 +20,7 @@ def so_path():
 def _declared_symbols():
     text = open(os.path.join(ROOT, "include", "flacarray_b200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    names = re.findall(r"\b(?:int|void|int64_t|const char\*)\s+\*?\s*([a-z_0-9]+)\s*\(", text)
+    names = re.findall(r"\b(?:int|void|int64_t|double|const char\*)\s+\*?\s*([a-z_0-9]+)\s*\(", text)
     return sorted(set(names))
 
 

@@ -104,8 +104,8 @@ def test_decode_oracle_encoded(fa, oracle, level):
     rng = np.random.default_rng(32)
     for name, x in _cases(rng).items():
         c, s, n = oracle.encode(x, level)
-        y = fa.array_decompress(c, x.shape[1], s, n)
-        assert np.array_equal(y, x), name
+        y = fa.array_decompress(c, x.shape[1], s, n)   # a single stream comes back flattened (decompress.py:138-141)
+        assert np.array_equal(y.reshape(x.shape), x), name
         if x.shape[1] > 20:
             f, l = x.shape[1] // 2 - 5, x.shape[1] // 2 + 5
             y = fa.array_decompress(c, x.shape[1], s, n, first_stream_sample=f, last_stream_sample=l)
@@ -142,7 +142,7 @@ def test_encode_decodes_through_oracle_and_size(fa, oracle, level):
         fs, fn = s.reshape(-1), n.reshape(-1)
         assert fs[0] == 0 and np.array_equal(np.cumsum(fn) - fn, fs) and fn.sum() == c.size  # compress.c:402-411
         assert np.array_equal(oracle.decode(c, fs, fn, x.shape[1]), x), name
-        assert np.array_equal(fa.array_decompress(c, x.shape[1], s, n), x), name
+        assert np.array_equal(fa.array_decompress(c, x.shape[1], s, n).reshape(x.shape), x), name
         oc, _, _ = oracle.encode(x, level)
         if x.size >= 10000:
             assert c.size <= 1.02 * oc.size, (name, level, c.size, oc.size)
