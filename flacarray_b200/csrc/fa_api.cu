@@ -16,6 +16,7 @@
 
 #include "../../include/flacarray_b200.h"
 #include "fa_decode.h"
+#include "fa_decode_tile.h"
 #include "fa_encode.h"
 #include "fa_quant.h"
 
@@ -169,6 +170,47 @@ __global__ void __launch_bounds__(kDecThreads) k_dec_frames(const DecParams P, i
     int64_t j = j0 + idx % nwin;
     if (j > j1) return;
     frame_body(P, k, j);
+}
+
+// throughput path: one warp = 32 (stream, frame) items, see fa_decode_tile.h
+template <bool CRC>
+__global__ void __launch_bounds__(kTileWarps * 32) k_dec_tile(const TileParams P) {
+    __shared__ uint16_t crc_tab[4 * 256];
+    __shared__ TileShared ws[kTileWarps];
+    for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) crc_tab[i] = P.D.crc->crc16[i >> 8][i & 255];
+    __syncthreads();
+    int64_t item0 = ((int64_t)blockIdx.x * kTileWarps + (threadIdx.x >> 5)) * 32;
+    if (item0 >= P.D.n_sel * P.nwin) return;
+    tile_warp_body<CRC>(P, item0, &ws[threadIdx.x >> 5], crc_tab);
+}
+
+// int32 -> float32 for the sample ranges that were NOT written by the fused tile path (frames left to
+// the general decoder, streams left to the walker).  grid = (nwin, n_sel)
+__global__ void __launch_bounds__(256) k_restore_fixup(const TileParams P) {
+    const DecParams& D = P.D;
+    const int64_t k = blockIdx.y;
+    const int sflag = D.stream_flag[k];
+    if (sflag == 4) return;
+    const int bs = D.meta[k].blocksize > 0 ? D.meta[k].blocksize : 4096;
+    int64_t j0 = D.first / bs, j1 = (D.first + D.n_decode - 1) / bs;
+    int64_t nfr = j1 - j0 + 1;
+    float* out = (float*)D.data + k * D.n_decode;
+    const int32_t* in = D.data + k * D.n_decode;
+    const float off = P.offsets[k], coeff = restore_coeff_f32(P.gains[k]);
+    if (sflag != 0) {
+        // whole window of this stream was (re)written as integers by the walker
+        for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < D.n_decode; i += (int64_t)gridDim.x * 256)
+            out[i] = restore_f32(in[i], off, coeff);
+        return;
+    }
+    for (int64_t jj = blockIdx.x; jj < nfr; jj += gridDim.x) {
+        int64_t j = j0 + jj;
+        if (j >= D.nframes_cap || !P.frame_flag[k * (int64_t)D.nframes_cap + j]) continue;
+        int64_t lo = j * bs - D.first, hi = lo + bs;
+        if (lo < 0) lo = 0;
+        if (hi > D.n_decode) hi = D.n_decode;
+        for (int64_t i = lo + threadIdx.x; i < hi; i += 256) out[i] = restore_f32(in[i], off, coeff);
+    }
 }
 
 __global__ void k_dec_walker(const DecParams P) {
@@ -471,12 +513,14 @@ extern "C" int fab_decode(fab_ctx* ctx, const unsigned char* d_bytes, const int6
     size_t meta_b = align256((size_t)n_stream * sizeof(StreamMeta));
     size_t fo_b = align256((size_t)n_stream * (size_t)(nframes_cap + 1) * 8);
     size_t flag_b = align256((size_t)n_stream * 4);
+    size_t fflag_b = align256((size_t)n_stream * (size_t)nframes_cap);
     unsigned char* scr;
-    int rc = ctx_scratch(ctx, meta_b + fo_b + flag_b + 256, &scr);
+    int rc = ctx_scratch(ctx, meta_b + fo_b + flag_b + fflag_b + 256, &scr);
     if (rc) return rc;
+    unsigned char* frame_flag = scr + meta_b + fo_b + flag_b;
 
     if (max_nbytes <= 0) {
-        long long* d_max = (long long*)(scr + meta_b + fo_b + flag_b);
+        long long* d_max = (long long*)(scr + meta_b + fo_b + flag_b + fflag_b);
         k_max_i64<<<1, 256, 0, st>>>((const long long*)d_nbytes, n_stream, d_max);
         ctx->launches++;
         long long h = 0;
@@ -490,7 +534,7 @@ extern "C" int fab_decode(fab_ctx* ctx, const unsigned char* d_bytes, const int6
     P.n_sel = n_stream; P.stream_size = stream_size; P.nch = nch;
     P.first = first_decode; P.n_decode = n_decode; P.data = (int32_t*)d_out; P.crc = ctx->d_crc;
     P.meta = (StreamMeta*)scr; P.frame_off = (long long*)(scr + meta_b); P.nframes_cap = nframes_cap;
-    P.stream_flag = (int*)(scr + meta_b + fo_b); P.err = ctx->d_err; P.verify_crc16 = 1;
+    P.stream_flag = (int*)(scr + meta_b + fo_b); P.err = ctx->d_err; P.verify_crc16 = 1; P.frame_flag = frame_flag;
 
     k_dec_meta<<<(unsigned)((n_stream + 127) / 128), 128, 0, st>>>(P);
     ctx->launches++;
@@ -507,33 +551,48 @@ extern "C" int fab_decode(fab_ctx* ctx, const unsigned char* d_bytes, const int6
             ctx->launches++;
         }
     }
+    const bool fuse_restore = d_offsets && d_gains && !is_int64;
+    TileParams TP;
     {
-        // frames overlapping the window, for the hinted blocksize (streams with another blocksize that
-        // need more frames than the table holds were flagged for the walker by k_dec_meta)
+        // frames overlapping the window, for the hinted blocksize (a stream whose real blocksize needs
+        // more frames than that is handed to the walker by the kernels)
         int64_t nwin = (first_decode + n_decode - 1) / bsh - first_decode / bsh + 1;
         int64_t total = n_stream * nwin;
+        FAB_CUDA(ctx, cudaMemsetAsync(frame_flag, 0, fflag_b, st));
+        TP.D = P; TP.j0 = first_decode / bsh; TP.nwin = nwin; TP.frame_flag = frame_flag;
+        TP.restore = fuse_restore ? 1 : 0; TP.offsets = (const float*)d_offsets; TP.gains = (const float*)d_gains;
+        int64_t per_cta = (int64_t)kTileWarps * 32;
         prof_begin(ctx, 1, st);
-        k_dec_frames<<<(unsigned)((total + kDecThreads - 1) / kDecThreads), kDecThreads, 0, st>>>(P, nwin);
+        k_dec_tile<true><<<(unsigned)((total + per_cta - 1) / per_cta), kTileWarps * 32, 0, st>>>(TP);
         prof_end(ctx, st);
+        ctx->launches++;
+        // general per-thread decoder: only the frames the tile path flagged
+        k_dec_frames<<<(unsigned)((total + kDecThreads - 1) / kDecThreads), kDecThreads, 0, st>>>(P, nwin);
         ctx->launches++;
     }
     k_dec_walker<<<(unsigned)((n_stream + 31) / 32), 32, 0, st>>>(P);
     ctx->launches++;
 
-    if (d_offsets && d_gains) {
+    if (fuse_restore) {
+        for (int64_t s0 = 0; s0 < n_stream; s0 += 65535) {
+            int64_t ns = std::min<int64_t>(65535, n_stream - s0);
+            TileParams Q = TP;
+            Q.D.starts += s0; Q.D.nbytes += s0; Q.D.meta += s0; Q.D.frame_off += s0 * (int64_t)(nframes_cap + 1);
+            Q.D.stream_flag += s0; Q.D.data += s0 * n_decode; Q.D.n_sel = ns;
+            Q.frame_flag += s0 * (int64_t)nframes_cap; Q.offsets += s0; Q.gains += s0;
+            dim3 grid((unsigned)std::min<int64_t>(TP.nwin, 64), (unsigned)ns);
+            k_restore_fixup<<<grid, 256, 0, st>>>(Q);
+            ctx->launches++;
+        }
+    } else if (d_offsets && d_gains) {
         int64_t per_cta = 256 * 16;
         int64_t gx = (n_decode + per_cta - 1) / per_cta;
         for (int64_t s0 = 0; s0 < n_stream; s0 += 65535) {
             int64_t ns = std::min<int64_t>(65535, n_stream - s0);
             dim3 grid((unsigned)gx, (unsigned)ns);
-            if (is_int64)
-                k_restore<long long, double><<<grid, 256, 0, st>>>((const long long*)d_out + s0 * n_decode, n_decode, per_cta,
-                                                                   (const double*)d_offsets + s0, (const double*)d_gains + s0,
-                                                                   (double*)d_out + s0 * n_decode);
-            else
-                k_restore<int32_t, float><<<grid, 256, 0, st>>>((const int32_t*)d_out + s0 * n_decode, n_decode, per_cta,
-                                                                (const float*)d_offsets + s0, (const float*)d_gains + s0,
-                                                                (float*)d_out + s0 * n_decode);
+            k_restore<long long, double><<<grid, 256, 0, st>>>((const long long*)d_out + s0 * n_decode, n_decode, per_cta,
+                                                               (const double*)d_offsets + s0, (const double*)d_gains + s0,
+                                                               (double*)d_out + s0 * n_decode);
             ctx->launches++;
         }
     }

@@ -258,6 +258,7 @@ struct DecParams {
     int* stream_flag;          // [n_sel] 0 = ok, !=0 = needs the sequential walker
     int* err;
     int verify_crc16;
+    const unsigned char* frame_flag;  // optional [n_sel][nframes_cap]: when set, frame_body only decodes flagged frames
 };
 
 // number of frames / size of frame j for a fixed-blocksize stream
@@ -322,6 +323,7 @@ FA_D void sync_body(const DecParams& P, int64_t k, int64_t p) {
 // ---- stage 3: one thread per (selected stream, frame overlapping the sample window) ---------------
 FA_D void frame_body(const DecParams& P, int64_t k, int64_t j) {
     if (P.stream_flag[k] != 0) return;
+    if (P.frame_flag && !P.frame_flag[k * (int64_t)P.nframes_cap + j]) return;
     const StreamMeta m = P.meta[k];
     const long long* fo = P.frame_off + k * (int64_t)(P.nframes_cap + 1);
     long long off = fo[j], next = fo[j + 1];

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../flacarray_b200/csrc/fa_decode.h"
+#include "../../flacarray_b200/csrc/fa_decode_tile.h"
 #include "../../flacarray_b200/csrc/fa_encode.h"
 
 namespace fasim {
@@ -98,7 +99,43 @@ int hs_decode(const uint8_t* bytes, const long long* starts, const long long* nb
     P.bytes = bytes; P.starts = starts; P.nbytes = nbytes; P.n_sel = n_sel; P.stream_size = stream_size;
     P.nch = nch; P.first = first_decode; P.n_decode = n_decode; P.data = data; P.crc = crc();
     P.meta = meta.data(); P.frame_off = fo.data(); P.nframes_cap = nframes_cap; P.stream_flag = flag.data();
-    P.err = &err; P.verify_crc16 = 0;
+    P.err = &err; P.verify_crc16 = 1; P.frame_flag = nullptr;
+    std::vector<unsigned char> fflag((size_t)n_sel * (size_t)nframes_cap, 0);
+    if (mode == 2) {
+        // throughput path emulation: meta -> sync scan -> warp-tile kernel -> general decoder on the
+        // flagged frames -> walker on the flagged streams
+        fasim::launch(1, 1, 0, [&](int) {
+            for (int64_t k = 0; k < n_sel; ++k) meta_body(P, k);
+            for (int64_t k = 0; k < n_sel; ++k)
+                for (int64_t p = 0; p < nbytes[k]; ++p) sync_body(P, k, p);
+        });
+        int bsh = 4096;
+        for (int64_t k = 0; k < n_sel; ++k) if (meta[(size_t)k].blocksize > 0) { bsh = meta[(size_t)k].blocksize; break; }
+        int64_t nwin = (first_decode + n_decode - 1) / bsh - first_decode / bsh + 1;
+        TileParams TP;
+        TP.D = P; TP.j0 = first_decode / bsh; TP.nwin = nwin; TP.frame_flag = fflag.data();
+        TP.restore = 0; TP.offsets = nullptr; TP.gains = nullptr;
+        int64_t total = n_sel * nwin;
+        std::vector<uint16_t> tab(4 * 256);
+        for (int i = 0; i < 4 * 256; ++i) tab[(size_t)i] = crc()->crc16[i >> 8][i & 255];
+        fasim::launch((int)((total + 31) / 32), 32, sizeof(TileShared) + 64, [&](int b) {
+            tile_warp_body<true>(TP, (int64_t)b * 32, (TileShared*)fasim::smem(), tab.data());
+        });
+        int walked = 0, general = 0;
+        fasim::launch(1, 1, 0, [&](int) {
+            DecParams Q = P;
+            Q.frame_flag = fflag.data();
+            for (int64_t k = 0; k < n_sel; ++k) {
+                if (flag[(size_t)k]) continue;
+                int bs = meta[(size_t)k].blocksize;
+                int64_t j0 = first_decode / bs, j1 = (first_decode + n_decode - 1) / bs;
+                for (int64_t j = j0; j <= j1; ++j) { if (fflag[(size_t)(k * nframes_cap + j)]) general++; frame_body(Q, k, j); }
+            }
+            for (int64_t k = 0; k < n_sel; ++k) { if (flag[(size_t)k] && flag[(size_t)k] != 4) walked++; walker_body(P, k); }
+        });
+        if (n_walked) *n_walked = walked + 1000 * general;
+        return err;
+    }
     fasim::launch(1, 1, 0, [&](int) {
         for (int64_t k = 0; k < n_sel; ++k) meta_body(P, k);
         if (mode == 1) for (int64_t k = 0; k < n_sel; ++k) if (flag[(size_t)k] == 0) flag[(size_t)k] = 1;

@@ -51,6 +51,8 @@ def test_decoder_bodies_on_own_and_foreign_streams(H, oracle):
         for comp, st, nb in ((c, s, n), (oc, os_, on)):
             y, walked = H.decode(comp, st, nb, x.shape[1])
             assert np.array_equal(y, x) and walked == 0, name
+            y, walked = H.decode(comp, st, nb, x.shape[1], mode=2)  # warp-tile throughput path
+            assert np.array_equal(y, x) and walked == 0, name
             y, walked = H.decode(comp, st, nb, x.shape[1], mode=1)  # sequential walker
             assert np.array_equal(y, x) and walked == x.shape[0], name
             if x.shape[1] > 20:
@@ -83,10 +85,11 @@ def test_decoder_bodies_on_golden_third_party_streams(H, golden_dir):
         n, nch = samples.shape
         st = np.zeros(1, np.int64)
         nb = np.array([stream.size], np.int64)
-        y, walked = H.decode(stream, st, nb, n, is_int64=(nch == 2))
         want = samples.reshape(1, -1).view(np.int64) if nch == 2 else samples.reshape(1, -1)
-        assert np.array_equal(y, want), p
-        assert walked == 0, p
+        for mode in (0, 2):
+            y, walked = H.decode(stream, st, nb, n, is_int64=(nch == 2), mode=mode)
+            assert np.array_equal(y, want), (p, mode)
+            assert walked % 1000 == 0, (p, mode)   # no stream needed the sequential walker
 
 
 def test_float_bodies_match_reference_vectors(H, golden_dir):
