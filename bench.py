@@ -98,7 +98,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -107,7 +107,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def mark(self):
+        """Only samples that arrive after this call are reported (the sampler is started before the
+        warm-up because nvidia-smi's start-up briefly stalls the GPU it attaches to)."""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
@@ -118,7 +123,10 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        t_mark = getattr(self, "t_mark", 0.0)
+        for t, r in self.rows:
+            if t < t_mark:
+                continue
             f = [x.strip() for x in r.split(",")]
             if len(f) < 9:
                 continue
@@ -262,14 +270,16 @@ def run_ours(args):
     del comp, out
 
     # ---- device-resident timed region (separate encode / decode timings inside one loop) ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.5)
     for _ in range(args.warmup):
         step_device()
     ctx.profile(True)
     launches0 = ctx.launches()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
         ev[k][0].record()

@@ -2,7 +2,10 @@
 //
 // Same role as frame_body() in fa_decode.h (libFLAC frame decode + the write callback
 // decompress.c:66-101), restructured for the machine:
-//   * predictor history and coefficients live in registers (order <= 12, 32-bit samples);
+//   * compressed bytes are fetched 16 B at a time per lane with one chunk always in flight
+//     (software prefetch: the DRAM latency overlaps ~8 samples of decode work);
+//   * predictor history and coefficients live in registers (order <= 12, 32-bit samples), four
+//     samples per loop trip so the history "shift" is register renaming;
 //   * every lane appends its samples to a [32 lanes][32 samples] shared-memory tile; after 32 samples
 //     the warp transposes the tile so that each store instruction writes 128 contiguous bytes of one
 //     frame (fully coalesced), optionally restoring int32 -> float32 on the way (utils.c:350-368);
@@ -30,16 +33,18 @@ struct TileShared {       // per warp
     TileRow row[32];
 };
 
-// Bit reader with a CRC-16 that lags two words behind the fetch pointer (so that the frame end, which
-// is only known after the last sample, can be handled exactly).
+// Bit reader: 16-byte chunk prefetch queue -> 64-bit MSB-aligned buffer, with a CRC-16 that lags two
+// words behind (so that the frame end, only known after the last sample, is handled exactly).
 struct BitRdC {
-    const uint32_t* wp;
-    const uint32_t* wend;
+    const U4* cp;      // next chunk to prefetch
+    const U4* cend;    // first chunk holding no valid byte
+    U4 cur, nxt;       // words still to be taken (cur.x first) / chunk in flight
+    int cnt;           // words left in cur
     uint64_t buf;
     int n;
-    int nwords;        // words fetched so far
-    uint32_t crc;      // CRC state before word (nwords - 2)
-    uint32_t w1, w2;   // last fetched word (w1) and the one before (w2)
+    int nwords;        // words taken after word 0
+    uint32_t crc;      // CRC state before word (nwords - 1) [absolute numbering, see brc_finish_crc]
+    uint32_t w1, w2;   // last taken word (w1) and the one before (w2)
     int err;
 };
 
@@ -52,11 +57,23 @@ FA_D uint32_t crc16_b(const uint16_t* T, uint32_t c, uint32_t byte) {
     return ((c << 8) & 0xFFFF) ^ T[((c >> 8) ^ byte) & 0xFF];
 }
 
+FA_D U4 u4_zero() { U4 z; z.x = z.y = z.z = z.w = 0; return z; }
+
+FA_D uint32_t brc_take(BitRdC& br) {
+    uint32_t w = bswap32(br.cur.x);
+    br.cur.x = br.cur.y; br.cur.y = br.cur.z; br.cur.z = br.cur.w;
+    if (--br.cnt == 0) {
+        br.cur = br.nxt;
+        br.cnt = 4;
+        br.nxt = (br.cp < br.cend) ? ldg128(br.cp) : u4_zero();
+        br.cp++;
+    }
+    return w;
+}
+
 template <bool CRC>
 FA_D void brc_fetch(BitRdC& br, const uint16_t* T) {
-    uint32_t w = 0;
-    if (br.wp < br.wend) w = bswap32(ldg32(br.wp));
-    br.wp++;
+    uint32_t w = brc_take(br);
     if (CRC) {
         if (br.nwords >= 2) br.crc = crc16_word(T, br.crc, br.w2);
         br.w2 = br.w1;
@@ -71,16 +88,20 @@ FA_D void brc_fetch(BitRdC& br, const uint16_t* T) {
 template <bool CRC>
 FA_D void brc_init(BitRdC& br, const uint8_t* start, const uint8_t* end, uint32_t crc0, const uint16_t* T) {
     uintptr_t s = (uintptr_t)start;
-    br.wp = (const uint32_t*)(s & ~(uintptr_t)3);
-    br.wend = (const uint32_t*)(((uintptr_t)end + 3) & ~(uintptr_t)3);
+    const U4* c0 = (const U4*)(s & ~(uintptr_t)15);
+    br.cend = (const U4*)(((uintptr_t)end + 15) & ~(uintptr_t)15);
+    br.cur = (c0 < br.cend) ? ldg128(c0) : u4_zero();
+    br.nxt = (c0 + 1 < br.cend) ? ldg128(c0 + 1) : u4_zero();
+    br.cp = c0 + 2;
+    br.cnt = 4;
+    int skip = (int)((s & 15) >> 2);
+    for (int i = 0; i < skip; ++i) (void)brc_take(br);   // cnt stays >= 1: skip <= 3
     int a = (int)(s & 3);
     br.buf = 0; br.n = 0; br.nwords = 0; br.err = 0; br.w1 = br.w2 = 0;
     br.crc = crc0;
-    uint32_t w = 0;
-    if (br.wp < br.wend) w = bswap32(ldg32(br.wp));
-    br.wp++;
-    // the first word is consumed byte-wise by the CRC (its leading `a` bytes precede `start`), so it
-    // does not enter the lagging word queue
+    uint32_t w = brc_take(br);
+    // word 0 is consumed byte-wise by the CRC (its leading `a` bytes precede `start`), so it does not
+    // enter the lagging word queue
     if (CRC) for (int b = a; b < 4; ++b) br.crc = crc16_b(T, br.crc, (w >> (24 - 8 * b)) & 0xFF);
     br.buf = ((uint64_t)w << 32) << (8 * a);
     br.n = 32 - 8 * a;
@@ -120,7 +141,7 @@ FA_D uint32_t brc_unary(BitRdC& br, const uint16_t* T) {
         }
         q += (uint32_t)br.n;
         br.n = 0;
-        if (br.wp > br.wend + 1) { br.err = 1; return q; }
+        if (br.cp > br.cend + 4) { br.err = 1; return q; }  // ran off the end of the stream
     }
 }
 // Rice code with parameter k (< 32): fast path when the whole code sits in the buffer.
@@ -143,22 +164,42 @@ FA_D int32_t brc_rice(BitRdC& br, int k, const uint16_t* T) {
     return (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
 }
 
-// Bits consumed since brc_init, and the frame-relative end / CRC check.
+// Bits consumed since brc_init (a = start byte offset inside word 0).
 FA_D int64_t brc_pos_bits(const BitRdC& br, int a) { return (int64_t)(br.nwords + 1) * 32 - br.n - 8 * a; }
 
+// CRC-16 over [frame start, first CRC byte).  E = byte index of the first CRC byte counted from the
+// start of word 0.  Words are numbered absolutely: word 0 (brc_init), then takes 1..nwords.  With
+// F = nwords takes, br.crc covers words 0..F-2 (F >= 2) or word 0 only (F == 1); the queue holds the
+// rest.  Because at most 64 unread bits remain, E lies in word F-1, F or right after F.
+FA_D uint32_t brc_finish_crc(const BitRdC& br, const uint16_t* T, int64_t E) {
+    uint32_t c16 = br.crc;
+    int64_t covered = (br.nwords >= 2) ? (int64_t)br.nwords - 1 : 1;
+    uint32_t q[2] = {br.w2, br.w1};
+    int qn = br.nwords >= 2 ? 2 : br.nwords;
+    if (br.nwords == 1) q[0] = br.w1;
+    int64_t wE = E >> 2;
+    for (int t = 0; t < qn; ++t) {
+        int64_t wabs = covered + t;
+        if (wabs > wE) break;
+        int nb = wabs < wE ? 4 : (int)(E & 3);
+        for (int b = 0; b < nb; ++b) c16 = crc16_b(T, c16, (q[t] >> (24 - 8 * b)) & 0xFF);
+    }
+    return c16;
+}
+
 struct TileLane {
-    int mode;       // 0 const, 1 verbatim, 2 predictive, -1 idle
+    int mode;       // 0 const, 1 verbatim, 2 predictive
     int lpc;        // predictive: 1 = LPC subframe (parameters follow the warm-up), 0 = fixed predictor
     int order, shift, wasted, bps;
-    int raw_left;
+    int raw_left;   // warm-up / verbatim samples still to read
+    int need_params;
     int32_t cval;
     int plen, esc, psize, part, nparts, left, k, rawbits;
     int32_t h[kTileOrd];
     int32_t c[kTileOrd];
 };
 
-// Parse one subframe header (up to and including the residual header).  Returns false if this path
-// cannot decode the subframe (caller flags the frame for the general decoder) or the stream is bad.
+// Subframe header.  false => this path cannot decode it (br.err tells a bad stream from "unsupported").
 template <bool CRC>
 FA_D bool tile_subframe_begin(BitRdC& br, const uint16_t* T, int bs, int bps, TileLane& L) {
     if (brc_read<CRC>(br, 1, T) != 0) return false;
@@ -174,7 +215,9 @@ FA_D bool tile_subframe_begin(BitRdC& br, const uint16_t* T, int bs, int bps, Ti
     L.shift = 0;
     L.left = 0;
     L.part = -1;
+    L.nparts = 0;
     L.k = 0;
+    L.need_params = 0;
 #pragma unroll
     for (int j = 0; j < kTileOrd; ++j) { L.h[j] = 0; L.c[j] = 0; }
     if (type == 0) {
@@ -198,6 +241,7 @@ FA_D bool tile_subframe_begin(BitRdC& br, const uint16_t* T, int bs, int bps, Ti
     L.lpc = lpc ? 1 : 0;
     L.order = order;
     L.raw_left = order;
+    L.need_params = 1;
     return true;
 }
 
@@ -205,6 +249,7 @@ FA_D bool tile_subframe_begin(BitRdC& br, const uint16_t* T, int bs, int bps, Ti
 template <bool CRC>
 FA_D bool tile_subframe_params(BitRdC& br, const uint16_t* T, int bs, TileLane& L) {
     const int order = L.order;
+    L.need_params = 0;
     if (L.lpc) {
         int prec = (int)brc_read<CRC>(br, 4, T) + 1;
         if (prec == 16) return false;
@@ -234,6 +279,19 @@ FA_D bool tile_subframe_params(BitRdC& br, const uint16_t* T, int bs, TileLane& 
 }
 
 template <bool CRC>
+FA_D void tile_open_partition(BitRdC& br, const uint16_t* T, TileLane& L) {
+    while (L.left == 0) {
+        L.part++;
+        if (L.part >= L.nparts) { br.err = 1; L.left = 1 << 30; L.k = 0; return; }
+        L.left = L.psize - (L.part == 0 ? L.order : 0);
+        int k = (int)brc_read<CRC>(br, L.plen, T);
+        if (k == L.esc) { L.k = -1; L.rawbits = (int)brc_read<CRC>(br, 5, T); }
+        else L.k = k;
+    }
+}
+
+// One sample, any mode (slow path: warm-up, verbatim, constant, partition edges, escapes).
+template <bool CRC, int ORD>
 FA_D int32_t tile_next_sample(BitRdC& br, const uint16_t* T, TileLane& L) {
     int32_t v;
     if (L.mode == 0) {
@@ -242,35 +300,103 @@ FA_D int32_t tile_next_sample(BitRdC& br, const uint16_t* T, TileLane& L) {
         v = brc_read_signed<CRC>(br, L.bps, T);
         L.raw_left--;
     } else {
-        while (L.left == 0) {
-            L.part++;
-            if (L.part >= L.nparts) { br.err = 1; return 0; }
-            L.left = L.psize - (L.part == 0 ? L.order : 0);
-            int k = (int)brc_read<CRC>(br, L.plen, T);
-            if (k == L.esc) { L.k = -1; L.rawbits = (int)brc_read<CRC>(br, 5, T); }
-            else L.k = k;
-        }
+        if (L.left == 0) tile_open_partition<CRC>(br, T, L);
         L.left--;
         int32_t r = (L.k >= 0) ? brc_rice<CRC>(br, L.k, T) : brc_read_signed<CRC>(br, L.rawbits, T);
         int64_t sum = 0;
 #pragma unroll
-        for (int j = 0; j < kTileOrd; ++j) sum += (int64_t)L.c[j] * (int64_t)L.h[j];
+        for (int j = 0; j < ORD; ++j) sum += (int64_t)L.c[j] * (int64_t)L.h[j];
         v = (int32_t)((int64_t)r + (sum >> L.shift));
     }
 #pragma unroll
-    for (int j = kTileOrd - 1; j > 0; --j) L.h[j] = L.h[j - 1];
-    L.h[0] = v;
+    for (int j = ORD - 1; j > 0; --j) L.h[j] = L.h[j - 1];
+    if (ORD > 0) L.h[0] = v;
     return (int32_t)((uint32_t)v << L.wasted);
+}
+
+// Four residual samples of one partition (k >= 0): the steady-state inner loop.
+template <bool CRC, int ORD>
+FA_D void tile_next4(BitRdC& br, const uint16_t* T, TileLane& L, int32_t* out4) {
+    int32_t r[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) r[q] = brc_rice<CRC>(br, L.k, T);
+    L.left -= 4;
+    int32_t s[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        int64_t sum = 0;
+#pragma unroll
+        for (int j = 0; j < ORD; ++j) {
+            // history as seen by sample q: s[q-1], .., s[0], h[0], h[1], ...
+            int32_t hv = (j < q) ? s[q - 1 - j] : L.h[j - q];
+            sum += (int64_t)L.c[j] * (int64_t)hv;
+        }
+        s[q] = (int32_t)((int64_t)r[q] + (sum >> L.shift));
+    }
+#pragma unroll
+    for (int j = ORD - 1; j >= 4; --j) L.h[j] = L.h[j - 4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        if (3 - q < ORD) L.h[3 - q] = s[q];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) out4[q] = (int32_t)((uint32_t)s[q] << L.wasted);
 }
 
 struct TileParams {
     DecParams D;
-    int64_t j0, nwin;        // frame window (for the hinted blocksize)
+    int64_t j0, nwin;           // frame window (for the hinted blocksize)
     unsigned char* frame_flag;  // [n_sel][nframes_cap]: 1 = leave to the general decoder
-    int restore;             // 1: nch == 1 and D.data receives float32 (offsets/gains given)
+    int restore;                // 1: nch == 1 and D.data receives float32 (offsets/gains given)
     const float* offsets;
     const float* gains;
 };
+
+// Decode + flush all tiles of one channel pass with a compile-time upper bound on the predictor order.
+template <bool CRC, int ORD>
+FA_D void tile_channel_pass(const TileParams& P, TileShared* ws, const uint16_t* T, BitRdC& br, TileLane& L, bool& run,
+                            bool& fail, bool& punt, int bs, uint32_t bsmax, int c, int nch) {
+    const int ln = lane();
+    int32_t* trow = ws->tile + ln * kTileStride;
+    for (uint32_t base = 0; base < bsmax; base += 32) {
+#pragma unroll 1
+        for (int s = 0; s < 32; s += 4) {
+            int i = (int)base + s;
+            if (run && i < bs) {
+                bool fast = L.mode == 2 && L.raw_left == 0 && !L.need_params && L.left >= 4 && L.k >= 0 && i + 4 <= bs;
+                if (fast) {
+                    tile_next4<CRC, ORD>(br, T, L, trow + s);
+                } else {
+                    for (int q = 0; q < 4; ++q) {
+                        int32_t v = 0;
+                        if (run && i + q < bs) {
+                            if (L.need_params && L.raw_left == 0) {
+                                if (!tile_subframe_params<CRC>(br, T, bs, L)) {
+                                    run = false;
+                                    if (br.err) fail = true; else punt = true;
+                                }
+                            }
+                            if (run) v = tile_next_sample<CRC, ORD>(br, T, L);
+                        }
+                        trow[s + q] = v;
+                    }
+                }
+            }
+        }
+        syncwarp();
+        // transpose: each iteration stores 32 consecutive samples of one frame (128 B)
+        const int i = (int)base + ln;
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+            const TileRow row = ws->row[r];
+            if ((uint32_t)(i - row.lo) < (uint32_t)(row.hi - row.lo)) {
+                int32_t v = ws->tile[r * kTileStride + ln];
+                if (P.restore) ((float*)row.out)[i] = restore_f32(v, row.off, row.coeff);
+                else row.out[(int64_t)i * nch + c] = v;
+            }
+        }
+        syncwarp();
+    }
+}
 
 // One warp: 32 consecutive (stream, frame) work items.  `ws` = this warp's shared storage, `T` = CRC
 // slice tables in shared memory.
@@ -346,19 +472,19 @@ FA_D void tile_warp_body(const TileParams& P, int64_t item0, TileShared* ws, con
     for (int m = 16; m >= 1; m >>= 1) { uint32_t o = shfl_xor(bsmax, m); bsmax = o > bsmax ? o : bsmax; }
 
     BitRdC br;
-    br.err = 0;
     int a = 0;
     if (active) {
         const uint8_t* body = fp + fh.hdr_bytes;
         a = (int)((uintptr_t)body & 3);
         brc_init<CRC>(br, body, end, crc0, T);
     } else {
-        br.wp = br.wend = nullptr; br.buf = 0; br.n = 64; br.nwords = 0; br.crc = 0; br.w1 = br.w2 = 0;
+        br.cp = br.cend = nullptr; br.cur = br.nxt = u4_zero(); br.cnt = 4;
+        br.buf = 0; br.n = 64; br.nwords = 0; br.crc = 0; br.w1 = br.w2 = 0; br.err = 0;
     }
     bool fail = false;      // stream problem -> walker
     bool punt = false;      // unsupported subframe -> general decoder
     TileLane L;
-    L.mode = -1;
+    L.mode = 0; L.order = 0; L.raw_left = 0; L.need_params = 0; L.left = 0; L.k = 0; L.wasted = 0; L.shift = 0; L.cval = 0;
     for (int c = 0; c < nch; ++c) {
         if (active && !fail && !punt) {
             if (!tile_subframe_begin<CRC>(br, T, bs, 32, L)) {
@@ -366,35 +492,12 @@ FA_D void tile_warp_body(const TileParams& P, int64_t item0, TileShared* ws, con
             }
         }
         bool run = active && !fail && !punt;
-        // The warm-up samples are read inside the main loop (raw_left); the LPC parameters and the
-        // residual header follow them in the stream and are parsed when the warm-up is exhausted.
-        bool need_params = run && L.mode == 2;
-        for (uint32_t base = 0; base < bsmax; base += 32) {
-            for (int s = 0; s < 32; ++s) {
-                int i = (int)base + s;
-                int32_t v = 0;
-                if (run && i < bs) {
-                    if (need_params && L.raw_left == 0) {
-                        if (!tile_subframe_params<CRC>(br, T, bs, L)) { run = false; if (br.err) fail = true; else punt = true; }
-                        need_params = false;
-                    }
-                    if (run) v = tile_next_sample<CRC>(br, T, L);
-                }
-                ws->tile[ln * kTileStride + s] = v;
-            }
-            syncwarp();
-            // transpose: each iteration stores 32 consecutive samples of one frame (128 B)
-            for (int r = 0; r < 32; ++r) {
-                const TileRow row = ws->row[r];
-                int i = (int)base + ln;
-                if (row.out != nullptr && i >= row.lo && i < row.hi) {
-                    int32_t v = ws->tile[r * kTileStride + ln];
-                    if (P.restore) ((float*)row.out)[i] = restore_f32(v, row.off, row.coeff);
-                    else row.out[(int64_t)i * nch + c] = v;
-                }
-            }
-            syncwarp();
-        }
+        // warp-uniform bound on the predictor order picks the instantiation of the sample loop
+        uint32_t omax = (uint32_t)((run && L.mode == 2) ? L.order : 0);
+        for (int m = 16; m >= 1; m >>= 1) { uint32_t o = shfl_xor(omax, m); omax = o > omax ? o : omax; }
+        if (omax <= 4) tile_channel_pass<CRC, 4>(P, ws, T, br, L, run, fail, punt, bs, bsmax, c, nch);
+        else if (omax <= 8) tile_channel_pass<CRC, 8>(P, ws, T, br, L, run, fail, punt, bs, bsmax, c, nch);
+        else tile_channel_pass<CRC, kTileOrd>(P, ws, T, br, L, run, fail, punt, bs, bsmax, c, nch);
         if (run && br.err) fail = true;
     }
     if (active) {
@@ -408,25 +511,8 @@ FA_D void tile_warp_body(const TileParams& P, int64_t item0, TileShared* ws, con
             if (fp + len > end) fail = true;
             if (!fail && next >= 0 && off + len != next) fail = true;
             if (!fail && CRC) {
-                // bytes of the body counted from the first fetched word: E = a + body_bytes
-                int64_t E = a + body_bytes;
-                int64_t wE = E >> 2;                       // word holding the first CRC byte
-                uint32_t c16 = br.crc;                     // state before word (nwords + 1 - 2) in absolute numbering
-                // absolute word numbering: word 0 = first word (consumed byte-wise in brc_init);
-                // fetched word t (t = 1..nwords) ; br.crc covers words < nwords - 1 (i.e. up to t = nwords - 2)
-                int64_t covered = (br.nwords >= 2) ? (int64_t)br.nwords - 1 : 1;   // first uncovered absolute word
-                // when fewer than two words were fetched nothing sits in the lag queue beyond w1
-                uint32_t q[2] = {br.w2, br.w1};
-                int qn = br.nwords >= 2 ? 2 : br.nwords;   // words in the queue: absolute indices covered .. covered+qn-1
-                if (br.nwords == 1) q[0] = br.w1;
-                for (int t = 0; t < qn; ++t) {
-                    int64_t wabs = covered + t;
-                    if (wabs > wE) break;
-                    int nb = wabs < wE ? 4 : (int)(E & 3);
-                    for (int b = 0; b < nb; ++b) c16 = crc16_b(T, c16, (q[t] >> (24 - 8 * b)) & 0xFF);
-                }
                 uint32_t want = ((uint32_t)fp[len - 2] << 8) | fp[len - 1];
-                if (c16 != want) fail = true;
+                if (brc_finish_crc(br, T, a + body_bytes) != want) fail = true;
             }
         }
         if (fail) atom_or_global(&D.stream_flag[k], 2);

@@ -56,6 +56,12 @@ FA_D unsigned long long ld_acquire_u64(const unsigned long long* p) {
 }
 FA_D void spin_pause() { __nanosleep(20); }
 FA_D uint32_t ldg32(const uint32_t* p) { return __ldg(p); }
+struct U4 { uint32_t x, y, z, w; };
+FA_D U4 ldg128(const void* p) {  // 16-byte aligned, read-only path
+    uint4 v = __ldg((const uint4*)p);
+    U4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+    return r;
+}
 // float ops with the rounding and (non-)contraction spelled out
 FA_D float fadd(float a, float b) { return __fadd_rn(a, b); }
 FA_D float fsub(float a, float b) { return __fsub_rn(a, b); }
@@ -185,6 +191,8 @@ inline void st_release_u64(unsigned long long* p, unsigned long long v) { __atom
 inline unsigned long long ld_acquire_u64(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 inline void spin_pause() { std::this_thread::yield(); }
 inline uint32_t ldg32(const uint32_t* p) { return *p; }
+struct U4 { uint32_t x, y, z, w; };
+inline U4 ldg128(const void* p) { U4 r; memcpy(&r, p, 16); return r; }
 // host build is compiled with -ffp-contract=off so these are the IEEE single operations
 inline float fadd(float a, float b) { return a + b; }
 inline float fsub(float a, float b) { return a - b; }
