@@ -26,16 +26,17 @@ using namespace fa;
 // Kernels
 // =================================================================================================
 
-__global__ void __launch_bounds__(kEncThreads, 2) k_encode(const EncParams P) {
+// persistent CTAs: each loops over (stream, frame) tickets; H = predictor history kept in registers
+template <int H>
+__global__ void __launch_bounds__(kEncThreads, 4) k_encode(const EncParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
-    encode_frame_cta(P, smem);
+    encode_frames_cta<H>(P, smem);
 }
 
-__global__ void k_enc_finalize(const long long* __restrict__ starts, const long long* __restrict__ ends,
-                               long long* __restrict__ nbytes, int64_t n, long long* __restrict__ total) {
+// stream headers, frame-size tables, stream_starts / stream_nbytes / total from the look-back descriptors
+__global__ void k_enc_finalize(const EncParams P, long long* __restrict__ nbytes, long long* __restrict__ total) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) nbytes[i] = ends[i] - starts[i];
-    if (i == n - 1 && total) *total = ends[i];
+    if (i < P.n_stream * P.nframes) finalize_entry(P, i / P.nframes, (int)(i % P.nframes), nbytes, total);
 }
 
 // ---- float -> int: per-stream min/max (utils.c:182-193 / :267-278), chunked over the stream ------
@@ -236,6 +237,9 @@ __global__ void k_max_i64(const long long* __restrict__ v, int64_t n, long long*
 struct fab_ctx {
     int device = -1;
     CrcTables* d_crc = nullptr;
+    EncTables* d_tab = nullptr;
+    int n_sm = 0;
+    int enc_ctas_per_sm[2][2] = {{0, 0}, {0, 0}};   // [H == 12][nch - 1]
     float* d_window[2] = {nullptr, nullptr};  // [0] 1152, [1] 4096
     int* d_err = nullptr;
     int* h_err = nullptr;  // pinned
@@ -318,11 +322,16 @@ extern "C" int fab_create(fab_ctx** out) {
     ctx->device = dev;
     CrcTables* h = new CrcTables();
     crc_tables_init(h);
+    EncTables* ht = new EncTables();
+    enc_tables_init(ht);
+    cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, dev);
     std::vector<float> w0(1152), w1(4096);
     make_tukey_window(w0.data(), 1152);
     make_tukey_window(w1.data(), 4096);
     bool ok = cudaMalloc((void**)&ctx->d_crc, sizeof(CrcTables)) == cudaSuccess &&
               cudaMemcpy(ctx->d_crc, h, sizeof(CrcTables), cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMalloc((void**)&ctx->d_tab, sizeof(EncTables)) == cudaSuccess &&
+              cudaMemcpy(ctx->d_tab, ht, sizeof(EncTables), cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMalloc((void**)&ctx->d_window[0], 1152 * 4) == cudaSuccess &&
               cudaMemcpy(ctx->d_window[0], w0.data(), 1152 * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMalloc((void**)&ctx->d_window[1], 4096 * 4) == cudaSuccess &&
@@ -330,6 +339,7 @@ extern "C" int fab_create(fab_ctx** out) {
               cudaMalloc((void**)&ctx->d_err, 4) == cudaSuccess && cudaMemset(ctx->d_err, 0, 4) == cudaSuccess &&
               cudaMallocHost((void**)&ctx->h_err, 4) == cudaSuccess;
     delete h;
+    delete ht;
     if (!ok) {
         cudaGetLastError();
         fab_destroy(ctx);
@@ -342,6 +352,7 @@ extern "C" int fab_create(fab_ctx** out) {
 extern "C" void fab_destroy(fab_ctx* ctx) {
     if (!ctx) return;
     if (ctx->d_crc) cudaFree(ctx->d_crc);
+    if (ctx->d_tab) cudaFree(ctx->d_tab);
     if (ctx->d_window[0]) cudaFree(ctx->d_window[0]);
     if (ctx->d_window[1]) cudaFree(ctx->d_window[1]);
     if (ctx->d_err) cudaFree(ctx->d_err);
@@ -453,7 +464,6 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
     long long* ends = (long long*)(scr + pre + desc_b);
     uint32_t* ticket = (uint32_t*)(scr + pre + desc_b + ends_b);
     FAB_CUDA(ctx, cudaMemsetAsync(desc, 0, desc_b + ends_b + 256, st));
-    FAB_CUDA(ctx, cudaMemsetAsync(d_starts, 0xFF, (size_t)n_stream * 8, st));
 
     EncParams P;
     P.data = d_data; P.dtype = dtype; P.offsets = d_offsets; P.gains = d_gains;
@@ -462,22 +472,30 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
     P.max_lpc_order = lp.max_lpc_order; P.max_porder = lp.max_porder;
     P.qlp_precision = lp.blocksize <= 384 ? 13 : (lp.blocksize <= 1152 ? 14 : 15);
     P.window = ctx->d_window[lp.blocksize == 1152 ? 0 : 1];
-    P.crc = ctx->d_crc;
+    P.crc = ctx->d_crc; P.tab = ctx->d_tab;
     P.out = d_out; P.out_capacity = out_capacity;
     P.starts = (long long*)d_starts; P.ends = ends; P.desc = desc; P.ticket = ticket; P.err = ctx->d_err;
     P.hdr_bytes = stream_header_bytes((int)nf);
 
     size_t smem = enc_smem_bytes(nch);
     if (!ctx->smem_configured) {
-        FAB_CUDA(ctx, cudaFuncSetAttribute(k_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_smem_bytes(2)));
+        FAB_CUDA(ctx, cudaFuncSetAttribute(k_encode<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_smem_bytes(2)));
+        FAB_CUDA(ctx, cudaFuncSetAttribute(k_encode<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_smem_bytes(2)));
+        for (int c = 0; c < 2; ++c) {
+            FAB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->enc_ctas_per_sm[0][c], k_encode<8>, kEncThreads, enc_smem_bytes(c + 1)));
+            FAB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->enc_ctas_per_sm[1][c], k_encode<12>, kEncThreads, enc_smem_bytes(c + 1)));
+        }
         ctx->smem_configured = true;
     }
+    const int h12 = lp.max_lpc_order > 8 ? 1 : 0;
+    int64_t resident = (int64_t)ctx->n_sm * std::max(1, ctx->enc_ctas_per_sm[h12][nch - 1]);
+    unsigned grid = (unsigned)std::min<int64_t>(n_stream * nf, resident);
     prof_begin(ctx, 0, st);
-    k_encode<<<(unsigned)(n_stream * nf), kEncThreads, smem, st>>>(P);
+    if (h12) k_encode<12><<<grid, kEncThreads, smem, st>>>(P);
+    else k_encode<8><<<grid, kEncThreads, smem, st>>>(P);
     prof_end(ctx, st);
     ctx->launches++;
-    k_enc_finalize<<<(unsigned)((n_stream + 255) / 256), 256, 0, st>>>((const long long*)d_starts, ends, (long long*)d_nbytes,
-                                                                     n_stream, (long long*)d_total);
+    k_enc_finalize<<<(unsigned)((n_stream * nf + 255) / 256), 256, 0, st>>>(P, (long long*)d_nbytes, (long long*)d_total);
     ctx->launches++;
     FAB_CUDA(ctx, cudaGetLastError());
     return 0;

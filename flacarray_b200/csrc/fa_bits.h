@@ -78,6 +78,17 @@ FA_D uint32_t crc16_shift(const CrcTables* t, uint32_t crc, uint32_t n) {
     return crc;
 }
 
+// CRC-16 over one big-endian word / one byte with the slice-by-4 tables copied to shared memory
+// (T = [4][256] uint16, T[k][b] = state after byte b followed by k zero bytes).
+FA_D uint32_t crc16_word(const uint16_t* T, uint32_t c, uint32_t w) {
+    // T: [4][256] slice tables in shared memory
+    return (uint32_t)(T[3 * 256 + (((c >> 8) ^ (w >> 24)) & 0xFF)] ^ T[2 * 256 + (((c & 0xFF) ^ (w >> 16)) & 0xFF)] ^
+                      T[256 + ((w >> 8) & 0xFF)] ^ T[w & 0xFF]);
+}
+FA_D uint32_t crc16_b(const uint16_t* T, uint32_t c, uint32_t byte) {
+    return ((c << 8) & 0xFFFF) ^ T[((c >> 8) ^ byte) & 0xFF];
+}
+
 // ---- Bit reader ---------------------------------------------------------------------------------
 // Reads aligned 32-bit words (coalescing-friendly, L1/L2 sector reuse) and never touches a word
 // that holds no valid byte of [start, end).

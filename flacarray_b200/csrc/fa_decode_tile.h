@@ -48,14 +48,6 @@ struct BitRdC {
     int err;
 };
 
-FA_D uint32_t crc16_word(const uint16_t* T, uint32_t c, uint32_t w) {
-    // T: [4][256] slice tables in shared memory
-    return (uint32_t)(T[3 * 256 + (((c >> 8) ^ (w >> 24)) & 0xFF)] ^ T[2 * 256 + (((c & 0xFF) ^ (w >> 16)) & 0xFF)] ^
-                      T[256 + ((w >> 8) & 0xFF)] ^ T[w & 0xFF]);
-}
-FA_D uint32_t crc16_b(const uint16_t* T, uint32_t c, uint32_t byte) {
-    return ((c << 8) & 0xFFFF) ^ T[((c >> 8) ^ byte) & 0xFF];
-}
 
 FA_D U4 u4_zero() { U4 z; z.x = z.y = z.z = z.w = 0; return z; }
 

@@ -1,17 +1,27 @@
-// fa_encode.h -- FLAC frame encoder body: one 256-thread CTA encodes one (stream, frame).
+// fa_encode.h -- FLAC frame encoder body: one 128-thread CTA encodes one (stream, frame) at a time
+// and loops over frames (persistent CTAs, ticket order).
 //
 // Replaces the libFLAC encoder the reference drives per stream in compress.c:184-237 (serial) and
 // compress.c:337-390 (OpenMP), plus the byte bookkeeping of the write callbacks
 // (compress.c:13-104) and the final prefix-sum/concatenation (compress.c:402-429).
 //
-// Per (frame, channel): wasted-bits/constant detection -> fixed-predictor error sums (orders 0-4)
-// -> tukey window + autocorrelation (FP64 accumulate, fixed reduction order => deterministic)
-// -> Levinson-Durbin + order choice + coefficient quantisation (one thread, FP64)
-// -> residual partition sums for the fixed and the LPC candidate -> Rice partition/parameter search
-// (one warp per candidate) -> exact code lengths -> block prefix sum -> bit packing into a
-// shared-memory staged frame -> CRC-8 / CRC-16 -> decoupled look-back scan over frame sizes gives the
-// frame's final byte offset -> coalesced copy to HBM.  Input is read from HBM exactly once and the
-// compressed bytes are written exactly once.
+// Layout of the work: every thread owns 32 consecutive samples of the frame (plus the predictor
+// history before them) in registers; nothing but the packed output frame is staged in shared memory.
+//
+// Two code paths per (frame, channel):
+//   * fast path  -- full 4096-sample frames whose samples fit 22 bits and have no wasted bits (the
+//     benchmark's quantised detector data): all integer work in 32-bit registers, one fused pass for
+//     the sample statistics, the five fixed-predictor error sums (VABSDIFF accumulate) and the
+//     windowed autocorrelation (FP64 FMA), REDUX warp reductions, LPC residual with 32-bit IMADs
+//     (the coefficient precision is lowered until sum|q|*max|x| provably fits, as libFLAC does for
+//     <= 16-bit input), per-thread Rice packing into a 64-bit accumulator with the CRC-16 folded
+//     into every flushed word (positions are fixed up with one GF(2) multiply per thread).
+//   * general path -- anything else (short last frames, wasted bits, wide samples, residuals that do
+//     not fit 32 bits, VERBATIM/CONSTANT subframes): the same stages with 64-bit arithmetic and
+//     per-sample bounds checks.  Slow, but only reached by frames the fast path rejects.
+//
+// Frame placement: decoupled look-back over frame sizes in ticket order gives every frame its final
+// byte offset, so the compressed bytes are written to HBM exactly once.
 #pragma once
 #include "fa_bits.h"
 #include "fa_quant.h"
@@ -19,12 +29,14 @@
 
 namespace fa {
 
-constexpr int kEncThreads = 256;
-constexpr int kSpt = 16;        // samples per thread
-constexpr int kMaxBs = kEncThreads * kSpt;  // 4096
-constexpr int kMaxOrd = 12;     // libFLAC presets never exceed order 12
-constexpr int kMaxParts = 64;   // partition order <= 6
-constexpr int kSmpWords = kMaxBs + kMaxBs / 16 + 16;
+constexpr int kEncThreads = 128;
+constexpr int kEncWarps = kEncThreads / 32;
+constexpr int kSpt = 32;                     // samples per thread
+constexpr int kMaxBs = kEncThreads * kSpt;   // 4096
+constexpr int kMaxOrd = 12;                  // libFLAC presets never exceed order 12
+constexpr int kMaxParts = 64;                // partition order <= 6
+constexpr int kX32Len = 8704;                // >= words of the largest (2-channel VERBATIM) frame + 1
+constexpr int kNarrowBits = 22;              // fast path: -2^22 <= x < 2^22
 
 enum { kI32 = 0, kI64 = 1, kF32 = 2, kF64 = 3 };
 
@@ -51,6 +63,33 @@ inline void make_tukey_window(float* w, int L) {
     }
 }
 
+// CRC-16 position tables (host-initialised): x32[m] = x^(32 m) mod P, inv8[k] = x^(-8 k) mod P.
+struct EncTables {
+    uint16_t x32[kX32Len];
+    uint16_t inv8[4];
+};
+inline uint32_t gf16_mul_host(uint32_t a, uint32_t b) {
+    uint32_t r = 0;
+    for (int i = 15; i >= 0; --i) {
+        r <<= 1;
+        if (r & 0x10000u) r ^= 0x18005u;
+        if ((b >> i) & 1u) r ^= a;
+    }
+    return r & 0xFFFFu;
+}
+inline void enc_tables_init(EncTables* t) {
+    uint32_t x8 = 1;
+    for (int i = 0; i < 8; ++i) { x8 <<= 1; if (x8 & 0x10000u) x8 ^= 0x18005u; }
+    uint32_t x32 = gf16_mul_host(gf16_mul_host(x8, x8), gf16_mul_host(x8, x8));
+    uint32_t v = 1;
+    for (int m = 0; m < kX32Len; ++m) { t->x32[m] = (uint16_t)v; v = gf16_mul_host(v, x32); }
+    // P = (x + 1)(x^15 + x + 1): x has multiplicative order 32767 mod P, so x^-8 = x^(32767 - 8)
+    uint32_t inv = 1, base = 2;
+    for (int e = 32767 - 8; e; e >>= 1) { if (e & 1) inv = gf16_mul_host(inv, base); base = gf16_mul_host(base, base); }
+    t->inv8[0] = 1;
+    for (int k = 1; k < 4; ++k) t->inv8[k] = (uint16_t)gf16_mul_host(t->inv8[k - 1], inv);
+}
+
 // Bytes before the first frame of every stream: "fLaC" + STREAMINFO + APPLICATION(faB2 table, last).
 inline int stream_header_bytes(int nframes) { return 4 + 4 + 34 + 4 + 8 + 3 * nframes; }
 
@@ -65,6 +104,7 @@ struct EncParams {
     int max_lpc_order, max_porder, qlp_precision;
     const float* window;       // tukey(0.5) of length blocksize
     const CrcTables* crc;
+    const EncTables* tab;
     uint8_t* out;
     int64_t out_capacity;
     long long* starts;         // [n_stream] byte offset of every stream; must be preset to -1
@@ -78,63 +118,53 @@ struct EncParams {
 struct Plan {
     int type;      // 0 constant, 1 verbatim, 2 fixed, 3 lpc
     int order, wasted, shift, prec, porder, rice2;
+    int wide;      // lpc: residual needs 64-bit accumulation
     uint32_t res_bits;  // estimated bits of the residual section
     int32_t qlp[kMaxOrd];
 };
 
 struct EncShared {
+    // per-warp partials of the block reductions
+    uint32_t w_or[kEncWarps];
+    int32_t w_mn[kEncWarps], w_mx[kEncWarps];
+    uint32_t w_bad[kEncWarps];
+    unsigned long long w_fe[kEncWarps][5];
+    double w_ac[kEncWarps][kMaxOrd + 1];
+    // totals
+    uint32_t t_or;
+    int32_t t_mn, t_mx;
+    unsigned long long t_fe[5];
+    double t_ac[kMaxOrd + 1];
+    // design
     Plan cand[2];  // [0] fixed, [1] lpc
-    Plan plan;     // winner
     int cand_ok[2];
     int maxp[2];
+    int mode;      // fast path: 0 = rejected, 1 = constant, 2 = predictive
+    int wasted;
+    double lpc_hist[kMaxOrd][kMaxOrd];
+    unsigned long long csum[2][kEncThreads];   // per-thread-chunk sum |residual|
     unsigned long long psum[2][kMaxParts];
-    uint8_t kpar[2][2 * kMaxParts];  // params for porder p at offset (1 << p) - 1
-    uint8_t params[kMaxParts];
-    double autoc[kMaxOrd + 1];
-    unsigned long long fix_err[5];
-    uint32_t fix_bad;
-    uint32_t red[8];
-    uint32_t scan[8];
-    uint32_t crc_part[kEncThreads];
-    int bitpos;
-    int sub_total_bits;
-    long long frame_off;
-    long long stream_start;
+    uint8_t kpar[2][2 * kMaxParts];            // params for porder p at offset (1 << p) - 1
+    uint32_t scan[kEncWarps];
+    uint32_t crc_part[kEncWarps];
+    // deferred tail words of the packing sessions (OR-ed in when the frame is retired)
+    uint32_t tail_val[2][kEncThreads];
+    int tail_word[2][kEncThreads];
+    // the frame that is packed in `out` and waits to be retired (look-back, CRC-16, copy-out)
+    int prev_valid, prev_f, prev_nbytes;
+    uint32_t prev_g;
+    long long prev_off;
     uint32_t g;
 };
 
-FA_D int pidx(int i) { return i + (i >> 4); }
-
-// ---- block-wide helpers (256 threads = 8 warps) ---------------------------------------------------
-FA_D uint32_t block_or(uint32_t v, uint32_t* red) {
-    for (int m = 16; m >= 1; m >>= 1) v |= shfl_xor(v, m);
-    if (lane() == 0) red[warp()] = v;
-    sync();
-    uint32_t r = 0;
-    for (int w = 0; w < kEncThreads / 32; ++w) r |= red[w];
-    sync();
-    return r;
+FA_HD size_t enc_out_words(int nch) { return ((size_t)nch * (kMaxBs * 4 + 64) + 64) / 4; }
+FA_D int ow(int w) { return w + (w >> 4); }   // padded word index: per-thread strides of ~16 words stay off one bank
+inline size_t enc_smem_bytes(int nch) {
+    size_t words = enc_out_words(nch);
+    return ((sizeof(EncShared) + 15) & ~(size_t)15) + 4 * 256 * 2 + (words + (words >> 4) + 8) * 4 + 16;
 }
 
-FA_D uint32_t block_excl_scan(uint32_t v, uint32_t* wt, uint32_t& total) {
-    uint32_t inc = v;
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t n = shfl_up(inc, d);
-        if (lane() >= d) inc += n;
-    }
-    if (lane() == 31) wt[warp()] = inc;
-    sync();
-    uint32_t base = 0, tot = 0;
-    for (int w = 0; w < kEncThreads / 32; ++w) {
-        uint32_t x = wt[w];
-        if (w < warp()) base += x;
-        tot += x;
-    }
-    sync();
-    total = tot;
-    return base + inc - v;
-}
-
+// ---- small helpers -----------------------------------------------------------------------------------
 FA_D double shfl_xor_d(double v, int m) {
     unsigned long long u;
     memcpy(&u, &v, 8);
@@ -147,89 +177,55 @@ FA_D unsigned long long shfl_xor_u64(unsigned long long u, int m) {
     uint32_t lo = shfl_xor((uint32_t)u, m), hi = shfl_xor((uint32_t)(u >> 32), m);
     return ((unsigned long long)hi << 32) | lo;
 }
-
-// ---- per-thread bit packer into the shared-memory frame buffer ------------------------------------
-// The buffer is pre-zeroed, so runs of zero bits (unary quotients) only advance the position.
-// A thread owns every word that lies entirely inside its bit range (plain store); its first and last
-// words may be shared with neighbours (atomic OR).
-struct BitPk {
-    uint32_t* out;
-    uint32_t cur;
-    int pos;
-    bool first;
-};
-FA_D void pk_begin(BitPk& pk, uint32_t* out, int pos) { pk.out = out; pk.cur = 0; pk.pos = pos; pk.first = true; }
-FA_D void pk_flush(BitPk& pk, int word) {
-    if (pk.cur) {
-        if (pk.first) atom_or_shared(&pk.out[word], pk.cur);
-        else pk.out[word] = pk.cur;
-    }
-    pk.first = false;
-    pk.cur = 0;
+FA_D unsigned long long warp_sum_u64(unsigned long long v) {
+    for (int m = 16; m >= 1; m >>= 1) v += shfl_xor_u64(v, m);
+    return v;
 }
-// nb in [1, 32], v < 2^nb
-FA_D void pk_emit(BitPk& pk, uint32_t v, int nb) {
-    int off = pk.pos & 31, space = 32 - off;
-    if (nb < space) {
-        pk.cur |= v << (space - nb);
-    } else if (nb == space) {
-        pk.cur |= v;
-        pk_flush(pk, pk.pos >> 5);
-    } else {
-        int rem = nb - space;  // 1..31
-        pk.cur |= v >> rem;
-        pk_flush(pk, pk.pos >> 5);
-        pk.cur = v << (32 - rem);
-    }
-    pk.pos += nb;
+// exact warp sum of 32-bit partials as a 64-bit value: two REDUX over the 16-bit halves
+FA_D unsigned long long warp_sum_u32_wide(uint32_t v) {
+    uint32_t lo = redux_add(v & 0xFFFFu), hi = redux_add(v >> 16);
+    return ((unsigned long long)hi << 16) + lo;
 }
-FA_D void pk_emit64(BitPk& pk, uint64_t v, int nb) {  // nb in [1, 64]
-    if (nb > 32) { pk_emit(pk, (uint32_t)(v >> 32) & (nb == 64 ? 0xFFFFFFFFu : ((1u << (nb - 32)) - 1u)), nb - 32); nb = 32; }
-    pk_emit(pk, nb == 32 ? (uint32_t)v : ((uint32_t)v & ((1u << nb) - 1u)), nb);
+FA_D double warp_sum_d(double v) {
+    for (int m = 16; m >= 1; m >>= 1) v = dadd(v, shfl_xor_d(v, m));
+    return v;
 }
-FA_D void pk_skip(BitPk& pk, uint32_t q) {
-    int np = pk.pos + (int)q;
-    if ((np >> 5) != (pk.pos >> 5)) pk_flush(pk, pk.pos >> 5);
-    pk.pos = np;
-}
-FA_D void pk_end(BitPk& pk) {
-    if (pk.cur) atom_or_shared(&pk.out[pk.pos >> 5], pk.cur);
-    pk.cur = 0;
-}
-
-// ---- residual of the thread's 16 samples for a compile-time predictor order ------------------------
-// xw[j] = sample (i0 - kMaxOrd + j).  res[j] valid for i0 + j in [order, bs).
-template <int ORD>
-FA_D void residual_block(const int32_t* xw, const int32_t* coef, int shift, int64_t* res) {
+// Sum 8 doubles across the warp with 18 shuffles: every step halves the values a lane carries.
+// Afterwards lane l holds the total of value index ((l >> 4) & 1) * 4 + ((l >> 3) & 1) * 2 + ((l >> 2) & 1).
+FA_D double warp_sum8_d(const double* v) {
+    const int ln = lane();
+    double a[4], b[2], c;
+    const bool u16 = (ln & 16) != 0;
 #pragma unroll
-    for (int j = 0; j < kSpt; ++j) {
-        int64_t sum = 0;
+    for (int i = 0; i < 4; ++i) {
+        double keep = u16 ? v[4 + i] : v[i], send = u16 ? v[i] : v[4 + i];
+        a[i] = dadd(keep, shfl_xor_d(send, 16));
+    }
+    const bool u8 = (ln & 8) != 0;
 #pragma unroll
-        for (int m = 0; m < ORD; ++m) sum += (int64_t)coef[m] * (int64_t)xw[kMaxOrd + j - 1 - m];
-        res[j] = (int64_t)xw[kMaxOrd + j] - (sum >> shift);
+    for (int i = 0; i < 2; ++i) {
+        double keep = u8 ? a[2 + i] : a[i], send = u8 ? a[i] : a[2 + i];
+        b[i] = dadd(keep, shfl_xor_d(send, 8));
     }
-}
-FA_D void residual_dispatch(int order, const int32_t* xw, const int32_t* coef, int shift, int64_t* res) {
-    switch (order) {
-    case 0: residual_block<0>(xw, coef, shift, res); break;
-    case 1: residual_block<1>(xw, coef, shift, res); break;
-    case 2: residual_block<2>(xw, coef, shift, res); break;
-    case 3: residual_block<3>(xw, coef, shift, res); break;
-    case 4: residual_block<4>(xw, coef, shift, res); break;
-    case 5: residual_block<5>(xw, coef, shift, res); break;
-    case 6: residual_block<6>(xw, coef, shift, res); break;
-    case 7: residual_block<7>(xw, coef, shift, res); break;
-    case 8: residual_block<8>(xw, coef, shift, res); break;
-    case 9: residual_block<9>(xw, coef, shift, res); break;
-    case 10: residual_block<10>(xw, coef, shift, res); break;
-    case 11: residual_block<11>(xw, coef, shift, res); break;
-    default: residual_block<12>(xw, coef, shift, res); break;
+    const bool u4 = (ln & 4) != 0;
+    {
+        double keep = u4 ? b[1] : b[0], send = u4 ? b[0] : b[1];
+        c = dadd(keep, shfl_xor_d(send, 4));
     }
+    c = dadd(c, shfl_xor_d(c, 2));
+    c = dadd(c, shfl_xor_d(c, 1));
+    return c;
 }
 
-FA_D void fixed_coefs(int order, int32_t* c) {
-    const int32_t fx[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};
-    for (int j = 0; j < kMaxOrd; ++j) c[j] = (j < 4) ? fx[order][j] : 0;
+FA_D uint32_t gf16_mul(uint32_t a, uint32_t b) {  // a * b mod x^16 + x^15 + x^2 + 1
+    uint32_t r = 0;
+#pragma unroll
+    for (int i = 15; i >= 0; --i) {
+        r <<= 1;
+        r ^= (r & 0x10000u) ? 0x18005u : 0u;
+        r ^= ((b >> i) & 1u) ? a : 0u;
+    }
+    return r & 0xFFFFu;
 }
 
 FA_D bool fits_res(int64_t v) { return v >= -2147483647LL && v <= 2147483647LL; }
@@ -241,53 +237,261 @@ FA_D int max_porder_for(int bs, int order, int level_max) {
     return p;
 }
 
-// Accumulate |res| of the thread's samples into the finest-level partition sums (shared atomics at
-// partition boundaries only).  Returns false if some residual does not fit the Rice coder.
-FA_D bool partition_sums(const int64_t* res, int i0, int bs, int order, int psize, unsigned long long* psum) {
-    bool ok = true;
-    int i = i0 < order ? order : i0;
-    int iend = i0 + kSpt < bs ? i0 + kSpt : bs;
-    if (i >= iend) return true;
-    int part = i / psize;
-    int next = (part + 1) * psize;
-    unsigned long long acc = 0;
-    for (; i < iend; ++i) {
-        if (i == next) {
-            atom_add_shared64(&psum[part], acc);
-            acc = 0;
-            part++;
-            next += psize;
-        }
-        int64_t r = res[i - i0];
-        ok = ok && fits_res(r);
-        acc += (unsigned long long)(r < 0 ? -r : r);
-    }
-    atom_add_shared64(&psum[part], acc);
-    return ok;
+FA_D int utf8_put(uint8_t* p, uint64_t v) {
+    if (v < 0x80) { p[0] = (uint8_t)v; return 1; }
+    int n = v < 0x800 ? 2 : v < 0x10000 ? 3 : v < 0x200000 ? 4 : v < 0x4000000 ? 5 : v < 0x80000000ull ? 6 : 7;
+    const uint8_t lead[8] = {0, 0, 0xC0, 0xE0, 0xF0, 0xF8, 0xFC, 0xFE};
+    for (int i = n - 1; i > 0; --i) { p[i] = (uint8_t)(0x80 | (v & 0x3F)); v >>= 6; }
+    p[0] = (uint8_t)(lead[n] | v);
+    return n;
+}
+FA_D int utf8_len(uint64_t v) {
+    return v < 0x80 ? 1 : v < 0x800 ? 2 : v < 0x10000 ? 3 : v < 0x200000 ? 4 : v < 0x4000000 ? 5 : v < 0x80000000ull ? 6 : 7;
 }
 
-// One warp: libFLAC's estimate-based partition-order / Rice-parameter search
-// (find_best_partition_order_ / set_partitioned_rice_ without escape codes).
+FA_D int blocksize_code(int bs) {
+    if (bs == 192) return 1;
+    if (bs == 576) return 2;
+    if (bs == 1152) return 3;
+    if (bs == 2304) return 4;
+    if (bs == 4608) return 5;
+    for (int c = 8; c <= 15; ++c) if (bs == (256 << (c - 8))) return c;
+    return bs <= 256 ? 6 : 7;
+}
+FA_D int frame_header_bytes(int bs, int f) {
+    int bc = blocksize_code(bs);
+    return 4 + utf8_len((uint64_t)f) + (bc == 6 ? 1 : bc == 7 ? 2 : 0) + 1;
+}
+
+// ---- bit packer: 64-bit accumulator -> staged frame words ----------------------------------------------
+// Write protocol of the staged frame (pre-zeroed): while packing, a thread plain-stores every word it
+// completes -- including its first one, whose leading bits may belong to the previous thread and are
+// stored as zeros.  The trailing partial word of a session is NOT stored: it is recorded and OR-ed in
+// after a barrier, when the frame is retired.  Each word has exactly one plain-storing thread, and all
+// ORs come after all plain stores, so no atomics and no "first word" test are needed in the hot loop.
+struct Pk {
+    uint32_t* out;
+    uint64_t acc;
+    int fill;            // bits pending in acc (MSB side), < 32 between calls
+    int word;            // next word to write
+};
+FA_D void pk_begin(Pk& pk, uint32_t* out, int bitpos) {
+    pk.out = out; pk.acc = 0; pk.fill = bitpos & 31; pk.word = bitpos >> 5;
+}
+FA_D void pk_flush(Pk& pk) {
+    pk.out[ow(pk.word)] = (uint32_t)(pk.acc >> 32);
+    pk.word++;
+    pk.acc <<= 32;
+    pk.fill -= 32;
+}
+// nb in [1, 32], v < 2^nb
+FA_D void pk_emit(Pk& pk, uint32_t v, int nb) {
+    pk.acc |= (uint64_t)v << (64 - pk.fill - nb);
+    pk.fill += nb;
+    if (pk.fill >= 32) pk_flush(pk);
+}
+FA_D void pk_zeros(Pk& pk, uint32_t q) {
+    while (q >= 32) { pk_emit(pk, 0u, 32); q -= 32; }
+    if (q) pk_emit(pk, 0u, (int)q);
+}
+FA_D void pk_rice(Pk& pk, uint32_t u, int k) {
+    uint32_t q = u >> k;
+    uint32_t low = (u & ((1u << k) - 1u)) | (1u << k);
+    uint32_t len = q + (uint32_t)k + 1u;
+    if (len <= 32u) {
+        pk_emit(pk, low, (int)len);
+    } else {
+        pk_zeros(pk, q);
+        pk_emit(pk, low, k + 1);
+    }
+}
+// record the trailing partial word (value 0 when the session ended on a word boundary)
+FA_D void pk_end(const Pk& pk, uint32_t& tail_val, int& tail_word) {
+    tail_val = (uint32_t)(pk.acc >> 32);
+    tail_word = pk.word;
+}
+
+// ---- decoupled look-back descriptors: [63:62] status (0 empty, 1 aggregate, 2 inclusive prefix), [61:0] bytes
+constexpr unsigned long long kDescAgg = 1ull << 62, kDescPre = 2ull << 62, kDescMask = (1ull << 62) - 1;
+
+// Thread 0, as soon as the size of the frame is known (before packing): successors can start summing.
+FA_D void publish_aggregate(const EncParams& P, uint32_t g, int f, int bitpos_end) {
+    unsigned long long mine = (unsigned long long)(((bitpos_end + 7) >> 3) + 2) + (f == 0 ? (unsigned long long)P.hdr_bytes : 0ull);
+    st_release_u64(&P.desc[g], (g == 0 ? kDescPre : kDescAgg) | mine);
+}
+
+// Warp 0: exclusive prefix of frame g over all earlier frames, 32 descriptors per round trip.
+FA_D unsigned long long lookback_warp(const EncParams& P, uint32_t g) {
+    const int ln = lane();
+    unsigned long long excl = 0;
+    long long base = (long long)g - 1;
+    for (;;) {
+        long long idx = base - ln;
+        unsigned long long d = idx >= 0 ? ld_acquire_u64(&P.desc[idx]) : kDescPre;   // virtual prefix 0 before frame 0
+        uint32_t st = (uint32_t)(d >> 62);
+        uint32_t pre = ballot(st == 2), empty = ballot(st == 0);
+        int first_pre = pre ? ctz32(pre) : 32;
+        uint32_t need = first_pre >= 31 ? 0xFFFFFFFFu : ((2u << first_pre) - 1u);   // lanes 0..first_pre
+        if (empty & need) { spin_pause(); continue; }
+        unsigned long long v = (ln <= first_pre) ? (d & kDescMask) : 0ull;
+        excl += warp_sum_u64(v);
+        if (first_pre < 32) break;
+        base -= 32;
+    }
+    return excl;
+}
+
+// ---- sample source ------------------------------------------------------------------------------------
+struct FrameSrc {
+    const void* base;   // element (stream s, frame sample 0)
+    int dtype, bs;
+    bool vec;           // 16-byte vector loads are aligned
+    float off32, gain32;
+    double off64, gain64;
+};
+
+// channel c of in-frame sample i (general path; 0 <= i < bs)
+FA_D int32_t src_sample(const FrameSrc& S, int c, int i) {
+    if (S.dtype == kI32) return ((const int32_t*)S.base)[i];
+    if (S.dtype == kF32) return quant_f32(((const float*)S.base)[i], S.off32, S.gain32);
+    long long v;
+    if (S.dtype == kI64) v = ((const long long*)S.base)[i];
+    else v = quant_f64(((const double*)S.base)[i], S.off64, S.gain64);
+    return c == 0 ? (int32_t)(uint32_t)((unsigned long long)v & 0xFFFFFFFFull) : (int32_t)(v >> 32);
+}
+
+// Fast path: xw[H + j] = sample (32 t + j), xw[0..H) = the H samples before them (zeros for thread 0).
+// FULL: the frame has 4096 samples; otherwise samples at or beyond S.bs read as zero.
+template <int H, bool FULL>
+FA_D void load_chunk(const FrameSrc& S, int c, int t, int32_t* xw) {
+    const int i0 = t * kSpt - H;
+    const int bs = S.bs;
+    if (S.dtype == kI32 || S.dtype == kF32) {
+        const uint32_t* p = (const uint32_t*)S.base + i0;
+#pragma unroll
+        for (int q = 0; q < (H + kSpt) / 4; ++q) {
+            U4 v;
+            v.x = v.y = v.z = v.w = 0;
+            const bool hist = q * 4 < H;
+            const int i = i0 + 4 * q;
+            if (!(hist && t == 0) && (FULL || i < bs)) {
+                if (S.vec && (FULL || i + 4 <= bs)) v = ldg128(p + 4 * q);
+                else {
+                    v.x = ldg32(p + 4 * q);
+                    if (FULL || i + 1 < bs) v.y = ldg32(p + 4 * q + 1);
+                    if (FULL || i + 2 < bs) v.z = ldg32(p + 4 * q + 2);
+                    if (FULL || i + 3 < bs) v.w = ldg32(p + 4 * q + 3);
+                }
+                if (S.dtype == kF32) {
+                    float f0, f1, f2, f3;
+                    memcpy(&f0, &v.x, 4); memcpy(&f1, &v.y, 4); memcpy(&f2, &v.z, 4); memcpy(&f3, &v.w, 4);
+                    v.x = (uint32_t)quant_f32(f0, S.off32, S.gain32);
+                    v.y = (FULL || i + 1 < bs) ? (uint32_t)quant_f32(f1, S.off32, S.gain32) : 0u;
+                    v.z = (FULL || i + 2 < bs) ? (uint32_t)quant_f32(f2, S.off32, S.gain32) : 0u;
+                    v.w = (FULL || i + 3 < bs) ? (uint32_t)quant_f32(f3, S.off32, S.gain32) : 0u;
+                }
+            }
+            xw[4 * q] = (int32_t)v.x; xw[4 * q + 1] = (int32_t)v.y; xw[4 * q + 2] = (int32_t)v.z; xw[4 * q + 3] = (int32_t)v.w;
+        }
+    } else {
+        const unsigned long long* p = (const unsigned long long*)S.base + i0;
+#pragma unroll
+        for (int q = 0; q < (H + kSpt) / 2; ++q) {
+            unsigned long long e0 = 0, e1 = 0;
+            const bool hist = q * 2 < H;
+            const int i = i0 + 2 * q;
+            const bool v1 = FULL || i + 1 < bs;
+            if (!(hist && t == 0) && (FULL || i < bs)) {
+                if (S.vec && v1) {
+                    U4 v = ldg128(p + 2 * q);
+                    e0 = ((unsigned long long)v.y << 32) | v.x;
+                    e1 = ((unsigned long long)v.w << 32) | v.z;
+                } else {
+                    e0 = p[2 * q];
+                    if (v1) e1 = p[2 * q + 1];
+                }
+                if (S.dtype == kF64) {
+                    double d0, d1;
+                    memcpy(&d0, &e0, 8); memcpy(&d1, &e1, 8);
+                    e0 = (unsigned long long)quant_f64(d0, S.off64, S.gain64);
+                    e1 = v1 ? (unsigned long long)quant_f64(d1, S.off64, S.gain64) : 0ull;
+                }
+            }
+            xw[2 * q] = c == 0 ? (int32_t)(uint32_t)e0 : (int32_t)(uint32_t)(e0 >> 32);
+            xw[2 * q + 1] = c == 0 ? (int32_t)(uint32_t)e1 : (int32_t)(uint32_t)(e1 >> 32);
+        }
+    }
+}
+
+// ---- frame / subframe headers (thread 0, through its packing session) ----------------------------------
+FA_D void emit_frame_header(Pk& pk, const CrcTables* crc, int bs, int f, int nch) {
+    uint8_t h[16];
+    int n = 0;
+    int bc = blocksize_code(bs);
+    h[n++] = 0xFF; h[n++] = 0xF8;
+    h[n++] = (uint8_t)((bc << 4) | 9);                       // 44.1 kHz like the reference's default
+    h[n++] = (uint8_t)(((nch == 2 ? 1 : 0) << 4) | (7 << 1));  // independent channels, 32 bps
+    n += utf8_put(h + n, (uint64_t)f);
+    if (bc == 6) h[n++] = (uint8_t)(bs - 1);
+    else if (bc == 7) { h[n++] = (uint8_t)((bs - 1) >> 8); h[n++] = (uint8_t)(bs - 1); }
+    uint32_t c = 0;
+    for (int i = 0; i < n; ++i) c = crc->crc8[c ^ h[i]];
+    h[n++] = (uint8_t)c;
+    for (int i = 0; i < n; ++i) pk_emit(pk, h[i], 8);
+}
+
+// subframe header byte (+ wasted-bits unary), warm-up samples are emitted by the caller
+FA_D void emit_subframe_header(Pk& pk, int ptype, int order, int wasted) {
+    int typebits = ptype == 0 ? 0 : ptype == 1 ? 1 : ptype == 2 ? (8 + order) : (32 + order - 1);
+    pk_emit(pk, ((uint32_t)typebits << 1) | (wasted ? 1u : 0u), 8);
+    if (wasted) { pk_zeros(pk, (uint32_t)(wasted - 1)); pk_emit(pk, 1u, 1); }
+}
+FA_D void emit_sample(Pk& pk, int32_t v, int bps) {  // bps in [1, 32]
+    pk_emit(pk, bps == 32 ? (uint32_t)v : ((uint32_t)v & ((1u << bps) - 1u)), bps);
+}
+FA_D void emit_lpc_params(Pk& pk, const Plan& pl) {
+    pk_emit(pk, (uint32_t)(pl.prec - 1), 4);
+    pk_emit(pk, (uint32_t)pl.shift & 31u, 5);
+    for (int j = 0; j < pl.order; ++j) pk_emit(pk, (uint32_t)pl.qlp[j] & ((1u << pl.prec) - 1u), pl.prec);
+}
+FA_D int subframe_header_bits(int ptype, int order, int wasted, int bps, int prec) {
+    int b = 8 + wasted;
+    if (ptype == 0) return b + bps;
+    if (ptype == 1) return b;
+    return b + order * bps + 6 + (ptype == 3 ? 9 + order * prec : 0);
+}
+
+// ---- Rice partition search: one warp per candidate ------------------------------------------------------
+// libFLAC's estimate-based partition-order / Rice-parameter search (find_best_partition_order_ /
+// set_partitioned_rice_ without escape codes) over the finest-level sums in sh->psum[cand].
 FA_D void rice_search_warp(EncShared* sh, int cand, int bs, int order, int maxp) {
     unsigned long long* ps = sh->psum[cand];
     uint32_t best_bits = 0xFFFFFFFFu;
-    int best_p = maxp;
+    int best_p = maxp, best_r2 = 0;
     for (int p = maxp; p >= 0; --p) {
         int nparts = 1 << p;
         uint32_t bits = 0;
+        bool big = false;
         for (int part = lane(); part < nparts; part += 32) {
             unsigned long long sum = ps[part];
             uint32_t n = (uint32_t)(bs >> p) - (part == 0 ? (uint32_t)order : 0u);
             int k = 0;
-            while (k < 30 && ((unsigned long long)n << k) < sum) k++;
+            if (sum > n) {
+                k = (64 - clz64(sum - 1)) - (32 - clz32(n));
+                if (k < 0) k = 0;
+                while (k < 30 && ((unsigned long long)n << k) < sum) k++;
+                if (k > 30) k = 30;
+            }
             sh->kpar[cand][(1 << p) - 1 + part] = (uint8_t)k;
+            big = big || k >= 15;
             unsigned long long pb = 4ull + (unsigned long long)(1 + k) * n + (k ? (sum >> (k - 1)) : (sum << 1));
             pb -= (n >> 1);
             bits += pb > (1ull << 25) ? (1u << 25) : (uint32_t)pb;
         }
-        for (int m = 16; m >= 1; m >>= 1) bits += shfl_xor(bits, m);
-        bits += 6;
-        if (bits < best_bits) { best_bits = bits; best_p = p; }
+        bits = redux_add(bits) + 6;
+        int r2 = ballot(big) != 0 ? 1 : 0;
+        if (r2) bits += (uint32_t)nparts;   // 5-bit parameters
+        if (bits < best_bits) { best_bits = bits; best_p = p; best_r2 = r2; }
         // merge to the next coarser level
         if (p > 0) {
             unsigned long long a[2] = {0, 0};
@@ -303,17 +507,70 @@ FA_D void rice_search_warp(EncShared* sh, int cand, int bs, int order, int maxp)
     if (lane() == 0) {
         sh->cand[cand].porder = best_p;
         sh->cand[cand].res_bits = best_bits;
+        sh->cand[cand].rice2 = best_r2;
     }
     syncwarp();
 }
 
-// Levinson-Durbin, order choice and coefficient quantisation (libFLAC lpc.c procedure), one thread.
-FA_D void lpc_design(EncShared* sh, int bs, int bps, int max_order, int precision) {
+// ---- design (one thread): fixed order choice, Levinson-Durbin, order choice, coefficient quantisation --
+// libFLAC fixed.c / lpc.c procedure.  `narrow_maxabs` > 0 selects the fast path's rule for the
+// coefficient precision: the largest precision <= `precision` for which every prediction sum and
+// residual provably fits 32-bit arithmetic; if that would cost more than 3 bits the plan is marked
+// `wide` (64-bit residual) at full precision instead.
+FA_D void design_fixed(EncShared* sh, int bs, int bps, uint32_t bad, int level_maxp) {
+    unsigned long long te[5];
+    for (int k = 0; k < 5; ++k) te[k] = ((bad >> k) & 1) ? ~0ull : sh->t_fe[k];
+    unsigned long long m34 = te[3] < te[4] ? te[3] : te[4];
+    unsigned long long m234 = te[2] < m34 ? te[2] : m34;
+    unsigned long long m1234 = te[1] < m234 ? te[1] : m234;
+    int order;
+    if (te[0] < m1234) order = 0;
+    else if (te[1] < m234) order = 1;
+    else if (te[2] < m34) order = 2;
+    else if (te[3] < te[4]) order = 3;
+    else order = 4;
+    Plan& pl = sh->cand[0];
+    pl.type = 2; pl.order = order; pl.shift = 0; pl.prec = 0; pl.wide = 0;
+    bool ok = te[order] != ~0ull;
+    if (ok && te[order] > 0) {
+        float rb = flog2(0.6931472f * (float)te[order] / (float)(bs - 4));
+        ok = rb < (float)bps;
+    }
+    sh->cand_ok[0] = ok ? 1 : 0;
+    sh->maxp[0] = max_porder_for(bs, order, level_maxp);
+}
+
+FA_D bool quantize_coefs(const double* coefs, int order, int precision, int32_t* q, int& shift_out) {
+    int prec = precision - 1;
+    int32_t qmax = (1 << prec) - 1, qmin = -(1 << prec);
+    double cmax = 0.0;
+    for (int i = 0; i < order; ++i) { double d = fabs(coefs[i]); if (d > cmax) cmax = d; }
+    if (!(cmax > 0.0)) return false;
+    int log2cmax;
+    (void)frexp(cmax, &log2cmax);
+    log2cmax--;
+    int shift = prec - log2cmax - 1;
+    if (shift > 15) shift = 15;
+    if (shift < 0) return false;
+    double e = 0.0;
+    for (int i = 0; i < order; ++i) {
+        e += coefs[i] * (double)(1 << shift);
+        double rq = e < 0.0 ? -floor(-e + 0.5) : floor(e + 0.5);  // lround: half away from zero
+        long long v = (long long)rq;
+        if (v > qmax) v = qmax; else if (v < qmin) v = qmin;
+        e -= (double)v;
+        q[i] = (int32_t)v;
+    }
+    shift_out = shift;
+    return true;
+}
+
+FA_D void design_lpc(EncShared* sh, int bs, int bps, int max_order, int precision, int level_maxp, uint32_t narrow_maxabs) {
     Plan& pl = sh->cand[1];
     sh->cand_ok[1] = 0;
-    const double* autoc = sh->autoc;
-    if (!(autoc[0] != 0.0)) return;
-    double lpc[kMaxOrd], coefs[kMaxOrd][kMaxOrd], error[kMaxOrd];
+    const double* autoc = sh->t_ac;
+    if (max_order <= 0 || !(autoc[0] != 0.0)) return;
+    double lpc[kMaxOrd], error[kMaxOrd];
     double err = autoc[0];
     int mo = max_order;
     for (int i = 0; i < mo; ++i) {
@@ -329,573 +586,979 @@ FA_D void lpc_design(EncShared* sh, int bs, int bps, int max_order, int precisio
         }
         if (i & 1) lpc[j] += lpc[j] * r;
         err *= (1.0 - r * r);
-        for (j = 0; j <= i; ++j) coefs[i][j] = (double)(float)(-lpc[j]);
+        for (j = 0; j <= i; ++j) sh->lpc_hist[i][j] = (double)(float)(-lpc[j]);
         error[i] = err;
         if (err == 0.0) { mo = i + 1; break; }
     }
-    // FLAC__lpc_compute_best_order
-    const double ln2 = 0.69314718055994530942;
-    double escale = 0.5 / (double)bs;
-    double best_bits = 1e300;
+    // FLAC__lpc_compute_best_order (log2 in single precision: only the order choice depends on it)
+    float escale = 0.5f / (float)bs;
+    float best_bits = 3.0e38f;
     int order = 1;
     for (int idx = 0; idx < mo; ++idx) {
-        double e = error[idx], b;
-        if (e > 0.0) { b = 0.5 * log(escale * e) / ln2; if (b < 0.0) b = 0.0; }
-        else if (e < 0.0) b = 1e32;
-        else b = 0.0;
-        double bits = b * (double)(bs - (idx + 1)) + (double)((idx + 1) * (bps + precision));
+        double e = error[idx];
+        float b;
+        if (e > 0.0) { b = 0.5f * flog2(escale * (float)e); if (b < 0.0f) b = 0.0f; }
+        else if (e < 0.0) b = 1e32f;
+        else b = 0.0f;
+        float bits = b * (float)(bs - (idx + 1)) + (float)((idx + 1) * (bps + precision));
         if (bits < best_bits) { best_bits = bits; order = idx + 1; }
     }
     {
-        double e = error[order - 1], b;
-        double es = 0.5 / (double)(bs - order);
-        if (e > 0.0) { b = 0.5 * log(es * e) / ln2; if (b < 0.0) b = 0.0; }
-        else if (e < 0.0) b = 1e32;
-        else b = 0.0;
-        if (!(b < (double)bps)) return;
+        double e = error[order - 1];
+        float b;
+        float es = 0.5f / (float)(bs - order);
+        if (e > 0.0) { b = 0.5f * flog2(es * (float)e); if (b < 0.0f) b = 0.0f; }
+        else if (e < 0.0) b = 1e32f;
+        else b = 0.0f;
+        if (!(b < (float)bps)) return;
     }
-    // FLAC__lpc_quantize_coefficients
-    int prec = precision - 1;
-    int32_t qmax = (1 << prec) - 1, qmin = -(1 << prec);
-    double cmax = 0.0;
-    for (int i = 0; i < order; ++i) { double d = fabs(coefs[order - 1][i]); if (d > cmax) cmax = d; }
-    if (!(cmax > 0.0)) return;
-    int log2cmax;
-    (void)frexp(cmax, &log2cmax);
-    log2cmax--;
-    int shift = prec - log2cmax - 1;
-    if (shift > 15) shift = 15;
-    if (shift < 0) return;
-    double e = 0.0;
-    for (int i = 0; i < order; ++i) {
-        e += coefs[order - 1][i] * (double)(1 << shift);
-        double rq = e < 0.0 ? -floor(-e + 0.5) : floor(e + 0.5);  // lround: half away from zero
-        long long q = (long long)rq;
-        if (q > qmax) q = qmax; else if (q < qmin) q = qmin;
-        e -= (double)q;
-        pl.qlp[i] = (int32_t)q;
+    const double* coefs = sh->lpc_hist[order - 1];
+    int shift = 0;
+    int prec = precision;
+    bool have = false;
+    pl.wide = 1;
+    if (narrow_maxabs) {
+        // 32-bit datapath conditions: |sum q x| <= sumq * maxabs < 2^30 and |x - pred| < 2^26.
+        // sumq ~ sumc * 2^shift with shift = p - 2 - floor(log2 cmax): solve for the largest p, verify.
+        double sumc = 0.0, cmax = 0.0;
+        for (int i = 0; i < order; ++i) { double d = fabs(coefs[i]); sumc += d; if (d > cmax) cmax = d; }
+        if (cmax > 0.0) {
+            int e, lc;
+            (void)frexp(sumc * (double)narrow_maxabs, &e);   // sumc * maxabs < 2^e
+            (void)frexp(cmax, &lc);                          // floor(log2 cmax) = lc - 1
+            int p = 32 - e + (lc - 1);
+            if (p > precision) p = precision;
+            for (int tries = 0; tries < 2 && p >= 5 && p >= precision - 6; ++tries, --p) {
+                int32_t q[kMaxOrd];
+                int sft;
+                if (!quantize_coefs(coefs, order, p, q, sft)) break;
+                unsigned long long sumq = 0;
+                for (int i = 0; i < order; ++i) sumq += (unsigned long long)(q[i] < 0 ? -q[i] : q[i]);
+                unsigned long long mac = sumq * narrow_maxabs;
+                // lowering the precision must stay invisible next to the residual itself: coefficient
+                // rounding error ~ 2^-(shift+1) per tap against the predicted residual RMS
+                double qerr = (double)narrow_maxabs * sqrt((double)order) / (double)(2u << sft);
+                double sigma = sqrt(error[order - 1] / (double)bs);
+                bool harmless = p == precision || qerr < 0.25 * sigma;
+                if (harmless && mac < (1ull << 30) && (unsigned long long)narrow_maxabs + (mac >> sft) < (1ull << 26)) {
+                    for (int i = 0; i < order; ++i) pl.qlp[i] = q[i];
+                    shift = sft;
+                    prec = p;
+                    pl.wide = 0;
+                    have = true;
+                    break;
+                }
+            }
+        }
     }
+    if (!have && !quantize_coefs(coefs, order, prec, pl.qlp, shift)) return;
     for (int i = order; i < kMaxOrd; ++i) pl.qlp[i] = 0;
     pl.type = 3;
     pl.order = order;
     pl.shift = shift;
-    pl.prec = precision;
+    pl.prec = prec;
     sh->cand_ok[1] = 1;
+    sh->maxp[1] = max_porder_for(bs, order, level_maxp);
 }
 
-FA_D int utf8_put(uint8_t* p, uint64_t v) {
-    if (v < 0x80) { p[0] = (uint8_t)v; return 1; }
-    int n = v < 0x800 ? 2 : v < 0x10000 ? 3 : v < 0x200000 ? 4 : v < 0x4000000 ? 5 : v < 0x80000000ull ? 6 : 7;
-    const uint8_t lead[8] = {0, 0, 0xC0, 0xE0, 0xF0, 0xF8, 0xFC, 0xFE};
-    for (int i = n - 1; i > 0; --i) { p[i] = (uint8_t)(0x80 | (v & 0x3F)); v >>= 6; }
-    p[0] = (uint8_t)(lead[n] | v);
-    return n;
+// ---- residuals of the thread's 32 samples for a compile-time predictor order ---------------------------
+// xw[H + j] = sample j of the chunk.  r[j] = x[j] - ((sum_m coef[m] * x[j - 1 - m]) >> shift).
+template <int H, int ORD>
+FA_D void residual32(const int32_t* xw, const int32_t* coef, int shift, int32_t* r) {
+#pragma unroll
+    for (int j = 0; j < kSpt; ++j) {
+        int32_t sum = 0;
+#pragma unroll
+        for (int m = 0; m < ORD; ++m) sum += coef[m] * xw[H + j - 1 - m];
+        r[j] = xw[H + j] - (sum >> shift);
+    }
+}
+template <int H>
+FA_D void residual32_dispatch(int order, const int32_t* xw, const int32_t* coef, int shift, int32_t* r) {
+    switch (order) {
+    case 0: residual32<H, 0>(xw, coef, shift, r); break;
+    case 1: residual32<H, 1>(xw, coef, shift, r); break;
+    case 2: residual32<H, 2>(xw, coef, shift, r); break;
+    case 3: residual32<H, 3>(xw, coef, shift, r); break;
+    case 4: residual32<H, 4>(xw, coef, shift, r); break;
+    case 5: residual32<H, 5>(xw, coef, shift, r); break;
+    case 6: residual32<H, 6>(xw, coef, shift, r); break;
+    case 7: residual32<H, 7>(xw, coef, shift, r); break;
+    case 8: residual32<H, 8>(xw, coef, shift, r); break;
+    default:
+        if constexpr (H > 8) {
+            switch (order) {
+            case 9: residual32<H, 9>(xw, coef, shift, r); break;
+            case 10: residual32<H, 10>(xw, coef, shift, r); break;
+            case 11: residual32<H, 11>(xw, coef, shift, r); break;
+            default: residual32<H, 12>(xw, coef, shift, r); break;
+            }
+        }
+        break;
+    }
+}
+// 64-bit accumulation (narrow samples, full-precision coefficients); bit j of the result is set when
+// residual j fits the Rice coder
+template <int H>
+FA_D uint32_t residual64(int order, const int32_t* xw, const int32_t* coef, int shift, int32_t* r) {
+    uint32_t ok = 0;
+#pragma unroll
+    for (int j = 0; j < kSpt; ++j) {
+        int64_t sum = 0;
+#pragma unroll
+        for (int m = 0; m < H; ++m) sum += (int64_t)coef[m] * (int64_t)xw[H + j - 1 - m];   // coef[m] = 0 beyond `order`
+        int64_t v = (int64_t)xw[H + j] - (sum >> shift);
+        if (fits_res(v)) ok |= 1u << j;
+        r[j] = (int32_t)v;
+    }
+    (void)order;
+    return ok;
 }
 
-FA_D int blocksize_code(int bs) {
-    if (bs == 192) return 1;
-    if (bs == 576) return 2;
-    if (bs == 1152) return 3;
-    if (bs == 2304) return 4;
-    if (bs == 4608) return 5;
-    for (int c = 8; c <= 15; ++c) if (bs == (256 << (c - 8))) return c;
-    return bs <= 256 ? 6 : 7;
+FA_D void fixed_coefs(int order, int32_t* c, int n) {
+    const int32_t fx[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};
+    for (int j = 0; j < n; ++j) c[j] = (j < 4) ? fx[order][j] : 0;
 }
 
-// byte k of the staged frame (words hold the bit-stream MSB first)
-FA_D uint32_t out_byte(const uint32_t* out, int k) { return (out[k >> 2] >> (24 - 8 * (k & 3))) & 0xFFu; }
 
-// ------------------------------------------------------------------------------------------------
-// The CTA body.  `smem_raw` is the dynamic shared memory base (>= enc_smem_bytes(nch)).
-// ------------------------------------------------------------------------------------------------
-inline size_t enc_out_words(int nch) { return (size_t)(nch * (kMaxBs * 32 / 8 + 8) + 64) / 4; }
-inline size_t enc_smem_bytes(int nch) {
-    return ((sizeof(EncShared) + 15) & ~(size_t)15) + (size_t)nch * kSmpWords * 4 + (size_t)kSmpWords * 4 +
-           enc_out_words(nch) * 4 + 16;
-}
+// ------------------------------------------------------------------------------------------------------
+// Retiring a packed frame: look-back -> byte offset, CRC-16, copy to HBM.  The frame packed during
+// iteration n of the CTA loop is retired during iteration n + 1 (before the staged buffer is needed
+// again), which gives every predecessor a whole frame time to publish its size: no spinning.
+// ------------------------------------------------------------------------------------------------------
+struct EncCtx {
+    EncShared* sh;
+    const uint16_t* crcT;
+    uint32_t* out;
+    int out_words_padded;
+    bool retired;   // block-uniform: the previous frame has left `out` and `out` is zeroed
+};
 
-FA_D void encode_frame_cta(const EncParams& P, unsigned char* smem_raw) {
-    EncShared* sh = (EncShared*)smem_raw;
-    int32_t* smp = (int32_t*)(smem_raw + ((sizeof(EncShared) + 15) & ~(size_t)15));
-    float* wd = (float*)(smp + (size_t)P.nch * kSmpWords);      // also reduction scratch
-    uint32_t* out = (uint32_t*)(wd + kSmpWords);
-    const int out_words = (int)(((size_t)P.nch * (kMaxBs * 32 / 8 + 8) + 64) / 4);
-    const int t = tid();
-
-    // ---- work assignment: tickets are handed out in launch order so that look-back never waits on
-    // a CTA that has not started (decoupled look-back, Merrill & Garland).
-    if (t == 0) sh->g = atom_add_global(P.ticket, 1u);
-    sync();
-    const uint32_t g = sh->g;
-    const int64_t s = (int64_t)(g / (uint32_t)P.nframes);
-    const int f = (int)(g % (uint32_t)P.nframes);
-    const int64_t samp0 = (int64_t)f * P.blocksize;
-    const int bs = (int)((P.stream_size - samp0) < P.blocksize ? (P.stream_size - samp0) : P.blocksize);
-    const int nch = P.nch;
-
-    // ---- load (and quantise) the frame: coalesced reads, padded-blocked layout in shared memory
-    {
-        float off32 = 0.f, gain32 = 0.f;
-        double off64 = 0., gain64 = 0.;
-        if (P.dtype == kF32) { off32 = ((const float*)P.offsets)[s]; gain32 = ((const float*)P.gains)[s]; }
-        if (P.dtype == kF64) { off64 = ((const double*)P.offsets)[s]; gain64 = ((const double*)P.gains)[s]; }
-        const int64_t base = s * P.stream_size + samp0;
-        for (int i = t; i < bs; i += kEncThreads) {
-            if (P.dtype == kI32) {
-                smp[pidx(i)] = ((const int32_t*)P.data)[base + i];
-            } else if (P.dtype == kF32) {
-                smp[pidx(i)] = quant_f32(((const float*)P.data)[base + i], off32, gain32);
-            } else {
-                long long v;
-                if (P.dtype == kI64) v = ((const long long*)P.data)[base + i];
-                else v = quant_f64(((const double*)P.data)[base + i], off64, gain64);
-                smp[pidx(i)] = (int32_t)(uint32_t)((unsigned long long)v & 0xFFFFFFFFull);  // ch0 = low word
-                smp[kSmpWords + pidx(i)] = (int32_t)(v >> 32);                              // ch1 = high word
-            }
-        }
-        for (int w = t; w < out_words; w += kEncThreads) out[w] = 0;
-    }
-    sync();
-
-    // ---- frame header (thread 0): RFC 9639 9.1
-    if (t == 0) {
-        uint8_t h[16];
-        int n = 0;
-        int bc = blocksize_code(bs);
-        h[n++] = 0xFF; h[n++] = 0xF8;
-        h[n++] = (uint8_t)((bc << 4) | 9);                       // 44.1 kHz like the reference's default
-        h[n++] = (uint8_t)(((nch == 2 ? 1 : 0) << 4) | (7 << 1));  // independent channels, 32 bps
-        n += utf8_put(h + n, (uint64_t)f);
-        if (bc == 6) h[n++] = (uint8_t)(bs - 1);
-        else if (bc == 7) { h[n++] = (uint8_t)((bs - 1) >> 8); h[n++] = (uint8_t)(bs - 1); }
-        uint32_t c = 0;
-        for (int i = 0; i < n; ++i) c = P.crc->crc8[c ^ h[i]];
-        h[n++] = (uint8_t)c;
-        for (int i = 0; i < n; ++i) out[i >> 2] |= (uint32_t)h[i] << (24 - 8 * (i & 3));
-        sh->bitpos = n * 8;
-    }
-    sync();
-
-    const int i0 = t * kSpt;
-    for (int c = 0; c < nch; ++c) {
-        int32_t* x = smp + (size_t)c * kSmpWords;
-        // ---- wasted bits / constant ----
-        uint32_t orv = 0, diff = 0;
-        {
-            int32_t x0 = x[0];
-            for (int j = 0; j < kSpt; ++j) {
-                int i = i0 + j;
-                if (i < bs) { int32_t v = x[pidx(i)]; orv |= (uint32_t)v; diff |= (uint32_t)(v ^ x0); }
-            }
-        }
-        orv = block_or(orv, sh->red);
-        diff = block_or(diff, sh->red);
-        int wasted = (orv == 0) ? 0 : ctz32(orv);
-        const int bps = 32 - wasted;
-        if (wasted) {
-            for (int j = 0; j < kSpt; ++j) { int i = i0 + j; if (i < bs) x[pidx(i)] >>= wasted; }
-            sync();
-        }
-        const bool constant = (diff == 0);
-        const uint32_t verbatim_bits = (uint32_t)bps * (uint32_t)bs;
-        const bool try_pred = !constant && bs > 4;
-
-        // thread-local window of samples: xw[j] = x[i0 - kMaxOrd + j]
-        int32_t xw[kMaxOrd + kSpt];
-#pragma unroll
-        for (int j = 0; j < kMaxOrd + kSpt; ++j) {
-            int i = i0 - kMaxOrd + j;
-            xw[j] = (i >= 0 && i < bs) ? x[pidx(i)] : 0;
-        }
-
-        if (t == 0) { sh->cand_ok[0] = 0; sh->cand_ok[1] = 0; sh->fix_bad = 0; }
-        if (t < 2 * kMaxParts) ((unsigned long long*)sh->psum)[t] = 0;
-
-        if (try_pred) {
-            // ---- fixed predictors: sum |e_k| over i >= 4, k = 0..4 (libFLAC fixed.c) ----
-            unsigned long long fe[5] = {0, 0, 0, 0, 0};
-            uint32_t bad = 0;
-#pragma unroll
-            for (int j = 0; j < kSpt; ++j) {
-                int i = i0 + j;
-                if (i >= 4 && i < bs) {
-                    int64_t a0 = xw[kMaxOrd + j], a1 = xw[kMaxOrd + j - 1], a2 = xw[kMaxOrd + j - 2],
-                            a3 = xw[kMaxOrd + j - 3], a4 = xw[kMaxOrd + j - 4];
-                    int64_t e0 = a0, e1 = a0 - a1, e2 = e1 - (a1 - a2), e3 = e2 - (a1 - 2 * a2 + a3),
-                            e4 = e3 - (a1 - 3 * a2 + 3 * a3 - a4);
-                    int64_t e[5] = {e0, e1, e2, e3, e4};
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) {
-                        if (!fits_res(e[k])) bad |= 1u << k;
-                        fe[k] += (unsigned long long)(e[k] < 0 ? -e[k] : e[k]);
-                    }
-                }
-            }
-            // reduce: pairs by shuffle, then [k][128] in scratch, warps 0..4 finish
-            unsigned long long* scr = (unsigned long long*)wd;
-#pragma unroll
-            for (int k = 0; k < 5; ++k) {
-                unsigned long long o = shfl_xor_u64(fe[k], 1);
-                if (!(t & 1)) scr[k * 128 + (t >> 1)] = fe[k] + o;
-            }
-            bad = block_or(bad, sh->red);  // includes barriers: scratch visible
-            if (warp() < 5) {
-                int k = warp();
-                unsigned long long v = scr[k * 128 + lane()] + scr[k * 128 + 32 + lane()] + scr[k * 128 + 64 + lane()] +
-                                       scr[k * 128 + 96 + lane()];
-                for (int m = 16; m >= 1; m >>= 1) v += shfl_xor_u64(v, m);
-                if (lane() == 0) sh->fix_err[k] = v;
-            }
-            sync();
-            if (t == 0) {
-                unsigned long long te[5];
-                for (int k = 0; k < 5; ++k) te[k] = ((bad >> k) & 1) ? ~0ull : sh->fix_err[k];
-                unsigned long long m34 = te[3] < te[4] ? te[3] : te[4];
-                unsigned long long m234 = te[2] < m34 ? te[2] : m34;
-                unsigned long long m1234 = te[1] < m234 ? te[1] : m234;
-                int order;
-                if (te[0] < m1234) order = 0;
-                else if (te[1] < m234) order = 1;
-                else if (te[2] < m34) order = 2;
-                else if (te[3] < te[4]) order = 3;
-                else order = 4;
-                Plan& pl = sh->cand[0];
-                pl.type = 2; pl.order = order; pl.shift = 0; pl.prec = 0;
-                bool ok = te[order] != ~0ull;
-                if (ok) {
-                    double n = (double)(bs - 4);
-                    double rb = te[order] > 0 ? log(0.69314718055994530942 * (double)te[order] / n) / 0.69314718055994530942 : 0.0;
-                    ok = rb < (double)bps;
-                }
-                sh->cand_ok[0] = ok ? 1 : 0;
-                sh->maxp[0] = max_porder_for(bs, order, P.max_porder);
-            }
-            sync();  // scratch (wd) is free again
-
-            // ---- LPC analysis ----
-            int max_order = P.max_lpc_order;
-            if (max_order >= bs) max_order = bs - 1;
-            if (max_order > 0) {
-                // window (libFLAC lpc.c FLAC__lpc_window_data: float data * float window)
-#pragma unroll
-                for (int j = 0; j < kSpt; ++j) {
-                    int i = i0 + j;
-                    if (i < bs) wd[pidx(i)] = fmul((float)xw[kMaxOrd + j], P.window[i]);
-                }
-                sync();
-                double ac[kMaxOrd + 1];
-#pragma unroll
-                for (int l = 0; l <= kMaxOrd; ++l) ac[l] = 0.0;
-                {
-                    double w[kMaxOrd + kSpt];
-#pragma unroll
-                    for (int j = 0; j < kMaxOrd + kSpt; ++j) {
-                        int i = i0 - kMaxOrd + j;
-                        w[j] = (i >= 0 && i < bs) ? (double)wd[pidx(i)] : 0.0;
-                    }
-#pragma unroll
-                    for (int l = 0; l <= kMaxOrd; ++l) {
-                        if (l <= max_order) {
-#pragma unroll
-                            for (int j = 0; j < kSpt; ++j) ac[l] = dfma(w[kMaxOrd + j], w[kMaxOrd + j - l], ac[l]);
-                        }
-                    }
-                }
-                sync();  // everyone has read wd: reuse it as reduction scratch
-                double* dscr = (double*)wd;
-#pragma unroll
-                for (int l = 0; l <= kMaxOrd; ++l) {
-                    double o = shfl_xor_d(ac[l], 1);
-                    if (!(t & 1)) dscr[l * 128 + (t >> 1)] = ac[l] + o;
-                }
-                sync();
-                for (int l = warp(); l <= max_order; l += kEncThreads / 32) {
-                    double v = (dscr[l * 128 + lane()] + dscr[l * 128 + 32 + lane()]) +
-                               (dscr[l * 128 + 64 + lane()] + dscr[l * 128 + 96 + lane()]);
-                    for (int m = 16; m >= 1; m >>= 1) v += shfl_xor_d(v, m);
-                    if (lane() == 0) sh->autoc[l] = v;
-                }
-                sync();
-                if (t == 0) {
-                    lpc_design(sh, bs, bps, max_order, P.qlp_precision);
-                    if (sh->cand_ok[1]) sh->maxp[1] = max_porder_for(bs, sh->cand[1].order, P.max_porder);
-                }
-                sync();
-            }
-
-            // ---- residual partition sums for both candidates ----
-            uint32_t resbad = 0;
-            for (int cd = 0; cd < 2; ++cd) {
-                if (!sh->cand_ok[cd]) continue;   // block-uniform
-                int32_t coef[kMaxOrd];
-                const Plan& pl = sh->cand[cd];
-                if (cd == 0) fixed_coefs(pl.order, coef);
-                else { for (int m = 0; m < kMaxOrd; ++m) coef[m] = pl.qlp[m]; }
-                int64_t res[kSpt];
-                residual_dispatch(pl.order, xw, coef, pl.shift, res);
-                int psize = bs >> sh->maxp[cd];
-                if (!partition_sums(res, i0, bs, pl.order, psize, sh->psum[cd])) resbad |= 1u << cd;
-            }
-            resbad = block_or(resbad, sh->red);
-            if (warp() < 2 && sh->cand_ok[warp()] && !((resbad >> warp()) & 1))
-                rice_search_warp(sh, warp(), bs, sh->cand[warp()].order, sh->maxp[warp()]);
-            sync();
-            if (t == 0) {
-                // ---- choose: verbatim vs fixed vs lpc by estimated size (stream_encoder.c process_subframe_)
-                uint32_t best = verbatim_bits;
-                int win = -1;
-                for (int cd = 0; cd < 2; ++cd) {
-                    if (!sh->cand_ok[cd] || ((resbad >> cd) & 1)) continue;
-                    const Plan& pl = sh->cand[cd];
-                    uint32_t bits = (uint32_t)pl.order * (uint32_t)bps + pl.res_bits;
-                    if (cd == 1) bits += 4 + 5 + (uint32_t)pl.order * (uint32_t)pl.prec;
-                    if (bits < best) { best = bits; win = cd; }
-                }
-                if (win < 0) { sh->plan.type = 1; sh->plan.order = 0; }
-                else sh->plan = sh->cand[win];
-                if (win >= 0) {
-                    int p = sh->plan.porder;
-                    int rice2 = 0;
-                    for (int q = 0; q < (1 << p); ++q) {
-                        uint8_t k = sh->kpar[win][(1 << p) - 1 + q];
-                        sh->params[q] = k;
-                        if (k >= 15) rice2 = 1;
-                    }
-                    sh->plan.rice2 = rice2;
-                }
-                sh->plan.wasted = wasted;
-            }
-            sync();
-        } else {
-            if (t == 0) { sh->plan.type = constant ? 0 : 1; sh->plan.order = 0; sh->plan.wasted = wasted; }
-            sync();
-        }
-
-        // ---- exact size of the predictive subframe; fall back to verbatim if it does not pay ----
-        int64_t res[kSpt];
-        uint32_t lens = 0;
-        int ptype = sh->plan.type;
-        int order = sh->plan.order;
-        int porder = sh->plan.porder;
-        int psize = bs >> porder;
-        int plen = sh->plan.rice2 ? 5 : 4;
-        if (ptype >= 2) {
-            int32_t coef[kMaxOrd];
-            if (ptype == 2) fixed_coefs(order, coef);
-            else { for (int m = 0; m < kMaxOrd; ++m) coef[m] = sh->plan.qlp[m]; }
-            residual_dispatch(order, xw, coef, sh->plan.shift, res);
-            int i = i0 < order ? order : i0;
-            int iend = i0 + kSpt < bs ? i0 + kSpt : bs;
-            if (i < iend) {
-                int part = i / psize;
-                int next = (part + 1) * psize;
-                int k = sh->params[part];
-                if (i == (part == 0 ? order : part * psize)) lens += plen;
-                for (; i < iend; ++i) {
-                    if (i == next) { part++; next += psize; k = sh->params[part]; lens += plen; }
-                    int64_t r = res[i - i0];
-                    uint32_t u = ((uint32_t)r << 1) ^ (uint32_t)(r >> 63);
-                    lens += (u >> k) + 1 + k;
-                }
-            }
-        }
-        uint32_t total;
-        uint32_t excl = block_excl_scan(lens, sh->scan, total);
-        if (ptype >= 2) {
-            uint32_t hdr_bits = (uint32_t)order * (uint32_t)bps + 6 + (ptype == 3 ? 9 + (uint32_t)order * (uint32_t)sh->plan.prec : 0);
-            if (hdr_bits + total >= verbatim_bits) ptype = 1;  // block-uniform
-        }
-
-        // ---- pack ----
-        int pos0 = sh->bitpos;
-        int sub_hdr_bits = 8 + (wasted ? wasted : 0);
-        if (t == 0) {
-            BitPk pk;
-            pk_begin(pk, out, pos0);
-            int typebits = ptype == 0 ? 0 : ptype == 1 ? 1 : ptype == 2 ? (8 + order) : (32 + order - 1);
-            pk_emit(pk, (uint32_t)typebits << 1 | (wasted ? 1u : 0u), 8);
-            if (wasted) { pk_skip(pk, (uint32_t)(wasted - 1)); pk_emit(pk, 1, 1); }
-            if (ptype == 0) {
-                pk_emit64(pk, (uint64_t)(uint32_t)x[0], bps);
-            } else if (ptype >= 2) {
-                for (int j = 0; j < order; ++j) pk_emit64(pk, (uint64_t)(uint32_t)x[pidx(j)], bps);
-                if (ptype == 3) {
-                    pk_emit(pk, (uint32_t)(sh->plan.prec - 1), 4);
-                    pk_emit(pk, (uint32_t)sh->plan.shift & 31u, 5);
-                    for (int j = 0; j < order; ++j)
-                        pk_emit(pk, (uint32_t)sh->plan.qlp[j] & ((1u << sh->plan.prec) - 1u), sh->plan.prec);
-                }
-                pk_emit(pk, (uint32_t)sh->plan.rice2, 2);
-                pk_emit(pk, (uint32_t)porder, 4);
-            }
-            pk_end(pk);
-        }
-        int body0;  // first bit of the per-sample payload
-        if (ptype == 0) body0 = pos0 + sub_hdr_bits + bps;
-        else if (ptype == 1) body0 = pos0 + sub_hdr_bits;
-        else body0 = pos0 + sub_hdr_bits + order * bps + 6 + (ptype == 3 ? 9 + order * sh->plan.prec : 0);
-        int sub_end;
-        if (ptype == 0) {
-            sub_end = body0;
-        } else if (ptype == 1) {
-            BitPk pk;
-            int start = i0 < bs ? i0 : bs;
-            pk_begin(pk, out, body0 + start * bps);
-            for (int j = 0; j < kSpt; ++j) {
-                int i = i0 + j;
-                if (i < bs) pk_emit64(pk, (uint64_t)(uint32_t)xw[kMaxOrd + j] & (bps == 32 ? 0xFFFFFFFFull : ((1ull << bps) - 1)), bps);
-            }
-            pk_end(pk);
-            sub_end = body0 + bs * bps;
-        } else {
-            BitPk pk;
-            pk_begin(pk, out, body0 + (int)excl);
-            int i = i0 < order ? order : i0;
-            int iend = i0 + kSpt < bs ? i0 + kSpt : bs;
-            if (i < iend) {
-                int part = i / psize;
-                int next = (part + 1) * psize;
-                int k = sh->params[part];
-                if (i == (part == 0 ? order : part * psize)) pk_emit(pk, (uint32_t)k, plen);
-                for (; i < iend; ++i) {
-                    if (i == next) { part++; next += psize; k = sh->params[part]; pk_emit(pk, (uint32_t)k, plen); }
-                    int64_t r = res[i - i0];
-                    uint32_t u = ((uint32_t)r << 1) ^ (uint32_t)(r >> 63);
-                    pk_skip(pk, u >> k);
-                    pk_emit(pk, (1u << k) | (u & ((1u << k) - 1u)), k + 1);
-                }
-            }
-            pk_end(pk);
-            sub_end = body0 + (int)total;
-        }
-        sync();
-        if (t == 0) sh->bitpos = sub_end;
-        sync();
-    }
-
-    // ---- frame footer: pad to a byte, CRC-16 over the whole frame ----
-    const int nbytes_body = (sh->bitpos + 7) >> 3;
-    {
-        // each thread: CRC of a contiguous chunk (front-padded so that all chunks have equal length),
-        // then a log-step combine with the "advance by 2^j zero bytes" tables.
-        const CrcTables* T = P.crc;
-        int chunk = (nbytes_body + kEncThreads - 1) / kEncThreads;
-        int lg = 0;
-        while ((1 << lg) < chunk) lg++;
-        chunk = 1 << lg;                      // power of two => combine uses one table level per step
-        int pad = chunk * kEncThreads - nbytes_body;
-        int b0 = t * chunk - pad, b1 = b0 + chunk;
-        uint32_t c = 0;
-        int k = b0 < 0 ? 0 : b0;
-        // byte-wise to a word boundary, then slice-by-4
-        for (; k < b1 && (k & 3); ++k) c = crc16_byte(T, c, out_byte(out, k));
-        for (; k + 4 <= b1; k += 4) {
-            uint32_t w = out[k >> 2];
-            c = (uint32_t)(T->crc16[3][((c >> 8) ^ (w >> 24)) & 0xFF] ^ T->crc16[2][((c & 0xFF) ^ (w >> 16)) & 0xFF] ^
-                           T->crc16[1][(w >> 8) & 0xFF] ^ T->crc16[0][w & 0xFF]);
-        }
-        for (; k < b1; ++k) c = crc16_byte(T, c, out_byte(out, k));
-        // combine: at step j, thread t (with bit j clear) merges partner t + 2^j whose block is 2^j chunks long
-        sh->crc_part[t] = c;
-        sync();
-        for (int j = 0; j < 8; ++j) {
-            if ((t & ((2 << j) - 1)) == 0) {
-                uint32_t a = sh->crc_part[t], b = sh->crc_part[t + (1 << j)];
-                sh->crc_part[t] = crc16_shift_pow2(T, a, lg + j) ^ b;
-            }
-            sync();
-        }
-    }
-    const int frame_bytes = nbytes_body + 2;
-    if (t == 0) {
-        uint32_t c = sh->crc_part[0];
-        int k = nbytes_body;
-        out[k >> 2] |= ((c >> 8) & 0xFF) << (24 - 8 * (k & 3));
-        k++;
-        out[k >> 2] |= (c & 0xFF) << (24 - 8 * (k & 3));
-    }
-
-    // ---- decoupled look-back over frame sizes: exclusive prefix = final byte offset ----
-    if (t == 0) {
-        const unsigned long long kAgg = 1ull << 62, kPre = 2ull << 62, kMask = (1ull << 62) - 1;
+// One warp: exclusive prefix of the frame waiting in `out`, publishes its inclusive prefix.
+FA_D void retire_lookback(const EncParams& P, EncShared* sh) {
+    if (!sh->prev_valid) return;
+    const uint32_t g = sh->prev_g;
+    const int f = sh->prev_f;
+    unsigned long long excl = g == 0 ? 0ull : lookback_warp(P, g);
+    if (lane() == 0) {
+        const int frame_bytes = sh->prev_nbytes + 2;
         unsigned long long mine = (unsigned long long)frame_bytes + (f == 0 ? (unsigned long long)P.hdr_bytes : 0ull);
-        unsigned long long excl = 0;
-        if (g == 0) {
-            st_release_u64(&P.desc[0], kPre | mine);
-        } else {
-            st_release_u64(&P.desc[g], kAgg | mine);
-            long long j = (long long)g - 1;
-            for (;;) {
-                unsigned long long d = ld_acquire_u64(&P.desc[j]);
-                unsigned long long st = d >> 62;
-                if (st == 0) { spin_pause(); continue; }
-                excl += d & kMask;
-                if (st == 2) break;
-                j--;
-            }
-            st_release_u64(&P.desc[g], kPre | (excl + mine));
-        }
+        if (g != 0) st_release_u64(&P.desc[g], kDescPre | (excl + mine));
         long long off = (long long)excl + (f == 0 ? P.hdr_bytes : 0);
-        sh->frame_off = off;
-        if (f == 0) {
-            st_release_u64((unsigned long long*)&P.starts[s], excl);
-            sh->stream_start = (long long)excl;
-        } else {
-            unsigned long long v;
-            while ((long long)(v = ld_acquire_u64((const unsigned long long*)&P.starts[s])) < 0) spin_pause();
-            sh->stream_start = (long long)v;
-        }
-        if (f == P.nframes - 1) P.ends[s] = off + frame_bytes;
-        if (off + frame_bytes > P.out_capacity) { atom_or_global(P.err, kErrEncodeCollect); sh->frame_off = -1; }
+        if (off + frame_bytes > P.out_capacity) { atom_or_global(P.err, kErrEncodeCollect); off = -1; }
+        sh->prev_off = off;
     }
-    sync();
-    const long long off = sh->frame_off;
+}
+
+// All threads, after a barrier behind retire_lookback: CRC-16 partials of the staged frame (uniform
+// pass, one contiguous run of words per thread, positions fixed up with one GF(2) multiply) and the
+// coalesced copy to HBM.
+FA_D void retire_copyout(const EncParams& P, const EncCtx& X) {
+    EncShared* sh = X.sh;
+    if (!sh->prev_valid) return;
+    const int t = tid();
+    const uint32_t* out = X.out;
+    const int nbytes_body = sh->prev_nbytes;
+    const int wtot = (nbytes_body + 3) >> 2;
+    {
+        const int per = (wtot + kEncThreads - 1) / kEncThreads;
+        int w0 = t * per, w1 = w0 + per < wtot ? w0 + per : wtot;
+        uint32_t crc = 0;
+        for (int w = w0; w < w1; ++w) crc = crc16_word(X.crcT, crc, out[ow(w)]);
+        uint32_t contrib = w0 < w1 ? gf16_mul(crc, P.tab->x32[wtot - w1]) : 0u;
+        contrib = redux_xor(contrib);
+        if (lane() == 0) sh->crc_part[warp()] = contrib;
+    }
+    const long long off = sh->prev_off;
     if (off >= 0) {
         uint8_t* dst = P.out + off;
         // aligned 32-bit stores in the middle, byte stores at the ragged ends
         int a = (int)((uintptr_t)dst & 3);
         int head = a ? 4 - a : 0;
-        if (head > frame_bytes) head = frame_bytes;
-        if (t < head) dst[t] = (uint8_t)out_byte(out, t);
-        int nwords = (frame_bytes - head) >> 2;
+        if (head > nbytes_body) head = nbytes_body;
+        if (t < head) dst[t] = (uint8_t)((out[ow(t >> 2)] >> (24 - 8 * (t & 3))) & 0xFFu);
+        int nwords = (nbytes_body - head) >> 2;
         uint32_t* dw = (uint32_t*)(dst + head);
         for (int w = t; w < nwords; w += kEncThreads) {
             int b = head + 4 * w;   // stream byte index of this word's first byte
-            uint32_t hi = out[b >> 2], lo = out[(b >> 2) + 1];
+            uint32_t hi = out[ow(b >> 2)], lo = out[ow((b >> 2) + 1)];
             uint32_t v = funnel_l(lo, hi, 8u * (uint32_t)(b & 3));
             dw[w] = bswap32(v);
         }
         int tail0 = head + 4 * nwords;
-        if (t < frame_bytes - tail0) dst[tail0 + t] = (uint8_t)out_byte(out, tail0 + t);
-
-        // stream header (frame 0) and this frame's entry in the frame-size table
-        uint8_t* sp = P.out + sh->stream_start;
-        if (f == 0 && t == 0) {
-            sp[0] = 'f'; sp[1] = 'L'; sp[2] = 'a'; sp[3] = 'C';
-            sp[4] = 0x00; sp[5] = 0; sp[6] = 0; sp[7] = 34;
-            uint8_t* si = sp + 8;
-            for (int i = 0; i < 34; ++i) si[i] = 0;
-            si[0] = si[2] = (uint8_t)(P.blocksize >> 8);
-            si[1] = si[3] = (uint8_t)P.blocksize;
-            const uint32_t sr = 44100;
-            si[10] = (uint8_t)(sr >> 12); si[11] = (uint8_t)(sr >> 4);
-            si[12] = (uint8_t)(((sr & 0xF) << 4) | ((nch - 1) << 1) | 1);
-            unsigned long long ts = (unsigned long long)P.stream_size;
-            if (ts >> 36) ts = 0;  // does not fit the 36-bit field: "unknown"
-            si[13] = (uint8_t)(0xF0 | ((ts >> 32) & 0xF));
-            si[14] = (uint8_t)(ts >> 24); si[15] = (uint8_t)(ts >> 16); si[16] = (uint8_t)(ts >> 8); si[17] = (uint8_t)ts;
-            uint8_t* ap = sp + 42;
-            uint32_t alen = 8 + 3 * (uint32_t)P.nframes;
-            ap[0] = 0x82; ap[1] = (uint8_t)(alen >> 16); ap[2] = (uint8_t)(alen >> 8); ap[3] = (uint8_t)alen;
-            ap[4] = 'f'; ap[5] = 'a'; ap[6] = 'B'; ap[7] = '2';
-            uint32_t nf = (uint32_t)P.nframes;
-            ap[8] = (uint8_t)(nf >> 24); ap[9] = (uint8_t)(nf >> 16); ap[10] = (uint8_t)(nf >> 8); ap[11] = (uint8_t)nf;
-        }
-        if (t == 0) {
-            uint8_t* e = sp + 54 + 3 * f;
-            e[0] = (uint8_t)(frame_bytes >> 16); e[1] = (uint8_t)(frame_bytes >> 8); e[2] = (uint8_t)frame_bytes;
+        if (t < nbytes_body - tail0) {
+            int k = tail0 + t;
+            dst[k] = (uint8_t)((out[ow(k >> 2)] >> (24 - 8 * (k & 3))) & 0xFFu);
         }
     }
+}
+
+// Thread 0, after a barrier behind retire_copyout: the two CRC-16 bytes.
+FA_D void retire_crc(const EncParams& P, EncShared* sh) {
+    if (!sh->prev_valid || sh->prev_off < 0) return;
+    const int nbytes_body = sh->prev_nbytes;
+    const int wtot = (nbytes_body + 3) >> 2;
+    uint32_t crc = sh->crc_part[0] ^ sh->crc_part[1] ^ sh->crc_part[2] ^ sh->crc_part[3];
+    crc = gf16_mul(crc, P.tab->inv8[4 * wtot - nbytes_body]);   // the staged words carry 0..3 pad bytes
+    st_global_u8x2(P.out + sh->prev_off + nbytes_body, (crc >> 8) & 0xFFu, crc & 0xFFu);
+}
+
+FA_D void zero_out(const EncCtx& X) {
+    U4 z; z.x = z.y = z.z = z.w = 0;
+    for (int w = 4 * tid(); w < X.out_words_padded; w += 4 * kEncThreads) sts128(X.out + w, z);
+}
+
+// Generic (non-overlapped) retire sequence with its own barriers; leaves `out` zeroed.
+FA_D void retire_full(const EncParams& P, EncCtx& X) {
+    if (X.retired) return;
+    if (warp() == 0) retire_lookback(P, X.sh);
+    sync();
+    retire_copyout(P, X);
+    sync();
+    if (tid() == 0) retire_crc(P, X.sh);
+    zero_out(X);
+    sync();
+    X.retired = true;
+}
+
+// Stream header and frame-size table, from the finished look-back descriptors (one thread per stream
+// header, one per table entry).  desc[g] holds the inclusive byte prefix of frame g.
+FA_D void finalize_entry(const EncParams& P, int64_t s, int f, long long* nbytes_out, long long* total_out) {
+    const uint32_t g = (uint32_t)(s * P.nframes + f);
+    const unsigned long long pre_prev = g == 0 ? 0ull : (P.desc[g - 1] & kDescMask);
+    const unsigned long long pre = P.desc[g] & kDescMask;
+    const uint32_t g0 = (uint32_t)(s * P.nframes);
+    const unsigned long long sstart = g0 == 0 ? 0ull : (P.desc[g0 - 1] & kDescMask);
+    uint8_t* sp = P.out + sstart;
+    if ((long long)pre > P.out_capacity) return;   // error already flagged by the encoder
+    const uint32_t frame_bytes = (uint32_t)(pre - pre_prev) - (f == 0 ? (uint32_t)P.hdr_bytes : 0u);
+    uint8_t* e = sp + 54 + 3 * f;
+    e[0] = (uint8_t)(frame_bytes >> 16); e[1] = (uint8_t)(frame_bytes >> 8); e[2] = (uint8_t)frame_bytes;
+    if (f == 0) {
+        sp[0] = 'f'; sp[1] = 'L'; sp[2] = 'a'; sp[3] = 'C';
+        sp[4] = 0x00; sp[5] = 0; sp[6] = 0; sp[7] = 34;
+        uint8_t* si = sp + 8;
+        for (int i = 0; i < 34; ++i) si[i] = 0;
+        si[0] = si[2] = (uint8_t)(P.blocksize >> 8);
+        si[1] = si[3] = (uint8_t)P.blocksize;
+        const uint32_t sr = 44100;
+        si[10] = (uint8_t)(sr >> 12); si[11] = (uint8_t)(sr >> 4);
+        si[12] = (uint8_t)(((sr & 0xF) << 4) | ((P.nch - 1) << 1) | 1);
+        unsigned long long ts = (unsigned long long)P.stream_size;
+        if (ts >> 36) ts = 0;  // does not fit the 36-bit field: "unknown"
+        si[13] = (uint8_t)(0xF0 | ((ts >> 32) & 0xF));
+        si[14] = (uint8_t)(ts >> 24); si[15] = (uint8_t)(ts >> 16); si[16] = (uint8_t)(ts >> 8); si[17] = (uint8_t)ts;
+        uint8_t* ap = sp + 42;
+        uint32_t alen = 8 + 3 * (uint32_t)P.nframes;
+        ap[0] = 0x82; ap[1] = (uint8_t)(alen >> 16); ap[2] = (uint8_t)(alen >> 8); ap[3] = (uint8_t)alen;
+        ap[4] = 'f'; ap[5] = 'a'; ap[6] = 'B'; ap[7] = '2';
+        uint32_t nf = (uint32_t)P.nframes;
+        ap[8] = (uint8_t)(nf >> 24); ap[9] = (uint8_t)(nf >> 16); ap[10] = (uint8_t)(nf >> 8); ap[11] = (uint8_t)nf;
+        // bookkeeping: compress.c:402-411 (starts = exclusive prefix), pyx:331-332 (nbytes = diff)
+        const unsigned long long send = P.desc[g0 + (uint32_t)P.nframes - 1] & kDescMask;
+        P.starts[s] = (long long)sstart;
+        nbytes_out[s] = (long long)(send - sstart);
+        if (s == P.n_stream - 1 && total_out) *total_out = (long long)send;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Fast path: full frame, narrow samples, no wasted bits.  Returns false (block-uniform) when the frame
+// does not qualify or the predictive subframe would not beat VERBATIM; nothing has been emitted then.
+// ------------------------------------------------------------------------------------------------------
+template <int H, bool FULL>
+FA_D bool enc_channel_fast(const EncParams& P, EncCtx& X, const FrameSrc& S, int c, int f, uint32_t g, int bitpos0,
+                           int& bitpos_end) {
+    EncShared* sh = X.sh;
+    uint32_t* out = X.out;
+    const int t = tid();
+    const int ln = lane(), wp = warp();
+    const int bs = FULL ? kMaxBs : S.bs;
+    const int i0 = t * kSpt;
+    const int nvalid = FULL ? kSpt : (bs - i0 >= kSpt ? kSpt : (bs > i0 ? bs - i0 : 0));
+    // partitions must be whole thread chunks: partition size a multiple of 32 (or a single partition)
+    const int level_maxp = FULL ? P.max_porder : (P.max_porder < ctz32((uint32_t)bs) - 5 ? P.max_porder : (ctz32((uint32_t)bs) > 5 ? ctz32((uint32_t)bs) - 5 : 0));
+    int32_t xw[H + kSpt];
+    load_chunk<H, FULL>(S, c, t, xw);
+
+    // ---- pass 1: statistics, fixed-predictor error sums (libFLAC fixed.c: sum |e_k| over i >= 4),
+    //      windowed autocorrelation (lpc.c: float data * float window, double accumulation)
+    uint32_t orv = 0;
+    int32_t mn = 0x7fffffff, mx = (int32_t)0x80000000u;
+    uint32_t fe0 = 0, fe1 = 0, fe2 = 0, fe3 = 0, fe4 = 0;
+    {
+        uint32_t p1 = (uint32_t)xw[H - 1] - (uint32_t)xw[H - 2];
+        uint32_t p1b = (uint32_t)xw[H - 2] - (uint32_t)xw[H - 3];
+        uint32_t p1c = (uint32_t)xw[H - 3] - (uint32_t)xw[H - 4];
+        uint32_t p2 = p1 - p1b, p2b = p1b - p1c;
+        uint32_t p3 = p2 - p2b;
+#pragma unroll
+        for (int j = 0; j < kSpt; ++j) {
+            int32_t a0 = xw[H + j];
+            if (FULL || j < nvalid) {
+                orv |= (uint32_t)a0;
+                mn = a0 < mn ? a0 : mn;
+                mx = a0 > mx ? a0 : mx;
+            }
+            uint32_t d1 = (uint32_t)a0 - (uint32_t)xw[H + j - 1];
+            uint32_t d2 = d1 - p1, d3 = d2 - p2, d4 = d3 - p3;
+            p1 = d1; p2 = d2; p3 = d3;
+            if ((j >= 4 || t != 0) && (FULL || j < nvalid)) {
+                fe0 = sad_acc(a0, 0, fe0);
+                fe1 = sad_acc((int32_t)d1, 0, fe1);
+                fe2 = sad_acc((int32_t)d2, 0, fe2);
+                fe3 = sad_acc((int32_t)d3, 0, fe3);
+                fe4 = sad_acc((int32_t)d4, 0, fe4);
+            }
+        }
+    }
+    const bool do_lpc = P.max_lpc_order > 0;
+    double ac[H + 1];
+#pragma unroll
+    for (int l = 0; l <= H; ++l) ac[l] = 0.0;
+    if (do_lpc) {
+        double wv[H + 1];
+#pragma unroll
+        for (int l = 0; l <= H; ++l) wv[l] = 0.0;
+        const float* win = P.window + i0 - H;
+        // history: wv[l] = windowed sample (i0 - l)
+#pragma unroll
+        for (int q = 0; q < H / 4; ++q) {
+            if (t != 0) {
+                U4 w4 = ldg128(win + 4 * q);
+                float w0, w1, w2, w3;
+                memcpy(&w0, &w4.x, 4); memcpy(&w1, &w4.y, 4); memcpy(&w2, &w4.z, 4); memcpy(&w3, &w4.w, 4);
+                wv[H - 4 * q] = (double)fmul((float)xw[4 * q], w0);
+                wv[H - 4 * q - 1] = (double)fmul((float)xw[4 * q + 1], w1);
+                wv[H - 4 * q - 2] = (double)fmul((float)xw[4 * q + 2], w2);
+                wv[H - 4 * q - 3] = (double)fmul((float)xw[4 * q + 3], w3);
+            }
+        }
+        float wq[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < kSpt; ++j) {
+            if ((j & 3) == 0) {
+                U4 w4 = ldg128(win + H + j);
+                memcpy(&wq[0], &w4.x, 4); memcpy(&wq[1], &w4.y, 4); memcpy(&wq[2], &w4.z, 4); memcpy(&wq[3], &w4.w, 4);
+            }
+            wv[0] = (double)fmul((float)xw[H + j], wq[j & 3]);
+#pragma unroll
+            for (int l = 0; l <= H; ++l) ac[l] = dfma(wv[0], wv[l], ac[l]);
+#pragma unroll
+            for (int l = H; l >= 1; --l) wv[l] = wv[l - 1];
+        }
+    }
+
+    // ---- block reduction: REDUX for the integers, transposing butterfly for the doubles
+    {
+        uint32_t wor = redux_or(orv);
+        int32_t wmn = redux_min(mn), wmx = redux_max(mx);
+        unsigned long long s0 = warp_sum_u32_wide(fe0), s1 = warp_sum_u32_wide(fe1), s2 = warp_sum_u32_wide(fe2),
+                           s3 = warp_sum_u32_wide(fe3), s4 = warp_sum_u32_wide(fe4);
+        if (ln == 0) {
+            sh->w_or[wp] = wor; sh->w_mn[wp] = wmn; sh->w_mx[wp] = wmx;
+            sh->w_fe[wp][0] = s0; sh->w_fe[wp][1] = s1; sh->w_fe[wp][2] = s2; sh->w_fe[wp][3] = s3; sh->w_fe[wp][4] = s4;
+        }
+        if (do_lpc) {
+            double v8 = warp_sum8_d(ac);
+            if ((ln & 3) == 0) sh->w_ac[wp][((ln >> 4) & 1) * 4 + ((ln >> 3) & 1) * 2 + ((ln >> 2) & 1)] = v8;
+#pragma unroll
+            for (int l = 8; l <= H; ++l) {
+                double v = warp_sum_d(ac[l]);
+                if (ln == 0) sh->w_ac[wp][l] = v;
+            }
+        }
+    }
+    sync();   // B1
+    if (wp == 3 && !X.retired) retire_lookback(P, sh);   // overlaps the serial design below
+    if (wp == 0) {
+        if (ln < 5) {
+            unsigned long long v = 0;
+            for (int w = 0; w < kEncWarps; ++w) v += sh->w_fe[w][ln];
+            sh->t_fe[ln] = v;
+        } else if (ln >= 8 && ln < 8 + H + 1) {
+            int l = ln - 8;
+            double v = dadd(dadd(sh->w_ac[0][l], sh->w_ac[1][l]), dadd(sh->w_ac[2][l], sh->w_ac[3][l]));
+            sh->t_ac[l] = v;
+        } else if (ln == 31) {
+            uint32_t o = 0;
+            int32_t a = 0x7fffffff, b = (int32_t)0x80000000u;
+            for (int w = 0; w < kEncWarps; ++w) {
+                o |= sh->w_or[w];
+                a = sh->w_mn[w] < a ? sh->w_mn[w] : a;
+                b = sh->w_mx[w] > b ? sh->w_mx[w] : b;
+            }
+            sh->t_or = o; sh->t_mn = a; sh->t_mx = b;
+        }
+        syncwarp();
+        if (ln == 0) {
+            const int32_t a = sh->t_mn, b = sh->t_mx;
+            int mode = 2;
+            if (a == b) mode = 1;                                           // CONSTANT
+            else if ((sh->t_or & 1u) == 0) mode = 0;                        // wasted bits
+            else if (a < -(1 << kNarrowBits) || b >= (1 << kNarrowBits)) mode = 0;   // wide samples
+            sh->mode = mode;
+            sh->wasted = 0;
+            if (mode == 2) {
+                uint32_t maxabs = (uint32_t)(-(int64_t)a > (int64_t)b ? -(int64_t)a : (int64_t)b);
+                design_fixed(sh, bs, 32, 0u, level_maxp);
+                design_lpc(sh, bs, 32, P.max_lpc_order < H ? P.max_lpc_order : H, P.qlp_precision, level_maxp, maxabs);
+            }
+        }
+    }
+    sync();   // B2
+    const int mode = sh->mode;
+    const bool retiring = !X.retired;
+    if (retiring) retire_copyout(P, X);   // previous frame: CRC partials + copy to HBM (offset known since B2)
+    if (mode != 2) {
+        if (retiring) {
+            sync();
+            if (t == 0) retire_crc(P, sh);
+            zero_out(X);
+            sync();
+            X.retired = true;
+        }
+        if (mode == 0) return false;
+        bitpos_end = bitpos0 + (c == 0 ? 8 * frame_header_bytes(bs, f) : 0) + subframe_header_bits(0, 0, 0, 32, 0);
+        if (t == 0) {
+            if (c == P.nch - 1) publish_aggregate(P, g, f, bitpos_end);
+            Pk pk;
+            pk_begin(pk, out, bitpos0);
+            if (c == 0) emit_frame_header(pk, P.crc, bs, f, P.nch);
+            emit_subframe_header(pk, 0, 0, 0);
+            emit_sample(pk, xw[H], 32);
+            pk_end(pk, sh->tail_val[c][0], sh->tail_word[c][0]);
+        }
+        return true;
+    }
+
+    // ---- pass 2: per-chunk sums of |residual| for both candidates
+    const int js = (t == 0) ? 0 : -1;   // thread 0 skips its first `order` samples (warm-up)
+    int32_t r[kSpt];
+    const int ok0 = sh->cand_ok[0], ok1 = sh->cand_ok[1];
+    const int ord0 = sh->cand[0].order;
+    if (ok0) {
+        uint32_t sel = ord0 == 0 ? fe0 : ord0 == 1 ? fe1 : ord0 == 2 ? fe2 : ord0 == 3 ? fe3 : fe4;
+        if (t == 0) {
+            // samples order..3 belong to the residual but not to libFLAC's selection sums
+            int32_t cf[4];
+            fixed_coefs(ord0, cf, 4);
+            for (int j = ord0; j < 4; ++j) {
+                int32_t pred = 0;
+                for (int m = 0; m < ord0; ++m) pred += cf[m] * xw[H + j - 1 - m];
+                sel = sad_acc(xw[H + j], pred, sel);
+            }
+        }
+        sh->csum[0][t] = sel;
+    }
+    int ord1 = 0, shift1 = 0, wide1 = 0;
+    if (ok1) {
+        const Plan& pl = sh->cand[1];
+        ord1 = pl.order; shift1 = pl.shift; wide1 = pl.wide;
+        int32_t coef[H];
+#pragma unroll
+        for (int m = 0; m < H; ++m) coef[m] = pl.qlp[m];
+        unsigned long long asum = 0;
+        if (!wide1) {
+            residual32_dispatch<H>(ord1, xw, coef, shift1, r);
+            uint32_t a32 = 0;
+#pragma unroll
+            for (int j = 0; j < kSpt; ++j)
+                if ((j >= H || js < 0 || j >= ord1) && (FULL || j < nvalid)) a32 = sad_acc(r[j], 0, a32);
+            asum = a32;
+        } else {
+            uint32_t fitmask = residual64<H>(ord1, xw, coef, shift1, r);
+#pragma unroll
+            for (int j = 0; j < kSpt; ++j)
+                if ((j >= H || js < 0 || j >= ord1) && (FULL || j < nvalid))
+                    asum += (unsigned long long)(r[j] < 0 ? -(int64_t)r[j] : (int64_t)r[j]);
+            uint32_t vmask = nvalid >= 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
+            if (t == 0) vmask &= ~((1u << ord1) - 1u);
+            if ((fitmask & vmask) != vmask) asum = ~0ull;   // a residual does not fit: poisons the candidate
+        }
+        sh->csum[1][t] = asum;
+    }
+    sync();   // B3
+    if (retiring) {
+        if (t == 0) retire_crc(P, sh);
+        zero_out(X);     // ordered before the packing below by B4 and B5
+        X.retired = true;
+    }
+    if (wp < 2 && sh->cand_ok[wp]) {
+        const int cd = wp;
+        const int maxp = sh->maxp[cd];
+        const int cpp = FULL ? (kEncThreads >> maxp) : (maxp > 0 ? ((bs >> maxp) >> 5) : kEncThreads);   // chunks per finest partition
+        bool poisoned = false;
+        for (int part = ln; part < (1 << maxp); part += 32) {
+            unsigned long long v = 0;
+            for (int q = 0; q < cpp; ++q) {
+                unsigned long long cs = sh->csum[cd][part * cpp + q];
+                poisoned = poisoned || cs == ~0ull;
+                v += cs;
+            }
+            sh->psum[cd][part] = v;
+        }
+        if (ballot(poisoned) != 0) {
+            if (ln == 0) sh->cand_ok[cd] = 0;
+            syncwarp();
+        } else {
+            syncwarp();
+            rice_search_warp(sh, cd, bs, sh->cand[cd].order, maxp);
+        }
+    }
+    sync();   // B4
+    // ---- every thread: pick the winner (stream_encoder.c process_subframe_: smallest estimate wins)
+    const uint32_t verbatim_bits = 32u * (uint32_t)bs;
+    int win = -1;
+    {
+        uint32_t best = verbatim_bits;
+        for (int cd = 0; cd < 2; ++cd) {
+            if (!sh->cand_ok[cd]) continue;
+            const Plan& pl = sh->cand[cd];
+            uint32_t bits = (uint32_t)pl.order * 32u + pl.res_bits + (cd == 1 ? 9u + (uint32_t)pl.order * (uint32_t)pl.prec : 0u);
+            if (bits < best) { best = bits; win = cd; }
+        }
+    }
+    if (win < 0) return false;
+    const Plan& pl = sh->cand[win];
+    const int order = pl.order, porder = pl.porder, plen = pl.rice2 ? 5 : 4;
+    if (win == 0) {
+        int32_t cf[H];
+        fixed_coefs(order, cf, H);
+        residual32_dispatch<H>(order, xw, cf, 0, r);
+    }
+    // ---- exact code lengths of the chunk, block scan
+    int part;
+    bool part_start;
+    if (FULL) {
+        const int psh = 12 - porder;             // log2(partition size)
+        part = i0 >> psh;
+        part_start = (i0 & ((1 << psh) - 1)) == 0;
+    } else {
+        const int psize = bs >> porder;          // a multiple of 32 when porder > 0
+        part = porder > 0 ? i0 / psize : 0;
+        part_start = nvalid > 0 && i0 == part * psize;
+        if (nvalid == 0) part = 0;
+    }
+    const int k = sh->kpar[win][(1 << porder) - 1 + part];
+    uint32_t lens = part_start ? (uint32_t)plen : 0u;
+    uint32_t qmax = 0;
+    int nres = 0;
+#pragma unroll
+    for (int j = 0; j < kSpt; ++j) {
+        if ((j >= H || js < 0 || j >= order) && (FULL || j < nvalid)) {
+            uint32_t u = ((uint32_t)r[j] << 1) ^ (uint32_t)(r[j] >> 31);
+            uint32_t q = u >> k;
+            lens += q;
+            qmax = q > qmax ? q : qmax;
+            nres++;
+        }
+    }
+    lens += (uint32_t)nres * (uint32_t)(k + 1);
+    uint32_t inc = lens;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t n = shfl_up(inc, d);
+        if (ln >= d) inc += n;
+    }
+    if (ln == 31) sh->scan[wp] = inc;
+    sync();   // B5
+    uint32_t wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kEncWarps; ++w) {
+        uint32_t x = sh->scan[w];
+        if (w < wp) wbase += x;
+        total += x;
+    }
+    const uint32_t excl = wbase + inc - lens;
+    const int ptype = win == 0 ? 2 : 3;
+    const int hdr_bits = subframe_header_bits(ptype, order, 0, 32, pl.prec);
+    if ((uint32_t)hdr_bits + total >= verbatim_bits + 8u) return false;   // VERBATIM is smaller: general path
+    const int sub0 = bitpos0 + (c == 0 ? 8 * frame_header_bytes(bs, f) : 0);
+    const int body0 = sub0 + hdr_bits;
+
+    // ---- pack
+    bitpos_end = body0 + (int)total;
+    Pk pk;
+    if (t == 0) {
+        if (c == P.nch - 1) publish_aggregate(P, g, f, bitpos_end);
+        pk_begin(pk, out, bitpos0);
+        if (c == 0) emit_frame_header(pk, P.crc, bs, f, P.nch);
+        emit_subframe_header(pk, ptype, order, 0);
+        for (int j = 0; j < order; ++j) emit_sample(pk, xw[H + j], 32);
+        if (ptype == 3) emit_lpc_params(pk, pl);
+        pk_emit(pk, (uint32_t)pl.rice2, 2);
+        pk_emit(pk, (uint32_t)porder, 4);
+    } else {
+        pk_begin(pk, out, body0 + (int)excl);
+    }
+    if (FULL || nvalid > 0) {
+        if (part_start) pk_emit(pk, (uint32_t)k, plen);
+        if (qmax + (uint32_t)k + 1u <= 32u) {
+            // every code of the chunk fits one emit: branch-free loop on a (hi, lo) register pair
+            uint32_t hi = (uint32_t)(pk.acc >> 32), lo = 0;
+            int fill = pk.fill, word = pk.word;
+            const uint32_t kbit = 1u << k, kmask = kbit - 1u;
+            const int k1 = k + 1;
+#pragma unroll
+            for (int j = 0; j < kSpt; ++j) {
+                if ((j >= H || js < 0 || j >= order) && (FULL || j < nvalid)) {
+                    uint32_t u = ((uint32_t)r[j] << 1) ^ (uint32_t)(r[j] >> 31);
+                    uint32_t low = (u & kmask) | kbit;
+                    int len = (int)(u >> k) + k1;
+                    uint64_t v = (uint64_t)low << (64 - fill - len);
+                    hi |= (uint32_t)(v >> 32);
+                    lo |= (uint32_t)v;
+                    fill += len;
+                    if (fill >= 32) {
+                        out[ow(word)] = hi;
+                        word++;
+                        hi = lo;
+                        lo = 0;
+                        fill -= 32;
+                    }
+                }
+            }
+            pk.acc = (uint64_t)hi << 32;
+            pk.fill = fill;
+            pk.word = word;
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < kSpt; ++j) {
+                if ((j >= H || js < 0 || j >= order) && (FULL || j < nvalid)) {
+                    int32_t rv = r[0];
+#pragma unroll
+                    for (int q = 1; q < kSpt; ++q) rv = (q == j) ? r[q] : rv;   // keeps r[] in registers
+                    uint32_t u = ((uint32_t)rv << 1) ^ (uint32_t)(rv >> 31);
+                    pk_rice(pk, u, k);
+                }
+            }
+        }
+        pk_end(pk, sh->tail_val[c][t], sh->tail_word[c][t]);
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// General path: any blocksize <= 4096, any sample width, wasted bits, CONSTANT / VERBATIM / FIXED / LPC.
+// ------------------------------------------------------------------------------------------------------
+struct GenChunk {                 // thread-local copy of the chunk (local memory: this path is not tuned)
+    int32_t x[kMaxOrd + kSpt];    // x[kMaxOrd + j] = sample (32 t + j) >> wasted; history before it
+};
+
+FA_D int64_t gen_residual(const GenChunk& G, int j, int order, const int32_t* coef, int shift) {
+    int64_t sum = 0;
+    for (int m = 0; m < order; ++m) sum += (int64_t)coef[m] * (int64_t)G.x[kMaxOrd + j - 1 - m];
+    return (int64_t)G.x[kMaxOrd + j] - (sum >> shift);
+}
+
+FA_D void enc_channel_general(const EncParams& P, EncCtx& X, const FrameSrc& S, int c, int f, uint32_t g, int bitpos0,
+                              int& bitpos_end) {
+    EncShared* sh = X.sh;
+    uint32_t* out = X.out;
+    retire_full(P, X);
+    const int t = tid();
+    const int ln = lane(), wp = warp();
+    const int bs = S.bs;
+    const int i0 = t * kSpt;
+    const int nmine = i0 >= bs ? 0 : (bs - i0 < kSpt ? bs - i0 : kSpt);
+    GenChunk G;
+    for (int j = 0; j < kMaxOrd + kSpt; ++j) {
+        int i = i0 - kMaxOrd + j;
+        G.x[j] = (i >= 0 && i < bs) ? src_sample(S, c, i) : 0;
+    }
+    // ---- statistics
+    {
+        uint32_t orv = 0;
+        int32_t mn = 0x7fffffff, mx = (int32_t)0x80000000u;
+        for (int j = 0; j < nmine; ++j) {
+            int32_t v = G.x[kMaxOrd + j];
+            orv |= (uint32_t)v;
+            mn = v < mn ? v : mn;
+            mx = v > mx ? v : mx;
+        }
+        uint32_t wor = redux_or(orv);
+        int32_t wmn = redux_min(mn), wmx = redux_max(mx);
+        if (ln == 0) { sh->w_or[wp] = wor; sh->w_mn[wp] = wmn; sh->w_mx[wp] = wmx; }
+    }
+    sync();
+    uint32_t t_or = 0;
+    int32_t t_mn = 0x7fffffff, t_mx = (int32_t)0x80000000u;
+    for (int w = 0; w < kEncWarps; ++w) {
+        t_or |= sh->w_or[w];
+        t_mn = sh->w_mn[w] < t_mn ? sh->w_mn[w] : t_mn;
+        t_mx = sh->w_mx[w] > t_mx ? sh->w_mx[w] : t_mx;
+    }
+    const int wasted = t_or == 0 ? 0 : ctz32(t_or);
+    const int bps = 32 - wasted;
+    const bool constant = t_mn == t_mx;
+    if (wasted)
+        for (int j = 0; j < kMaxOrd + kSpt; ++j) G.x[j] >>= wasted;
+    const int sub0 = bitpos0 + (c == 0 ? 8 * frame_header_bytes(bs, f) : 0);
+    const uint32_t verbatim_bits = (uint32_t)bps * (uint32_t)bs;
+    const bool try_pred = !constant && bs > 4;
+
+    int ptype = constant ? 0 : 1;
+    int win = -1;
+    if (try_pred) {
+        // ---- fixed-predictor error sums (64-bit) and windowed autocorrelation
+        unsigned long long fe[5] = {0, 0, 0, 0, 0};
+        uint32_t bad = 0;
+        for (int j = 0; j < nmine; ++j) {
+            if (i0 + j < 4) continue;
+            int64_t a0 = G.x[kMaxOrd + j], a1 = G.x[kMaxOrd + j - 1], a2 = G.x[kMaxOrd + j - 2], a3 = G.x[kMaxOrd + j - 3],
+                    a4 = G.x[kMaxOrd + j - 4];
+            int64_t e[5];
+            e[0] = a0; e[1] = a0 - a1; e[2] = e[1] - (a1 - a2); e[3] = e[2] - (a1 - 2 * a2 + a3);
+            e[4] = e[3] - (a1 - 3 * a2 + 3 * a3 - a4);
+            for (int k = 0; k < 5; ++k) {
+                if (!fits_res(e[k])) bad |= 1u << k;
+                fe[k] += (unsigned long long)(e[k] < 0 ? -e[k] : e[k]);
+            }
+        }
+        int max_order = P.max_lpc_order;
+        if (max_order >= bs) max_order = bs - 1;
+        double ac[kMaxOrd + 1];
+        for (int l = 0; l <= kMaxOrd; ++l) ac[l] = 0.0;
+        if (max_order > 0) {
+            for (int j = 0; j < nmine; ++j) {
+                double w0 = (double)fmul((float)G.x[kMaxOrd + j], P.window[i0 + j]);
+                for (int l = 0; l <= max_order; ++l) {
+                    int i = i0 + j - l;
+                    if (i < 0) break;
+                    double wl = (double)fmul((float)G.x[kMaxOrd + j - l], P.window[i]);
+                    ac[l] = dfma(w0, wl, ac[l]);
+                }
+            }
+        }
+        uint32_t wbad = redux_or(bad);
+        for (int k = 0; k < 5; ++k) {
+            unsigned long long v = warp_sum_u64(fe[k]);
+            if (ln == 0) sh->w_fe[wp][k] = v;
+        }
+        for (int l = 0; l <= max_order; ++l) {
+            double v = warp_sum_d(ac[l]);
+            if (ln == 0) sh->w_ac[wp][l] = v;
+        }
+        if (ln == 0) sh->w_bad[wp] = wbad;
+        sync();
+        if (t == 0) {
+            uint32_t tb = 0;
+            for (int w = 0; w < kEncWarps; ++w) tb |= sh->w_bad[w];
+            for (int k = 0; k < 5; ++k) {
+                unsigned long long v = 0;
+                for (int w = 0; w < kEncWarps; ++w) v += sh->w_fe[w][k];
+                sh->t_fe[k] = v;
+            }
+            for (int l = 0; l <= max_order; ++l)
+                sh->t_ac[l] = dadd(dadd(sh->w_ac[0][l], sh->w_ac[1][l]), dadd(sh->w_ac[2][l], sh->w_ac[3][l]));
+            design_fixed(sh, bs, bps, tb, P.max_porder);
+            design_lpc(sh, bs, bps, max_order, P.qlp_precision, P.max_porder, 0u);
+        }
+        if (t < 2 * kMaxParts) ((unsigned long long*)sh->psum)[t] = 0;
+        sync();
+        // ---- residual partition sums (shared atomics at partition boundaries only)
+        uint32_t resbad = 0;
+        for (int cd = 0; cd < 2; ++cd) {
+            if (!sh->cand_ok[cd]) continue;   // block-uniform
+            const Plan& pl = sh->cand[cd];
+            int32_t coef[kMaxOrd];
+            if (cd == 0) fixed_coefs(pl.order, coef, kMaxOrd);
+            else for (int m = 0; m < kMaxOrd; ++m) coef[m] = pl.qlp[m];
+            const int psize = bs >> sh->maxp[cd];
+            int j = i0 < pl.order ? pl.order - i0 : 0;
+            if (j < nmine) {
+                int part = (i0 + j) / psize;
+                int next = (part + 1) * psize;
+                unsigned long long acc = 0;
+                for (; j < nmine; ++j) {
+                    if (i0 + j == next) {
+                        atom_add_shared64(&sh->psum[cd][part], acc);
+                        acc = 0;
+                        part++;
+                        next += psize;
+                    }
+                    int64_t rv = gen_residual(G, j, pl.order, coef, pl.shift);
+                    if (!fits_res(rv)) resbad |= 1u << cd;
+                    acc += (unsigned long long)(rv < 0 ? -rv : rv);
+                }
+                atom_add_shared64(&sh->psum[cd][part], acc);
+            }
+        }
+        resbad = redux_or(resbad);
+        if (ln == 0) sh->w_bad[wp] = resbad;
+        sync();
+        resbad = sh->w_bad[0] | sh->w_bad[1] | sh->w_bad[2] | sh->w_bad[3];
+        if (wp < 2 && sh->cand_ok[wp] && !((resbad >> wp) & 1))
+            rice_search_warp(sh, wp, bs, sh->cand[wp].order, sh->maxp[wp]);
+        sync();
+        {
+            uint32_t best = verbatim_bits;
+            for (int cd = 0; cd < 2; ++cd) {
+                if (!sh->cand_ok[cd] || ((resbad >> cd) & 1)) continue;
+                const Plan& pl = sh->cand[cd];
+                uint32_t bits = (uint32_t)pl.order * (uint32_t)bps + pl.res_bits +
+                                (cd == 1 ? 9u + (uint32_t)pl.order * (uint32_t)pl.prec : 0u);
+                if (bits < best) { best = bits; win = cd; }
+            }
+        }
+        if (win >= 0) ptype = win == 0 ? 2 : 3;
+    }
+
+    // ---- exact size of the predictive subframe; fall back to VERBATIM if it does not pay
+    int order = 0, porder = 0, plen = 4, shift = 0, prec = 0;
+    int32_t coef[kMaxOrd];
+    for (int m = 0; m < kMaxOrd; ++m) coef[m] = 0;
+    uint32_t lens = 0;
+    if (ptype >= 2) {
+        const Plan& pl = sh->cand[win];
+        order = pl.order; porder = pl.porder; plen = pl.rice2 ? 5 : 4; shift = pl.shift; prec = pl.prec;
+        if (win == 0) fixed_coefs(order, coef, kMaxOrd);
+        else for (int m = 0; m < kMaxOrd; ++m) coef[m] = pl.qlp[m];
+        const int psize = bs >> porder;
+        const uint8_t* kp = &sh->kpar[win][(1 << porder) - 1];
+        int j = i0 < order ? order - i0 : 0;
+        if (j < nmine) {
+            int part = (i0 + j) / psize;
+            int next = (part + 1) * psize;
+            int k = kp[part];
+            if (i0 + j == (part == 0 ? order : part * psize)) lens += (uint32_t)plen;
+            for (; j < nmine; ++j) {
+                if (i0 + j == next) { part++; next += psize; k = kp[part]; lens += (uint32_t)plen; }
+                int64_t rv = gen_residual(G, j, order, coef, shift);
+                uint32_t u = ((uint32_t)rv << 1) ^ (uint32_t)(rv >> 63);
+                lens += (u >> k) + 1u + (uint32_t)k;
+            }
+        }
+    }
+    uint32_t inc = lens;
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t n = shfl_up(inc, d);
+        if (ln >= d) inc += n;
+    }
+    if (ln == 31) sh->scan[wp] = inc;
+    sync();
+    uint32_t wbase = 0, total = 0;
+    for (int w = 0; w < kEncWarps; ++w) {
+        uint32_t x = sh->scan[w];
+        if (w < wp) wbase += x;
+        total += x;
+    }
+    const uint32_t excl = wbase + inc - lens;
+    if (ptype >= 2 && (uint32_t)subframe_header_bits(ptype, order, 0, bps, prec) + total >= verbatim_bits + 8u) ptype = 1;
+    const int hdr_bits = subframe_header_bits(ptype, order, wasted, bps, prec);
+    const int body0 = sub0 + hdr_bits;   // for CONSTANT this already includes the value
+
+    // ---- pack
+    bitpos_end = ptype == 1 ? body0 + bs * bps : ptype >= 2 ? body0 + (int)total : body0;
+    Pk pk;
+    bool open = false;
+    if (t == 0) {
+        if (c == P.nch - 1) publish_aggregate(P, g, f, bitpos_end);
+        pk_begin(pk, out, bitpos0);
+        open = true;
+        if (c == 0) emit_frame_header(pk, P.crc, bs, f, P.nch);
+        emit_subframe_header(pk, ptype, order, wasted);
+        if (ptype == 0) {
+            emit_sample(pk, G.x[kMaxOrd], bps);
+        } else if (ptype >= 2) {
+            for (int j = 0; j < order; ++j) emit_sample(pk, G.x[kMaxOrd + j], bps);
+            if (ptype == 3) emit_lpc_params(pk, sh->cand[win]);
+            pk_emit(pk, (uint32_t)sh->cand[win].rice2, 2);
+            pk_emit(pk, (uint32_t)porder, 4);
+        }
+    }
+    if (ptype == 1) {
+        if (nmine > 0) {
+            if (!open) { pk_begin(pk, out, body0 + i0 * bps); open = true; }
+            for (int j = 0; j < nmine; ++j) emit_sample(pk, G.x[kMaxOrd + j], bps);
+        }
+    } else if (ptype >= 2) {
+        const int psize = bs >> porder;
+        const uint8_t* kp = &sh->kpar[win][(1 << porder) - 1];
+        int j = i0 < order ? order - i0 : 0;
+        if (j < nmine) {
+            if (!open) { pk_begin(pk, out, body0 + (int)excl); open = true; }
+            int part = (i0 + j) / psize;
+            int next = (part + 1) * psize;
+            int k = kp[part];
+            if (i0 + j == (part == 0 ? order : part * psize)) pk_emit(pk, (uint32_t)k, plen);
+            for (; j < nmine; ++j) {
+                if (i0 + j == next) { part++; next += psize; k = kp[part]; pk_emit(pk, (uint32_t)k, plen); }
+                int64_t rv = gen_residual(G, j, order, coef, shift);
+                uint32_t u = ((uint32_t)rv << 1) ^ (uint32_t)(rv >> 63);
+                pk_rice(pk, u, k);
+            }
+        }
+    }
+    if (open) pk_end(pk, sh->tail_val[c][t], sh->tail_word[c][t]);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// The CTA body: loops over (stream, frame) tickets.  `smem_raw` >= enc_smem_bytes(nch).
+// ------------------------------------------------------------------------------------------------------
+template <int H>
+FA_D void encode_frames_cta(const EncParams& P, unsigned char* smem_raw) {
+    EncShared* sh = (EncShared*)smem_raw;
+    uint16_t* crcT = (uint16_t*)(smem_raw + ((sizeof(EncShared) + 15) & ~(size_t)15));
+    const int t = tid();
+    const int nch = P.nch;
+    const uint32_t total_frames = (uint32_t)(P.n_stream * P.nframes);
+    EncCtx X;
+    X.sh = sh; X.crcT = crcT; X.out = (uint32_t*)(crcT + 4 * 256);
+    X.out_words_padded = (int)(enc_out_words(nch) + (enc_out_words(nch) >> 4) + 8);
+    X.retired = false;
+
+    for (int i = t; i < 4 * 256; i += kEncThreads) crcT[i] = P.crc->crc16[i >> 8][i & 255];
+    if (t == 0) sh->prev_valid = 0;
+    sh->tail_val[0][t] = 0; sh->tail_val[1][t] = 0;
+    zero_out(X);
+
+    for (;;) {
+        // ---- work assignment: tickets are handed out in launch order so that look-back never waits
+        // on a frame that has not started (decoupled look-back, Merrill & Garland).
+        if (t == 0) sh->g = atom_add_global(P.ticket, 1u);
+        sync();   // also: every thread has finished packing the previous frame (all plain stores done)
+        const uint32_t g = sh->g;
+        // trailing partial words of the previous frame's packing sessions
+        for (int c = 0; c < nch; ++c) {
+            uint32_t tv = sh->tail_val[c][t];
+            if (tv) { atom_or_shared(&X.out[ow(sh->tail_word[c][t])], tv); sh->tail_val[c][t] = 0; }
+        }
+        X.retired = false;
+        if (g >= total_frames) break;
+        const int64_t s = (int64_t)(g / (uint32_t)P.nframes);
+        const int f = (int)(g % (uint32_t)P.nframes);
+        const int64_t samp0 = (int64_t)f * P.blocksize;
+        const int bs = (int)((P.stream_size - samp0) < P.blocksize ? (P.stream_size - samp0) : P.blocksize);
+
+        FrameSrc S;
+        S.dtype = P.dtype; S.bs = bs;
+        S.off32 = 0.f; S.gain32 = 0.f; S.off64 = 0.; S.gain64 = 0.;
+        if (P.dtype == kF32) { S.off32 = ((const float*)P.offsets)[s]; S.gain32 = ((const float*)P.gains)[s]; }
+        if (P.dtype == kF64) { S.off64 = ((const double*)P.offsets)[s]; S.gain64 = ((const double*)P.gains)[s]; }
+        const int esize = (P.dtype == kI32 || P.dtype == kF32) ? 4 : 8;
+        S.base = (const unsigned char*)P.data + (s * P.stream_size + samp0) * esize;
+        S.vec = (((uintptr_t)S.base) & 15) == 0;
+
+        int bitpos = 0;
+        for (int c = 0; c < nch; ++c) {
+            int bend = 0;
+            bool done = false;
+            if (bs == kMaxBs) done = enc_channel_fast<H, true>(P, X, S, c, f, g, bitpos, bend);
+            else if (bs >= 64) done = enc_channel_fast<H, false>(P, X, S, c, f, g, bitpos, bend);
+            if (!done) enc_channel_general(P, X, S, c, f, g, bitpos, bend);
+            bitpos = bend;
+        }
+        // the frame now waits in `out`; it is retired during the next iteration (or the drain below).
+        // The writes below are ordered before their readers by the barrier at the top of the loop.
+        if (t == 0) {
+            sh->prev_valid = 1; sh->prev_g = g; sh->prev_f = f; sh->prev_nbytes = (bitpos + 7) >> 3;
+        }
+    }
+    // ---- drain: the last frame of this CTA (its tails were OR-ed in above)
+    sync();
+    retire_full(P, X);
 }
 
 }  // namespace fa

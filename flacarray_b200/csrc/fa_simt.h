@@ -16,6 +16,7 @@
 // ------------------------------------------------------------------------------------------------
 #define FA_D __device__ __forceinline__
 #define FA_DNOINL __device__ __noinline__
+#define FA_HD __host__ __device__ inline
 #define FA_SHARED_BASE(name) extern __shared__ __align__(16) unsigned char name[]
 #define FA_RESTRICT __restrict__
 
@@ -62,6 +63,18 @@ FA_D U4 ldg128(const void* p) {  // 16-byte aligned, read-only path
     U4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
     return r;
 }
+FA_D void sts128(void* p, U4 v) { *(uint4*)p = make_uint4(v.x, v.y, v.z, v.w); }   // 16-byte aligned shared/global store
+FA_D U4 lds128(const void* p) { uint4 v = *(const uint4*)p; U4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r; }
+// |a - b| + acc in one instruction (VABSDIFF)
+FA_D uint32_t sad_acc(int32_t a, int32_t b, uint32_t acc) { return __sad(a, b, acc); }
+// warp-wide integer reductions (REDUX / CREDUX)
+FA_D uint32_t redux_add(uint32_t v) { return __reduce_add_sync(0xffffffffu, v); }
+FA_D uint32_t redux_or(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
+FA_D uint32_t redux_xor(uint32_t v) { return __reduce_xor_sync(0xffffffffu, v); }
+FA_D int32_t redux_min(int32_t v) { return __reduce_min_sync(0xffffffffu, v); }
+FA_D int32_t redux_max(int32_t v) { return __reduce_max_sync(0xffffffffu, v); }
+FA_D float flog2(float v) { return __log2f(v); }
+FA_D void st_global_u8x2(uint8_t* p, uint32_t hi, uint32_t lo) { p[0] = (uint8_t)hi; p[1] = (uint8_t)lo; }
 // float ops with the rounding and (non-)contraction spelled out
 FA_D float fadd(float a, float b) { return __fadd_rn(a, b); }
 FA_D float fsub(float a, float b) { return __fsub_rn(a, b); }
@@ -87,6 +100,7 @@ FA_D double dfma(double a, double b, double c) { return __fma_rn(a, b, c); }
 
 #define FA_D inline
 #define FA_DNOINL inline
+#define FA_HD inline
 #define FA_RESTRICT __restrict__
 
 namespace fasim {
@@ -193,6 +207,30 @@ inline void spin_pause() { std::this_thread::yield(); }
 inline uint32_t ldg32(const uint32_t* p) { return *p; }
 struct U4 { uint32_t x, y, z, w; };
 inline U4 ldg128(const void* p) { U4 r; memcpy(&r, p, 16); return r; }
+inline void sts128(void* p, U4 v) { memcpy(p, &v, 16); }
+inline U4 lds128(const void* p) { U4 r; memcpy(&r, p, 16); return r; }
+inline uint32_t sad_acc(int32_t a, int32_t b, uint32_t acc) {
+    int64_t d = (int64_t)a - (int64_t)b;
+    return acc + (uint32_t)(d < 0 ? -d : d);
+}
+template <class F>
+inline uint32_t redux_(uint32_t v, F f) {
+    auto* b = fasim::tls.blk;
+    int base = fasim::tls.tid & ~31;
+    b->xchg[(size_t)fasim::tls.tid] = v;
+    syncwarp();
+    uint32_t r = (uint32_t)b->xchg[(size_t)base];
+    for (int l = 1; l < 32 && base + l < b->nthreads; ++l) r = f(r, (uint32_t)b->xchg[(size_t)(base + l)]);
+    syncwarp();
+    return r;
+}
+inline uint32_t redux_add(uint32_t v) { return redux_(v, [](uint32_t a, uint32_t b) { return a + b; }); }
+inline uint32_t redux_or(uint32_t v) { return redux_(v, [](uint32_t a, uint32_t b) { return a | b; }); }
+inline uint32_t redux_xor(uint32_t v) { return redux_(v, [](uint32_t a, uint32_t b) { return a ^ b; }); }
+inline int32_t redux_min(int32_t v) { return (int32_t)redux_((uint32_t)v, [](uint32_t a, uint32_t b) { return (int32_t)a < (int32_t)b ? a : b; }); }
+inline int32_t redux_max(int32_t v) { return (int32_t)redux_((uint32_t)v, [](uint32_t a, uint32_t b) { return (int32_t)a > (int32_t)b ? a : b; }); }
+inline float flog2(float v) { return log2f(v); }
+inline void st_global_u8x2(uint8_t* p, uint32_t hi, uint32_t lo) { p[0] = (uint8_t)hi; p[1] = (uint8_t)lo; }
 // host build is compiled with -ffp-contract=off so these are the IEEE single operations
 inline float fadd(float a, float b) { return a + b; }
 inline float fsub(float a, float b) { return a - b; }

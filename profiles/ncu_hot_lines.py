@@ -5,7 +5,7 @@ top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 cur = None; hdr = None; data = []
 for r in rows:
     if not r: continue
-    if r[0] == 'File Name': cur = r[1].split('/')[-1]; continue
+    if r[0] in ('File Name', 'File Path'): cur = r[1].split('/')[-1]; continue
     if r[0] == 'Line No': hdr = r; continue
     if hdr is None or r[0] == '': continue
     try:

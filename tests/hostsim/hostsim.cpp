@@ -61,20 +61,27 @@ int hs_encode(const void* data, int dtype, int64_t n_stream, int64_t stream_size
     for (int64_t s = 0; s < n_stream; ++s) starts[s] = -1;
     uint32_t ticket = 0;
     int err = 0;
+    static EncTables tab;
+    static bool tab_ready = false;
+    if (!tab_ready) { enc_tables_init(&tab); tab_ready = true; }
     EncParams P;
     P.data = data; P.dtype = dtype; P.offsets = offsets; P.gains = gains;
     P.n_stream = n_stream; P.stream_size = stream_size; P.nch = nch;
     P.blocksize = lp.blocksize; P.nframes = nf;
     P.max_lpc_order = lp.max_lpc_order; P.max_porder = lp.max_porder;
     P.qlp_precision = lp.blocksize <= 384 ? 13 : (lp.blocksize <= 1152 ? 14 : 15);
-    P.window = window.data(); P.crc = crc();
+    P.window = window.data(); P.crc = crc(); P.tab = &tab;
     P.out = out; P.out_capacity = cap; P.starts = starts; P.ends = ends.data(); P.desc = desc.data();
     P.ticket = &ticket; P.err = &err; P.hdr_bytes = stream_header_bytes(nf);
-    fasim::launch((int)(n_stream * nf), kEncThreads, enc_smem_bytes(nch), [&](int) {
-        encode_frame_cta(P, fasim::smem());
+    // persistent CTAs: the emulator runs blocks one after the other, so one block drains every ticket
+    fasim::launch(1, kEncThreads, enc_smem_bytes(nch), [&](int) {
+        if (lp.max_lpc_order > 8) encode_frames_cta<12>(P, fasim::smem());
+        else encode_frames_cta<8>(P, fasim::smem());
     });
-    for (int64_t s = 0; s < n_stream; ++s) nbytes[s] = ends[s] - starts[s];
-    *total = n_stream ? ends[n_stream - 1] : 0;
+    fasim::launch(1, 1, 0, [&](int) {
+        for (int64_t s = 0; s < n_stream; ++s)
+            for (int f = 0; f < nf; ++f) finalize_entry(P, s, f, nbytes, total);
+    });
     return err;
 }
 
