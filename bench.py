@@ -339,7 +339,7 @@ def run_ours(args):
         alg_dec = comp_bytes + raw
         enc_gbs = alg_enc * enc_n / (enc_ms / 1e3) / 1e9 if enc_ms > 0 else None
         dec_gbs = alg_dec * dec_n / (dec_ms / 1e3) / 1e9 if dec_ms > 0 else None
-        dominant = "k_encode" if (enc_ms / max(enc_n, 1)) >= (dec_ms / max(dec_n, 1)) else "k_dec_frames"
+        dominant = "k_encode" if (enc_ms / max(enc_n, 1)) >= (dec_ms / max(dec_n, 1)) else "k_dec_tile"
         ach = enc_gbs if dominant == "k_encode" else dec_gbs
         # CPU baseline beside it (bounded sample, all host cores)
         cores = os.cpu_count() or 1
@@ -372,7 +372,7 @@ def run_ours(args):
                          "ms_per_launch": (enc_ms / max(enc_n, 1)) if dominant == "k_encode" else (dec_ms / max(dec_n, 1))},
             "roofline_encode": {"kernel": "k_encode", "achieved": enc_gbs, "frac": enc_gbs / peak if enc_gbs else None,
                                 "ms_per_launch": enc_ms / max(enc_n, 1)},
-            "roofline_decode": {"kernel": "k_dec_frames", "achieved": dec_gbs, "frac": dec_gbs / peak if dec_gbs else None,
+            "roofline_decode": {"kernel": "k_dec_tile", "achieved": dec_gbs, "frac": dec_gbs / peak if dec_gbs else None,
                                 "ms_per_launch": dec_ms / max(dec_n, 1)},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d // e2e_steps,
