@@ -172,13 +172,8 @@ def wrap_int64_to_float64(idata, n_stream, stream_size, offsets, gains):
 # encode (pyx:285-594)
 # -------------------------------------------------------------------------------------------------
 
-def encode_device(d, n_stream, stream_size, level, quanta=None):
-    """Device-level encode.  d: CUDA tensor (int32/int64/float32/float64), flat or 2-D.
-
-    Returns CUDA tensors (compressed u8[total], starts i64[n], nbytes i64[n], offsets, gains); offsets /
-    gains are None for integer input.  For float input the quantisation (utils.c:160-328) is fused in
-    front of the encoder; `quanta` is None (auto) or a CUDA tensor [n_stream].
-    """
+def _encode_device_raw(d, n_stream, stream_size, level, quanta=None):
+    """fab_encode into a worst-case device buffer.  Returns (buffer, starts, nbytes, total, offsets, gains)."""
     dev = d.device
     dt = _TORCH2NP[d.dtype]
     with torch.cuda.device(dev):
@@ -199,16 +194,198 @@ def encode_device(d, n_stream, stream_size, level, quanta=None):
                           _ptr(gain), _ptr(out), bound, _ptr(starts), _ptr(nbytes), _ptr(total), st)
         _check(rc, ctx, st, "Encoding")
         n_total = int(total.item())
+    return out, starts, nbytes, n_total, off, gain
+
+
+def encode_device(d, n_stream, stream_size, level, quanta=None):
+    """Device-level encode.  d: CUDA tensor (int32/int64/float32/float64), flat or 2-D.
+
+    Returns CUDA tensors (compressed u8[total], starts i64[n], nbytes i64[n], offsets, gains); offsets /
+    gains are None for integer input.  For float input the quantisation (utils.c:160-328) is fused in
+    front of the encoder; `quanta` is None (auto) or a CUDA tensor [n_stream].
+    """
+    out, starts, nbytes, n_total, off, gain = _encode_device_raw(d, n_stream, stream_size, level, quanta)
     return out[:n_total], starts, nbytes, off, gain
+
+
+# -------------------------------------------------------------------------------------------------
+# Host-buffer pipelines: H2D of chunk i+1, the kernels of chunk i and D2H of chunk i-1 overlap on three
+# CUDA streams (the PCIe link is full duplex).  Chunks are whole streams, so every chunk is an
+# independent call of the device path; only byte offsets have to be rebased on the host.
+# -------------------------------------------------------------------------------------------------
+_PIPE_CHUNK_BYTES = 192 << 20     # raw bytes per chunk
+_PIPE_MIN_BYTES = 64 << 20        # smaller arrays go in one shot
+_side = {}
+
+
+def _side_streams(dev):
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _side:
+        _side[key] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+    return _side[key]
+
+
+def _chunk_ranges(n_stream, bytes_per_stream):
+    total = n_stream * bytes_per_stream
+    if n_stream < 2 or total < _PIPE_MIN_BYTES:
+        return [(0, n_stream)]
+    nchunk = min(n_stream, max(2, -(-total // _PIPE_CHUNK_BYTES)))
+    edges = [(n_stream * i) // nchunk for i in range(nchunk + 1)]
+    return [(edges[i], edges[i + 1]) for i in range(nchunk) if edges[i + 1] > edges[i]]
+
+
+def _as_host_tensor(a):
+    a = np.ascontiguousarray(a)
+    if not a.flags.writeable:
+        a = a.copy()
+    return torch.from_numpy(a)
+
+
+def _encode_host(flat, n_stream, stream_size, level, quanta, dt):
+    """numpy [n_stream * stream_size] -> (compressed u8 numpy, starts, nbytes, offsets, gains) (numpy)."""
+    dev = _device()
+    tdt = _NP2TORCH[dt]
+    src = _as_host_tensor(flat)
+    if src.dtype != tdt:
+        src = src.to(tdt)
+    src = src.view(n_stream, stream_size)
+    isz = src.element_size()
+    ranges = _chunk_ranges(n_stream, stream_size * isz)
+    q = None
+    if quanta is not None:
+        q = to_device(quanta, dev, tdt)
+    if len(ranges) == 1:
+        d = src.to(dev, non_blocking=True)
+        comp, starts, nbytes, off, gain = encode_device(d.view(-1), n_stream, stream_size, level, q)
+        return (to_host(comp), to_host(starts), to_host(nbytes), None if off is None else to_host(off),
+                None if gain is None else to_host(gain))
+    with torch.cuda.device(dev):
+        cur = torch.cuda.current_stream(dev)
+        s_in, s_out = _side_streams(dev)
+        ev_in = []
+        d_chunks = []
+        with torch.cuda.stream(s_in):
+            for a, b in ranges:
+                dc = torch.empty((b - a, stream_size), dtype=tdt, device=dev)   # owned by s_in's pool
+                dc.copy_(src[a:b], non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(s_in)
+                ev_in.append(e)
+                d_chunks.append(dc)
+        raw_total = n_stream * stream_size * isz
+        host = None
+        cap = 0
+        pos = 0
+        overflow = False
+        keep = []
+        parts = []
+        for i, (a, b) in enumerate(ranges):
+            cur.wait_event(ev_in[i])
+            d_chunks[i].record_stream(cur)
+            out, starts, nbytes, tot, off, gain = _encode_device_raw(d_chunks[i].view(-1), b - a, stream_size, level,
+                                                                     None if q is None else q[a:b])
+            d_chunks[i] = None    # input chunk can go back to the pool
+            if host is None:
+                # capacity from the first chunk's ratio (+3 %); a wrong guess is repaired below
+                cap = min(int(tot / ((b - a) * stream_size * isz) * raw_total * 1.03) + (1 << 20),
+                          int(_lib.lib().fab_encode_bound(n_stream, stream_size, _FAB[dt], level)))
+                host = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+            e = torch.cuda.Event()
+            e.record(cur)
+            if pos + tot > cap:
+                overflow = True
+            if not overflow:
+                out.record_stream(s_out)
+                s_out.wait_event(e)
+                with torch.cuda.stream(s_out):
+                    host[pos:pos + tot].copy_(out[:tot], non_blocking=True)
+            keep.append((out, tot, pos))
+            parts.append((starts + pos, nbytes, off, gain))
+            pos += tot
+        if overflow:
+            s_out.synchronize()
+            host = torch.empty(pos, dtype=torch.uint8, pin_memory=True)
+            for out, tot, p0 in keep:
+                host[p0:p0 + tot].copy_(out[:tot], non_blocking=True)
+            cur.synchronize()
+        starts = to_host(torch.cat([p[0] for p in parts]))
+        nbytes = to_host(torch.cat([p[1] for p in parts]))
+        off = gain = None
+        if parts[0][2] is not None:
+            off = to_host(torch.cat([p[2] for p in parts]))
+            gain = to_host(torch.cat([p[3] for p in parts]))
+        s_out.synchronize()
+        del keep
+    return host[:pos].numpy(), starts, nbytes, off, gain
+
+
+def _decode_host(compressed, h_starts, h_nbytes, n_stream, stream_size, first_sample, last_sample, is_int64,
+                 offsets=None, gains=None):
+    """Host compressed bytes -> host samples (numpy, flat); optional int->float restore on the device."""
+    dev = _device()
+    n_decode = stream_size
+    if first_sample >= 0 and last_sample >= 0:
+        n_decode = last_sample - first_sample
+    h_starts = np.asarray(h_starts, dtype=np.int64).reshape(-1)
+    h_nbytes = np.asarray(h_nbytes, dtype=np.int64).reshape(-1)
+    restore = offsets is not None and gains is not None
+    if is_int64:
+        odt = torch.float64 if restore else torch.int64
+    else:
+        odt = torch.float32 if restore else torch.int32
+    isz = 8 if is_int64 else 4
+    hint = blocksize_hint(compressed, h_starts)
+    src = _as_host_tensor(compressed)
+    ranges = _chunk_ranges(n_stream, max(n_decode, 1) * isz)
+    h_ends = h_starts + h_nbytes
+    with torch.cuda.device(dev):
+        cur = torch.cuda.current_stream(dev)
+        s_in, s_out = _side_streams(dev)
+        fdt = torch.float64 if is_int64 else torch.float32
+        d_off = to_device(np.asarray(offsets).reshape(-1), dev, fdt) if restore else None
+        d_gain = to_device(np.asarray(gains).reshape(-1), dev, fdt) if restore else None
+        out_host = torch.empty((n_stream, max(n_decode, 0)), dtype=odt, pin_memory=True)
+        staged = []
+        with torch.cuda.stream(s_in):
+            for a, b in ranges:
+                # the byte range covering this chunk's streams (keep masks select sparse subsets)
+                lo = int(h_starts[a:b].min())
+                hi = int(h_ends[a:b].max())
+                dc = torch.empty(max(hi - lo, 1), dtype=torch.uint8, device=dev)
+                dc[:hi - lo].copy_(src[lo:hi], non_blocking=True)
+                d_st = torch.from_numpy(h_starts[a:b] - lo).to(dev, non_blocking=True)
+                d_nb = torch.from_numpy(np.ascontiguousarray(h_nbytes[a:b])).to(dev, non_blocking=True)
+                e = torch.cuda.Event()
+                e.record(s_in)
+                staged.append((dc, d_st, d_nb, e, int(h_nbytes[a:b].max())))
+        for i, (a, b) in enumerate(ranges):
+            dc, d_st, d_nb, e, max_nb = staged[i]
+            cur.wait_event(e)
+            for t in (dc, d_st, d_nb):
+                t.record_stream(cur)
+            out = decode_device(dc, d_st, d_nb, b - a, int(stream_size), int(first_sample), int(last_sample), is_int64,
+                                max_nb, hint, None if d_off is None else d_off[a:b], None if d_gain is None else d_gain[a:b])
+            staged[i] = None
+            e2 = torch.cuda.Event()
+            e2.record(cur)
+            out.record_stream(s_out)
+            s_out.wait_event(e2)
+            with torch.cuda.stream(s_out):
+                out_host[a:b].view(-1).copy_(out.view(odt), non_blocking=True)
+        s_out.synchronize()
+    return out_host.view(-1).numpy()
 
 
 def _wrap_encode(flatdata, n_stream, stream_size, level, dt):
     on_dev = is_torch(flatdata) and flatdata.is_cuda
+    if not on_dev:
+        if is_torch(flatdata):
+            flatdata = flatdata.numpy()
+        comp, starts, nbytes, _, _ = _encode_host(flatdata, int(n_stream), int(stream_size), int(level), None, dt)
+        return comp, starts, nbytes
     d = to_device(flatdata, dtype=_NP2TORCH[dt])
     comp, starts, nbytes, _, _ = encode_device(d, int(n_stream), int(stream_size), int(level))
-    if on_dev:
-        return comp, starts, nbytes
-    return to_host(comp), to_host(starts), to_host(nbytes)
+    return comp, starts, nbytes
 
 
 def wrap_encode_i32(flatdata, n_stream, stream_size, level):
@@ -304,21 +481,17 @@ def _wrap_decode(compressed, starts, nbytes, n_stream, stream_size, first_sample
     on_dev = is_torch(compressed) and compressed.is_cuda
     h_starts = starts.cpu().numpy() if is_torch(starts) else np.asarray(starts)
     h_nbytes = nbytes.cpu().numpy() if is_torch(nbytes) else np.asarray(nbytes)
+    if not on_dev:
+        if is_torch(compressed):
+            compressed = compressed.numpy()
+        return _decode_host(compressed, h_starts, h_nbytes, int(n_stream), int(stream_size), int(first_sample),
+                            int(last_sample), is_int64)
     max_nb = int(h_nbytes.max()) if h_nbytes.size else 0
     hint = blocksize_hint(compressed, h_starts)
-    if on_dev:
-        comp = compressed
-        d_starts = to_device(h_starts, comp.device, torch.int64)
-    else:
-        # upload only the byte range the selected streams cover (keep masks select sparse subsets)
-        lo = int(h_starts.min())
-        hi = int((h_starts + h_nbytes).max())
-        comp = to_device(compressed[lo:hi])
-        d_starts = to_device(h_starts - lo, comp.device, torch.int64)
-    d_nbytes = to_device(h_nbytes, comp.device, torch.int64)
-    out = decode_device(comp, d_starts, d_nbytes, int(n_stream), int(stream_size), int(first_sample),
-                        int(last_sample), is_int64, max_nb, hint)
-    return out if on_dev else to_host(out)
+    d_starts = to_device(h_starts, compressed.device, torch.int64)
+    d_nbytes = to_device(h_nbytes, compressed.device, torch.int64)
+    return decode_device(compressed, d_starts, d_nbytes, int(n_stream), int(stream_size), int(first_sample),
+                         int(last_sample), is_int64, max_nb, hint)
 
 
 def wrap_decode_i32(compressed, starts, nbytes, n_stream, stream_size, first_sample, last_sample, use_threads):
@@ -393,15 +566,18 @@ def encode_flac_float(data, level, quanta):
     else:
         n_stream, lead = int(np.prod(shape[:-1])), shape[:-1]
     on_dev = is_torch(data) and data.is_cuda
-    d = to_device(data.reshape((-1,)), dtype=_NP2TORCH[dt])
-    q = None
     if quanta is not None:
-        q = to_device(quanta.reshape((-1,)), d.device, _NP2TORCH[dt])
-        if q.numel() != n_stream:
-            q = None
-    comp, starts, nbytes, off, gain = encode_device(d, n_stream, stream_size, int(level), q)
+        quanta = quanta.reshape((-1,))
+        if (quanta.numel() if is_torch(quanta) else quanta.size) != n_stream:
+            quanta = None
     if not on_dev:
-        comp, starts, nbytes, off, gain = (to_host(comp), to_host(starts), to_host(nbytes), to_host(off), to_host(gain))
+        if is_torch(data):
+            data = data.numpy()
+        comp, starts, nbytes, off, gain = _encode_host(data.reshape((-1,)), n_stream, stream_size, int(level), quanta, dt)
+        return comp, starts.reshape(lead), nbytes.reshape(lead), off, gain
+    d = to_device(data.reshape((-1,)), dtype=_NP2TORCH[dt])
+    q = None if quanta is None else to_device(quanta, d.device, _NP2TORCH[dt])
+    comp, starts, nbytes, off, gain = encode_device(d, n_stream, stream_size, int(level), q)
     return comp, starts.reshape(lead), nbytes.reshape(lead), off, gain
 
 
@@ -416,21 +592,20 @@ def decode_flac_float(compressed, starts, nbytes, stream_size, offsets, gains, f
     on_dev = is_torch(compressed) and compressed.is_cuda
     h_starts = (starts.cpu().numpy() if is_torch(starts) else np.asarray(starts)).reshape(-1)
     h_nbytes = (nbytes.cpu().numpy() if is_torch(nbytes) else np.asarray(nbytes)).reshape(-1)
+    if not on_dev:
+        if is_torch(compressed):
+            compressed = compressed.numpy()
+        out = _decode_host(compressed, h_starts, h_nbytes, n_stream, int(stream_size), int(first_sample), int(last_sample),
+                           is_int64, offsets, gains)
+        return out.reshape(output_shape)
     max_nb = int(h_nbytes.max()) if h_nbytes.size else 0
     hint = blocksize_hint(compressed, h_starts)
-    if on_dev:
-        comp = compressed
-        d_starts = to_device(h_starts, comp.device, torch.int64)
-    else:
-        lo = int(h_starts.min())
-        hi = int((h_starts + h_nbytes).max())
-        comp = to_device(compressed[lo:hi])
-        d_starts = to_device(h_starts - lo, comp.device, torch.int64)
+    comp = compressed
+    d_starts = to_device(h_starts, comp.device, torch.int64)
     d_nbytes = to_device(h_nbytes, comp.device, torch.int64)
     fdt = torch.float64 if is_int64 else torch.float32
     off = to_device(offsets.reshape((-1,)), comp.device, fdt)
     gain = to_device(gains.reshape((-1,)), comp.device, fdt)
     out = decode_device(comp, d_starts, d_nbytes, n_stream, int(stream_size), int(first_sample), int(last_sample),
                         is_int64, max_nb, hint, off, gain)
-    out = out if on_dev else to_host(out)
     return out.reshape(output_shape)

@@ -144,3 +144,54 @@ def test_quantization_error_bounds(fa):
         pre = np.round(data / quanta) * quanta
         far = fa.FlacArray.from_array(pre, quanta=quanta)
         assert np.max(np.abs(far.to_array() - pre)) <= 2 * np.max(np.abs(pre)) * np.finfo(np.float64).eps + 1e-15
+
+
+def test_host_pipeline_matches_single_shot(fa, monkeypatch):
+    """The chunked host-buffer pipeline (H2D / kernels / D2H on three streams) returns exactly what one
+    device call returns: same bytes, starts, nbytes, offsets, gains; decode with keep + slice; the
+    capacity-overflow repair path (first chunk compresses far better than the rest)."""
+    import torch
+    from flacarray_b200 import libflacarray as lf
+
+    rng = np.random.default_rng(11)
+    n, L = 37, 9000
+    cases = []
+    walk = (np.cumsum(rng.integers(-300, 301, (n, L)), axis=1)).astype(np.int32)
+    cases.append((walk, {}))
+    w64 = np.cumsum(rng.integers(-(1 << 33), 1 << 33, (n, L)), axis=1).astype(np.int64)
+    cases.append((w64, {}))
+    f32 = (rng.normal(0, 1, (n, L)) + np.linspace(-3, 3, n)[:, None]).astype(np.float32)
+    cases.append((f32, {"quanta": 1e-4}))
+    f64 = rng.normal(0, 1, (n, L))
+    cases.append((f64, {"precision": 6}))
+    skew = walk.copy()
+    skew[:6] = 7                      # constant streams first: the capacity guess is far too small
+    skew[6:] = rng.integers(-2 ** 31, 2 ** 31 - 1, (n - 6, L), dtype=np.int64).astype(np.int32)
+    cases.append((skew, {}))
+    for data, kw in cases:
+        monkeypatch.setattr(lf, "_PIPE_MIN_BYTES", 1 << 40)
+        ref = fa.array_compress(data, level=5, **kw)
+        monkeypatch.setattr(lf, "_PIPE_MIN_BYTES", 1 << 10)
+        monkeypatch.setattr(lf, "_PIPE_CHUNK_BYTES", 6 * L * data.itemsize)
+        got = fa.array_compress(data, level=5, **kw)
+        for a, b in zip(ref, got):
+            assert (a is None) == (b is None)
+            if a is not None:
+                assert a.dtype == b.dtype and np.array_equal(a, b)
+        comp, starts, nbytes, off, gain = got
+        is64 = data.itemsize == 8
+        full = fa.array_decompress(comp, L, starts, nbytes, stream_offsets=off, stream_gains=gain, is_int64=is64)
+        monkeypatch.setattr(lf, "_PIPE_MIN_BYTES", 1 << 40)
+        full1 = fa.array_decompress(comp, L, starts, nbytes, stream_offsets=off, stream_gains=gain, is_int64=is64)
+        assert np.array_equal(full, full1) and full.dtype == data.dtype
+        if data.dtype.kind == "i":
+            assert np.array_equal(full, data)
+        monkeypatch.setattr(lf, "_PIPE_MIN_BYTES", 1 << 10)
+        keep = (np.arange(n) % 3) != 1
+        part, idx = fa.array_decompress_slice(comp, L, starts, nbytes, stream_offsets=off, stream_gains=gain, keep=keep,
+                                              first_stream_sample=4000, last_stream_sample=4700, is_int64=is64)
+        assert np.array_equal(part, full[keep][:, 4000:4700]) and len(idx) == int(keep.sum())
+    # torch host tensors (pinned) are accepted like numpy arrays
+    pin = torch.from_numpy(walk).pin_memory()
+    c2 = lf.encode_flac(pin, 5)
+    assert np.array_equal(c2[0], fa.array_compress(walk, level=5)[0])
