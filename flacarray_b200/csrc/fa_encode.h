@@ -993,16 +993,28 @@ FA_D bool enc_channel_fast(const EncParams& P, EncCtx& X, const FrameSrc& S, int
         syncwarp();
         if (ln == 0) {
             const int32_t a = sh->t_mn, b = sh->t_mx;
-            int mode = 2;
+            int mode = 2, wasted = 0;
             if (a == b) mode = 1;                                           // CONSTANT
-            else if ((sh->t_or & 1u) == 0) mode = 0;                        // wasted bits
-            else if (a < -(1 << kNarrowBits) || b >= (1 << kNarrowBits)) mode = 0;   // wide samples
+            else {
+                wasted = ctz32(sh->t_or);                                   // t_or != 0: the samples differ
+                // the 32-bit sums of pass 1 are only valid for narrow (unshifted) samples
+                if (a < -(1 << kNarrowBits) || b >= (1 << kNarrowBits)) mode = 3;   // wide: 64-bit statistics below
+            }
             sh->mode = mode;
-            sh->wasted = 0;
+            sh->wasted = wasted;
+            if (wasted && mode >= 2) {
+                // statistics of the samples >> wasted: every difference is a multiple of 2^wasted and
+                // float(x) * w scales exactly, so shifting the sums is exact
+                unsigned long long den = 1ull << (2 * wasted);
+                double sc = 1.0 / (double)den;
+                for (int l = 0; l <= H; ++l) sh->t_ac[l] *= sc;
+                for (int k = 0; k < 5; ++k) sh->t_fe[k] >>= wasted;
+            }
             if (mode == 2) {
-                uint32_t maxabs = (uint32_t)(-(int64_t)a > (int64_t)b ? -(int64_t)a : (int64_t)b);
-                design_fixed(sh, bs, 32, 0u, level_maxp);
-                design_lpc(sh, bs, 32, P.max_lpc_order < H ? P.max_lpc_order : H, P.qlp_precision, level_maxp, maxabs);
+                const int32_t as = a >> wasted, bsft = b >> wasted;
+                uint32_t maxabs = (uint32_t)(-(int64_t)as > (int64_t)bsft ? -(int64_t)as : (int64_t)bsft);
+                design_fixed(sh, bs, 32 - wasted, 0u, level_maxp);
+                design_lpc(sh, bs, 32 - wasted, P.max_lpc_order < H ? P.max_lpc_order : H, P.qlp_precision, level_maxp, maxabs);
             }
         }
     }
@@ -1010,7 +1022,7 @@ FA_D bool enc_channel_fast(const EncParams& P, EncCtx& X, const FrameSrc& S, int
     const int mode = sh->mode;
     const bool retiring = !X.retired;
     if (retiring) retire_copyout(P, X);   // previous frame: CRC partials + copy to HBM (offset known since B2)
-    if (mode != 2) {
+    if (mode < 2) {
         if (retiring) {
             sync();
             if (t == 0) retire_crc(P, sh);
@@ -1032,12 +1044,82 @@ FA_D bool enc_channel_fast(const EncParams& P, EncCtx& X, const FrameSrc& S, int
         return true;
     }
 
+    // ---- wide samples (up to the full int32 range, e.g. the low word of an int64): the 32-bit sums of
+    //      pass 1 may have wrapped, so the fixed-predictor statistics are redone with 64-bit
+    //      differences (libFLAC: FLAC__fixed_compute_best_predictor_wide); predictor orders whose
+    //      residual leaves the int32 range are excluded.  The autocorrelation of pass 1 stays valid.
+    const bool wide = mode == 3;
+    const int wasted = sh->wasted;
+    const int bps = 32 - wasted;
+    if (wasted) {
+#pragma unroll
+        for (int i = 0; i < H + kSpt; ++i) xw[i] >>= wasted;
+        fe0 >>= wasted; fe1 >>= wasted; fe2 >>= wasted; fe3 >>= wasted; fe4 >>= wasted;
+    }
+    if (wide) {
+        unsigned long long we[5] = {0, 0, 0, 0, 0};
+        uint32_t bad = 0;
+        int64_t q1 = (int64_t)xw[H - 1] - (int64_t)xw[H - 2];
+        int64_t q1b = (int64_t)xw[H - 2] - (int64_t)xw[H - 3];
+        int64_t q1c = (int64_t)xw[H - 3] - (int64_t)xw[H - 4];
+        int64_t q2 = q1 - q1b, q2b = q1b - q1c;
+        int64_t q3 = q2 - q2b;
+#pragma unroll
+        for (int j = 0; j < kSpt; ++j) {
+            int64_t e[5];
+            e[0] = (int64_t)xw[H + j];
+            e[1] = e[0] - (int64_t)xw[H + j - 1];
+            e[2] = e[1] - q1; e[3] = e[2] - q2; e[4] = e[3] - q3;
+            q1 = e[1]; q2 = e[2]; q3 = e[3];
+            if ((j >= 4 || t != 0) && (FULL || j < nvalid)) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    if (!fits_res(e[k])) bad |= 1u << k;
+                    we[k] += (unsigned long long)(e[k] < 0 ? -e[k] : e[k]);
+                }
+            }
+        }
+        uint32_t wbad = redux_or(bad);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            unsigned long long v = warp_sum_u64(we[k]);
+            if (ln == 0) sh->w_fe[wp][k] = v;
+        }
+        if (ln == 0) sh->w_bad[wp] = wbad;
+        sync();
+        if (t == 0) {
+            uint32_t tb = 0;
+            for (int w = 0; w < kEncWarps; ++w) tb |= sh->w_bad[w];
+            for (int k = 0; k < 5; ++k) {
+                unsigned long long v = 0;
+                for (int w = 0; w < kEncWarps; ++w) v += sh->w_fe[w][k];
+                sh->t_fe[k] = v;
+            }
+            design_fixed(sh, bs, bps, tb, level_maxp);
+            design_lpc(sh, bs, bps, P.max_lpc_order < H ? P.max_lpc_order : H, P.qlp_precision, level_maxp, 0u);
+        }
+        sync();
+    }
+
     // ---- pass 2: per-chunk sums of |residual| for both candidates
     const int js = (t == 0) ? 0 : -1;   // thread 0 skips its first `order` samples (warm-up)
     int32_t r[kSpt];
     const int ok0 = sh->cand_ok[0], ok1 = sh->cand_ok[1];
     const int ord0 = sh->cand[0].order;
-    if (ok0) {
+    if (ok0 && wide) {
+        int32_t cf[H];
+        fixed_coefs(ord0, cf, H);
+        uint32_t fitmask = residual64<H>(ord0, xw, cf, 0, r);
+        unsigned long long asum = 0;
+#pragma unroll
+        for (int j = 0; j < kSpt; ++j)
+            if ((j >= H || js < 0 || j >= ord0) && (FULL || j < nvalid))
+                asum += (unsigned long long)(r[j] < 0 ? -(int64_t)r[j] : (int64_t)r[j]);
+        uint32_t vmask = nvalid >= 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
+        if (t == 0) vmask &= ~((1u << ord0) - 1u);
+        if ((fitmask & vmask) != vmask) asum = ~0ull;
+        sh->csum[0][t] = asum;
+    } else if (ok0) {
         uint32_t sel = ord0 == 0 ? fe0 : ord0 == 1 ? fe1 : ord0 == 2 ? fe2 : ord0 == 3 ? fe3 : fe4;
         if (t == 0) {
             // samples order..3 belong to the residual but not to libFLAC's selection sums
@@ -1108,14 +1190,14 @@ FA_D bool enc_channel_fast(const EncParams& P, EncCtx& X, const FrameSrc& S, int
     }
     sync();   // B4
     // ---- every thread: pick the winner (stream_encoder.c process_subframe_: smallest estimate wins)
-    const uint32_t verbatim_bits = 32u * (uint32_t)bs;
+    const uint32_t verbatim_bits = (uint32_t)bps * (uint32_t)bs;
     int win = -1;
     {
         uint32_t best = verbatim_bits;
         for (int cd = 0; cd < 2; ++cd) {
             if (!sh->cand_ok[cd]) continue;
             const Plan& pl = sh->cand[cd];
-            uint32_t bits = (uint32_t)pl.order * 32u + pl.res_bits + (cd == 1 ? 9u + (uint32_t)pl.order * (uint32_t)pl.prec : 0u);
+            uint32_t bits = (uint32_t)pl.order * (uint32_t)bps + pl.res_bits + (cd == 1 ? 9u + (uint32_t)pl.order * (uint32_t)pl.prec : 0u);
             if (bits < best) { best = bits; win = cd; }
         }
     }
@@ -1125,7 +1207,8 @@ FA_D bool enc_channel_fast(const EncParams& P, EncCtx& X, const FrameSrc& S, int
     if (win == 0) {
         int32_t cf[H];
         fixed_coefs(order, cf, H);
-        residual32_dispatch<H>(order, xw, cf, 0, r);
+        if (wide) (void)residual64<H>(order, xw, cf, 0, r);
+        else residual32_dispatch<H>(order, xw, cf, 0, r);
     }
     // ---- exact code lengths of the chunk, block scan
     int part;
@@ -1172,7 +1255,7 @@ FA_D bool enc_channel_fast(const EncParams& P, EncCtx& X, const FrameSrc& S, int
     }
     const uint32_t excl = wbase + inc - lens;
     const int ptype = win == 0 ? 2 : 3;
-    const int hdr_bits = subframe_header_bits(ptype, order, 0, 32, pl.prec);
+    const int hdr_bits = subframe_header_bits(ptype, order, wasted, bps, pl.prec);
     if ((uint32_t)hdr_bits + total >= verbatim_bits + 8u) return false;   // VERBATIM is smaller: general path
     const int sub0 = bitpos0 + (c == 0 ? 8 * frame_header_bytes(bs, f) : 0);
     const int body0 = sub0 + hdr_bits;
@@ -1184,8 +1267,8 @@ FA_D bool enc_channel_fast(const EncParams& P, EncCtx& X, const FrameSrc& S, int
         if (c == P.nch - 1) publish_aggregate(P, g, f, bitpos_end);
         pk_begin(pk, out, bitpos0);
         if (c == 0) emit_frame_header(pk, P.crc, bs, f, P.nch);
-        emit_subframe_header(pk, ptype, order, 0);
-        for (int j = 0; j < order; ++j) emit_sample(pk, xw[H + j], 32);
+        emit_subframe_header(pk, ptype, order, wasted);
+        for (int j = 0; j < order; ++j) emit_sample(pk, xw[H + j], bps);
         if (ptype == 3) emit_lpc_params(pk, pl);
         pk_emit(pk, (uint32_t)pl.rice2, 2);
         pk_emit(pk, (uint32_t)porder, 4);

@@ -56,7 +56,7 @@ def cfg2(scale):
     far, t_enc = timed(lambda: fa.FlacArray.from_array(x, quanta=1e-4))
     y, t_dec = timed(lambda: far.to_array())
     err = float((y - x).abs().max())
-    return dict(cfg=2, workload=f"float32 TOD ({n}, {L}) quanta 1e-4", ok=err <= 0.5e-4 * 1.001, max_err=err,
+    return dict(cfg=2, workload=f"float32 TOD ({n}, {L}) quanta 1e-4", ok=err <= 0.5e-4 + 2e-6, max_err=err,
                 ratio=far.nbytes / (x.numel() * 4), enc_ms=t_enc, dec_ms=t_dec, raw_gb=x.numel() * 4 / 1e9,
                 enc_gbs=x.numel() * 4 / t_enc / 1e6, dec_gbs=x.numel() * 4 / t_dec / 1e6)
 

@@ -28,6 +28,10 @@ def _cases(rng):
         "walk": walk, "full": full, "const": np.full((1, 5000), -77, np.int32),
         "wasted": (walk[:1] << 5).astype(np.int32), "tiny": rng.integers(-5, 6, (2, 7)).astype(np.int32),
         "one": np.array([[42]], np.int32), "odd": rng.integers(-100, 100, (1, 1000)).astype(np.int32),
+        # wide samples (64-bit statistics path): a 2^29-range walk, and one that wraps like the low word of an int64
+        "widewalk": np.cumsum(rng.integers(-2 ** 22, 2 ** 22, (2, 9000)), axis=1).astype(np.int32),
+        "widewasted": (np.cumsum(rng.integers(-2 ** 15, 2 ** 15, (1, 9000)), axis=1) << 9).astype(np.int32),
+        "wrap": np.cumsum(rng.integers(-2 ** 26, 2 ** 26, (1, 9000)), axis=1).astype(np.uint32).astype(np.int32),
     }
 
 
@@ -66,7 +70,9 @@ def test_int64_bodies(H, oracle):
     a = rng.integers(-2 ** 63, 2 ** 63 - 1, (1, 5000), dtype=np.int64)
     a[0, :4] = [-2 ** 63, 2 ** 63 - 1, 2 ** 32, -2 ** 32]
     b = (np.cumsum(rng.integers(-2 ** 20, 2 ** 20, (1, 9000)), axis=1) + 2 ** 40 * 3).astype(np.int64)
-    for x in (a, b):
+    # BASELINE configs[2] model: the high word is a multiple of 256 (wasted bits) while the walk is positive
+    c3 = (np.cumsum(rng.integers(-2 ** 20, 2 ** 20 + 1, (2, 9000)), axis=1) + 2 ** 40 * rng.integers(-4, 5, (2, 9000))).astype(np.int64)
+    for x in (a, b, c3):
         c, s, n, _, _ = H.encode(x, 5)
         assert np.array_equal(oracle.decode(c, s, n, x.shape[1], is_int64=True), x)
         oc, os_, on = oracle.encode(x, 5)  # stereo search: exercises side/mid decoding
