@@ -27,8 +27,11 @@ using namespace fa;
 // =================================================================================================
 
 // persistent CTAs: each loops over (stream, frame) tickets; H = predictor history kept in registers
+#ifndef FAB_ENC_CTAS
+#define FAB_ENC_CTAS 4
+#endif
 template <int H>
-__global__ void __launch_bounds__(kEncThreads, 4) k_encode(const EncParams P) {
+__global__ void __launch_bounds__(kEncThreads, FAB_ENC_CTAS) k_encode(const EncParams P) {
     extern __shared__ __align__(16) unsigned char smem[];
     encode_frames_cta<H>(P, smem);
 }

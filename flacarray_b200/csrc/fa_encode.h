@@ -317,7 +317,7 @@ constexpr unsigned long long kDescAgg = 1ull << 62, kDescPre = 2ull << 62, kDesc
 // Thread 0, as soon as the size of the frame is known (before packing): successors can start summing.
 FA_D void publish_aggregate(const EncParams& P, uint32_t g, int f, int bitpos_end) {
     unsigned long long mine = (unsigned long long)(((bitpos_end + 7) >> 3) + 2) + (f == 0 ? (unsigned long long)P.hdr_bytes : 0ull);
-    st_release_u64(&P.desc[g], (g == 0 ? kDescPre : kDescAgg) | mine);
+    st_relaxed_u64(&P.desc[g], (g == 0 ? kDescPre : kDescAgg) | mine);   // the word is its own payload
 }
 
 // Warp 0: exclusive prefix of frame g over all earlier frames, 32 descriptors per round trip.
@@ -327,7 +327,7 @@ FA_D unsigned long long lookback_warp(const EncParams& P, uint32_t g) {
     long long base = (long long)g - 1;
     for (;;) {
         long long idx = base - ln;
-        unsigned long long d = idx >= 0 ? ld_acquire_u64(&P.desc[idx]) : kDescPre;   // virtual prefix 0 before frame 0
+        unsigned long long d = idx >= 0 ? ld_relaxed_u64(&P.desc[idx]) : kDescPre;   // virtual prefix 0 before frame 0
         uint32_t st = (uint32_t)(d >> 62);
         uint32_t pre = ballot(st == 2), empty = ballot(st == 0);
         int first_pre = pre ? ctz32(pre) : 32;
@@ -346,6 +346,7 @@ struct FrameSrc {
     const void* base;   // element (stream s, frame sample 0)
     int dtype, bs;
     bool vec;           // 16-byte vector loads are aligned
+    bool posgain;       // kF32: gain > 0 (block-uniform; lets the quantiser skip its sign test)
     float off32, gain32;
     double off64, gain64;
 };
@@ -743,7 +744,7 @@ FA_D void retire_lookback(const EncParams& P, EncShared* sh) {
     if (lane() == 0) {
         const int frame_bytes = sh->prev_nbytes + 2;
         unsigned long long mine = (unsigned long long)frame_bytes + (f == 0 ? (unsigned long long)P.hdr_bytes : 0ull);
-        if (g != 0) st_release_u64(&P.desc[g], kDescPre | (excl + mine));
+        if (g != 0) st_relaxed_u64(&P.desc[g], kDescPre | (excl + mine));
         long long off = (long long)excl + (f == 0 ? P.hdr_bytes : 0);
         if (off + frame_bytes > P.out_capacity) { atom_or_global(P.err, kErrEncodeCollect); off = -1; }
         sh->prev_off = off;
@@ -1623,6 +1624,7 @@ FA_D void encode_frames_cta(const EncParams& P, unsigned char* smem_raw) {
         const int esize = (P.dtype == kI32 || P.dtype == kF32) ? 4 : 8;
         S.base = (const unsigned char*)P.data + (s * P.stream_size + samp0) * esize;
         S.vec = (((uintptr_t)S.base) & 15) == 0;
+        S.posgain = S.gain32 > 0.0f;
 
         int bitpos = 0;
         for (int c = 0; c < nch; ++c) {

@@ -55,6 +55,14 @@ FA_D unsigned long long ld_acquire_u64(const unsigned long long* p) {
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+FA_D void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+FA_D unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 FA_D void spin_pause() { __nanosleep(20); }
 FA_D uint32_t ldg32(const uint32_t* p) { return __ldg(p); }
 struct U4 { uint32_t x, y, z, w; };
@@ -203,6 +211,8 @@ inline int atom_cas_global32(int* p, int cmp, int v) {
 }
 inline void st_release_u64(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 inline unsigned long long ld_acquire_u64(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+inline void st_relaxed_u64(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
+inline unsigned long long ld_relaxed_u64(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
 inline void spin_pause() { std::this_thread::yield(); }
 inline uint32_t ldg32(const uint32_t* p) { return *p; }
 struct U4 { uint32_t x, y, z, w; };
