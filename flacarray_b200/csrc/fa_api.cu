@@ -177,8 +177,11 @@ __global__ void __launch_bounds__(kDecThreads) k_dec_frames(const DecParams P, i
 }
 
 // throughput path: one warp = 32 (stream, frame) items, see fa_decode_tile.h
+#ifndef FAB_DEC_CTAS
+#define FAB_DEC_CTAS 6
+#endif
 template <bool CRC>
-__global__ void __launch_bounds__(kTileWarps * 32) k_dec_tile(const TileParams P) {
+__global__ void __launch_bounds__(kTileWarps * 32, FAB_DEC_CTAS) k_dec_tile(const TileParams P) {
     __shared__ uint16_t crc_tab[4 * 256];
     __shared__ TileShared ws[kTileWarps];
     for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) crc_tab[i] = P.D.crc->crc16[i >> 8][i & 255];

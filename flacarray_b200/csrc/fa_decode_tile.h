@@ -2,8 +2,8 @@
 //
 // Same role as frame_body() in fa_decode.h (libFLAC frame decode + the write callback
 // decompress.c:66-101), restructured for the machine:
-//   * compressed bytes are fetched 16 B at a time per lane with one chunk always in flight
-//     (software prefetch: the DRAM latency overlaps ~8 samples of decode work);
+//   * compressed bytes stream through a per-lane shared-memory ring filled by cp.async at one
+//     warp-uniform point per group of 4 samples (see BitRdC: register prefetch stalls the whole warp);
 //   * predictor history and coefficients live in registers (order <= 12, 32-bit samples), four
 //     samples per loop trip so the history "shift" is register renaming;
 //   * every lane appends its samples to a [32 lanes][32 samples] shared-memory tile; after 32 samples
@@ -22,6 +22,9 @@ constexpr int kTileOrd = 12;
 constexpr int kTileStride = 33;
 constexpr int kTileWarps = 4;  // warps per CTA
 
+constexpr int kRingChunks = 4;                 // 16-byte chunks per lane in the shared-memory ring
+constexpr int kRingStride = kRingChunks * 4 + 4;   // words per lane row (16-byte aligned, spreads the banks)
+
 struct TileRow {          // per-lane output description, read by all lanes during the flush
     int32_t* out;         // address of (frame sample 0, channel 0)
     int lo, hi;           // valid sample range inside the frame
@@ -31,15 +34,24 @@ struct TileRow {          // per-lane output description, read by all lanes duri
 struct TileShared {       // per warp
     int32_t tile[32 * kTileStride];
     TileRow row[32];
+    uint32_t ring[32 * kRingStride];   // compressed bytes in flight: one ring of kRingChunks chunks per lane
 };
 
-// Bit reader: 16-byte chunk prefetch queue -> 64-bit MSB-aligned buffer, with a CRC-16 that lags two
-// words behind (so that the frame end, only known after the last sample, is handled exactly).
+// Bit reader.  The compressed bytes of every lane's frame stream through a small ring in shared memory
+// that is topped up with asynchronous 16-byte copies (cp.async) at ONE warp-uniform point per group of
+// samples (brc_service).  A register prefetch queue does not work here: register scoreboards are per
+// warp, so whenever one lane consumed its prefetched chunk the whole warp waited for the most recent
+// load of ANY lane -- the DRAM/L2 latency was exposed at almost every refill (30 % of the stall samples
+// of the previous version).  With the ring, loads never target a register; the 64-bit MSB-aligned
+// buffer is refilled with (short-latency) shared-memory reads.  The CRC-16 lags two words behind so
+// that the frame end, only known after the last sample, is handled exactly.
 struct BitRdC {
-    const U4* cp;      // next chunk to prefetch
-    const U4* cend;    // first chunk holding no valid byte
-    U4 cur, nxt;       // words still to be taken (cur.x first) / chunk in flight
-    int cnt;           // words left in cur
+    const U4* gp;      // next chunk to copy
+    const U4* gend;    // first chunk holding no valid byte
+    uint32_t* ring;    // this lane's ring
+    uint32_t rd;       // words taken so far (absolute, counted from the first chunk)
+    uint32_t wr;       // chunks issued so far
+    uint32_t landed;   // chunks known to be complete in the ring
     uint64_t buf;
     int n;
     int nwords;        // words taken after word 0
@@ -48,19 +60,40 @@ struct BitRdC {
     int err;
 };
 
-
 FA_D U4 u4_zero() { U4 z; z.x = z.y = z.z = z.w = 0; return z; }
 
-FA_D uint32_t brc_take(BitRdC& br) {
-    uint32_t w = bswap32(br.cur.x);
-    br.cur.x = br.cur.y; br.cur.y = br.cur.z; br.cur.z = br.cur.w;
-    if (--br.cnt == 0) {
-        br.cur = br.nxt;
-        br.cnt = 4;
-        br.nxt = (br.cp < br.cend) ? ldg128(br.cp) : u4_zero();
-        br.cp++;
+// Top the ring up (called at a warp-uniform point; lanes with nothing to do predicate off).
+FA_D void brc_service(BitRdC& br) {
+    cp_async_wait_all();          // copies issued at the previous service point: a whole sample group old
+    br.landed = br.wr;
+#pragma unroll
+    for (int i = 0; i < kRingChunks; ++i) {
+        if (br.ring != nullptr && br.wr - (br.rd >> 2) < (uint32_t)kRingChunks) {
+            uint32_t* slot = br.ring + (br.wr & (kRingChunks - 1)) * 4;
+            if (br.gp < br.gend) cp_async16(slot, br.gp);
+            else sts128(slot, u4_zero());     // past the end of the stream: zeros
+            br.gp++;
+            br.wr++;
+        }
     }
-    return w;
+    cp_async_commit();
+}
+
+FA_D uint32_t brc_take(BitRdC& br) {
+    if ((br.rd >> 2) >= br.landed) {
+        // ran ahead of the copies (long codes, or the first words of a frame): wait for what is in
+        // flight; if the ring is empty, fetch now
+        cp_async_wait_all();
+        br.landed = br.wr;
+        if ((br.rd >> 2) >= br.landed) {
+            brc_service(br);
+            cp_async_wait_all();
+            br.landed = br.wr;
+        }
+    }
+    uint32_t w = br.ring[((br.rd >> 2) & (kRingChunks - 1)) * 4 + (br.rd & 3)];
+    br.rd++;
+    return bswap32(w);
 }
 
 template <bool CRC>
@@ -78,19 +111,18 @@ FA_D void brc_fetch(BitRdC& br, const uint16_t* T) {
 
 // Start reading at byte `start` (crc0 = CRC state over the frame bytes before `start`).
 template <bool CRC>
-FA_D void brc_init(BitRdC& br, const uint8_t* start, const uint8_t* end, uint32_t crc0, const uint16_t* T) {
+FA_D void brc_init(BitRdC& br, uint32_t* ring, const uint8_t* start, const uint8_t* end, uint32_t crc0, const uint16_t* T) {
     uintptr_t s = (uintptr_t)start;
-    const U4* c0 = (const U4*)(s & ~(uintptr_t)15);
-    br.cend = (const U4*)(((uintptr_t)end + 15) & ~(uintptr_t)15);
-    br.cur = (c0 < br.cend) ? ldg128(c0) : u4_zero();
-    br.nxt = (c0 + 1 < br.cend) ? ldg128(c0 + 1) : u4_zero();
-    br.cp = c0 + 2;
-    br.cnt = 4;
-    int skip = (int)((s & 15) >> 2);
-    for (int i = 0; i < skip; ++i) (void)brc_take(br);   // cnt stays >= 1: skip <= 3
+    br.gp = (const U4*)(s & ~(uintptr_t)15);
+    br.gend = (const U4*)(((uintptr_t)end + 15) & ~(uintptr_t)15);
+    br.ring = ring;
+    br.rd = (uint32_t)((s & 15) >> 2);      // words of the first chunk that precede `start`
+    br.wr = 0;
+    br.landed = 0;
     int a = (int)(s & 3);
     br.buf = 0; br.n = 0; br.nwords = 0; br.err = 0; br.w1 = br.w2 = 0;
     br.crc = crc0;
+    brc_service(br);
     uint32_t w = brc_take(br);
     // word 0 is consumed byte-wise by the CRC (its leading `a` bytes precede `start`), so it does not
     // enter the lagging word queue
@@ -133,7 +165,7 @@ FA_D uint32_t brc_unary(BitRdC& br, const uint16_t* T) {
         }
         q += (uint32_t)br.n;
         br.n = 0;
-        if (br.cp > br.cend + 4) { br.err = 1; return q; }  // ran off the end of the stream
+        if (br.gp > br.gend + 4 + kRingChunks) { br.err = 1; return q; }  // ran off the end of the stream
     }
 }
 // Rice code with parameter k (< 32): fast path when the whole code sits in the buffer.
@@ -353,6 +385,7 @@ FA_D void tile_channel_pass(const TileParams& P, TileShared* ws, const uint16_t*
 #pragma unroll 1
         for (int s = 0; s < 32; s += 4) {
             int i = (int)base + s;
+            brc_service(br);      // warp-uniform refill point of the compressed-byte rings
             if (run && i < bs) {
                 bool fast = L.mode == 2 && L.raw_left == 0 && !L.need_params && L.left >= 4 && L.k >= 0 && i + 4 <= bs;
                 if (fast) {
@@ -468,9 +501,9 @@ FA_D void tile_warp_body(const TileParams& P, int64_t item0, TileShared* ws, con
     if (active) {
         const uint8_t* body = fp + fh.hdr_bytes;
         a = (int)((uintptr_t)body & 3);
-        brc_init<CRC>(br, body, end, crc0, T);
+        brc_init<CRC>(br, ws->ring + ln * kRingStride, body, end, crc0, T);
     } else {
-        br.cp = br.cend = nullptr; br.cur = br.nxt = u4_zero(); br.cnt = 4;
+        br.gp = br.gend = nullptr; br.ring = nullptr; br.rd = 0; br.wr = 0; br.landed = 0;
         br.buf = 0; br.n = 64; br.nwords = 0; br.crc = 0; br.w1 = br.w2 = 0; br.err = 0;
     }
     bool fail = false;      // stream problem -> walker

@@ -64,6 +64,13 @@ FA_D unsigned long long ld_relaxed_u64(const unsigned long long* p) {
     return v;
 }
 FA_D void spin_pause() { __nanosleep(20); }
+// 16-byte asynchronous copy global -> shared (LDGSTS): no destination register, so no scoreboard stall
+FA_D void cp_async16(void* smem_dst, const void* gsrc) {
+    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+FA_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+FA_D void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 FA_D uint32_t ldg32(const uint32_t* p) { return __ldg(p); }
 struct U4 { uint32_t x, y, z, w; };
 FA_D U4 ldg128(const void* p) {  // 16-byte aligned, read-only path
@@ -214,6 +221,9 @@ inline unsigned long long ld_acquire_u64(const unsigned long long* p) { return _
 inline void st_relaxed_u64(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
 inline unsigned long long ld_relaxed_u64(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_RELAXED); }
 inline void spin_pause() { std::this_thread::yield(); }
+inline void cp_async16(void* smem_dst, const void* gsrc) { memcpy(smem_dst, gsrc, 16); }
+inline void cp_async_commit() {}
+inline void cp_async_wait_all() {}
 inline uint32_t ldg32(const uint32_t* p) { return *p; }
 struct U4 { uint32_t x, y, z, w; };
 inline U4 ldg128(const void* p) { U4 r; memcpy(&r, p, 16); return r; }

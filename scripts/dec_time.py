@@ -1,0 +1,22 @@
+"""Decode-only timing (kernel experiments): python scripts/dec_time.py [streams]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from flacarray_b200 import _lib, libflacarray as lf
+dev = torch.device("cuda", 0)
+n_stream, n_samp = int(sys.argv[1]) if len(sys.argv) > 1 else 1000, 1000000
+data = bench.make_tod_torch(n_stream, n_samp, 1, dev)
+quanta = torch.full((n_stream,), 1e-4, dtype=torch.float32, device=dev)
+flat = data.reshape(-1)
+ctx = _lib.context(dev)
+comp, starts, nbytes, off, gain = lf.encode_device(flat, n_stream, n_samp, 5, quanta)
+mx = int(nbytes.max().item())
+for it in range(4):
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    if it == 3: ctx.profile(True)
+    e0.record()
+    out = lf.decode_device(comp, starts, nbytes, n_stream, n_samp, -1, -1, False, mx, 4096, off, gain)
+    e1.record(); torch.cuda.synchronize()
+    print(f"it{it}: dec gpu {e0.elapsed_time(e1):.2f} ms")
+print("k_dec_tile ms", ctx.profile_ms(1))
