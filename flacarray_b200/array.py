@@ -395,3 +395,50 @@ class FlacArray:
             mpi_comm=mpi_comm,
             mpi_dist=mpi_dist,
         )
+
+    # ---- file I/O (array.py:639-884): format version 1 group layout, see io_common.py ----
+    def _write_group(self, grp):
+        from . import __version__
+        from .io_common import write_compressed
+
+        write_compressed(
+            grp, self._leading_shape, self._global_leading_shape, self._stream_size, self._stream_starts,
+            self._global_stream_starts, self._stream_nbytes, self._stream_offsets, self._stream_gains, self._compressed,
+            2 if self._is_int64 else 1, self._local_nbytes, self._global_nbytes, self._global_proc_nbytes,
+            self._mpi_comm, self._mpi_dist, software_version=__version__)
+
+    @classmethod
+    def _read_group(cls, grp, keep, mpi_comm, mpi_dist, no_flatten):
+        from .io_common import read_compressed
+        from .utils import compressed_dtype
+
+        (local_shape, global_shape, compressed, n_channels, starts, nbytes, offsets, gains, mpi_dist, _) = read_compressed(
+            grp, keep=keep, mpi_comm=mpi_comm, mpi_dist=mpi_dist)
+        if compressed is None:
+            raise RuntimeError("No streams selected on this process")
+        dt = compressed_dtype(n_channels, offsets, gains)
+        if len(local_shape) == 2 and local_shape[0] == 1 and not no_flatten:
+            shape = (local_shape[1],)
+        else:
+            shape = local_shape
+        return FlacArray(None, shape=shape, global_shape=global_shape, compressed=compressed, dtype=dt,
+                         stream_starts=starts, stream_nbytes=nbytes, stream_offsets=offsets, stream_gains=gains,
+                         mpi_comm=mpi_comm, mpi_dist=mpi_dist)
+
+    def write_hdf5(self, hgrp):
+        """Write the compressed representation to an open HDF5 group (array.py:639-681)."""
+        self._write_group(hgrp)
+
+    @classmethod
+    def read_hdf5(cls, hgrp, keep=None, mpi_comm=None, mpi_dist=None, no_flatten=False):
+        """Construct a FlacArray from an HDF5 group (array.py:683-764)."""
+        return cls._read_group(hgrp, keep, mpi_comm, mpi_dist, no_flatten)
+
+    def write_zarr(self, zgrp):
+        """Write the compressed representation to an open zarr group (array.py:766-803)."""
+        self._write_group(zgrp)
+
+    @classmethod
+    def read_zarr(cls, zgrp, keep=None, mpi_comm=None, mpi_dist=None, no_flatten=False):
+        """Construct a FlacArray from a zarr group (array.py:805-884)."""
+        return cls._read_group(zgrp, keep, mpi_comm, mpi_dist, no_flatten)

@@ -64,6 +64,15 @@ class TorchComm:
         dist.broadcast_object_list(box, src=root, group=self.group)
         return box[0]
 
+    def send(self, obj, dest):
+        """Point-to-point object transfer (used by the serial-writer file I/O, io_common.py)."""
+        dist.send_object_list([obj], dst=dest, group=self.group)
+
+    def recv(self, source):
+        box = [None]
+        dist.recv_object_list(box, src=source, group=self.group)
+        return box[0]
+
     def barrier(self):
         dist.barrier(group=self.group)
 

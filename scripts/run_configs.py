@@ -111,10 +111,17 @@ def cfg4(scale):
     ok = bool(torch.equal(full[:, sl], part[:4]))
     err = float(((part[:4] - x[[0, 2, 4, 6]][:, sl]).abs() / quanta[[0, 2, 4, 6], None]).max())
     ok = ok and err <= 0.5 * 1.0001 and len(idx) == int(keep.sum())
-    a = ev()
-    y = far.to_array(keep=(np.arange(n) < min(n, 512)))
-    b = ev(); torch.cuda.synchronize()
-    t_dec512 = a.elapsed_time(b)
+    ctx = _lib.context(dev)
+    t_dec512 = 1e30
+    for rep in range(2):
+        ctx.profile(True)
+        a = ev()
+        y = far.to_array(keep=(np.arange(n) < min(n, 512)))
+        b = ev(); torch.cuda.synchronize()
+        print(f"# cfg4 decode of 512 streams, rep {rep}: {a.elapsed_time(b):.2f} ms, k_dec_tile {ctx.profile_ms(1)}", flush=True)
+        t_dec512 = min(t_dec512, a.elapsed_time(b))
+        del y
+    ctx.profile(False)
     return dict(cfg=4, workload=f"float64 ({n}, {L}) precision 5; keep rows%2==0 + slice 100k", ok=ok, max_err_quanta=err,
                 ratio=far.nbytes / (x.numel() * 8), enc_ms=t_enc, raw_gb=x.numel() * 8 / 1e9,
                 enc_gbs=x.numel() * 8 / t_enc / 1e6, partial_ms=t_part, partial_out_gb=part.numel() * 8 / 1e9,

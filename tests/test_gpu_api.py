@@ -195,3 +195,41 @@ def test_host_pipeline_matches_single_shot(fa, monkeypatch):
     pin = torch.from_numpy(walk).pin_memory()
     c2 = lf.encode_flac(pin, 5)
     assert np.array_equal(c2[0], fa.array_compress(walk, level=5)[0])
+
+
+@pytest.mark.parametrize("zarr_style", [False, True])
+def test_write_read_array_through_group_layout(fa, zarr_style):
+    """reference tests/hdf5.py:27-173 and tests/zarr.py: write_array -> read_array (full, keep mask,
+    stream slice) and FlacArray.write_* / read_* with the compression and decompression on the GPU."""
+    from flacarray_b200 import hdf5 as fh5
+    from flacarray_b200 import zarr as fzr
+    from flacarray_b200.demo import create_fake_data
+    from flacarray_b200.memgroup import MemGroup
+
+    mod = fzr if zarr_style else fh5
+    for dt, kw, tol in ((np.int32, {}, 0), (np.int64, {}, 0), (np.float32, {"quanta": 1e-5}, 1e-5),
+                        (np.float64, {"precision": 7}, 1e-6)):
+        sig = None if np.dtype(dt).kind == "i" else 1.0
+        data, _ = create_fake_data((4, 3, 5000), sigma=sig, dtype=dt)
+        grp = MemGroup(zarr_style=zarr_style)
+        mod.write_array(data, grp, level=5, **kw)
+        assert grp.attrs["flacarray_format_version"] == "1" and grp["stream_starts"].shape == (4, 3)
+        assert ("stream_offsets" in grp) == (np.dtype(dt).kind == "f")
+        full = mod.read_array(grp)
+        assert full.shape == data.shape and full.dtype == np.dtype(dt)
+        assert np.allclose(full, data, rtol=0, atol=tol)
+        keep = np.zeros((4, 3), bool)
+        keep[0, 2] = keep[3, 1] = True
+        part, idx = mod.read_array(grp, keep=keep, stream_slice=slice(1000, 1200), keep_indices=True)
+        assert part.shape == (2, 200) and idx == [(0, 2), (3, 1)]
+        assert np.array_equal(part, full[keep][:, 1000:1200])
+        far = fa.FlacArray.from_array(data, **kw)
+        g2 = MemGroup(zarr_style=zarr_style)
+        (far.write_zarr if zarr_style else far.write_hdf5)(g2)
+        back = (fa.FlacArray.read_zarr if zarr_style else fa.FlacArray.read_hdf5)(g2)
+        assert back == far and np.array_equal(back.to_array(), far.to_array())
+        assert np.array_equal(g2["compressed"][...], grp["compressed"][...])     # deterministic bytes
+    one, _ = create_fake_data((6000,), sigma=1.0, dtype=np.float32)
+    g3 = MemGroup(zarr_style=zarr_style)
+    mod.write_array(one, g3, quanta=1e-6)
+    assert g3["stream_starts"].shape == (1,) and mod.read_array(g3).shape == (6000,)
