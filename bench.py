@@ -37,6 +37,15 @@ QUANTA = 1e-4
 METRIC = "encode+decode GB/s of raw samples (float32 TOD, quanta 1e-4, level 5)"
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r01_traffic.json)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[kernel]
+        return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -372,7 +381,9 @@ def run_ours(args):
             "encode_gbs": raw * world * args.steps / t_enc_m / 1e9, "decode_gbs": raw * world * args.steps / t_dec_m / 1e9,
             "ratio": ratio, "wall_ms_per_step": 1e3 * wall_m / args.steps,
             "roofline": {"bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src,
+                         "frac": (ach / peak) if ach else None,
+                         "traffic": ncu_traffic(dominant) if (n_stream, n_samp) == (1000, 1000000) else None,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_enc if dominant == "k_encode" else alg_dec,
                          "ms_per_launch": (enc_ms / max(enc_n, 1)) if dominant == "k_encode" else (dec_ms / max(dec_n, 1))},
             "roofline_encode": {"kernel": "k_encode", "achieved": enc_gbs, "frac": enc_gbs / peak if enc_gbs else None,
