@@ -95,62 +95,115 @@ def make_tod_torch(n_stream, n_samp, seed, device):
 # clocks sampler (B200_PROFILING.md recipe)
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).
+
+    Uses NVML in-process (nvidia_ml_py) from a thread: a query costs microseconds.  (The first version
+    spawned `nvidia-smi -lms 50`; with one poller per rank the driver-side cost of those queries showed up
+    as tens of milliseconds of launch/sync latency in multi-GPU runs.)  Falls back to nvidia-smi.
+    """
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.rows = []
-        self.proc = None
+        self.rows = []          # (t, sm_mhz, sm_max_mhz, set(reasons))
         self.gpu_index = gpu_index
+        self.proc = None
+        self.thread = None
+        self.stop_flag = False
+        self.t_mark = 0.0
+        self.nvml = None
 
     def start(self):
         try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            # torch's device index follows CUDA_VISIBLE_DEVICES; map through the UUID-free common case
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu_index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu_index])
+                except Exception:
+                    idx = self.gpu_index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), line.strip()))
-
-    def mark(self):
-        """Only samples that arrive after this call are reported (the sampler is started before the
-        warm-up because nvidia-smi's start-up briefly stalls the GPU it attaches to)."""
-        self.t_mark = time.perf_counter()
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
+    def _poll_nvml(self):
+        n = self.nvml
+        R = {
+            "hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+            "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown",
+                                           getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+            "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown",
+                                           getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+            "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)),
+        }
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
         try:
-            self.proc.wait(timeout=5)
+            mx = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
         except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        t_mark = getattr(self, "t_mark", 0.0)
-        for t, r in self.rows:
-            if t < t_mark:
-                continue
-            f = [x.strip() for x in r.split(",")]
+            mx = 0.0
+        while not self.stop_flag:
+            try:
+                sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                mask = int(get_reasons(self.handle))
+                self.rows.append((time.perf_counter(), sm, mx, {k for k, b in R.items() if mask & b}))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def _read_smi(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.strip().split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                sm, mx = float(f[1]), float(f[2])
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+            rs = {name for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9])
+                  if v.lower().startswith("active")}
+            self.rows.append((time.perf_counter(), sm, mx, rs))
+
+    def mark(self):
+        """Only samples that arrive after this call are reported (start of the timed region)."""
+        self.t_mark = time.perf_counter()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        rows = [r for r in self.rows if r[0] >= self.t_mark]
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        busy = sorted(sm)[len(sm) // 2:]  # upper half ~ samples under load
-        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        sm = sorted(r[1] for r in rows)
+        reasons = set()
+        for r in rows:
+            reasons |= r[3]
+        busy = sm[len(sm) // 2:]  # upper half ~ samples under load
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(r[2] for r in rows)), "reasons": sorted(reasons),
+                "samples": len(rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -162,6 +215,10 @@ def cpu_pipeline(sample, threads, level=5):
     from oracle import oracle as O
 
     os.environ["OMP_NUM_THREADS"] = str(threads)
+    try:   # the runtime may already be initialised (torchrun exports OMP_NUM_THREADS=1)
+        O.lib().omp_set_num_threads(int(threads))
+    except Exception:
+        pass
     q = np.full(sample.shape[0], QUANTA, np.float32)
     t0 = time.perf_counter()
     ints, off, gain = O.float_to_int(sample, q)
@@ -282,19 +339,29 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.5)
+    # warm-up with the same object lifetimes as the timed loop (the previous step's results are still alive
+    # while the next step allocates), so that the caching allocator has reached its steady state
+    comp = out = None
     for _ in range(args.warmup):
-        step_device()
+        comp, out = step_device()
+    del comp, out
     ctx.profile(True)
     launches0 = ctx.launches()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     barrier()
     sampler.mark()
     t_wall0 = time.perf_counter()
+    dbg = os.environ.get("FAB_BENCH_DEBUG") == "1"
     for k in range(args.steps):
         ev[k][0].record()
+        th0 = time.perf_counter()
         comp, starts, nbytes, off, gain = lf.encode_device(flat, n_stream, n_samp, 5, quanta)
+        th1 = time.perf_counter()
         if comm is not None:
             global_bytes(int(comp.numel()), starts, comm)
+        if dbg:
+            print(f"[rank {rank}] step {k}: encode_device {1e3 * (th1 - th0):.2f} ms, global_bytes "
+                  f"{1e3 * (time.perf_counter() - th1):.2f} ms", file=sys.stderr, flush=True)
         ev[k][1].record()
         mx = int(nbytes.max().item())
         out = lf.decode_device(comp, starts, nbytes, n_stream, n_samp, -1, -1, False, mx, 4096, off, gain)
@@ -303,6 +370,9 @@ def run_ours(args):
     wall = time.perf_counter() - t_wall0
     clocks = sampler.stop()
     launches = ctx.launches() - launches0
+    if dbg:
+        print(f"[rank {rank}] events: " + ", ".join(f"enc {e[0].elapsed_time(e[1]):.1f} dec {e[1].elapsed_time(e[2]):.1f}" for e in ev)
+              + f" | wall {1e3 * wall:.1f} ms", file=sys.stderr, flush=True)
     t_enc = sum(e[0].elapsed_time(e[1]) for e in ev) / 1e3
     t_dec = sum(e[1].elapsed_time(e[2]) for e in ev) / 1e3
     enc_ms, enc_n = ctx.profile_ms(0)

@@ -172,8 +172,23 @@ def wrap_int64_to_float64(idata, n_stream, stream_size, offsets, gains):
 # encode (pyx:285-594)
 # -------------------------------------------------------------------------------------------------
 
-def _encode_device_raw(d, n_stream, stream_size, level, quanta=None):
-    """fab_encode into a worst-case device buffer.  Returns (buffer, starts, nbytes, total, offsets, gains)."""
+_enc_scratch = {}   # device index -> grow-only worst-case output buffer of the device-resident encode
+
+
+def _scratch_out(dev, nbytes):
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    buf = _enc_scratch.get(key)
+    if buf is None or buf.numel() < nbytes:
+        _enc_scratch[key] = None
+        buf = None
+        buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        _enc_scratch[key] = buf
+    return buf
+
+
+def _encode_device_raw(d, n_stream, stream_size, level, quanta=None, scratch=False):
+    """fab_encode into a worst-case device buffer (a fresh one, or the per-device scratch).
+    Returns (buffer, starts, nbytes, total, offsets, gains)."""
     dev = d.device
     dt = _TORCH2NP[d.dtype]
     with torch.cuda.device(dev):
@@ -182,7 +197,7 @@ def _encode_device_raw(d, n_stream, stream_size, level, quanta=None):
         if level < 0 or level > 8:
             raise RuntimeError("Encoding failed, return code = 2")
         bound = L.fab_encode_bound(n_stream, stream_size, _FAB[dt], level)
-        out = torch.empty(max(bound, 1), dtype=torch.uint8, device=dev)
+        out = _scratch_out(dev, bound) if scratch else torch.empty(max(bound, 1), dtype=torch.uint8, device=dev)
         aux = torch.empty(2 * n_stream + 1, dtype=torch.int64, device=dev)
         starts, nbytes, total = aux[:n_stream], aux[n_stream:2 * n_stream], aux[2 * n_stream:]
         off = gain = None
@@ -204,8 +219,11 @@ def encode_device(d, n_stream, stream_size, level, quanta=None):
     gains are None for integer input.  For float input the quantisation (utils.c:160-328) is fused in
     front of the encoder; `quanta` is None (auto) or a CUDA tensor [n_stream].
     """
-    out, starts, nbytes, n_total, off, gain = _encode_device_raw(d, n_stream, stream_size, level, quanta)
-    return out[:n_total], starts, nbytes, off, gain
+    # The encoder needs a worst-case (~ raw size) output buffer; the result handed back is an exact-size
+    # copy so that a device-resident FlacArray holds the compressed bytes only.  The worst-case buffer is
+    # a per-device scratch (stream-ordered: the copy is queued before the next encode can reuse it).
+    out, starts, nbytes, n_total, off, gain = _encode_device_raw(d, n_stream, stream_size, level, quanta, scratch=True)
+    return out[:n_total].clone(), starts, nbytes, off, gain
 
 
 # -------------------------------------------------------------------------------------------------
