@@ -36,6 +36,28 @@ __global__ void __launch_bounds__(kEncThreads, FAB_ENC_CTAS) k_encode(const EncP
     encode_frames_cta<H>(P, smem);
 }
 
+// sample statistics, fixed-predictor error sums and windowed autocorrelation of every (frame, channel)
+template <int H>
+__global__ void __launch_bounds__(kEncThreads, 4) k_enc_analyze(const EncParams P) {
+    __shared__ AnShared sh;
+    analyze_frame_cta<H>(P, P.g_begin + blockIdx.x, &sh);
+}
+
+// predictor design: one thread per (frame, channel)
+__global__ void __launch_bounds__(128) k_enc_design(const EncParams P, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) design_frame(P, i);
+}
+
+// frame sizes of a batch -> inclusive byte prefixes (one CTA)
+__global__ void __launch_bounds__(kScanThreads) k_enc_scan(const EncParams P) {
+    __shared__ unsigned long long part[kScanThreads / 32 + 1];
+    scan_batch_cta(P, part);
+}
+
+// frames of a batch from their slots to their final byte offsets
+__global__ void __launch_bounds__(128) k_enc_compact(const EncParams P) { compact_frame_cta(P, blockIdx.x); }
+
 // stream headers, frame-size tables, stream_starts / stream_nbytes / total from the look-back descriptors
 __global__ void k_enc_finalize(const EncParams P, long long* __restrict__ nbytes, long long* __restrict__ total) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -43,6 +65,7 @@ __global__ void k_enc_finalize(const EncParams P, long long* __restrict__ nbytes
 }
 
 // ---- float -> int: per-stream min/max (utils.c:182-193 / :267-278), chunked over the stream ------
+constexpr int64_t kEncBatchBytes = 1ll << 30;   // slot scratch of one batch of encoder launches
 constexpr int kMmThreads = 256;
 constexpr int kMmChunk = 32768;  // elements per CTA
 
@@ -258,8 +281,8 @@ struct fab_ctx {
     bool prof = false;
     struct Pending { cudaEvent_t a, b; int which; };
     std::vector<Pending> pending;
-    double prof_ms[2] = {0.0, 0.0};
-    int64_t prof_n[2] = {0, 0};
+    double prof_ms[3] = {0.0, 0.0, 0.0};   // [0] k_encode, [1] k_dec_tile, [2] k_enc_analyze
+    int64_t prof_n[3] = {0, 0, 0};
 };
 
 static void prof_begin(fab_ctx* ctx, int which, cudaStream_t st) {
@@ -374,11 +397,11 @@ extern "C" void fab_profile(fab_ctx* ctx, int enable) {
     if (!ctx) return;
     prof_collect(ctx);
     ctx->prof = enable != 0;
-    ctx->prof_ms[0] = ctx->prof_ms[1] = 0.0;
-    ctx->prof_n[0] = ctx->prof_n[1] = 0;
+    ctx->prof_ms[0] = ctx->prof_ms[1] = ctx->prof_ms[2] = 0.0;
+    ctx->prof_n[0] = ctx->prof_n[1] = ctx->prof_n[2] = 0;
 }
 extern "C" double fab_profile_ms(fab_ctx* ctx, int which, int64_t* count) {
-    if (!ctx || which < 0 || which > 1) return 0.0;
+    if (!ctx || which < 0 || which > 2) return 0.0;
     prof_collect(ctx);
     if (count) *count = ctx->prof_n[which];
     return ctx->prof_ms[which];
@@ -453,8 +476,19 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
         pre = 2 * align256((size_t)n_stream * nchunk * (dtype == FAB_F32 ? 4 : 8));
     }
     size_t desc_b = align256((size_t)(n_stream * nf) * 8), ends_b = align256((size_t)n_stream * 8);
+    // the three encoder kernels run over batches of (stream, frame) tickets so that the per-frame
+    // records between them stay small; one ticket counter per batch
+    const int64_t total_frames = n_stream * nf;
+    const int64_t slot_bytes = (int64_t)((16 + 2 + (int64_t)nch * (lp.blocksize * 4 + 8) + 15) & ~15ll);
+    const int64_t batch = std::min<int64_t>(total_frames, std::max<int64_t>(1024, kEncBatchBytes / slot_bytes));
+    const int64_t nbatch = (total_frames + batch - 1) / batch;
+    size_t stats_b = align256((size_t)batch * nch * sizeof(FrameStats));
+    size_t plans_b = align256((size_t)batch * nch * sizeof(FramePlan));
+    size_t tick_b = align256((size_t)nbatch * 4 + 16);
+    size_t fsize_b = align256((size_t)batch * 4);
+    size_t slots_b = align256((size_t)batch * (size_t)slot_bytes);
     unsigned char* scr;
-    int rc = ctx_scratch(ctx, pre + desc_b + ends_b + 256, &scr);
+    int rc = ctx_scratch(ctx, pre + desc_b + ends_b + tick_b + stats_b + plans_b + fsize_b + slots_b + 256, &scr);
     if (rc) return rc;
 
     if (dtype == FAB_F32) {
@@ -469,7 +503,11 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
     unsigned long long* desc = (unsigned long long*)(scr + pre);
     long long* ends = (long long*)(scr + pre + desc_b);
     uint32_t* ticket = (uint32_t*)(scr + pre + desc_b + ends_b);
-    FAB_CUDA(ctx, cudaMemsetAsync(desc, 0, desc_b + ends_b + 256, st));
+    FrameStats* stats = (FrameStats*)(scr + pre + desc_b + ends_b + tick_b);
+    FramePlan* plans = (FramePlan*)(scr + pre + desc_b + ends_b + tick_b + stats_b);
+    uint32_t* fsize = (uint32_t*)(scr + pre + desc_b + ends_b + tick_b + stats_b + plans_b);
+    uint8_t* slots = scr + pre + desc_b + ends_b + tick_b + stats_b + plans_b + fsize_b;
+    FAB_CUDA(ctx, cudaMemsetAsync(desc, 0, desc_b + ends_b + tick_b, st));
 
     EncParams P;
     P.data = d_data; P.dtype = dtype; P.offsets = d_offsets; P.gains = d_gains;
@@ -483,24 +521,44 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
     P.starts = (long long*)d_starts; P.ends = ends; P.desc = desc; P.ticket = ticket; P.err = ctx->d_err;
     P.hdr_bytes = stream_header_bytes((int)nf);
 
-    size_t smem = enc_smem_bytes(nch);
+#ifndef FAB_SMEM_PAD
+#define FAB_SMEM_PAD 0
+#endif
+    size_t smem = enc_smem_bytes(nch) + FAB_SMEM_PAD;   // (FAB_SMEM_PAD: experiment knob, shrinks the L1)
     if (!ctx->smem_configured) {
-        FAB_CUDA(ctx, cudaFuncSetAttribute(k_encode<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_smem_bytes(2)));
+        FAB_CUDA(ctx, cudaFuncSetAttribute(k_encode<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_smem_bytes(2) + FAB_SMEM_PAD));
         FAB_CUDA(ctx, cudaFuncSetAttribute(k_encode<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_smem_bytes(2)));
         for (int c = 0; c < 2; ++c) {
-            FAB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->enc_ctas_per_sm[0][c], k_encode<8>, kEncThreads, enc_smem_bytes(c + 1)));
+            FAB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->enc_ctas_per_sm[0][c], k_encode<8>, kEncThreads, enc_smem_bytes(c + 1) + FAB_SMEM_PAD));
             FAB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->enc_ctas_per_sm[1][c], k_encode<12>, kEncThreads, enc_smem_bytes(c + 1)));
         }
         ctx->smem_configured = true;
     }
+    P.stats = stats; P.plans = plans;
+    P.slots = slots; P.slot_bytes = slot_bytes; P.fsize = fsize;
+    P.base = (unsigned long long*)(ticket + ((nbatch + 3) & ~3ll));   // zeroed with the tickets (8-byte aligned)
     const int h12 = lp.max_lpc_order > 8 ? 1 : 0;
     int64_t resident = (int64_t)ctx->n_sm * std::max(1, ctx->enc_ctas_per_sm[h12][nch - 1]);
-    unsigned grid = (unsigned)std::min<int64_t>(n_stream * nf, resident);
-    prof_begin(ctx, 0, st);
-    if (h12) k_encode<12><<<grid, kEncThreads, smem, st>>>(P);
-    else k_encode<8><<<grid, kEncThreads, smem, st>>>(P);
-    prof_end(ctx, st);
-    ctx->launches++;
+    for (int64_t bi = 0; bi < nbatch; ++bi) {
+        P.g_begin = (uint32_t)(bi * batch);
+        P.g_end = (uint32_t)std::min<int64_t>(total_frames, (bi + 1) * batch);
+        P.ticket = ticket + bi;
+        const int64_t nfr = (int64_t)P.g_end - (int64_t)P.g_begin;
+        prof_begin(ctx, 2, st);
+        if (h12) k_enc_analyze<12><<<(unsigned)nfr, kEncThreads, 0, st>>>(P);
+        else k_enc_analyze<8><<<(unsigned)nfr, kEncThreads, 0, st>>>(P);
+        prof_end(ctx, st);
+        k_enc_design<<<(unsigned)((nfr * nch + 127) / 128), 128, 0, st>>>(P, nfr * nch);
+        unsigned grid = (unsigned)std::min<int64_t>(nfr, resident);
+        prof_begin(ctx, 0, st);
+        if (h12) k_encode<12><<<grid, kEncThreads, smem, st>>>(P);
+        else k_encode<8><<<grid, kEncThreads, smem, st>>>(P);
+        prof_end(ctx, st);
+        k_enc_scan<<<1, kScanThreads, 0, st>>>(P);
+        k_enc_compact<<<(unsigned)nfr, 128, 0, st>>>(P);
+        ctx->launches += 5;
+    }
+    P.g_begin = 0; P.g_end = (uint32_t)total_frames;
     k_enc_finalize<<<(unsigned)((n_stream * nf + 255) / 256), 256, 0, st>>>(P, (long long*)d_nbytes, (long long*)d_total);
     ctx->launches++;
     FAB_CUDA(ctx, cudaGetLastError());

@@ -20,7 +20,10 @@ namespace fa {
 
 constexpr int kTileOrd = 12;
 constexpr int kTileStride = 33;
-constexpr int kTileWarps = 4;  // warps per CTA
+#ifndef FAB_TILE_WARPS
+#define FAB_TILE_WARPS 4
+#endif
+constexpr int kTileWarps = FAB_TILE_WARPS;  // warps per CTA
 
 constexpr int kRingChunks = 4;                 // 16-byte chunks per lane in the shared-memory ring
 constexpr int kRingStride = kRingChunks * 4 + 4;   // words per lane row (16-byte aligned, spreads the banks)

@@ -8,6 +8,7 @@
 // Layout of the work: every thread owns 32 consecutive samples of the frame (plus the predictor
 // history before them) in registers; nothing but the packed output frame is staged in shared memory.
 //
+// Three kernels (see "Fast path" below): k_enc_analyze -> k_enc_design -> k_encode.
 // Two code paths per (frame, channel):
 //   * fast path  -- full 4096-sample frames whose samples fit 22 bits and have no wasted bits (the
 //     benchmark's quantised detector data): all integer work in 32-bit registers, one fused pass for
@@ -93,6 +94,9 @@ inline void enc_tables_init(EncTables* t) {
 // Bytes before the first frame of every stream: "fLaC" + STREAMINFO + APPLICATION(faB2 table, last).
 inline int stream_header_bytes(int nframes) { return 4 + 4 + 34 + 4 + 8 + 3 * nframes; }
 
+struct FrameStats;
+struct FramePlan;
+
 struct EncParams {
     const void* data;
     int dtype;                 // kI32 / kI64 / kF32 / kF64
@@ -110,9 +114,32 @@ struct EncParams {
     long long* starts;         // [n_stream] byte offset of every stream; must be preset to -1
     long long* ends;           // [n_stream]
     unsigned long long* desc;  // [n_stream * nframes] look-back descriptors, zeroed
-    uint32_t* ticket;          // zeroed
+    uint32_t* ticket;          // zeroed (one counter per launch)
     int* err;
     int hdr_bytes;
+    uint8_t* slots;            // batch scratch: frame (g - g_begin) is written at slots + (g - g_begin) * slot_bytes
+    int64_t slot_bytes;        // worst-case frame size rounded up to 16
+    uint32_t* fsize;           // [g - g_begin] bytes of the frame (body + CRC-16)
+    unsigned long long* base;  // running total of bytes before this batch (device scalar)
+    FrameStats* stats;         // [(g - g_begin) * nch + c]
+    FramePlan* plans;
+    uint32_t g_begin, g_end;   // (stream, frame) tickets covered by this batch of launches
+};
+
+// Records exchanged between the three encoder kernels, one per (frame, channel):
+//   k_enc_analyze -> FrameStats -> k_enc_design -> FramePlan -> k_encode
+struct FrameStats {
+    int32_t mode;              // 0 general path, 1 CONSTANT, 2 predictive (narrow samples), 3 predictive (wide samples)
+    int32_t wasted;
+    int32_t mn, mx;            // of the samples >> wasted
+    uint32_t bad, pad;         // wide: fixed-predictor orders whose residual leaves the int32 range
+    unsigned long long fe[5];  // fixed-predictor error sums of the samples >> wasted
+    double ac[kMaxOrd + 1];    // windowed autocorrelation of the samples >> wasted
+};
+struct FramePlan {             // 48 bytes, read with three 16-byte broadcast loads
+    uint8_t mode, wasted, ok0, ok1, ord0, ord1, shift1, prec1, wide1, maxp0, maxp1, pad[5];
+    int16_t qlp[kMaxOrd];
+    uint32_t pad2[2];
 };
 
 struct Plan {
@@ -121,6 +148,23 @@ struct Plan {
     int wide;      // lpc: residual needs 64-bit accumulation
     uint32_t res_bits;  // estimated bits of the residual section
     int32_t qlp[kMaxOrd];
+};
+
+struct AnShared {              // k_enc_analyze: per-warp partials of the block reductions
+    uint32_t w_or[kEncWarps];
+    int32_t w_mn[kEncWarps], w_mx[kEncWarps];
+    uint32_t w_bad[kEncWarps];
+    unsigned long long w_fe[kEncWarps][5];
+    double w_ac[kEncWarps][kMaxOrd + 1];
+};
+
+struct DesignIO {              // k_enc_design: thread-private working set of design_fixed / design_lpc
+    unsigned long long t_fe[5];
+    double t_ac[kMaxOrd + 1];
+    Plan cand[2];
+    int cand_ok[2];
+    int maxp[2];
+    double lpc_hist[kMaxOrd][kMaxOrd];
 };
 
 struct EncShared {
@@ -147,6 +191,11 @@ struct EncShared {
     uint8_t kpar[2][2 * kMaxParts];            // params for porder p at offset (1 << p) - 1
     uint32_t scan[kEncWarps];
     uint32_t crc_part[kEncWarps];
+    uint8_t crc8[256];                         // CRC-8 table (frame headers)
+    // full-frame path: per-warp partials of (estimated bits at the finest partition order, sum |residual|, flags)
+    uint32_t x_bits[2][kEncWarps];
+    unsigned long long x_sum[2][kEncWarps];
+    uint32_t x_flag[2][kEncWarps];             // bit 0: a residual does not fit, bit 1: some parameter >= 15
     // deferred tail words of the packing sessions (OR-ed in when the frame is retired)
     uint32_t tail_val[2][kEncThreads];
     int tail_word[2][kEncThreads];
@@ -161,7 +210,8 @@ FA_HD size_t enc_out_words(int nch) { return ((size_t)nch * (kMaxBs * 4 + 64) + 
 FA_D int ow(int w) { return w + (w >> 4); }   // padded word index: per-thread strides of ~16 words stay off one bank
 inline size_t enc_smem_bytes(int nch) {
     size_t words = enc_out_words(nch);
-    return ((sizeof(EncShared) + 15) & ~(size_t)15) + 4 * 256 * 2 + (words + (words >> 4) + 8) * 4 + 16;
+    // EncShared | CRC slice tables | staged frame (padded) | residuals of one full frame-channel
+    return ((sizeof(EncShared) + 15) & ~(size_t)15) + 4 * 256 * 2 + (words + (words >> 4) + 8) * 4 + 16 + kMaxBs * 4;
 }
 
 // ---- small helpers -----------------------------------------------------------------------------------
@@ -264,11 +314,13 @@ FA_D int frame_header_bytes(int bs, int f) {
 }
 
 // ---- bit packer: 64-bit accumulator -> staged frame words ----------------------------------------------
-// Write protocol of the staged frame (pre-zeroed): while packing, a thread plain-stores every word it
-// completes -- including its first one, whose leading bits may belong to the previous thread and are
-// stored as zeros.  The trailing partial word of a session is NOT stored: it is recorded and OR-ed in
-// after a barrier, when the frame is retired.  Each word has exactly one plain-storing thread, and all
-// ORs come after all plain stores, so no atomics and no "first word" test are needed in the hot loop.
+// Write protocol of the staged frame: while packing, a thread plain-stores every word it completes --
+// including its first one, whose leading bits may belong to the previous thread and are stored as
+// zeros.  The trailing partial word of a session is NOT stored: it is recorded and OR-ed in after a
+// barrier, when the frame is retired.  The sessions tile the frame, so every word except the frame's
+// final partial word has exactly one plain-storing thread (the one whose session contains its last
+// bit), and all ORs come after all plain stores: no atomics, no "first word" test and no pre-zeroed
+// buffer are needed.  The final partial word is cleared by thread 0 once the frame size is known.
 struct Pk {
     uint32_t* out;
     uint64_t acc;
@@ -314,39 +366,20 @@ FA_D void pk_end(const Pk& pk, uint32_t& tail_val, int& tail_word) {
 // ---- decoupled look-back descriptors: [63:62] status (0 empty, 1 aggregate, 2 inclusive prefix), [61:0] bytes
 constexpr unsigned long long kDescAgg = 1ull << 62, kDescPre = 2ull << 62, kDescMask = (1ull << 62) - 1;
 
-// Thread 0, as soon as the size of the frame is known (before packing): successors can start summing.
-FA_D void publish_aggregate(const EncParams& P, uint32_t g, int f, int bitpos_end) {
-    unsigned long long mine = (unsigned long long)(((bitpos_end + 7) >> 3) + 2) + (f == 0 ? (unsigned long long)P.hdr_bytes : 0ull);
-    st_relaxed_u64(&P.desc[g], (g == 0 ? kDescPre : kDescAgg) | mine);   // the word is its own payload
-}
-
-// Warp 0: exclusive prefix of frame g over all earlier frames, 32 descriptors per round trip.
-FA_D unsigned long long lookback_warp(const EncParams& P, uint32_t g) {
-    const int ln = lane();
-    unsigned long long excl = 0;
-    long long base = (long long)g - 1;
-    for (;;) {
-        long long idx = base - ln;
-        unsigned long long d = idx >= 0 ? ld_relaxed_u64(&P.desc[idx]) : kDescPre;   // virtual prefix 0 before frame 0
-        uint32_t st = (uint32_t)(d >> 62);
-        uint32_t pre = ballot(st == 2), empty = ballot(st == 0);
-        int first_pre = pre ? ctz32(pre) : 32;
-        uint32_t need = first_pre >= 31 ? 0xFFFFFFFFu : ((2u << first_pre) - 1u);   // lanes 0..first_pre
-        if (empty & need) { spin_pause(); continue; }
-        unsigned long long v = (ln <= first_pre) ? (d & kDescMask) : 0ull;
-        excl += warp_sum_u64(v);
-        if (first_pre < 32) break;
-        base -= 32;
-    }
-    return excl;
-}
+// Frame placement.  Every frame of a batch is first written to its own 16-byte aligned worst-case slot, so
+// the encoder CTAs are completely independent (no ticket order, no look-back, no waiting for stragglers:
+// with the decoupled look-back of the first version a single late CTA stalled the retire of every
+// successor, and the stall grew with the number of resident CTAs).  k_enc_scan then turns the frame
+// sizes into byte offsets and k_enc_compact moves the frames to their final place: the compressed
+// bytes cross HBM three times instead of once, which costs ~1 ms at cfg2 and is far cheaper than the
+// serialisation it removes.
+FA_D void publish_aggregate(const EncParams&, uint32_t, int, int) {}
 
 // ---- sample source ------------------------------------------------------------------------------------
 struct FrameSrc {
     const void* base;   // element (stream s, frame sample 0)
     int dtype, bs;
     bool vec;           // 16-byte vector loads are aligned
-    bool posgain;       // kF32: gain > 0 (block-uniform; lets the quantiser skip its sign test)
     float off32, gain32;
     double off64, gain64;
 };
@@ -425,7 +458,7 @@ FA_D void load_chunk(const FrameSrc& S, int c, int t, int32_t* xw) {
 }
 
 // ---- frame / subframe headers (thread 0, through its packing session) ----------------------------------
-FA_D void emit_frame_header(Pk& pk, const CrcTables* crc, int bs, int f, int nch) {
+FA_D void emit_frame_header(Pk& pk, const uint8_t* crc8, int bs, int f, int nch) {
     uint8_t h[16];
     int n = 0;
     int bc = blocksize_code(bs);
@@ -436,7 +469,7 @@ FA_D void emit_frame_header(Pk& pk, const CrcTables* crc, int bs, int f, int nch
     if (bc == 6) h[n++] = (uint8_t)(bs - 1);
     else if (bc == 7) { h[n++] = (uint8_t)((bs - 1) >> 8); h[n++] = (uint8_t)(bs - 1); }
     uint32_t c = 0;
-    for (int i = 0; i < n; ++i) c = crc->crc8[c ^ h[i]];
+    for (int i = 0; i < n; ++i) c = crc8[c ^ h[i]];
     h[n++] = (uint8_t)c;
     for (int i = 0; i < n; ++i) pk_emit(pk, h[i], 8);
 }
@@ -518,7 +551,8 @@ FA_D void rice_search_warp(EncShared* sh, int cand, int bs, int order, int maxp)
 // coefficient precision: the largest precision <= `precision` for which every prediction sum and
 // residual provably fits 32-bit arithmetic; if that would cost more than 3 bits the plan is marked
 // `wide` (64-bit residual) at full precision instead.
-FA_D void design_fixed(EncShared* sh, int bs, int bps, uint32_t bad, int level_maxp) {
+template <class D>
+FA_D void design_fixed(D* sh, int bs, int bps, uint32_t bad, int level_maxp) {
     unsigned long long te[5];
     for (int k = 0; k < 5; ++k) te[k] = ((bad >> k) & 1) ? ~0ull : sh->t_fe[k];
     unsigned long long m34 = te[3] < te[4] ? te[3] : te[4];
@@ -566,7 +600,8 @@ FA_D bool quantize_coefs(const double* coefs, int order, int precision, int32_t*
     return true;
 }
 
-FA_D void design_lpc(EncShared* sh, int bs, int bps, int max_order, int precision, int level_maxp, uint32_t narrow_maxabs) {
+template <class D>
+FA_D void design_lpc(D* sh, int bs, int bps, int max_order, int precision, int level_maxp, uint32_t narrow_maxabs) {
     Plan& pl = sh->cand[1];
     sh->cand_ok[1] = 0;
     const double* autoc = sh->t_ac;
@@ -717,8 +752,13 @@ FA_D uint32_t residual64(int order, const int32_t* xw, const int32_t* coef, int 
 }
 
 FA_D void fixed_coefs(int order, int32_t* c, int n) {
-    const int32_t fx[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};
-    for (int j = 0; j < n; ++j) c[j] = (j < 4) ? fx[order][j] : 0;
+    // (1), (2, -1), (3, -3, 1), (4, -6, 4, -1): selected arithmetically, no table in local memory
+    const int32_t c0 = order;
+    const int32_t c1 = order == 2 ? -1 : order == 3 ? -3 : order == 4 ? -6 : 0;
+    const int32_t c2 = order == 3 ? 1 : order == 4 ? 4 : 0;
+    const int32_t c3 = order == 4 ? -1 : 0;
+#pragma unroll
+    for (int q = 0; q < n; ++q) c[q] = q == 0 ? c0 : q == 1 ? c1 : q == 2 ? c2 : q == 3 ? c3 : 0;
 }
 
 
@@ -731,23 +771,22 @@ struct EncCtx {
     EncShared* sh;
     const uint16_t* crcT;
     uint32_t* out;
+    int32_t* res;        // [32][128]: residual j of thread t at res[j * 128 + t]
     int out_words_padded;
+#if defined(FAB_PHASE_TIMING) && defined(__CUDACC__)
+    long long ph[12];
+    long long last;
+#endif
     bool retired;   // block-uniform: the previous frame has left `out` and `out` is zeroed
 };
 
-// One warp: exclusive prefix of the frame waiting in `out`, publishes its inclusive prefix.
+// One warp: where the frame waiting in `out` goes (its slot) and its size.
 FA_D void retire_lookback(const EncParams& P, EncShared* sh) {
     if (!sh->prev_valid) return;
-    const uint32_t g = sh->prev_g;
-    const int f = sh->prev_f;
-    unsigned long long excl = g == 0 ? 0ull : lookback_warp(P, g);
     if (lane() == 0) {
-        const int frame_bytes = sh->prev_nbytes + 2;
-        unsigned long long mine = (unsigned long long)frame_bytes + (f == 0 ? (unsigned long long)P.hdr_bytes : 0ull);
-        if (g != 0) st_relaxed_u64(&P.desc[g], kDescPre | (excl + mine));
-        long long off = (long long)excl + (f == 0 ? P.hdr_bytes : 0);
-        if (off + frame_bytes > P.out_capacity) { atom_or_global(P.err, kErrEncodeCollect); off = -1; }
-        sh->prev_off = off;
+        const uint32_t i = sh->prev_g - P.g_begin;
+        P.fsize[i] = (uint32_t)(sh->prev_nbytes + 2);
+        sh->prev_off = (long long)i * P.slot_bytes;
     }
 }
 
@@ -772,7 +811,7 @@ FA_D void retire_copyout(const EncParams& P, const EncCtx& X) {
     }
     const long long off = sh->prev_off;
     if (off >= 0) {
-        uint8_t* dst = P.out + off;
+        uint8_t* dst = P.slots + off;
         // aligned 32-bit stores in the middle, byte stores at the ragged ends
         int a = (int)((uintptr_t)dst & 3);
         int head = a ? 4 - a : 0;
@@ -801,10 +840,10 @@ FA_D void retire_crc(const EncParams& P, EncShared* sh) {
     const int wtot = (nbytes_body + 3) >> 2;
     uint32_t crc = sh->crc_part[0] ^ sh->crc_part[1] ^ sh->crc_part[2] ^ sh->crc_part[3];
     crc = gf16_mul(crc, P.tab->inv8[4 * wtot - nbytes_body]);   // the staged words carry 0..3 pad bytes
-    st_global_u8x2(P.out + sh->prev_off + nbytes_body, (crc >> 8) & 0xFFu, crc & 0xFFu);
+    st_global_u8x2(P.slots + sh->prev_off + nbytes_body, (crc >> 8) & 0xFFu, crc & 0xFFu);
 }
 
-FA_D void zero_out(const EncCtx& X) {
+FA_D void zero_out(const EncCtx& X) {   // only used once, when the CTA starts
     U4 z; z.x = z.y = z.z = z.w = 0;
     for (int w = 4 * tid(); w < X.out_words_padded; w += 4 * kEncThreads) sts128(X.out + w, z);
 }
@@ -817,9 +856,77 @@ FA_D void retire_full(const EncParams& P, EncCtx& X) {
     retire_copyout(P, X);
     sync();
     if (tid() == 0) retire_crc(P, X.sh);
-    zero_out(X);
     sync();
     X.retired = true;
+}
+
+// Inclusive byte prefix of every frame of the batch (one CTA of kScanThreads threads): desc[g] = bytes of
+// everything up to and including frame g (stream headers included, at the first frame of each stream).
+// Every warp scans one contiguous segment with coalesced 32-wide steps, the 32 segment totals are
+// scanned by one thread, and a second coalesced pass adds the segment bases.
+constexpr int kScanThreads = 1024;
+FA_D void scan_batch_cta(const EncParams& P, unsigned long long* sh_part /*[kScanThreads / 32 + 1]*/) {
+    const int t = tid(), ln = lane(), wp = warp();
+    const uint32_t n = P.g_end - P.g_begin;
+    constexpr uint32_t kW = kScanThreads / 32;
+    const uint32_t seg = (((n + kW - 1) / kW) + 31u) & ~31u;      // elements per warp, a multiple of 32
+    const uint32_t lo = (uint32_t)wp * seg;
+    unsigned long long run = 0;
+    for (uint32_t i = lo; i < lo + seg && i < n; i += 32) {
+        const uint32_t j = i + (uint32_t)ln;
+        uint32_t v = 0;
+        if (j < n) v = P.fsize[j] + (((P.g_begin + j) % (uint32_t)P.nframes) == 0 ? (uint32_t)P.hdr_bytes : 0u);
+        uint32_t inc = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = shfl_up(inc, d);
+            if (ln >= d) inc += o;
+        }
+        if (j < n) P.desc[P.g_begin + j] = run + inc;
+        run += shfl(inc, 31);
+    }
+    if (ln == 0) sh_part[wp] = run;
+    sync();
+    if (t == 0) {
+        unsigned long long acc = *P.base;
+        for (uint32_t w = 0; w < kW; ++w) { unsigned long long v = sh_part[w]; sh_part[w] = acc; acc += v; }
+        sh_part[kW] = acc;
+    }
+    sync();
+    const unsigned long long base = sh_part[wp];
+    for (uint32_t i = lo; i < lo + seg && i < n; i += 32) {
+        const uint32_t j = i + (uint32_t)ln;
+        if (j < n) P.desc[P.g_begin + j] += base;
+    }
+    if (t == 0) *P.base = sh_part[kW];
+}
+
+// One CTA: frame i of the batch from its slot to its final place (any byte alignment).
+FA_D void compact_frame_cta(const EncParams& P, uint32_t i) {
+    const uint32_t g = P.g_begin + i;
+    const uint32_t len = P.fsize[i];
+    const unsigned long long end = P.desc[g];
+    if ((long long)end > P.out_capacity) {
+        if (tid() == 0) atom_or_global(P.err, kErrEncodeCollect);
+        return;
+    }
+    uint8_t* dst = P.out + (end - len);
+    const uint32_t* src = (const uint32_t*)(P.slots + (long long)i * P.slot_bytes);   // 16-byte aligned
+    const int t = tid(), nt = nthreads();
+    int head = (int)((4 - ((uintptr_t)dst & 3)) & 3);
+    if ((uint32_t)head > len) head = (int)len;
+    if (t < head) dst[t] = (uint8_t)(src[0] >> (8 * t));
+    const uint32_t nwords = (len - (uint32_t)head) >> 2;
+    uint32_t* dw = (uint32_t*)(dst + head);
+    const uint32_t sh8 = 8u * (uint32_t)head;     // source byte offset of dw[0] is `head` (0..3)
+    for (uint32_t w = (uint32_t)t; w < nwords; w += (uint32_t)nt) {
+        uint32_t a = src[w], b = head ? src[w + 1] : 0u;
+        dw[w] = head ? ((a >> sh8) | (b << (32u - sh8))) : a;
+    }
+    const uint32_t tail0 = (uint32_t)head + 4u * nwords;
+    if ((uint32_t)t < len - tail0) {
+        uint32_t k = tail0 + (uint32_t)t;
+        dst[k] = (uint8_t)(src[k >> 2] >> (8 * (k & 3)));
+    }
 }
 
 // Stream header and frame-size table, from the finished look-back descriptors (one thread per stream
@@ -864,21 +971,33 @@ FA_D void finalize_entry(const EncParams& P, int64_t s, int f, long long* nbytes
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Fast path: full frame, narrow samples, no wasted bits.  Returns false (block-uniform) when the frame
-// does not qualify or the predictive subframe would not beat VERBATIM; nothing has been emitted then.
+// Fast path, split over three kernels so that no thread ever waits for the serial predictor design:
+//   analyze_channel (k_enc_analyze, one CTA per frame): sample statistics, fixed-predictor error sums,
+//       windowed autocorrelation -> FrameStats;
+//   design_frame (k_enc_design, one THREAD per (frame, channel)): fixed order choice, Levinson-Durbin,
+//       order choice, coefficient quantisation -> FramePlan;
+//   enc_channel_fast (k_encode, persistent CTAs in ticket order): residuals, Rice partition search,
+//       bit packing, CRC-16, look-back placement, copy-out.
+// The samples are read (and float input quantised) twice; the path is instruction-bound, not
+// HBM-bound, and the second read buys a design stage that runs at full machine width.
+// Eligible frames: 64 <= blocksize <= 4096 samples; anything else (and any frame whose predictive
+// subframe would not beat VERBATIM) takes the general path below.
 // ------------------------------------------------------------------------------------------------------
+FA_D int fast_level_maxp(int bs, int level_max) {
+    if (bs == kMaxBs) return level_max;
+    // partitions must be whole thread chunks: partition size a multiple of 32 (or a single partition)
+    int z = ctz32((uint32_t)bs);
+    int lim = z > 5 ? z - 5 : 0;
+    return level_max < lim ? level_max : lim;
+}
+
 template <int H, bool FULL>
-FA_D bool enc_channel_fast(const EncParams& P, EncCtx& X, const FrameSrc& S, int c, int f, uint32_t g, int bitpos0,
-                           int& bitpos_end) {
-    EncShared* sh = X.sh;
-    uint32_t* out = X.out;
+FA_D void analyze_channel(const EncParams& P, AnShared* sh, const FrameSrc& S, int c, FrameStats* st) {
     const int t = tid();
     const int ln = lane(), wp = warp();
     const int bs = FULL ? kMaxBs : S.bs;
     const int i0 = t * kSpt;
     const int nvalid = FULL ? kSpt : (bs - i0 >= kSpt ? kSpt : (bs > i0 ? bs - i0 : 0));
-    // partitions must be whole thread chunks: partition size a multiple of 32 (or a single partition)
-    const int level_maxp = FULL ? P.max_porder : (P.max_porder < ctz32((uint32_t)bs) - 5 ? P.max_porder : (ctz32((uint32_t)bs) > 5 ? ctz32((uint32_t)bs) - 5 : 0));
     int32_t xw[H + kSpt];
     load_chunk<H, FULL>(S, c, t, xw);
 
@@ -968,96 +1087,35 @@ FA_D bool enc_channel_fast(const EncParams& P, EncCtx& X, const FrameSrc& S, int
                 double v = warp_sum_d(ac[l]);
                 if (ln == 0) sh->w_ac[wp][l] = v;
             }
+        } else if (ln <= H) {
+            sh->w_ac[wp][ln] = 0.0;
         }
     }
-    sync();   // B1
-    if (wp == 3 && !X.retired) retire_lookback(P, sh);   // overlaps the serial design below
-    if (wp == 0) {
-        if (ln < 5) {
-            unsigned long long v = 0;
-            for (int w = 0; w < kEncWarps; ++w) v += sh->w_fe[w][ln];
-            sh->t_fe[ln] = v;
-        } else if (ln >= 8 && ln < 8 + H + 1) {
-            int l = ln - 8;
-            double v = dadd(dadd(sh->w_ac[0][l], sh->w_ac[1][l]), dadd(sh->w_ac[2][l], sh->w_ac[3][l]));
-            sh->t_ac[l] = v;
-        } else if (ln == 31) {
-            uint32_t o = 0;
-            int32_t a = 0x7fffffff, b = (int32_t)0x80000000u;
-            for (int w = 0; w < kEncWarps; ++w) {
-                o |= sh->w_or[w];
-                a = sh->w_mn[w] < a ? sh->w_mn[w] : a;
-                b = sh->w_mx[w] > b ? sh->w_mx[w] : b;
-            }
-            sh->t_or = o; sh->t_mn = a; sh->t_mx = b;
-        }
-        syncwarp();
-        if (ln == 0) {
-            const int32_t a = sh->t_mn, b = sh->t_mx;
-            int mode = 2, wasted = 0;
-            if (a == b) mode = 1;                                           // CONSTANT
-            else {
-                wasted = ctz32(sh->t_or);                                   // t_or != 0: the samples differ
-                // the 32-bit sums of pass 1 are only valid for narrow (unshifted) samples
-                if (a < -(1 << kNarrowBits) || b >= (1 << kNarrowBits)) mode = 3;   // wide: 64-bit statistics below
-            }
-            sh->mode = mode;
-            sh->wasted = wasted;
-            if (wasted && mode >= 2) {
-                // statistics of the samples >> wasted: every difference is a multiple of 2^wasted and
-                // float(x) * w scales exactly, so shifting the sums is exact
-                unsigned long long den = 1ull << (2 * wasted);
-                double sc = 1.0 / (double)den;
-                for (int l = 0; l <= H; ++l) sh->t_ac[l] *= sc;
-                for (int k = 0; k < 5; ++k) sh->t_fe[k] >>= wasted;
-            }
-            if (mode == 2) {
-                const int32_t as = a >> wasted, bsft = b >> wasted;
-                uint32_t maxabs = (uint32_t)(-(int64_t)as > (int64_t)bsft ? -(int64_t)as : (int64_t)bsft);
-                design_fixed(sh, bs, 32 - wasted, 0u, level_maxp);
-                design_lpc(sh, bs, 32 - wasted, P.max_lpc_order < H ? P.max_lpc_order : H, P.qlp_precision, level_maxp, maxabs);
-            }
-        }
-    }
-    sync();   // B2
-    const int mode = sh->mode;
-    const bool retiring = !X.retired;
-    if (retiring) retire_copyout(P, X);   // previous frame: CRC partials + copy to HBM (offset known since B2)
-    if (mode < 2) {
-        if (retiring) {
-            sync();
-            if (t == 0) retire_crc(P, sh);
-            zero_out(X);
-            sync();
-            X.retired = true;
-        }
-        if (mode == 0) return false;
-        bitpos_end = bitpos0 + (c == 0 ? 8 * frame_header_bytes(bs, f) : 0) + subframe_header_bits(0, 0, 0, 32, 0);
-        if (t == 0) {
-            if (c == P.nch - 1) publish_aggregate(P, g, f, bitpos_end);
-            Pk pk;
-            pk_begin(pk, out, bitpos0);
-            if (c == 0) emit_frame_header(pk, P.crc, bs, f, P.nch);
-            emit_subframe_header(pk, 0, 0, 0);
-            emit_sample(pk, xw[H], 32);
-            pk_end(pk, sh->tail_val[c][0], sh->tail_word[c][0]);
-        }
-        return true;
-    }
-
-    // ---- wide samples (up to the full int32 range, e.g. the low word of an int64): the 32-bit sums of
-    //      pass 1 may have wrapped, so the fixed-predictor statistics are redone with 64-bit
-    //      differences (libFLAC: FLAC__fixed_compute_best_predictor_wide); predictor orders whose
-    //      residual leaves the int32 range are excluded.  The autocorrelation of pass 1 stays valid.
-    const bool wide = mode == 3;
-    const int wasted = sh->wasted;
-    const int bps = 32 - wasted;
-    if (wasted) {
+    sync();
+    // ---- every thread: frame totals of the sample statistics -> mode (block-uniform)
+    uint32_t t_or = 0;
+    int32_t a = 0x7fffffff, b = (int32_t)0x80000000u;
 #pragma unroll
-        for (int i = 0; i < H + kSpt; ++i) xw[i] >>= wasted;
-        fe0 >>= wasted; fe1 >>= wasted; fe2 >>= wasted; fe3 >>= wasted; fe4 >>= wasted;
+    for (int w = 0; w < kEncWarps; ++w) {
+        t_or |= sh->w_or[w];
+        a = sh->w_mn[w] < a ? sh->w_mn[w] : a;
+        b = sh->w_mx[w] > b ? sh->w_mx[w] : b;
     }
-    if (wide) {
+    int mode = 2, wasted = 0;
+    if (a == b) mode = 1;                                           // CONSTANT
+    else {
+        wasted = ctz32(t_or);                                       // t_or != 0: the samples differ
+        // the 32-bit sums of pass 1 are only valid for narrow (unshifted) samples
+        if (a < -(1 << kNarrowBits) || b >= (1 << kNarrowBits)) mode = 3;
+    }
+    if (mode == 3) {
+        // wide samples (up to the full int32 range, e.g. the low word of an int64): the fixed-predictor
+        // statistics are redone with 64-bit differences (libFLAC: FLAC__fixed_compute_best_predictor_wide);
+        // orders whose residual leaves the int32 range are excluded.  The autocorrelation stays valid.
+        if (wasted) {
+#pragma unroll
+            for (int i = 0; i < H + kSpt; ++i) xw[i] >>= wasted;
+        }
         unsigned long long we[5] = {0, 0, 0, 0, 0};
         uint32_t bad = 0;
         int64_t q1 = (int64_t)xw[H - 1] - (int64_t)xw[H - 2];
@@ -1088,59 +1146,196 @@ FA_D bool enc_channel_fast(const EncParams& P, EncCtx& X, const FrameSrc& S, int
         }
         if (ln == 0) sh->w_bad[wp] = wbad;
         sync();
-        if (t == 0) {
-            uint32_t tb = 0;
-            for (int w = 0; w < kEncWarps; ++w) tb |= sh->w_bad[w];
-            for (int k = 0; k < 5; ++k) {
-                unsigned long long v = 0;
-                for (int w = 0; w < kEncWarps; ++w) v += sh->w_fe[w][k];
-                sh->t_fe[k] = v;
-            }
-            design_fixed(sh, bs, bps, tb, level_maxp);
-            design_lpc(sh, bs, bps, P.max_lpc_order < H ? P.max_lpc_order : H, P.qlp_precision, level_maxp, 0u);
+    }
+    // ---- writers: statistics of the samples >> wasted.  Every difference is a multiple of 2^wasted and
+    //      float(x) * w scales exactly, so shifting / scaling the narrow sums is exact.
+    if (t < 5) {
+        unsigned long long v = 0;
+        for (int w = 0; w < kEncWarps; ++w) v += sh->w_fe[w][t];
+        if (mode == 2) v >>= wasted;
+        st->fe[t] = v;
+    } else if (t >= 8 && t < 8 + H + 1) {
+        int l = t - 8;
+        double v = dadd(dadd(sh->w_ac[0][l], sh->w_ac[1][l]), dadd(sh->w_ac[2][l], sh->w_ac[3][l]));
+        if (wasted) v *= 1.0 / (double)(1ull << (2 * wasted));
+        st->ac[l] = v;
+    } else if (t == 31) {
+        uint32_t tb = 0;
+        if (mode == 3) for (int w = 0; w < kEncWarps; ++w) tb |= sh->w_bad[w];
+        st->mode = mode; st->wasted = wasted; st->mn = a >> wasted; st->mx = b >> wasted; st->bad = tb; st->pad = 0;
+    }
+    sync();   // the partials are reused by the next channel
+}
+
+// One CTA: every channel of (stream, frame) ticket g.
+template <int H>
+FA_D void analyze_frame_cta(const EncParams& P, uint32_t g, AnShared* sh) {
+    const int64_t s = (int64_t)(g / (uint32_t)P.nframes);
+    const int f = (int)(g % (uint32_t)P.nframes);
+    const int64_t samp0 = (int64_t)f * P.blocksize;
+    const int bs = (int)((P.stream_size - samp0) < P.blocksize ? (P.stream_size - samp0) : P.blocksize);
+    FrameStats* st = P.stats + (size_t)(g - P.g_begin) * P.nch;
+    if (bs < 64) {
+        if (tid() < P.nch) st[tid()].mode = 0;
+        return;
+    }
+    FrameSrc S;
+    S.dtype = P.dtype; S.bs = bs;
+    S.off32 = 0.f; S.gain32 = 0.f; S.off64 = 0.; S.gain64 = 0.;
+    if (P.dtype == kF32) { S.off32 = ((const float*)P.offsets)[s]; S.gain32 = ((const float*)P.gains)[s]; }
+    if (P.dtype == kF64) { S.off64 = ((const double*)P.offsets)[s]; S.gain64 = ((const double*)P.gains)[s]; }
+    const int esize = (P.dtype == kI32 || P.dtype == kF32) ? 4 : 8;
+    S.base = (const unsigned char*)P.data + (s * P.stream_size + samp0) * esize;
+    S.vec = (((uintptr_t)S.base) & 15) == 0;
+    for (int c = 0; c < P.nch; ++c) {
+        if (bs == kMaxBs) analyze_channel<H, true>(P, sh, S, c, st + c);
+        else analyze_channel<H, false>(P, sh, S, c, st + c);
+    }
+}
+
+// One thread: the plan of (frame, channel) record i of the batch.
+FA_D void design_frame(const EncParams& P, int64_t i) {
+    const uint32_t g = P.g_begin + (uint32_t)(i / P.nch);
+    const int f = (int)(g % (uint32_t)P.nframes);
+    const int64_t samp0 = (int64_t)f * P.blocksize;
+    const int bs = (int)((P.stream_size - samp0) < P.blocksize ? (P.stream_size - samp0) : P.blocksize);
+    const FrameStats& st = P.stats[i];
+    FramePlan pl;
+    memset(&pl, 0, sizeof(pl));
+    pl.mode = (uint8_t)st.mode;
+    if (bs == kMaxBs && st.mode >= 2 && (P.max_porder < 2 || P.max_porder > 7)) pl.mode = 0;   // (no preset does this)
+    if (pl.mode >= 2) {
+        DesignIO d;
+        for (int k = 0; k < 5; ++k) d.t_fe[k] = st.fe[k];
+        for (int l = 0; l <= kMaxOrd; ++l) d.t_ac[l] = l <= P.max_lpc_order ? st.ac[l] : 0.0;
+        const int bps = 32 - st.wasted;
+        const int level_maxp = fast_level_maxp(bs, P.max_porder);
+        uint32_t maxabs = 0;
+        if (st.mode == 2) maxabs = (uint32_t)(-(int64_t)st.mn > (int64_t)st.mx ? -(int64_t)st.mn : (int64_t)st.mx);
+        design_fixed(&d, bs, bps, st.bad, level_maxp);
+        design_lpc(&d, bs, bps, P.max_lpc_order, P.qlp_precision, level_maxp, maxabs);
+        pl.wasted = (uint8_t)st.wasted;
+        pl.ok0 = (uint8_t)d.cand_ok[0];
+        pl.ok1 = (uint8_t)d.cand_ok[1];
+        pl.ord0 = (uint8_t)d.cand[0].order;
+        pl.maxp0 = (uint8_t)d.maxp[0];
+        if (d.cand_ok[1]) {
+            pl.ord1 = (uint8_t)d.cand[1].order;
+            pl.shift1 = (uint8_t)d.cand[1].shift;
+            pl.prec1 = (uint8_t)d.cand[1].prec;
+            pl.wide1 = (uint8_t)d.cand[1].wide;
+            pl.maxp1 = (uint8_t)d.maxp[1];
+            for (int j = 0; j < kMaxOrd; ++j) pl.qlp[j] = (int16_t)d.cand[1].qlp[j];
         }
-        sync();
+    }
+    P.plans[i] = pl;
+}
+
+// residuals of a fixed predictor by repeated differences (order <= 4 subtractions per sample)
+template <int H>
+FA_D void fixed_residual32(int order, const int32_t* xw, int32_t* r) {
+    uint32_t p1 = (uint32_t)xw[H - 1] - (uint32_t)xw[H - 2];
+    uint32_t p1b = (uint32_t)xw[H - 2] - (uint32_t)xw[H - 3];
+    uint32_t p1c = (uint32_t)xw[H - 3] - (uint32_t)xw[H - 4];
+    uint32_t p2 = p1 - p1b, p2b = p1b - p1c;
+    uint32_t p3 = p2 - p2b;
+#pragma unroll
+    for (int j = 0; j < kSpt; ++j) {
+        uint32_t d0 = (uint32_t)xw[H + j];
+        uint32_t d1 = d0 - (uint32_t)xw[H + j - 1];
+        uint32_t d2 = d1 - p1, d3 = d2 - p2, d4 = d3 - p3;
+        p1 = d1; p2 = d2; p3 = d3;
+        r[j] = (int32_t)(order == 0 ? d0 : order == 1 ? d1 : order == 2 ? d2 : order == 3 ? d3 : d4);
+    }
+}
+
+template <int H, bool FULL>
+FA_D bool enc_channel_fast(const EncParams& P, EncCtx& X, const FrameSrc& S, int c, int f, uint32_t g, int bitpos0,
+                           int& bitpos_end) {
+    EncShared* sh = X.sh;
+    uint32_t* out = X.out;
+    const int t = tid();
+    const int ln = lane(), wp = warp();
+    const int bs = FULL ? kMaxBs : S.bs;
+    const int i0 = t * kSpt;
+    const int nvalid = FULL ? kSpt : (bs - i0 >= kSpt ? kSpt : (bs > i0 ? bs - i0 : 0));
+    // ---- the plan of this (frame, channel): three broadcast loads, decoded in registers
+    const unsigned char* pp = (const unsigned char*)(P.plans + ((size_t)(g - P.g_begin) * P.nch + c));
+    const U4 pa = ldg128(pp), pb = ldg128(pp + 16), pc = ldg128(pp + 32);
+    const int mode = (int)(pa.x & 0xFFu);
+    if (mode == 0) return false;
+    const int wasted = (int)((pa.x >> 8) & 0xFFu);
+    const int bps = 32 - wasted;
+    const int ok0 = (int)((pa.x >> 16) & 0xFFu), ok1 = (int)(pa.x >> 24);
+    const int ord0 = (int)(pa.y & 0xFFu), ord1 = (int)((pa.y >> 8) & 0xFFu);
+    const int shift1 = (int)((pa.y >> 16) & 0xFFu), prec1 = (int)(pa.y >> 24);
+    const int wide1 = (int)(pa.z & 0xFFu), maxp0 = (int)((pa.z >> 8) & 0xFFu), maxp1 = (int)((pa.z >> 16) & 0xFFu);
+    const bool wide = mode == 3;
+    int32_t xw[H + kSpt];
+    load_chunk<H, FULL>(S, c, t, xw);
+    const bool retiring = !X.retired;
+    if (wp == 3 && retiring) retire_lookback(P, sh);   // previous frame: overlaps the loads above
+
+    if (mode == 1) {
+        if (retiring) {
+            sync();
+            retire_copyout(P, X);
+            sync();
+            if (t == 0) retire_crc(P, sh);
+            X.retired = true;
+        }
+        bitpos_end = bitpos0 + (c == 0 ? 8 * frame_header_bytes(bs, f) : 0) + subframe_header_bits(0, 0, 0, 32, 0);
+        if (t == 0) {
+            if (c == P.nch - 1) publish_aggregate(P, g, f, bitpos_end);
+            Pk pk;
+            pk_begin(pk, out, bitpos0);
+            if (c == 0) emit_frame_header(pk, sh->crc8, bs, f, P.nch);
+            emit_subframe_header(pk, 0, 0, 0);
+            emit_sample(pk, xw[H], 32);
+            pk_end(pk, sh->tail_val[c][0], sh->tail_word[c][0]);
+        }
+        return true;
+    }
+    if (wasted) {
+#pragma unroll
+        for (int i = 0; i < H + kSpt; ++i) xw[i] >>= wasted;
     }
 
     // ---- pass 2: per-chunk sums of |residual| for both candidates
     const int js = (t == 0) ? 0 : -1;   // thread 0 skips its first `order` samples (warm-up)
     int32_t r[kSpt];
-    const int ok0 = sh->cand_ok[0], ok1 = sh->cand_ok[1];
-    const int ord0 = sh->cand[0].order;
-    if (ok0 && wide) {
-        int32_t cf[H];
-        fixed_coefs(ord0, cf, H);
-        uint32_t fitmask = residual64<H>(ord0, xw, cf, 0, r);
-        unsigned long long asum = 0;
+    if (t < 2) sh->cand_ok[t] = t == 0 ? ok0 : ok1;
+    if (ok0) {
+        unsigned long long asum;
+        if (!wide) {
+            fixed_residual32<H>(ord0, xw, r);
+            uint32_t a32 = 0;
 #pragma unroll
-        for (int j = 0; j < kSpt; ++j)
-            if ((j >= H || js < 0 || j >= ord0) && (FULL || j < nvalid))
-                asum += (unsigned long long)(r[j] < 0 ? -(int64_t)r[j] : (int64_t)r[j]);
-        uint32_t vmask = nvalid >= 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
-        if (t == 0) vmask &= ~((1u << ord0) - 1u);
-        if ((fitmask & vmask) != vmask) asum = ~0ull;
-        sh->csum[0][t] = asum;
-    } else if (ok0) {
-        uint32_t sel = ord0 == 0 ? fe0 : ord0 == 1 ? fe1 : ord0 == 2 ? fe2 : ord0 == 3 ? fe3 : fe4;
-        if (t == 0) {
-            // samples order..3 belong to the residual but not to libFLAC's selection sums
-            int32_t cf[4];
-            fixed_coefs(ord0, cf, 4);
-            for (int j = ord0; j < 4; ++j) {
-                int32_t pred = 0;
-                for (int m = 0; m < ord0; ++m) pred += cf[m] * xw[H + j - 1 - m];
-                sel = sad_acc(xw[H + j], pred, sel);
-            }
+            for (int j = 0; j < kSpt; ++j)
+                if ((j >= H || js < 0 || j >= ord0) && (FULL || j < nvalid)) a32 = sad_acc(r[j], 0, a32);
+            asum = a32;
+        } else {
+            int32_t cf[H];
+            fixed_coefs(ord0, cf, H);
+            uint32_t fitmask = residual64<H>(ord0, xw, cf, 0, r);
+            asum = 0;
+#pragma unroll
+            for (int j = 0; j < kSpt; ++j)
+                if ((j >= H || js < 0 || j >= ord0) && (FULL || j < nvalid))
+                    asum += (unsigned long long)(r[j] < 0 ? -(int64_t)r[j] : (int64_t)r[j]);
+            uint32_t vmask = nvalid >= 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
+            if (t == 0) vmask &= ~((1u << ord0) - 1u);
+            if ((fitmask & vmask) != vmask) asum = ~0ull;
         }
-        sh->csum[0][t] = sel;
+        sh->csum[0][t] = asum;
     }
-    int ord1 = 0, shift1 = 0, wide1 = 0;
-    if (ok1) {
-        const Plan& pl = sh->cand[1];
-        ord1 = pl.order; shift1 = pl.shift; wide1 = pl.wide;
-        int32_t coef[H];
+    int32_t coef[H];
+    {
+        const uint32_t qw[8] = {pb.x, pb.y, pb.z, pb.w, pc.x, pc.y, pc.z, pc.w};
 #pragma unroll
-        for (int m = 0; m < H; ++m) coef[m] = pl.qlp[m];
+        for (int m = 0; m < H; ++m) coef[m] = (int32_t)(int16_t)(uint16_t)(qw[m >> 1] >> (16 * (m & 1)));
+    }
+    if (ok1) {
         unsigned long long asum = 0;
         if (!wide1) {
             residual32_dispatch<H>(ord1, xw, coef, shift1, r);
@@ -1161,15 +1356,11 @@ FA_D bool enc_channel_fast(const EncParams& P, EncCtx& X, const FrameSrc& S, int
         }
         sh->csum[1][t] = asum;
     }
-    sync();   // B3
-    if (retiring) {
-        if (t == 0) retire_crc(P, sh);
-        zero_out(X);     // ordered before the packing below by B4 and B5
-        X.retired = true;
-    }
+    sync();   // B3: chunk sums, cand_ok and (retiring) the byte offset of the previous frame are visible
+    if (retiring) retire_copyout(P, X);   // previous frame: CRC partials + copy to HBM
     if (wp < 2 && sh->cand_ok[wp]) {
         const int cd = wp;
-        const int maxp = sh->maxp[cd];
+        const int maxp = cd == 0 ? maxp0 : maxp1;
         const int cpp = FULL ? (kEncThreads >> maxp) : (maxp > 0 ? ((bs >> maxp) >> 5) : kEncThreads);   // chunks per finest partition
         bool poisoned = false;
         for (int part = ln; part < (1 << maxp); part += 32) {
@@ -1186,10 +1377,14 @@ FA_D bool enc_channel_fast(const EncParams& P, EncCtx& X, const FrameSrc& S, int
             syncwarp();
         } else {
             syncwarp();
-            rice_search_warp(sh, cd, bs, sh->cand[cd].order, maxp);
+            rice_search_warp(sh, cd, bs, cd == 0 ? ord0 : ord1, maxp);
         }
     }
     sync();   // B4
+    if (retiring) {
+        if (t == 0) retire_crc(P, sh);
+        X.retired = true;    // the copy-out (before B4) is ordered before the packing below by B5
+    }
     // ---- every thread: pick the winner (stream_encoder.c process_subframe_: smallest estimate wins)
     const uint32_t verbatim_bits = (uint32_t)bps * (uint32_t)bs;
     int win = -1;
@@ -1197,19 +1392,23 @@ FA_D bool enc_channel_fast(const EncParams& P, EncCtx& X, const FrameSrc& S, int
         uint32_t best = verbatim_bits;
         for (int cd = 0; cd < 2; ++cd) {
             if (!sh->cand_ok[cd]) continue;
-            const Plan& pl = sh->cand[cd];
-            uint32_t bits = (uint32_t)pl.order * (uint32_t)bps + pl.res_bits + (cd == 1 ? 9u + (uint32_t)pl.order * (uint32_t)pl.prec : 0u);
+            const uint32_t ord = (uint32_t)(cd == 0 ? ord0 : ord1);
+            uint32_t bits = ord * (uint32_t)bps + sh->cand[cd].res_bits + (cd == 1 ? 9u + ord * (uint32_t)prec1 : 0u);
             if (bits < best) { best = bits; win = cd; }
         }
     }
-    if (win < 0) return false;
-    const Plan& pl = sh->cand[win];
-    const int order = pl.order, porder = pl.porder, plen = pl.rice2 ? 5 : 4;
+    // (block-uniform; the barrier keeps the general path's writes to sh->cand behind the reads above)
+    if (win < 0) { sync(); return false; }
+    const int order = win == 0 ? ord0 : ord1;
+    const int porder = sh->cand[win].porder, rice2 = sh->cand[win].rice2, plen = rice2 ? 5 : 4;
     if (win == 0) {
-        int32_t cf[H];
-        fixed_coefs(order, cf, H);
-        if (wide) (void)residual64<H>(order, xw, cf, 0, r);
-        else residual32_dispatch<H>(order, xw, cf, 0, r);
+        if (wide) {
+            int32_t cf[H];
+            fixed_coefs(order, cf, H);
+            (void)residual64<H>(order, xw, cf, 0, r);
+        } else {
+            fixed_residual32<H>(order, xw, r);
+        }
     }
     // ---- exact code lengths of the chunk, block scan
     int part;
@@ -1256,7 +1455,8 @@ FA_D bool enc_channel_fast(const EncParams& P, EncCtx& X, const FrameSrc& S, int
     }
     const uint32_t excl = wbase + inc - lens;
     const int ptype = win == 0 ? 2 : 3;
-    const int hdr_bits = subframe_header_bits(ptype, order, wasted, bps, pl.prec);
+    const int prec = win == 0 ? 0 : prec1;
+    const int hdr_bits = subframe_header_bits(ptype, order, wasted, bps, prec);
     if ((uint32_t)hdr_bits + total >= verbatim_bits + 8u) return false;   // VERBATIM is smaller: general path
     const int sub0 = bitpos0 + (c == 0 ? 8 * frame_header_bytes(bs, f) : 0);
     const int body0 = sub0 + hdr_bits;
@@ -1267,11 +1467,15 @@ FA_D bool enc_channel_fast(const EncParams& P, EncCtx& X, const FrameSrc& S, int
     if (t == 0) {
         if (c == P.nch - 1) publish_aggregate(P, g, f, bitpos_end);
         pk_begin(pk, out, bitpos0);
-        if (c == 0) emit_frame_header(pk, P.crc, bs, f, P.nch);
+        if (c == 0) emit_frame_header(pk, sh->crc8, bs, f, P.nch);
         emit_subframe_header(pk, ptype, order, wasted);
         for (int j = 0; j < order; ++j) emit_sample(pk, xw[H + j], bps);
-        if (ptype == 3) emit_lpc_params(pk, pl);
-        pk_emit(pk, (uint32_t)pl.rice2, 2);
+        if (ptype == 3) {
+            pk_emit(pk, (uint32_t)(prec1 - 1), 4);
+            pk_emit(pk, (uint32_t)shift1 & 31u, 5);
+            for (int j = 0; j < order; ++j) pk_emit(pk, (uint32_t)coef[j] & ((1u << prec1) - 1u), prec1);
+        }
+        pk_emit(pk, (uint32_t)rice2, 2);
         pk_emit(pk, (uint32_t)porder, 4);
     } else {
         pk_begin(pk, out, body0 + (int)excl);
@@ -1323,6 +1527,504 @@ FA_D bool enc_channel_fast(const EncParams& P, EncCtx& X, const FrameSrc& S, int
     return true;
 }
 
+// short frames (the last frame of a stream, blocksize-1152 levels): the generic variant, out of line
+// (by value: a by-reference context would force the hot path's copy of it into local memory)
+template <int H>
+FA_DNOINL int enc_channel_short(const EncParams P, EncCtx X, const FrameSrc S, int c, int f, uint32_t g, int bitpos0) {
+    int bitpos_end = -1;
+    bool done = enc_channel_fast<H, false>(P, X, S, c, f, g, bitpos0, bitpos_end);
+    if (!done) {
+        // the short path has retired the previous frame before giving up
+        X.retired = true;
+        return -1;
+    }
+    return bitpos_end;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Full 4096-sample frames: the hot path.  Written as ROLLED loops over sub-blocks of 8 samples so that
+// the instruction stream of a frame fits the instruction caches (the fully unrolled predecessor was
+// instruction-fetch bound: 39 k SASS instructions, 18 % of the stall samples "no instruction"), which
+// also keeps the register count low enough for 5-6 resident CTAs per SM.  Residuals are parked in
+// shared memory (transposed: conflict-free) between the statistics, length and packing passes; the
+// Rice parameters come from shuffles inside the 2^(7 - max_porder) threads that share a finest
+// partition, and the partition order is chosen between the level's maximum and 0.  Three barriers per
+// (frame, channel): chunk statistics (B3), bit-offset scan (B5), and the ticket barrier of the CTA loop.
+// ------------------------------------------------------------------------------------------------------
+// Rice parameter and estimated bits of one partition (libFLAC set_partitioned_rice_, estimate mode)
+FA_D uint32_t rice_estimate(unsigned long long sum, uint32_t n, int& k_out) {
+    int k = 0;
+    if (sum > n) {
+        k = (64 - clz64(sum - 1)) - (32 - clz32(n));
+        if (k < 0) k = 0;
+        if (k < 30 && ((unsigned long long)n << k) < sum) k++;
+        if (k < 30 && ((unsigned long long)n << k) < sum) k++;
+        if (k > 30) k = 30;
+    }
+    k_out = k;
+    unsigned long long pb = 4ull + (unsigned long long)(1 + k) * n + (k ? (sum >> (k - 1)) : (sum << 1));
+    pb -= (n >> 1);
+    return pb > (1ull << 25) ? (1u << 25) : (uint32_t)pb;
+}
+
+// 8 consecutive samples of channel c starting at in-frame sample i (a multiple of 8, inside the frame)
+FA_D void load8(const FrameSrc& S, int c, int i, int32_t* x) {
+    if (S.dtype == kI32 || S.dtype == kF32) {
+        const uint32_t* p = (const uint32_t*)S.base + i;
+        U4 a, b;
+        if (S.vec) { a = ldg128(p); b = ldg128(p + 4); }
+        else {
+            a.x = ldg32(p); a.y = ldg32(p + 1); a.z = ldg32(p + 2); a.w = ldg32(p + 3);
+            b.x = ldg32(p + 4); b.y = ldg32(p + 5); b.z = ldg32(p + 6); b.w = ldg32(p + 7);
+        }
+        uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        if (S.dtype == kF32) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float fv;
+                memcpy(&fv, &v[q], 4);
+                v[q] = (uint32_t)quant_f32(fv, S.off32, S.gain32);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) x[q] = (int32_t)v[q];
+    } else {
+        const unsigned long long* p = (const unsigned long long*)S.base + i;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            unsigned long long e0, e1;
+            if (S.vec) {
+                U4 v = ldg128(p + 2 * q);
+                e0 = ((unsigned long long)v.y << 32) | v.x;
+                e1 = ((unsigned long long)v.w << 32) | v.z;
+            } else {
+                e0 = p[2 * q];
+                e1 = p[2 * q + 1];
+            }
+            if (S.dtype == kF64) {
+                double d0, d1;
+                memcpy(&d0, &e0, 8); memcpy(&d1, &e1, 8);
+                e0 = (unsigned long long)quant_f64(d0, S.off64, S.gain64);
+                e1 = (unsigned long long)quant_f64(d1, S.off64, S.gain64);
+            }
+            x[2 * q] = c == 0 ? (int32_t)(uint32_t)e0 : (int32_t)(uint32_t)(e0 >> 32);
+            x[2 * q + 1] = c == 0 ? (int32_t)(uint32_t)e1 : (int32_t)(uint32_t)(e1 >> 32);
+        }
+    }
+}
+
+// LPC residuals of 8 samples: w[0 .. H) = history, w[H .. H + 8) = the samples
+template <int H, int ORD>
+FA_D void lpc8(const int32_t* w, const int32_t* coef, int shift, int32_t* r) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int32_t sum = 0;
+#pragma unroll
+        for (int m = 0; m < ORD; ++m) sum += coef[m] * w[H + i - 1 - m];
+        r[i] = w[H + i] - (sum >> shift);
+    }
+}
+template <int H>
+FA_D void lpc8_dispatch(int order, const int32_t* w, const int32_t* coef, int shift, int32_t* r) {
+    switch (order) {
+    case 1: lpc8<H, 1>(w, coef, shift, r); break;
+    case 2: lpc8<H, 2>(w, coef, shift, r); break;
+    case 3: lpc8<H, 3>(w, coef, shift, r); break;
+    case 4: lpc8<H, 4>(w, coef, shift, r); break;
+    case 5: lpc8<H, 5>(w, coef, shift, r); break;
+    case 6: lpc8<H, 6>(w, coef, shift, r); break;
+    case 7: lpc8<H, 7>(w, coef, shift, r); break;
+    case 8: lpc8<H, 8>(w, coef, shift, r); break;
+    default:
+        if constexpr (H > 8) {
+            switch (order) {
+            case 9: lpc8<H, 9>(w, coef, shift, r); break;
+            case 10: lpc8<H, 10>(w, coef, shift, r); break;
+            case 11: lpc8<H, 11>(w, coef, shift, r); break;
+            default: lpc8<H, 12>(w, coef, shift, r); break;
+            }
+        } else {
+            lpc8<H, 0>(w, coef, shift, r);
+        }
+        break;
+    }
+}
+// 64-bit accumulation; bit i of the result is CLEAR when residual i does not fit the Rice coder
+template <int H>
+FA_D uint32_t lpc8_wide(const int32_t* w, const int32_t* coef, int shift, int32_t* r) {
+    uint32_t ok = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int64_t sum = 0;
+#pragma unroll
+        for (int m = 0; m < H; ++m) sum += (int64_t)coef[m] * (int64_t)w[H + i - 1 - m];   // coef[m] = 0 beyond the order
+        int64_t v = (int64_t)w[H + i] - (sum >> shift);
+        if (fits_res(v)) ok |= 1u << i;
+        r[i] = (int32_t)v;
+    }
+    return ok;
+}
+
+// Pass 2 of a full frame: the thread's 32 samples in 4 rolled sub-blocks of 8.  do0 / do1: accumulate the
+// sum |residual| of the fixed / LPC candidate into s0 / s1; the LPC residual (do1) or else the fixed one
+// is parked in res[j * 128 + t].  Thread 0 leaves its warm-up samples out of the sums.
+template <int H>
+FA_D void full_pass2(const FrameSrc& S, int c, int t, int wasted, bool wide, bool do0, int ord0, bool do1, int ord1,
+                     const int32_t* coef, int shift1, bool wide1, int32_t* res, unsigned long long& s0_out,
+                     unsigned long long& s1_out, bool& fit0, bool& fit1) {
+    int32_t w[H + 8];
+    // history: the H samples before the chunk (zeros for thread 0)
+    if (t == 0) {
+#pragma unroll
+        for (int i = 0; i < H; ++i) w[i] = 0;
+    } else {
+        if (H == 8) {
+            load8(S, c, t * kSpt - 8, w);
+        } else {
+            int32_t tmp[16];
+            load8(S, c, t * kSpt - 16, tmp);
+            load8(S, c, t * kSpt - 8, tmp + 8);
+#pragma unroll
+            for (int i = 0; i < H; ++i) w[i] = tmp[16 - H + i];
+        }
+        if (wasted) {
+#pragma unroll
+            for (int i = 0; i < H; ++i) w[i] >>= wasted;
+        }
+    }
+    int32_t cf[H];
+    fixed_coefs(ord0, cf, H);
+    const int skip0 = t == 0 ? ord0 : 0, skip1 = t == 0 ? ord1 : 0;
+    uint32_t a0 = 0, a1 = 0;                 // narrow sums
+    unsigned long long b0 = 0, b1 = 0;       // wide sums
+    uint32_t bad0 = 0, bad1 = 0;
+    // running differences of the fixed predictors (narrow path)
+    uint32_t p1 = (uint32_t)w[H - 1] - (uint32_t)w[H - 2];
+    uint32_t p1b = (uint32_t)w[H - 2] - (uint32_t)w[H - 3];
+    uint32_t p1c = (uint32_t)w[H - 3] - (uint32_t)w[H - 4];
+    uint32_t p2 = p1 - p1b, p2b = p1b - p1c;
+    uint32_t p3 = p2 - p2b;
+    int32_t nx[8];                            // next sub-block, in flight while the current one is processed
+    load8(S, c, t * kSpt, nx);
+#pragma unroll 1
+    for (int it = 0; it < kSpt / 8; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[H + i] = nx[i];
+        if (it + 1 < kSpt / 8) load8(S, c, t * kSpt + (it + 1) * 8, nx);
+        if (wasted) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[H + i] >>= wasted;
+        }
+        const int sk0 = skip0 - it * 8, sk1 = skip1 - it * 8;
+        int32_t r[8];
+        if (do0) {
+            if (!wide) {
+                // order-k residual = k-th running difference (the lower differences are carried anyway)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    uint32_t d0 = (uint32_t)w[H + i];
+                    uint32_t d1 = d0 - (uint32_t)w[H + i - 1];
+                    uint32_t d2 = d1 - p1, d3 = d2 - p2, d4 = d3 - p3;
+                    p1 = d1; p2 = d2; p3 = d3;
+                    r[i] = (int32_t)d4;
+                    if (ord0 < 4) r[i] = (int32_t)(ord0 == 0 ? d0 : ord0 == 1 ? d1 : ord0 == 2 ? d2 : d3);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (i >= sk0) a0 = sad_acc(r[i], 0, a0);
+            } else {
+                uint32_t ok = lpc8_wide<H>(w, cf, 0, r);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (i >= sk0) {
+                        b0 += (unsigned long long)(r[i] < 0 ? -(int64_t)r[i] : (int64_t)r[i]);
+                        if (!((ok >> i) & 1u)) bad0 = 1;
+                    }
+            }
+            if (!do1) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) res[(it * 8 + i) * kEncThreads + t] = i >= sk0 ? r[i] : w[H + i];   // warm-up: the sample
+            }
+        }
+        if (do1) {
+            if (!wide1) {
+                lpc8_dispatch<H>(ord1, w, coef, shift1, r);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (i >= sk1) a1 = sad_acc(r[i], 0, a1);
+            } else {
+                uint32_t ok = lpc8_wide<H>(w, coef, shift1, r);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (i >= sk1) {
+                        b1 += (unsigned long long)(r[i] < 0 ? -(int64_t)r[i] : (int64_t)r[i]);
+                        if (!((ok >> i) & 1u)) bad1 = 1;
+                    }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) res[(it * 8 + i) * kEncThreads + t] = i >= sk1 ? r[i] : w[H + i];       // warm-up: the sample
+        }
+#pragma unroll
+        for (int i = 0; i < H; ++i) w[i] = w[8 + i];
+    }
+    s0_out = wide ? b0 : (unsigned long long)a0;
+    s1_out = wide1 ? b1 : (unsigned long long)a1;
+    fit0 = bad0 == 0;
+    fit1 = bad1 == 0;
+}
+
+#if defined(FAB_PHASE_TIMING) && defined(__CUDACC__)
+#define FAB_TICK(k) do { long long now_ = clock64(); X.ph[k] += now_ - X.last; X.last = now_; } while (0)
+#else
+#define FAB_TICK(k) do { } while (0)
+#endif
+
+template <int H>
+FA_D bool enc_channel_full(const EncParams& P, EncCtx& X, const FrameSrc& S, int c, int f, uint32_t g, int bitpos0,
+                           int& bitpos_end) {
+    EncShared* sh = X.sh;
+    uint32_t* out = X.out;
+    int32_t* res = X.res;
+    const int t = tid();
+    const int ln = lane(), wp = warp();
+    constexpr int bs = kMaxBs;
+    // ---- the plan of this (frame, channel): three broadcast loads, decoded in registers
+    const unsigned char* pp = (const unsigned char*)(P.plans + ((size_t)(g - P.g_begin) * P.nch + c));
+    const U4 pa = ldg128(pp), pb = ldg128(pp + 16), pc = ldg128(pp + 32);
+    const int mode = (int)(pa.x & 0xFFu);
+    if (mode == 0) return false;
+    const int wasted = (int)((pa.x >> 8) & 0xFFu);
+    const int bps = 32 - wasted;
+    const int ok0 = (int)((pa.x >> 16) & 0xFFu), ok1 = (int)(pa.x >> 24);
+    const int ord0 = (int)(pa.y & 0xFFu), ord1 = (int)((pa.y >> 8) & 0xFFu);
+    const int shift1 = (int)((pa.y >> 16) & 0xFFu), prec1 = (int)(pa.y >> 24);
+    const bool wide = mode == 3;
+    const bool wide1 = wide || (pa.z & 0xFFu) != 0;
+    const bool retiring = !X.retired;
+    FAB_TICK(1);
+    if (wp == 3 && retiring) retire_lookback(P, sh);   // previous frame
+    FAB_TICK(2);
+
+    if (mode == 1) {
+        if (retiring) {
+            sync();
+            retire_copyout(P, X);
+            sync();
+            if (t == 0) retire_crc(P, sh);
+            X.retired = true;
+        }
+        bitpos_end = bitpos0 + (c == 0 ? 8 * frame_header_bytes(bs, f) : 0) + subframe_header_bits(0, 0, 0, 32, 0);
+        if (t == 0) {
+            if (c == P.nch - 1) publish_aggregate(P, g, f, bitpos_end);
+            Pk pk;
+            pk_begin(pk, out, bitpos0);
+            if (c == 0) emit_frame_header(pk, sh->crc8, bs, f, P.nch);
+            emit_subframe_header(pk, 0, 0, 0);
+            emit_sample(pk, src_sample(S, c, 0), 32);
+            pk_end(pk, sh->tail_val[c][0], sh->tail_word[c][0]);
+        }
+        return true;
+    }
+    int32_t coef[H];
+    {
+        const uint32_t qw[8] = {pb.x, pb.y, pb.z, pb.w, pc.x, pc.y, pc.z, pc.w};
+#pragma unroll
+        for (int m = 0; m < H; ++m) coef[m] = (int32_t)(int16_t)(uint16_t)(qw[m >> 1] >> (16 * (m & 1)));
+    }
+
+    // ---- pass 2: sum |residual| of the chunk for both candidates; the LPC residual (or the fixed one when
+    //      there is no LPC candidate) is parked in shared memory
+    unsigned long long s0 = 0, s1 = 0;
+    bool fit0 = true, fit1 = true;
+    full_pass2<H>(S, c, t, wasted, wide, ok0 != 0, ord0, ok1 != 0, ord1, coef, shift1, wide1, res, s0, s1, fit0, fit1);
+    FAB_TICK(3);
+
+    // ---- finest partitions: 2^gsh consecutive threads each; sums by butterfly, parameters and estimated
+    //      bits computed redundantly by every thread of the group
+    const int maxp = P.max_porder;
+    const int gsh = 7 - maxp;
+    unsigned long long g0 = s0, g1 = s1;
+    for (int m = 1; m < (1 << gsh); m <<= 1) {
+        g0 += shfl_xor_u64(g0, m);
+        g1 += shfl_xor_u64(g1, m);
+    }
+    const int part = t >> gsh;
+    const bool leader = (t & ((1 << gsh) - 1)) == 0;
+    const uint32_t npart0 = (uint32_t)(bs >> maxp) - (part == 0 ? (uint32_t)ord0 : 0u);
+    const uint32_t npart1 = (uint32_t)(bs >> maxp) - (part == 0 ? (uint32_t)ord1 : 0u);
+    int kf0 = 0, kf1 = 0;
+    const uint32_t e0 = rice_estimate(g0, npart0, kf0), e1 = rice_estimate(g1, npart1, kf1);
+    {
+        const uint32_t b0 = redux_add(leader ? e0 : 0u), b1 = redux_add(leader ? e1 : 0u);
+        const unsigned long long t0s = warp_sum_u64(s0), t1s = warp_sum_u64(s1);
+        const uint32_t f0 = (ballot(!fit0) ? 1u : 0u) | (ballot(kf0 >= 15) ? 2u : 0u);
+        const uint32_t f1 = (ballot(!fit1) ? 1u : 0u) | (ballot(kf1 >= 15) ? 2u : 0u);
+        if (ln == 0) {
+            sh->x_bits[0][wp] = b0; sh->x_bits[1][wp] = b1;
+            sh->x_sum[0][wp] = t0s; sh->x_sum[1][wp] = t1s;
+            sh->x_flag[0][wp] = f0; sh->x_flag[1][wp] = f1;
+        }
+    }
+    FAB_TICK(4);
+    sync();   // B3: the partials and (retiring) the byte offset of the previous frame are visible
+    FAB_TICK(5);
+    if (retiring) retire_copyout(P, X);   // previous frame: CRC partials + copy to HBM
+    FAB_TICK(6);
+
+    // ---- every thread: partition order (maximum or 0) and winner (smallest estimate, stream_encoder.c
+    //      process_subframe_); all inputs are block-uniform
+    const uint32_t verbatim_bits = (uint32_t)bps * (uint32_t)bs;
+    int win = -1, porder = 0, kwin = 0, rice2 = 0;
+    {
+        uint32_t best = verbatim_bits;
+#pragma unroll
+        for (int cd = 0; cd < 2; ++cd) {
+            if (!(cd == 0 ? ok0 : ok1)) continue;
+            uint32_t bits_hi = 0, flag = 0;
+            unsigned long long tot = 0;
+#pragma unroll
+            for (int w = 0; w < kEncWarps; ++w) { bits_hi += sh->x_bits[cd][w]; tot += sh->x_sum[cd][w]; flag |= sh->x_flag[cd][w]; }
+            if (flag & 1u) continue;                       // a residual does not fit the Rice coder
+            const uint32_t ord = (uint32_t)(cd == 0 ? ord0 : ord1);
+            int k0 = 0;
+            uint32_t bits_lo = rice_estimate(tot, (uint32_t)bs - ord, k0);
+            bits_lo += 6u + (k0 >= 15 ? 1u : 0u);
+            bits_hi += 6u + ((flag & 2u) ? (1u << maxp) : 0u);
+            const bool use_hi = bits_hi < bits_lo;
+            const uint32_t res_bits = use_hi ? bits_hi : bits_lo;
+            const uint32_t bits = ord * (uint32_t)bps + res_bits + (cd == 1 ? 9u + ord * (uint32_t)prec1 : 0u);
+            if (bits < best) {
+                best = bits; win = cd;
+                porder = use_hi ? maxp : 0;
+                kwin = use_hi ? (cd == 0 ? kf0 : kf1) : k0;
+                rice2 = use_hi ? ((flag & 2u) ? 1 : 0) : (k0 >= 15 ? 1 : 0);
+            }
+        }
+    }
+    if (win < 0) {            // (block-uniform) nothing beats VERBATIM: general path
+        sync();
+        if (retiring) { if (t == 0) retire_crc(P, sh); X.retired = true; }
+        return false;
+    }
+    const int order = win == 0 ? ord0 : ord1;
+    const int plen = rice2 ? 5 : 4;
+    const int k = kwin;
+    const int skip = t == 0 ? order : 0;
+    if (win == 0 && ok1) {
+        // the fixed predictor won but the parked residual is the LPC one: redo the fixed pass (L1/L2 hits)
+        unsigned long long d0, d1;
+        bool q0, q1;
+        full_pass2<H>(S, c, t, wasted, wide, true, ord0, false, 0, coef, 0, false, res, d0, d1, q0, q1);
+    }
+    // ---- exact code lengths of the chunk, block scan
+    const bool part_start = porder == 0 ? t == 0 : leader;
+    uint32_t lens = part_start ? (uint32_t)plen : 0u;
+    uint32_t qmax = 0;
+#pragma unroll 8
+    for (int j = 0; j < kSpt; ++j) {
+        int32_t rv = res[j * kEncThreads + t];
+        uint32_t u = ((uint32_t)rv << 1) ^ (uint32_t)(rv >> 31);
+        uint32_t q = j >= skip ? (u >> k) : 0u;
+        lens += q;
+        qmax = q > qmax ? q : qmax;
+    }
+    lens += (uint32_t)(kSpt - skip) * (uint32_t)(k + 1);
+    uint32_t inc = lens;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t n = shfl_up(inc, d);
+        if (ln >= d) inc += n;
+    }
+    if (ln == 31) sh->scan[wp] = inc;
+    FAB_TICK(7);
+    sync();   // B5: also orders the copy-out of the previous frame before the packing stores below
+    FAB_TICK(8);
+    if (retiring) {
+        if (t == 0) retire_crc(P, sh);
+        X.retired = true;
+    }
+    uint32_t wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kEncWarps; ++w) {
+        uint32_t x = sh->scan[w];
+        if (w < wp) wbase += x;
+        total += x;
+    }
+    const uint32_t excl = wbase + inc - lens;
+    const int ptype = win == 0 ? 2 : 3;
+    const int prec = win == 0 ? 0 : prec1;
+    const int hdr_bits = subframe_header_bits(ptype, order, wasted, bps, prec);
+    if ((uint32_t)hdr_bits + total >= verbatim_bits + 8u) return false;   // VERBATIM is smaller: general path
+    const int sub0 = bitpos0 + (c == 0 ? 8 * frame_header_bytes(bs, f) : 0);
+    const int body0 = sub0 + hdr_bits;
+
+    // ---- pack
+    bitpos_end = body0 + (int)total;
+    Pk pk;
+    if (t == 0) {
+        if (c == P.nch - 1) publish_aggregate(P, g, f, bitpos_end);
+        pk_begin(pk, out, bitpos0);
+        if (c == 0) emit_frame_header(pk, sh->crc8, bs, f, P.nch);
+        emit_subframe_header(pk, ptype, order, wasted);
+        for (int j = 0; j < order; ++j) emit_sample(pk, res[j * kEncThreads], bps);   // thread 0 parked its warm-up samples
+        if (ptype == 3) {
+            pk_emit(pk, (uint32_t)(prec1 - 1), 4);
+            pk_emit(pk, (uint32_t)shift1 & 31u, 5);
+            for (int j = 0; j < order; ++j) {
+                int32_t cj = coef[0];
+#pragma unroll
+                for (int q = 1; q < H; ++q) cj = (q == j) ? coef[q] : cj;
+                pk_emit(pk, (uint32_t)cj & ((1u << prec1) - 1u), prec1);
+            }
+        }
+        pk_emit(pk, (uint32_t)rice2, 2);
+        pk_emit(pk, (uint32_t)porder, 4);
+    } else {
+        pk_begin(pk, out, body0 + (int)excl);
+    }
+    if (part_start) pk_emit(pk, (uint32_t)k, plen);
+    if (qmax + (uint32_t)k + 1u <= 32u) {
+        // every code of the chunk fits one emit: branch-free loop on a (hi, lo) register pair
+        uint32_t hi = (uint32_t)(pk.acc >> 32), lo = 0;
+        int fill = pk.fill, word = pk.word;
+        const uint32_t kbit = 1u << k, kmask = kbit - 1u;
+        const int k1 = k + 1;
+#pragma unroll 4
+        for (int j = 0; j < kSpt; ++j) {
+            int32_t rv = res[j * kEncThreads + t];
+            if (j >= skip) {
+                uint32_t u = ((uint32_t)rv << 1) ^ (uint32_t)(rv >> 31);
+                uint32_t low = (u & kmask) | kbit;
+                int len = (int)(u >> k) + k1;
+                uint64_t v = (uint64_t)low << (64 - fill - len);
+                hi |= (uint32_t)(v >> 32);
+                lo |= (uint32_t)v;
+                fill += len;
+                if (fill >= 32) {
+                    out[ow(word)] = hi;
+                    word++;
+                    hi = lo;
+                    lo = 0;
+                    fill -= 32;
+                }
+            }
+        }
+        pk.acc = (uint64_t)hi << 32;
+        pk.fill = fill;
+        pk.word = word;
+    } else {
+#pragma unroll 1
+        for (int j = skip; j < kSpt; ++j) {
+            int32_t rv = res[j * kEncThreads + t];
+            uint32_t u = ((uint32_t)rv << 1) ^ (uint32_t)(rv >> 31);
+            pk_rice(pk, u, k);
+        }
+    }
+    pk_end(pk, sh->tail_val[c][t], sh->tail_word[c][t]);
+    FAB_TICK(9);
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // General path: any blocksize <= 4096, any sample width, wasted bits, CONSTANT / VERBATIM / FIXED / LPC.
 // ------------------------------------------------------------------------------------------------------
@@ -1336,8 +2038,8 @@ FA_D int64_t gen_residual(const GenChunk& G, int j, int order, const int32_t* co
     return (int64_t)G.x[kMaxOrd + j] - (sum >> shift);
 }
 
-FA_D void enc_channel_general(const EncParams& P, EncCtx& X, const FrameSrc& S, int c, int f, uint32_t g, int bitpos0,
-                              int& bitpos_end) {
+FA_D void enc_channel_general_body(const EncParams& P, EncCtx& X, const FrameSrc& S, int c, int f, uint32_t g, int bitpos0,
+                                   int& bitpos_end) {
     EncShared* sh = X.sh;
     uint32_t* out = X.out;
     retire_full(P, X);
@@ -1541,7 +2243,7 @@ FA_D void enc_channel_general(const EncParams& P, EncCtx& X, const FrameSrc& S, 
         if (c == P.nch - 1) publish_aggregate(P, g, f, bitpos_end);
         pk_begin(pk, out, bitpos0);
         open = true;
-        if (c == 0) emit_frame_header(pk, P.crc, bs, f, P.nch);
+        if (c == 0) emit_frame_header(pk, sh->crc8, bs, f, P.nch);
         emit_subframe_header(pk, ptype, order, wasted);
         if (ptype == 0) {
             emit_sample(pk, G.x[kMaxOrd], bps);
@@ -1578,6 +2280,12 @@ FA_D void enc_channel_general(const EncParams& P, EncCtx& X, const FrameSrc& S, 
     if (open) pk_end(pk, sh->tail_val[c][t], sh->tail_word[c][t]);
 }
 
+FA_DNOINL int enc_channel_general(const EncParams P, EncCtx X, const FrameSrc S, int c, int f, uint32_t g, int bitpos0) {
+    int bitpos_end = 0;
+    enc_channel_general_body(P, X, S, c, f, g, bitpos0, bitpos_end);
+    return bitpos_end;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // The CTA body: loops over (stream, frame) tickets.  `smem_raw` >= enc_smem_bytes(nch).
 // ------------------------------------------------------------------------------------------------------
@@ -1587,13 +2295,19 @@ FA_D void encode_frames_cta(const EncParams& P, unsigned char* smem_raw) {
     uint16_t* crcT = (uint16_t*)(smem_raw + ((sizeof(EncShared) + 15) & ~(size_t)15));
     const int t = tid();
     const int nch = P.nch;
-    const uint32_t total_frames = (uint32_t)(P.n_stream * P.nframes);
+    const uint32_t total_frames = P.g_end;
     EncCtx X;
     X.sh = sh; X.crcT = crcT; X.out = (uint32_t*)(crcT + 4 * 256);
     X.out_words_padded = (int)(enc_out_words(nch) + (enc_out_words(nch) >> 4) + 8);
+    X.res = (int32_t*)(X.out + ((X.out_words_padded + 3) & ~3));
     X.retired = false;
+#if defined(FAB_PHASE_TIMING) && defined(__CUDACC__)
+    for (int k = 0; k < 12; ++k) X.ph[k] = 0;
+    X.last = clock64();
+#endif
 
     for (int i = t; i < 4 * 256; i += kEncThreads) crcT[i] = P.crc->crc16[i >> 8][i & 255];
+    for (int i = t; i < 256; i += kEncThreads) sh->crc8[i] = P.crc->crc8[i];
     if (t == 0) sh->prev_valid = 0;
     sh->tail_val[0][t] = 0; sh->tail_val[1][t] = 0;
     zero_out(X);
@@ -1601,8 +2315,10 @@ FA_D void encode_frames_cta(const EncParams& P, unsigned char* smem_raw) {
     for (;;) {
         // ---- work assignment: tickets are handed out in launch order so that look-back never waits
         // on a frame that has not started (decoupled look-back, Merrill & Garland).
-        if (t == 0) sh->g = atom_add_global(P.ticket, 1u);
+        FAB_TICK(10);
+        if (t == 0) sh->g = P.g_begin + atom_add_global(P.ticket, 1u);
         sync();   // also: every thread has finished packing the previous frame (all plain stores done)
+        FAB_TICK(0);
         const uint32_t g = sh->g;
         // trailing partial words of the previous frame's packing sessions
         for (int c = 0; c < nch; ++c) {
@@ -1624,26 +2340,39 @@ FA_D void encode_frames_cta(const EncParams& P, unsigned char* smem_raw) {
         const int esize = (P.dtype == kI32 || P.dtype == kF32) ? 4 : 8;
         S.base = (const unsigned char*)P.data + (s * P.stream_size + samp0) * esize;
         S.vec = (((uintptr_t)S.base) & 15) == 0;
-        S.posgain = S.gain32 > 0.0f;
 
         int bitpos = 0;
         for (int c = 0; c < nch; ++c) {
             int bend = 0;
             bool done = false;
-            if (bs == kMaxBs) done = enc_channel_fast<H, true>(P, X, S, c, f, g, bitpos, bend);
-            else if (bs >= 64) done = enc_channel_fast<H, false>(P, X, S, c, f, g, bitpos, bend);
-            if (!done) enc_channel_general(P, X, S, c, f, g, bitpos, bend);
+            if (bs == kMaxBs) done = enc_channel_full<H>(P, X, S, c, f, g, bitpos, bend);
+            else if (bs >= 64) {
+                // (the short path retires the previous frame on every return: its plans never have mode 0)
+                bend = enc_channel_short<H>(P, X, S, c, f, g, bitpos);
+                done = bend >= 0;
+                X.retired = true;
+            }
+            if (!done) {
+                bend = enc_channel_general(P, X, S, c, f, g, bitpos);
+                X.retired = true;
+            }
             bitpos = bend;
         }
         // the frame now waits in `out`; it is retired during the next iteration (or the drain below).
         // The writes below are ordered before their readers by the barrier at the top of the loop.
         if (t == 0) {
+            if (bitpos & 31) X.out[ow(bitpos >> 5)] = 0;   // final partial word: nobody plain-stores it, tails are OR-ed in
             sh->prev_valid = 1; sh->prev_g = g; sh->prev_f = f; sh->prev_nbytes = (bitpos + 7) >> 3;
         }
     }
     // ---- drain: the last frame of this CTA (its tails were OR-ed in above)
     sync();
     retire_full(P, X);
+#if defined(FAB_PHASE_TIMING) && defined(__CUDACC__)
+    if ((blockIdx.x == 7 || blockIdx.x == 300) && (t == 0 || t == 37 || t == 127 || t == 96))
+        printf("cta %d t %d: top %lld | plan %lld lookback %lld pass2 %lld est %lld B3 %lld copyout %lld lens %lld B5 %lld pack %lld rest %lld\n",
+               (int)blockIdx.x, t, X.ph[0], X.ph[1], X.ph[2], X.ph[3], X.ph[4], X.ph[5], X.ph[6], X.ph[7], X.ph[8], X.ph[9], X.ph[10]);
+#endif
 }
 
 }  // namespace fa

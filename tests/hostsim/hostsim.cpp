@@ -73,11 +73,36 @@ int hs_encode(const void* data, int dtype, int64_t n_stream, int64_t stream_size
     P.window = window.data(); P.crc = crc(); P.tab = &tab;
     P.out = out; P.out_capacity = cap; P.starts = starts; P.ends = ends.data(); P.desc = desc.data();
     P.ticket = &ticket; P.err = &err; P.hdr_bytes = stream_header_bytes(nf);
+    // the three encoder kernels: analyze (one CTA per frame) -> design (one thread per record) -> encode
+    const int64_t total_frames = n_stream * nf;
+    std::vector<FrameStats> stats((size_t)(total_frames * nch));
+    std::vector<FramePlan> plans((size_t)(total_frames * nch) + 1);
+    // ldg128 needs 16-byte aligned plan records
+    FramePlan* plan_base = (FramePlan*)(((uintptr_t)plans.data() + 15) & ~(uintptr_t)15);
+    if ((uintptr_t)plan_base + (size_t)(total_frames * nch) * sizeof(FramePlan) > (uintptr_t)(plans.data() + plans.size()))
+        return kErrAlloc;
+    P.stats = stats.data(); P.plans = plan_base; P.g_begin = 0; P.g_end = (uint32_t)total_frames;
+    fasim::launch((int)total_frames, kEncThreads, sizeof(AnShared), [&](int b) {
+        if (lp.max_lpc_order > 8) analyze_frame_cta<12>(P, (uint32_t)b, (AnShared*)fasim::smem());
+        else analyze_frame_cta<8>(P, (uint32_t)b, (AnShared*)fasim::smem());
+    });
+    fasim::launch(1, 1, 0, [&](int) {
+        for (int64_t i = 0; i < total_frames * nch; ++i) design_frame(P, i);
+    });
+    // slots for the frames of the (single) batch, then scan + compaction
+    const int64_t slot_bytes = (int64_t)((16 + 2 + (int64_t)nch * (lp.blocksize * 4 + 8) + 15) & ~15ll);
+    std::vector<uint32_t> slots_w((size_t)(total_frames * slot_bytes / 4) + 8);
+    std::vector<uint32_t> fsize((size_t)total_frames);
+    unsigned long long base = 0;
+    P.slots = (uint8_t*)(((uintptr_t)slots_w.data() + 15) & ~(uintptr_t)15); P.slot_bytes = slot_bytes;
+    P.fsize = fsize.data(); P.base = &base;
     // persistent CTAs: the emulator runs blocks one after the other, so one block drains every ticket
     fasim::launch(1, kEncThreads, enc_smem_bytes(nch), [&](int) {
         if (lp.max_lpc_order > 8) encode_frames_cta<12>(P, fasim::smem());
         else encode_frames_cta<8>(P, fasim::smem());
     });
+    fasim::launch(1, kScanThreads, (kScanThreads / 32 + 1) * 8, [&](int) { scan_batch_cta(P, (unsigned long long*)fasim::smem()); });
+    fasim::launch((int)total_frames, 128, 0, [&](int b) { compact_frame_cta(P, (uint32_t)b); });
     fasim::launch(1, 1, 0, [&](int) {
         for (int64_t s = 0; s < n_stream; ++s)
             for (int f = 0; f < nf; ++f) finalize_entry(P, s, f, nbytes, total);
