@@ -811,24 +811,16 @@ FA_D void retire_copyout(const EncParams& P, const EncCtx& X) {
     }
     const long long off = sh->prev_off;
     if (off >= 0) {
+        // the slot is 16-byte aligned: four staged (big-endian) words per 16-byte store; the bytes past the
+        // frame end inside the last store are don't-care (the slot is a worst-case frame rounded up to 16)
         uint8_t* dst = P.slots + off;
-        // aligned 32-bit stores in the middle, byte stores at the ragged ends
-        int a = (int)((uintptr_t)dst & 3);
-        int head = a ? 4 - a : 0;
-        if (head > nbytes_body) head = nbytes_body;
-        if (t < head) dst[t] = (uint8_t)((out[ow(t >> 2)] >> (24 - 8 * (t & 3))) & 0xFFu);
-        int nwords = (nbytes_body - head) >> 2;
-        uint32_t* dw = (uint32_t*)(dst + head);
-        for (int w = t; w < nwords; w += kEncThreads) {
-            int b = head + 4 * w;   // stream byte index of this word's first byte
-            uint32_t hi = out[ow(b >> 2)], lo = out[ow((b >> 2) + 1)];
-            uint32_t v = funnel_l(lo, hi, 8u * (uint32_t)(b & 3));
-            dw[w] = bswap32(v);
-        }
-        int tail0 = head + 4 * nwords;
-        if (t < nbytes_body - tail0) {
-            int k = tail0 + t;
-            dst[k] = (uint8_t)((out[ow(k >> 2)] >> (24 - 8 * (k & 3))) & 0xFFu);
+        const int nvec = (nbytes_body + 15) >> 4;
+        for (int v = t; v < nvec; v += kEncThreads) {
+            const int w = 4 * v;          // four consecutive words never straddle a pad word (ow pads every 16)
+            const int o = ow(w);
+            U4 q;
+            q.x = bswap32(out[o]); q.y = bswap32(out[o + 1]); q.z = bswap32(out[o + 2]); q.w = bswap32(out[o + 3]);
+            sts128(dst + 16 * (size_t)v, q);
         }
     }
 }
@@ -1627,6 +1619,7 @@ FA_D void lpc8(const int32_t* w, const int32_t* coef, int shift, int32_t* r) {
 template <int H>
 FA_D void lpc8_dispatch(int order, const int32_t* w, const int32_t* coef, int shift, int32_t* r) {
     switch (order) {
+    case 0: lpc8<H, 0>(w, coef, shift, r); break;
     case 1: lpc8<H, 1>(w, coef, shift, r); break;
     case 2: lpc8<H, 2>(w, coef, shift, r); break;
     case 3: lpc8<H, 3>(w, coef, shift, r); break;
@@ -1698,12 +1691,6 @@ FA_D void full_pass2(const FrameSrc& S, int c, int t, int wasted, bool wide, boo
     uint32_t a0 = 0, a1 = 0;                 // narrow sums
     unsigned long long b0 = 0, b1 = 0;       // wide sums
     uint32_t bad0 = 0, bad1 = 0;
-    // running differences of the fixed predictors (narrow path)
-    uint32_t p1 = (uint32_t)w[H - 1] - (uint32_t)w[H - 2];
-    uint32_t p1b = (uint32_t)w[H - 2] - (uint32_t)w[H - 3];
-    uint32_t p1c = (uint32_t)w[H - 3] - (uint32_t)w[H - 4];
-    uint32_t p2 = p1 - p1b, p2b = p1b - p1c;
-    uint32_t p3 = p2 - p2b;
     int32_t nx[8];                            // next sub-block, in flight while the current one is processed
     load8(S, c, t * kSpt, nx);
 #pragma unroll 1
@@ -1716,22 +1703,20 @@ FA_D void full_pass2(const FrameSrc& S, int c, int t, int wasted, bool wide, boo
             for (int i = 0; i < 8; ++i) w[H + i] >>= wasted;
         }
         const int sk0 = skip0 - it * 8, sk1 = skip1 - it * 8;
+        const bool plain = sk0 <= 0 && sk1 <= 0;     // no warm-up sample in this sub-block (all but thread 0's first)
         int32_t r[8];
         if (do0) {
             if (!wide) {
-                // order-k residual = k-th running difference (the lower differences are carried anyway)
+                // fixed predictor = LPC with the literal coefficients (1), (2,-1), (3,-3,1), (4,-6,4,-1), shift 0
+                lpc8_dispatch<H>(ord0, w, cf, 0, r);
+                if (plain) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    uint32_t d0 = (uint32_t)w[H + i];
-                    uint32_t d1 = d0 - (uint32_t)w[H + i - 1];
-                    uint32_t d2 = d1 - p1, d3 = d2 - p2, d4 = d3 - p3;
-                    p1 = d1; p2 = d2; p3 = d3;
-                    r[i] = (int32_t)d4;
-                    if (ord0 < 4) r[i] = (int32_t)(ord0 == 0 ? d0 : ord0 == 1 ? d1 : ord0 == 2 ? d2 : d3);
+                    for (int i = 0; i < 8; ++i) a0 = sad_acc(r[i], 0, a0);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (i >= sk0) a0 = sad_acc(r[i], 0, a0);
                 }
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (i >= sk0) a0 = sad_acc(r[i], 0, a0);
             } else {
                 uint32_t ok = lpc8_wide<H>(w, cf, 0, r);
 #pragma unroll
@@ -1742,16 +1727,26 @@ FA_D void full_pass2(const FrameSrc& S, int c, int t, int wasted, bool wide, boo
                     }
             }
             if (!do1) {
+                if (plain) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) res[(it * 8 + i) * kEncThreads + t] = i >= sk0 ? r[i] : w[H + i];   // warm-up: the sample
+                    for (int i = 0; i < 8; ++i) res[(it * 8 + i) * kEncThreads + t] = r[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) res[(it * 8 + i) * kEncThreads + t] = i >= sk0 ? r[i] : w[H + i];   // warm-up: the sample
+                }
             }
         }
         if (do1) {
             if (!wide1) {
                 lpc8_dispatch<H>(ord1, w, coef, shift1, r);
+                if (plain) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (i >= sk1) a1 = sad_acc(r[i], 0, a1);
+                    for (int i = 0; i < 8; ++i) a1 = sad_acc(r[i], 0, a1);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (i >= sk1) a1 = sad_acc(r[i], 0, a1);
+                }
             } else {
                 uint32_t ok = lpc8_wide<H>(w, coef, shift1, r);
 #pragma unroll
@@ -1761,8 +1756,13 @@ FA_D void full_pass2(const FrameSrc& S, int c, int t, int wasted, bool wide, boo
                         if (!((ok >> i) & 1u)) bad1 = 1;
                     }
             }
+            if (plain) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) res[(it * 8 + i) * kEncThreads + t] = i >= sk1 ? r[i] : w[H + i];       // warm-up: the sample
+                for (int i = 0; i < 8; ++i) res[(it * 8 + i) * kEncThreads + t] = r[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) res[(it * 8 + i) * kEncThreads + t] = i >= sk1 ? r[i] : w[H + i];   // warm-up: the sample
+            }
         }
 #pragma unroll
         for (int i = 0; i < H; ++i) w[i] = w[8 + i];
