@@ -37,10 +37,14 @@ __global__ void __launch_bounds__(kEncThreads, FAB_ENC_CTAS) k_encode(const EncP
 }
 
 // sample statistics, fixed-predictor error sums and windowed autocorrelation of every (frame, channel)
+// (persistent CTAs: the thread's slice of the tukey window is loaded into shared memory once)
 template <int H>
 __global__ void __launch_bounds__(kEncThreads, 4) k_enc_analyze(const EncParams P) {
     __shared__ AnShared sh;
-    analyze_frame_cta<H>(P, P.g_begin + blockIdx.x, &sh);
+    __shared__ __align__(16) float wsm[an_window_bytes(H) / 4];
+    analyze_fill_window<H>(P, wsm);
+    __syncthreads();
+    for (uint32_t g = P.g_begin + blockIdx.x; g < P.g_end; g += gridDim.x) analyze_frame_cta<H>(P, g, &sh, wsm);
 }
 
 // predictor design: one thread per (frame, channel)
@@ -539,25 +543,24 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
     P.base = (unsigned long long*)(ticket + ((nbatch + 3) & ~3ll));   // zeroed with the tickets (8-byte aligned)
     const int h12 = lp.max_lpc_order > 8 ? 1 : 0;
     int64_t resident = (int64_t)ctx->n_sm * std::max(1, ctx->enc_ctas_per_sm[h12][nch - 1]);
+    prof_begin(ctx, 0, st);     // slot 0: the whole encoder kernel sequence of this call (all batches)
     for (int64_t bi = 0; bi < nbatch; ++bi) {
         P.g_begin = (uint32_t)(bi * batch);
         P.g_end = (uint32_t)std::min<int64_t>(total_frames, (bi + 1) * batch);
         P.ticket = ticket + bi;
         const int64_t nfr = (int64_t)P.g_end - (int64_t)P.g_begin;
-        prof_begin(ctx, 2, st);
-        if (h12) k_enc_analyze<12><<<(unsigned)nfr, kEncThreads, 0, st>>>(P);
-        else k_enc_analyze<8><<<(unsigned)nfr, kEncThreads, 0, st>>>(P);
-        prof_end(ctx, st);
+        const unsigned agrid = (unsigned)std::min<int64_t>(nfr, (int64_t)ctx->n_sm * 4);
+        if (h12) k_enc_analyze<12><<<agrid, kEncThreads, 0, st>>>(P);
+        else k_enc_analyze<8><<<agrid, kEncThreads, 0, st>>>(P);
         k_enc_design<<<(unsigned)((nfr * nch + 127) / 128), 128, 0, st>>>(P, nfr * nch);
         unsigned grid = (unsigned)std::min<int64_t>(nfr, resident);
-        prof_begin(ctx, 0, st);
         if (h12) k_encode<12><<<grid, kEncThreads, smem, st>>>(P);
         else k_encode<8><<<grid, kEncThreads, smem, st>>>(P);
-        prof_end(ctx, st);
         k_enc_scan<<<1, kScanThreads, 0, st>>>(P);
         k_enc_compact<<<(unsigned)nfr, 128, 0, st>>>(P);
         ctx->launches += 5;
     }
+    prof_end(ctx, st);
     P.g_begin = 0; P.g_end = (uint32_t)total_frames;
     k_enc_finalize<<<(unsigned)((n_stream * nf + 255) / 256), 256, 0, st>>>(P, (long long*)d_nbytes, (long long*)d_total);
     ctx->launches++;

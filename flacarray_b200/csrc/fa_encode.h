@@ -192,6 +192,7 @@ struct EncShared {
     uint32_t scan[kEncWarps];
     uint32_t crc_part[kEncWarps];
     uint8_t crc8[256];                         // CRC-8 table (frame headers)
+    uint32_t hdr_tmp[40];                      // full-frame path: header words built by thread 0 ahead of the packing (ow-indexed)
     // full-frame path: per-warp partials of (estimated bits at the finest partition order, sum |residual|, flags)
     uint32_t x_bits[2][kEncWarps];
     unsigned long long x_sum[2][kEncWarps];
@@ -204,6 +205,7 @@ struct EncShared {
     uint32_t prev_g;
     long long prev_off;
     uint32_t g;
+    uint32_t gq[2];     // tickets, fetched one frame ahead (the atomic's latency is off the critical path)
 };
 
 FA_HD size_t enc_out_words(int nch) { return ((size_t)nch * (kMaxBs * 4 + 64) + 64) / 4; }
@@ -793,16 +795,18 @@ FA_D void retire_lookback(const EncParams& P, EncShared* sh) {
 // All threads, after a barrier behind retire_lookback: CRC-16 partials of the staged frame (uniform
 // pass, one contiguous run of words per thread, positions fixed up with one GF(2) multiply) and the
 // coalesced copy to HBM.
-FA_D void retire_copyout(const EncParams& P, const EncCtx& X) {
+// skip0: thread 0 takes no share of the work (it builds the next frame's header meanwhile)
+FA_D void retire_copyout(const EncParams& P, const EncCtx& X, bool skip0 = false) {
     EncShared* sh = X.sh;
     if (!sh->prev_valid) return;
-    const int t = tid();
+    const int nthr = skip0 ? kEncThreads - 1 : kEncThreads;
+    const int t = skip0 ? tid() - 1 : tid();
     const uint32_t* out = X.out;
     const int nbytes_body = sh->prev_nbytes;
     const int wtot = (nbytes_body + 3) >> 2;
     {
-        const int per = (wtot + kEncThreads - 1) / kEncThreads;
-        int w0 = t * per, w1 = w0 + per < wtot ? w0 + per : wtot;
+        const int per = (wtot + nthr - 1) / nthr;
+        int w0 = t < 0 ? wtot : t * per, w1 = w0 + per < wtot ? w0 + per : wtot;
         uint32_t crc = 0;
         for (int w = w0; w < w1; ++w) crc = crc16_word(X.crcT, crc, out[ow(w)]);
         uint32_t contrib = w0 < w1 ? gf16_mul(crc, P.tab->x32[wtot - w1]) : 0u;
@@ -815,7 +819,7 @@ FA_D void retire_copyout(const EncParams& P, const EncCtx& X) {
         // frame end inside the last store are don't-care (the slot is a worst-case frame rounded up to 16)
         uint8_t* dst = P.slots + off;
         const int nvec = (nbytes_body + 15) >> 4;
-        for (int v = t; v < nvec; v += kEncThreads) {
+        for (int v = t < 0 ? nvec : t; v < nvec; v += nthr) {
             const int w = 4 * v;          // four consecutive words never straddle a pad word (ow pads every 16)
             const int o = ow(w);
             U4 q;
@@ -984,7 +988,7 @@ FA_D int fast_level_maxp(int bs, int level_max) {
 }
 
 template <int H, bool FULL>
-FA_D void analyze_channel(const EncParams& P, AnShared* sh, const FrameSrc& S, int c, FrameStats* st) {
+FA_D void analyze_channel(const EncParams& P, AnShared* sh, const float* wsm, const FrameSrc& S, int c, FrameStats* st) {
     const int t = tid();
     const int ln = lane(), wp = warp();
     const int bs = FULL ? kMaxBs : S.bs;
@@ -1032,12 +1036,12 @@ FA_D void analyze_channel(const EncParams& P, AnShared* sh, const FrameSrc& S, i
         double wv[H + 1];
 #pragma unroll
         for (int l = 0; l <= H; ++l) wv[l] = 0.0;
-        const float* win = P.window + i0 - H;
+        // the thread's window values sit in shared memory, [q][t] x 4 floats (filled once per CTA)
         // history: wv[l] = windowed sample (i0 - l)
 #pragma unroll
         for (int q = 0; q < H / 4; ++q) {
             if (t != 0) {
-                U4 w4 = ldg128(win + 4 * q);
+                U4 w4 = lds128(wsm + (q * kEncThreads + t) * 4);
                 float w0, w1, w2, w3;
                 memcpy(&w0, &w4.x, 4); memcpy(&w1, &w4.y, 4); memcpy(&w2, &w4.z, 4); memcpy(&w3, &w4.w, 4);
                 wv[H - 4 * q] = (double)fmul((float)xw[4 * q], w0);
@@ -1050,7 +1054,7 @@ FA_D void analyze_channel(const EncParams& P, AnShared* sh, const FrameSrc& S, i
 #pragma unroll
         for (int j = 0; j < kSpt; ++j) {
             if ((j & 3) == 0) {
-                U4 w4 = ldg128(win + H + j);
+                U4 w4 = lds128(wsm + (((H + j) >> 2) * kEncThreads + t) * 4);
                 memcpy(&wq[0], &w4.x, 4); memcpy(&wq[1], &w4.y, 4); memcpy(&wq[2], &w4.z, 4); memcpy(&wq[3], &w4.w, 4);
             }
             wv[0] = (double)fmul((float)xw[H + j], wq[j & 3]);
@@ -1160,8 +1164,25 @@ FA_D void analyze_channel(const EncParams& P, AnShared* sh, const FrameSrc& S, i
 }
 
 // One CTA: every channel of (stream, frame) ticket g.
+// window values of thread t: samples 32 t - H .. 32 t + 31 (zeros outside the window)
 template <int H>
-FA_D void analyze_frame_cta(const EncParams& P, uint32_t g, AnShared* sh) {
+FA_D void analyze_fill_window(const EncParams& P, float* wsm) {
+    const int t = tid();
+    for (int q = 0; q < (H + kSpt) / 4; ++q) {
+        float v[4];
+        for (int e = 0; e < 4; ++e) {
+            int i = t * kSpt - H + 4 * q + e;
+            v[e] = (i >= 0 && i < P.blocksize) ? P.window[i] : 0.f;
+        }
+        U4 u;
+        memcpy(&u.x, &v[0], 4); memcpy(&u.y, &v[1], 4); memcpy(&u.z, &v[2], 4); memcpy(&u.w, &v[3], 4);
+        sts128(wsm + (q * kEncThreads + t) * 4, u);
+    }
+}
+FA_HD constexpr size_t an_window_bytes(int H) { return (size_t)((H + kSpt) / 4) * kEncThreads * 16; }
+
+template <int H>
+FA_D void analyze_frame_cta(const EncParams& P, uint32_t g, AnShared* sh, const float* wsm) {
     const int64_t s = (int64_t)(g / (uint32_t)P.nframes);
     const int f = (int)(g % (uint32_t)P.nframes);
     const int64_t samp0 = (int64_t)f * P.blocksize;
@@ -1180,8 +1201,8 @@ FA_D void analyze_frame_cta(const EncParams& P, uint32_t g, AnShared* sh) {
     S.base = (const unsigned char*)P.data + (s * P.stream_size + samp0) * esize;
     S.vec = (((uintptr_t)S.base) & 15) == 0;
     for (int c = 0; c < P.nch; ++c) {
-        if (bs == kMaxBs) analyze_channel<H, true>(P, sh, S, c, st + c);
-        else analyze_channel<H, false>(P, sh, S, c, st + c);
+        if (bs == kMaxBs) analyze_channel<H, true>(P, sh, wsm, S, c, st + c);
+        else analyze_channel<H, false>(P, sh, wsm, S, c, st + c);
     }
 }
 
@@ -1868,8 +1889,6 @@ FA_D bool enc_channel_full(const EncParams& P, EncCtx& X, const FrameSrc& S, int
     FAB_TICK(4);
     sync();   // B3: the partials and (retiring) the byte offset of the previous frame are visible
     FAB_TICK(5);
-    if (retiring) retire_copyout(P, X);   // previous frame: CRC partials + copy to HBM
-    FAB_TICK(6);
 
     // ---- every thread: partition order (maximum or 0) and winner (smallest estimate, stream_encoder.c
     //      process_subframe_); all inputs are block-uniform
@@ -1902,6 +1921,7 @@ FA_D bool enc_channel_full(const EncParams& P, EncCtx& X, const FrameSrc& S, int
         }
     }
     if (win < 0) {            // (block-uniform) nothing beats VERBATIM: general path
+        if (retiring) retire_copyout(P, X);
         sync();
         if (retiring) { if (t == 0) retire_crc(P, sh); X.retired = true; }
         return false;
@@ -1910,6 +1930,38 @@ FA_D bool enc_channel_full(const EncParams& P, EncCtx& X, const FrameSrc& S, int
     const int plen = rice2 ? 5 : 4;
     const int k = kwin;
     const int skip = t == 0 ? order : 0;
+    const int ptype = win == 0 ? 2 : 3;
+    const int prec = win == 0 ? 0 : prec1;
+    // ---- previous frame: CRC partials + copy to its slot, by threads 1..127; thread 0 meanwhile builds the
+    //      frame / subframe header of this channel into hdr_tmp (a serial job that used to sit behind the
+    //      scan barrier and made the other 127 threads wait)
+    if (retiring) retire_copyout(P, X, true);
+    Pk pk;
+    int hdr_words = 0;
+    if (t == 0) {
+        // same accumulator protocol as Pk, words go to hdr_tmp[0 ..); bit offset of the first word kept
+        pk_begin(pk, sh->hdr_tmp, bitpos0 & 31);          // word index 0 = frame word (bitpos0 >> 5)
+        if (c == 0) emit_frame_header(pk, sh->crc8, bs, f, P.nch);
+        emit_subframe_header(pk, ptype, order, wasted);
+        // warm-up samples: parked in res by the LPC pass; if the fixed predictor won after an LPC pass they
+        // are re-parked by the redo below, which has not run yet -> read them from the source
+        for (int j = 0; j < order; ++j)
+            emit_sample(pk, (win == 0 && ok1) ? (src_sample(S, c, j) >> wasted) : res[j * kEncThreads], bps);
+        if (ptype == 3) {
+            pk_emit(pk, (uint32_t)(prec1 - 1), 4);
+            pk_emit(pk, (uint32_t)shift1 & 31u, 5);
+            for (int j = 0; j < order; ++j) {
+                int32_t cj = coef[0];
+#pragma unroll
+                for (int q = 1; q < H; ++q) cj = (q == j) ? coef[q] : cj;
+                pk_emit(pk, (uint32_t)cj & ((1u << prec1) - 1u), prec1);
+            }
+        }
+        pk_emit(pk, (uint32_t)rice2, 2);
+        pk_emit(pk, (uint32_t)porder, 4);
+        hdr_words = pk.word;
+    }
+    FAB_TICK(6);
     if (win == 0 && ok1) {
         // the fixed predictor won but the parked residual is the LPC one: redo the fixed pass (L1/L2 hits)
         unsigned long long d0, d1;
@@ -1951,8 +2003,6 @@ FA_D bool enc_channel_full(const EncParams& P, EncCtx& X, const FrameSrc& S, int
         total += x;
     }
     const uint32_t excl = wbase + inc - lens;
-    const int ptype = win == 0 ? 2 : 3;
-    const int prec = win == 0 ? 0 : prec1;
     const int hdr_bits = subframe_header_bits(ptype, order, wasted, bps, prec);
     if ((uint32_t)hdr_bits + total >= verbatim_bits + 8u) return false;   // VERBATIM is smaller: general path
     const int sub0 = bitpos0 + (c == 0 ? 8 * frame_header_bytes(bs, f) : 0);
@@ -1960,25 +2010,12 @@ FA_D bool enc_channel_full(const EncParams& P, EncCtx& X, const FrameSrc& S, int
 
     // ---- pack
     bitpos_end = body0 + (int)total;
-    Pk pk;
     if (t == 0) {
-        if (c == P.nch - 1) publish_aggregate(P, g, f, bitpos_end);
-        pk_begin(pk, out, bitpos0);
-        if (c == 0) emit_frame_header(pk, sh->crc8, bs, f, P.nch);
-        emit_subframe_header(pk, ptype, order, wasted);
-        for (int j = 0; j < order; ++j) emit_sample(pk, res[j * kEncThreads], bps);   // thread 0 parked its warm-up samples
-        if (ptype == 3) {
-            pk_emit(pk, (uint32_t)(prec1 - 1), 4);
-            pk_emit(pk, (uint32_t)shift1 & 31u, 5);
-            for (int j = 0; j < order; ++j) {
-                int32_t cj = coef[0];
-#pragma unroll
-                for (int q = 1; q < H; ++q) cj = (q == j) ? coef[q] : cj;
-                pk_emit(pk, (uint32_t)cj & ((1u << prec1) - 1u), prec1);
-            }
-        }
-        pk_emit(pk, (uint32_t)rice2, 2);
-        pk_emit(pk, (uint32_t)porder, 4);
+        // move the finished header words into the staged frame and continue the same packing session there
+        const int w0 = bitpos0 >> 5;
+        for (int i = 0; i < hdr_words; ++i) out[ow(w0 + i)] = sh->hdr_tmp[ow(i)];
+        pk.out = out;
+        pk.word = w0 + hdr_words;
     } else {
         pk_begin(pk, out, body0 + (int)excl);
     }
@@ -2308,18 +2345,17 @@ FA_D void encode_frames_cta(const EncParams& P, unsigned char* smem_raw) {
 
     for (int i = t; i < 4 * 256; i += kEncThreads) crcT[i] = P.crc->crc16[i >> 8][i & 255];
     for (int i = t; i < 256; i += kEncThreads) sh->crc8[i] = P.crc->crc8[i];
-    if (t == 0) sh->prev_valid = 0;
+    if (t == 0) { sh->prev_valid = 0; sh->gq[0] = P.g_begin + atom_add_global(P.ticket, 1u); }
     sh->tail_val[0][t] = 0; sh->tail_val[1][t] = 0;
     zero_out(X);
 
-    for (;;) {
-        // ---- work assignment: tickets are handed out in launch order so that look-back never waits
-        // on a frame that has not started (decoupled look-back, Merrill & Garland).
+    for (int iter = 0;; ++iter) {
+        // ---- work assignment: dynamic tickets (any order: every frame has its own output slot)
         FAB_TICK(10);
-        if (t == 0) sh->g = P.g_begin + atom_add_global(P.ticket, 1u);
         sync();   // also: every thread has finished packing the previous frame (all plain stores done)
         FAB_TICK(0);
-        const uint32_t g = sh->g;
+        const uint32_t g = sh->gq[iter & 1];
+        if (t == 0) sh->gq[(iter + 1) & 1] = P.g_begin + atom_add_global(P.ticket, 1u);   // for the next iteration
         // trailing partial words of the previous frame's packing sessions
         for (int c = 0; c < nch; ++c) {
             uint32_t tv = sh->tail_val[c][t];

@@ -20,4 +20,4 @@ for it in range(4):
         print("err", ex)
     e1.record(); torch.cuda.synchronize()
     print(f"it{it}: enc gpu {e0.elapsed_time(e1):.2f} ms")
-print("k_encode ms", ctx.profile_ms(0), "k_enc_analyze ms", ctx.profile_ms(2))
+print("encoder kernels ms", ctx.profile_ms(0))

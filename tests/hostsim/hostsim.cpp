@@ -82,9 +82,15 @@ int hs_encode(const void* data, int dtype, int64_t n_stream, int64_t stream_size
     if ((uintptr_t)plan_base + (size_t)(total_frames * nch) * sizeof(FramePlan) > (uintptr_t)(plans.data() + plans.size()))
         return kErrAlloc;
     P.stats = stats.data(); P.plans = plan_base; P.g_begin = 0; P.g_end = (uint32_t)total_frames;
-    fasim::launch((int)total_frames, kEncThreads, sizeof(AnShared), [&](int b) {
-        if (lp.max_lpc_order > 8) analyze_frame_cta<12>(P, (uint32_t)b, (AnShared*)fasim::smem());
-        else analyze_frame_cta<8>(P, (uint32_t)b, (AnShared*)fasim::smem());
+    fasim::launch(1, kEncThreads, sizeof(AnShared) + 16 + an_window_bytes(12), [&](int) {
+        AnShared* ash = (AnShared*)fasim::smem();
+        float* wsm = (float*)(fasim::smem() + ((sizeof(AnShared) + 15) & ~(size_t)15));
+        if (lp.max_lpc_order > 8) analyze_fill_window<12>(P, wsm); else analyze_fill_window<8>(P, wsm);
+        fa::sync();
+        for (uint32_t g = 0; g < (uint32_t)total_frames; ++g) {
+            if (lp.max_lpc_order > 8) analyze_frame_cta<12>(P, g, ash, wsm);
+            else analyze_frame_cta<8>(P, g, ash, wsm);
+        }
     });
     fasim::launch(1, 1, 0, [&](int) {
         for (int64_t i = 0; i < total_frames * nch; ++i) design_frame(P, i);
