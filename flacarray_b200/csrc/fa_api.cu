@@ -38,8 +38,11 @@ __global__ void __launch_bounds__(kEncThreads, FAB_ENC_CTAS) k_encode(const EncP
 
 // sample statistics, fixed-predictor error sums and windowed autocorrelation of every (frame, channel)
 // (persistent CTAs: the thread's slice of the tukey window is loaded into shared memory once)
+#ifndef FAB_AN_CTAS
+#define FAB_AN_CTAS 6
+#endif
 template <int H>
-__global__ void __launch_bounds__(kEncThreads, 4) k_enc_analyze(const EncParams P) {
+__global__ void __launch_bounds__(kEncThreads, FAB_AN_CTAS) k_enc_analyze(const EncParams P) {
     __shared__ AnShared sh;
     __shared__ __align__(16) float wsm[an_window_bytes(H) / 4];
     analyze_fill_window<H>(P, wsm);
@@ -549,7 +552,7 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
         P.g_end = (uint32_t)std::min<int64_t>(total_frames, (bi + 1) * batch);
         P.ticket = ticket + bi;
         const int64_t nfr = (int64_t)P.g_end - (int64_t)P.g_begin;
-        const unsigned agrid = (unsigned)std::min<int64_t>(nfr, (int64_t)ctx->n_sm * 4);
+        const unsigned agrid = (unsigned)std::min<int64_t>(nfr, (int64_t)ctx->n_sm * FAB_AN_CTAS);
         if (h12) k_enc_analyze<12><<<agrid, kEncThreads, 0, st>>>(P);
         else k_enc_analyze<8><<<agrid, kEncThreads, 0, st>>>(P);
         k_enc_design<<<(unsigned)((nfr * nch + 127) / 128), 128, 0, st>>>(P, nfr * nch);
