@@ -221,6 +221,16 @@ __global__ void __launch_bounds__(kTileWarps * 32, FAB_DEC_CTAS) k_dec_tile(cons
     tile_warp_body<CRC>(P, item0, &ws[threadIdx.x >> 5], crc_tab);
 }
 
+// frame CRC-16 of every (stream, frame) item: one warp per item, see crc_frame_warp
+__global__ void __launch_bounds__(128) k_dec_crc(const TileParams P) {
+    __shared__ uint16_t crc_tab[4 * 256];
+    for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) crc_tab[i] = P.D.crc->crc16[i >> 8][i & 255];
+    __syncthreads();
+    int64_t idx = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (idx >= P.D.n_sel * P.nwin) return;
+    crc_frame_warp(P, idx, crc_tab);
+}
+
 // int32 -> float32 for the sample ranges that were NOT written by the fused tile path (frames left to
 // the general decoder, streams left to the walker).  grid = (nwin, n_sel)
 __global__ void __launch_bounds__(256) k_restore_fixup(const TileParams P) {
@@ -651,9 +661,10 @@ extern "C" int fab_decode(fab_ctx* ctx, const unsigned char* d_bytes, const int6
         TP.restore = fuse_restore ? 1 : 0; TP.offsets = (const float*)d_offsets; TP.gains = (const float*)d_gains;
         int64_t per_cta = (int64_t)kTileWarps * 32;
         prof_begin(ctx, 1, st);
-        k_dec_tile<true><<<(unsigned)((total + per_cta - 1) / per_cta), kTileWarps * 32, 0, st>>>(TP);
+        k_dec_tile<false><<<(unsigned)((total + per_cta - 1) / per_cta), kTileWarps * 32, 0, st>>>(TP);
+        k_dec_crc<<<(unsigned)((total + 3) / 4), 128, 0, st>>>(TP);
         prof_end(ctx, st);
-        ctx->launches++;
+        ctx->launches += 2;
         // general per-thread decoder: only the frames the tile path flagged
         k_dec_frames<<<(unsigned)((total + kDecThreads - 1) / kDecThreads), kDecThreads, 0, st>>>(P, nwin);
         ctx->launches++;

@@ -69,8 +69,10 @@ FA_D U4 u4_zero() { U4 z; z.x = z.y = z.z = z.w = 0; return z; }
 FA_D void brc_service(BitRdC& br) {
     cp_async_wait_all();          // copies issued at the previous service point: a whole sample group old
     br.landed = br.wr;
+    // at most two chunks per service point: 4 samples rarely consume more than 32 bytes (a lane that does
+    // runs into the underflow path of brc_take, which services again)
 #pragma unroll
-    for (int i = 0; i < kRingChunks; ++i) {
+    for (int i = 0; i < 2; ++i) {
         if (br.ring != nullptr && br.wr - (br.rd >> 2) < (uint32_t)kRingChunks) {
             uint32_t* slot = br.ring + (br.wr & (kRingChunks - 1)) * 4;
             if (br.gp < br.gend) cp_async16(slot, br.gp);
@@ -545,6 +547,51 @@ FA_D void tile_warp_body(const TileParams& P, int64_t item0, TileShared* ws, con
         }
         if (fail) atom_or_global(&D.stream_flag[k], 2);
     }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Frame CRC-16 as its own frame-parallel pass (k_dec_crc): one warp per (stream, frame) item of the tile
+// decoder's index space.  Inside the tile decoder the CRC was 23 % of the instructions, sitting on the
+// serial per-lane chain and doubled by divergence; here every lane folds a contiguous slice of the frame
+// (slice-by-4 over aligned words, tables in shared memory), the slice CRCs are advanced to the frame end
+// with the shift tables and XOR-reduced.  A mismatch flags the stream for the sequential walker exactly
+// like a mismatch found by the fused check (tile_warp_body<true>).
+// ------------------------------------------------------------------------------------------------------
+FA_D void crc_frame_warp(const TileParams& P, int64_t idx, const uint16_t* T) {
+    const DecParams& D = P.D;
+    const int ln = lane();
+    const int64_t k = idx / P.nwin;
+    if (k >= D.n_sel) return;
+    if (D.stream_flag[k] != 0) return;
+    const int bs_nom = D.meta[k].blocksize;
+    if (bs_nom <= 0) return;
+    const int64_t jj0 = D.first / bs_nom, jj1 = (D.first + D.n_decode - 1) / bs_nom;
+    if (jj1 - jj0 + 1 > P.nwin) return;               // (the tile kernel hands this stream to the walker)
+    const int64_t j = jj0 + idx % P.nwin;
+    if (j > jj1) return;
+    const long long* fo = D.frame_off + k * (int64_t)(D.nframes_cap + 1);
+    const long long off = fo[j], next = fo[j + 1];
+    if (off < 0) return;                              // (flagged by the tile kernel)
+    const long long nb = D.nbytes[k];
+    const long long len = (next >= 0 ? next : nb) - off;
+    if (len < 3 || off + len > nb) { if (ln == 0) atom_or_global(&D.stream_flag[k], 2); return; }
+    const uint8_t* fp = D.bytes + D.starts[k] + off;
+    const int64_t nbody = len - 2;
+    // contiguous slice of every lane, a multiple of 4 bytes long
+    const int64_t per = (((nbody + 31) / 32) + 3) & ~(int64_t)3;
+    int64_t lo = (int64_t)ln * per, hi = lo + per;
+    if (lo > nbody) lo = nbody;
+    if (hi > nbody) hi = nbody;
+    uint32_t c = 0;
+    const uint8_t* p = fp + lo;
+    const uint8_t* e = fp + hi;
+    while (p < e && ((uintptr_t)p & 3)) { c = crc16_b(T, c, *p); ++p; }
+    while (p + 4 <= e) { c = crc16_word(T, c, bswap32(ldg32((const uint32_t*)p))); p += 4; }
+    while (p < e) { c = crc16_b(T, c, *p); ++p; }
+    c = crc16_shift(D.crc, c, (uint32_t)(nbody - hi));
+    c = redux_xor(c);
+    const uint32_t want = ((uint32_t)fp[len - 2] << 8) | fp[len - 1];
+    if (ln == 0 && c != want) atom_or_global(&D.stream_flag[k], 2);
 }
 
 }  // namespace fa

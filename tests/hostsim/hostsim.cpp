@@ -156,9 +156,11 @@ int hs_decode(const uint8_t* bytes, const long long* starts, const long long* nb
         int64_t total = n_sel * nwin;
         std::vector<uint16_t> tab(4 * 256);
         for (int i = 0; i < 4 * 256; ++i) tab[(size_t)i] = crc()->crc16[i >> 8][i & 255];
+        // the product launches the tile decoder without the fused CRC and checks it in k_dec_crc
         fasim::launch((int)((total + 31) / 32), 32, sizeof(TileShared) + 64, [&](int b) {
-            tile_warp_body<true>(TP, (int64_t)b * 32, (TileShared*)fasim::smem(), tab.data());
+            tile_warp_body<false>(TP, (int64_t)b * 32, (TileShared*)fasim::smem(), tab.data());
         });
+        fasim::launch((int)total, 32, 0, [&](int b) { crc_frame_warp(TP, (int64_t)b, tab.data()); });
         int walked = 0, general = 0;
         fasim::launch(1, 1, 0, [&](int) {
             DecParams Q = P;

@@ -121,3 +121,18 @@ def test_float_bodies_match_reference_vectors(H, golden_dir):
         from oracle import oracle as O
         assert np.array_equal(O.decode(c, s, n, ss, is_int64=bool(is64)), g["ints0"])
         assert np.array_equal(off, g["off0"]) and np.array_equal(gain, g["gain0"])
+
+
+def test_corrupt_frame_is_caught_by_the_crc_pass(H):
+    """A flipped bit inside a frame body still decodes structurally; the frame-parallel CRC-16 pass
+    (crc_frame_warp) flags the stream and the walker reports ERROR_DECODE_PROCESS."""
+    rng = np.random.default_rng(25)
+    x = np.cumsum(rng.integers(-900, 901, (2, 9000)), axis=1).astype(np.int32)
+    c, s, n, _, _ = H.encode(x, 5)
+    y, walked = H.decode(c, s, n, 9000, mode=2)
+    assert np.array_equal(y, x) and walked == 0
+    bad = c.copy()
+    bad[s[1] + 3000] ^= 0x10
+    for mode in (0, 2):
+        with pytest.raises(RuntimeError, match="16384"):
+            H.decode(bad, s, n, 9000, mode=mode)
