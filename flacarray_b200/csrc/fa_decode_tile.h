@@ -413,15 +413,48 @@ FA_D void tile_channel_pass(const TileParams& P, TileShared* ws, const uint16_t*
             }
         }
         syncwarp();
-        // transpose: each iteration stores 32 consecutive samples of one frame (128 B)
-        const int i = (int)base + ln;
+        // transpose.  Common case (one channel, every active row holds all 32 samples of this block inside
+        // its window, 16-byte aligned destination): 8 trips, each lane moves 4 consecutive samples of one
+        // row with one 16-byte store (a group of 8 lanes covers a row: 128 contiguous bytes).
+        bool vec_ok;
+        {
+            const TileRow mine = ws->row[ln];
+            const bool inactive = mine.hi == 0;
+            const bool full = mine.lo <= (int)base && (int)base + 32 <= mine.hi &&
+                              ((((uintptr_t)(mine.out + base)) & 15) == 0);
+            vec_ok = nch == 1 && ballot(!(inactive || full)) == 0;
+        }
+        if (vec_ok) {
+            const int c4 = (ln & 7) * 4;
+#pragma unroll 2
+            for (int it = 0; it < 8; ++it) {
+                const int r = it * 4 + (ln >> 3);
+                const TileRow row = ws->row[r];
+                if (row.hi != 0) {
+                    const int32_t* tp = ws->tile + r * kTileStride + c4;
+                    const int32_t v0 = tp[0], v1 = tp[1], v2 = tp[2], v3 = tp[3];
+                    U4 q;
+                    if (P.restore) {
+                        float f0 = restore_f32(v0, row.off, row.coeff), f1 = restore_f32(v1, row.off, row.coeff);
+                        float f2 = restore_f32(v2, row.off, row.coeff), f3 = restore_f32(v3, row.off, row.coeff);
+                        memcpy(&q.x, &f0, 4); memcpy(&q.y, &f1, 4); memcpy(&q.z, &f2, 4); memcpy(&q.w, &f3, 4);
+                    } else {
+                        q.x = (uint32_t)v0; q.y = (uint32_t)v1; q.z = (uint32_t)v2; q.w = (uint32_t)v3;
+                    }
+                    sts128(row.out + base + c4, q);
+                }
+            }
+        } else {
+            // general: each iteration stores 32 consecutive samples of one frame (128 B)
+            const int i = (int)base + ln;
 #pragma unroll 4
-        for (int r = 0; r < 32; ++r) {
-            const TileRow row = ws->row[r];
-            if ((uint32_t)(i - row.lo) < (uint32_t)(row.hi - row.lo)) {
-                int32_t v = ws->tile[r * kTileStride + ln];
-                if (P.restore) ((float*)row.out)[i] = restore_f32(v, row.off, row.coeff);
-                else row.out[(int64_t)i * nch + c] = v;
+            for (int r = 0; r < 32; ++r) {
+                const TileRow row = ws->row[r];
+                if ((uint32_t)(i - row.lo) < (uint32_t)(row.hi - row.lo)) {
+                    int32_t v = ws->tile[r * kTileStride + ln];
+                    if (P.restore) ((float*)row.out)[i] = restore_f32(v, row.off, row.coeff);
+                    else row.out[(int64_t)i * nch + c] = v;
+                }
             }
         }
         syncwarp();
