@@ -178,13 +178,24 @@ template <bool CRC>
 FA_D int32_t brc_rice(BitRdC& br, int k, const uint16_t* T) {
     brc_refill<CRC>(br, T);
     uint32_t q, low;
-    int z = clz64(br.buf);
-    if (br.buf != 0 && z + 1 + k <= br.n) {
+    // fast path on 32-bit halves: the whole code (z zeros, the 1, k low bits) lies in the upper word
+    const uint32_t hi = (uint32_t)(br.buf >> 32), lo = (uint32_t)br.buf;
+    const int z = clz32(hi);                   // 32 when hi == 0
+    const int used = z + 1 + k;
+    if (used <= 32 && used <= br.n) {
         q = (uint32_t)z;
-        uint64_t t = (br.buf << z) << 1;
+        const uint32_t t = funnel_lc(lo, hi, (uint32_t)(z + 1));     // bits behind the unary part
+        low = k ? t >> (32 - k) : 0u;
+        const uint32_t nhi = funnel_lc(lo, hi, (uint32_t)used), nlo = funnel_lc(0u, lo, (uint32_t)used);
+        br.buf = ((uint64_t)nhi << 32) | nlo;
+        br.n -= used;
+    } else if (br.buf != 0 && clz64(br.buf) + 1 + k <= br.n) {
+        const int z64 = clz64(br.buf);
+        q = (uint32_t)z64;
+        uint64_t t = (br.buf << z64) << 1;
         low = k ? (uint32_t)(t >> (64 - k)) : 0u;
         br.buf = k ? (t << k) : t;
-        br.n -= z + 1 + k;
+        br.n -= z64 + 1 + k;
     } else {
         q = brc_unary<CRC>(br, T);
         low = brc_read<CRC>(br, k, T);
@@ -390,7 +401,7 @@ FA_D void tile_channel_pass(const TileParams& P, TileShared* ws, const uint16_t*
 #pragma unroll 1
         for (int s = 0; s < 32; s += 4) {
             int i = (int)base + s;
-            brc_service(br);      // warp-uniform refill point of the compressed-byte rings
+            if ((s & 4) == 0) brc_service(br);   // warp-uniform refill point of the compressed-byte rings (every 8 samples)
             if (run && i < bs) {
                 bool fast = L.mode == 2 && L.raw_left == 0 && !L.need_params && L.left >= 4 && L.k >= 0 && i + 4 <= bs;
                 if (fast) {

@@ -38,6 +38,8 @@ FA_D int ctz32(uint32_t v) { return __ffs((int)v) - 1; }
 FA_D int popc32(uint32_t v) { return __popc(v); }
 FA_D uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
 FA_D uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_l(lo, hi, s); }
+// upper word of (hi:lo) << min(s, 32)
+FA_D uint32_t funnel_lc(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_lc(lo, hi, s); }
 FA_D void atom_or_shared(uint32_t* p, uint32_t v) { atomicOr(p, v); }
 FA_D void atom_add_shared64(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }
 FA_D void atom_or_shared_u32(uint32_t* p, uint32_t v) { atomicOr(p, v); }
@@ -202,6 +204,10 @@ inline int popc32(uint32_t v) { return __builtin_popcount(v); }
 inline uint32_t bswap32(uint32_t v) { return __builtin_bswap32(v); }
 inline uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t s) {
     s &= 31;
+    return s ? (hi << s) | (lo >> (32 - s)) : hi;
+}
+inline uint32_t funnel_lc(uint32_t lo, uint32_t hi, uint32_t s) {
+    if (s >= 32) return lo;
     return s ? (hi << s) | (lo >> (32 - s)) : hi;
 }
 inline void atom_or_shared(uint32_t* p, uint32_t v) { __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
