@@ -988,7 +988,8 @@ FA_D int fast_level_maxp(int bs, int level_max) {
 }
 
 template <int H, bool FULL>
-FA_D void analyze_channel(const EncParams& P, AnShared* sh, const float* wsm, const FrameSrc& S, int c, FrameStats* st) {
+FA_D void analyze_channel(const EncParams& P, AnShared* sh, const float* wsm, const FrameSrc& S, int c, FrameStats* st,
+                          int32_t* park) {
     const int t = tid();
     const int ln = lane(), wp = warp();
     const int bs = FULL ? kMaxBs : S.bs;
@@ -996,6 +997,16 @@ FA_D void analyze_channel(const EncParams& P, AnShared* sh, const float* wsm, co
     const int nvalid = FULL ? kSpt : (bs - i0 >= kSpt ? kSpt : (bs > i0 ? bs - i0 : 0));
     int32_t xw[H + kSpt];
     load_chunk<H, FULL>(S, c, t, xw);
+    if (FULL && park != nullptr) {
+        // park the channel's int32 samples (quantised / split once, here) for k_encode: 128 B per thread
+#pragma unroll
+        for (int q = 0; q < kSpt / 4; ++q) {
+            U4 v;
+            v.x = (uint32_t)xw[H + 4 * q]; v.y = (uint32_t)xw[H + 4 * q + 1];
+            v.z = (uint32_t)xw[H + 4 * q + 2]; v.w = (uint32_t)xw[H + 4 * q + 3];
+            sts128(park + t * kSpt + 4 * q, v);
+        }
+    }
 
     // ---- pass 1: statistics, fixed-predictor error sums (libFLAC fixed.c: sum |e_k| over i >= 4),
     //      windowed autocorrelation (lpc.c: float data * float window, double accumulation)
@@ -1164,6 +1175,11 @@ FA_D void analyze_channel(const EncParams& P, AnShared* sh, const float* wsm, co
 }
 
 // One CTA: every channel of (stream, frame) ticket g.
+// 8-byte input types only: measured on B200, parking float32 costs k_enc_analyze as much (4 GB of extra
+// stores) as the second quantisation costs k_encode, while for int64 / float64 it saves the wasted half of
+// every 16-byte load and the double-precision quantiser (cfg3 38.5 -> 35.2 ms, cfg4 300 -> 273 ms)
+FA_D bool frame_parked(const EncParams& P) { return P.dtype == kI64 || P.dtype == kF64; }
+
 // window values of thread t: samples 32 t - H .. 32 t + 31 (zeros outside the window)
 template <int H>
 FA_D void analyze_fill_window(const EncParams& P, float* wsm) {
@@ -1200,9 +1216,12 @@ FA_D void analyze_frame_cta(const EncParams& P, uint32_t g, AnShared* sh, const 
     const int esize = (P.dtype == kI32 || P.dtype == kF32) ? 4 : 8;
     S.base = (const unsigned char*)P.data + (s * P.stream_size + samp0) * esize;
     S.vec = (((uintptr_t)S.base) & 15) == 0;
+    // full frames of the 8-byte types are parked as planar int32 in the frame's (still unused) output
+    // slot: k_encode then reads plain integers instead of converting / splitting the input a second time
+    int32_t* slot = frame_parked(P) ? (int32_t*)(P.slots + (int64_t)(g - P.g_begin) * P.slot_bytes) : nullptr;
     for (int c = 0; c < P.nch; ++c) {
-        if (bs == kMaxBs) analyze_channel<H, true>(P, sh, wsm, S, c, st + c);
-        else analyze_channel<H, false>(P, sh, wsm, S, c, st + c);
+        if (bs == kMaxBs) analyze_channel<H, true>(P, sh, wsm, S, c, st + c, slot ? slot + c * kMaxBs : nullptr);
+        else analyze_channel<H, false>(P, sh, wsm, S, c, st + c, nullptr);
     }
 }
 
@@ -2381,7 +2400,19 @@ FA_D void encode_frames_cta(const EncParams& P, unsigned char* smem_raw) {
         for (int c = 0; c < nch; ++c) {
             int bend = 0;
             bool done = false;
-            if (bs == kMaxBs) done = enc_channel_full<H>(P, X, S, c, f, g, bitpos, bend);
+            if (bs == kMaxBs) {
+                if (frame_parked(P)) {
+                    // planar int32 samples parked by k_enc_analyze in this frame's slot (the compressed frame
+                    // only replaces them when the frame is retired, one iteration from now)
+                    FrameSrc Sp;
+                    Sp.dtype = kI32; Sp.bs = bs; Sp.vec = true;
+                    Sp.off32 = 0.f; Sp.gain32 = 0.f; Sp.off64 = 0.; Sp.gain64 = 0.;
+                    Sp.base = P.slots + (int64_t)(g - P.g_begin) * P.slot_bytes + (int64_t)c * kMaxBs * 4;
+                    done = enc_channel_full<H>(P, X, Sp, c, f, g, bitpos, bend);
+                } else {
+                    done = enc_channel_full<H>(P, X, S, c, f, g, bitpos, bend);
+                }
+            }
             else if (bs >= 64) {
                 // (the short path retires the previous frame on every return: its plans never have mode 0)
                 bend = enc_channel_short<H>(P, X, S, c, f, g, bitpos);

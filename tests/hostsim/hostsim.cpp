@@ -82,6 +82,13 @@ int hs_encode(const void* data, int dtype, int64_t n_stream, int64_t stream_size
     if ((uintptr_t)plan_base + (size_t)(total_frames * nch) * sizeof(FramePlan) > (uintptr_t)(plans.data() + plans.size()))
         return kErrAlloc;
     P.stats = stats.data(); P.plans = plan_base; P.g_begin = 0; P.g_end = (uint32_t)total_frames;
+    // slots for the frames of the (single) batch (analyze parks samples there, encode writes frames)
+    const int64_t slot_bytes = (int64_t)((16 + 2 + (int64_t)nch * (lp.blocksize * 4 + 8) + 15) & ~15ll);
+    std::vector<uint32_t> slots_w((size_t)(total_frames * slot_bytes / 4) + 8);
+    std::vector<uint32_t> fsize((size_t)total_frames);
+    unsigned long long base = 0;
+    P.slots = (uint8_t*)(((uintptr_t)slots_w.data() + 15) & ~(uintptr_t)15); P.slot_bytes = slot_bytes;
+    P.fsize = fsize.data(); P.base = &base;
     fasim::launch(1, kEncThreads, sizeof(AnShared) + 16 + an_window_bytes(12), [&](int) {
         AnShared* ash = (AnShared*)fasim::smem();
         float* wsm = (float*)(fasim::smem() + ((sizeof(AnShared) + 15) & ~(size_t)15));
@@ -95,13 +102,6 @@ int hs_encode(const void* data, int dtype, int64_t n_stream, int64_t stream_size
     fasim::launch(1, 1, 0, [&](int) {
         for (int64_t i = 0; i < total_frames * nch; ++i) design_frame(P, i);
     });
-    // slots for the frames of the (single) batch, then scan + compaction
-    const int64_t slot_bytes = (int64_t)((16 + 2 + (int64_t)nch * (lp.blocksize * 4 + 8) + 15) & ~15ll);
-    std::vector<uint32_t> slots_w((size_t)(total_frames * slot_bytes / 4) + 8);
-    std::vector<uint32_t> fsize((size_t)total_frames);
-    unsigned long long base = 0;
-    P.slots = (uint8_t*)(((uintptr_t)slots_w.data() + 15) & ~(uintptr_t)15); P.slot_bytes = slot_bytes;
-    P.fsize = fsize.data(); P.base = &base;
     // persistent CTAs: the emulator runs blocks one after the other, so one block drains every ticket
     fasim::launch(1, kEncThreads, enc_smem_bytes(nch), [&](int) {
         if (lp.max_lpc_order > 8) encode_frames_cta<12>(P, fasim::smem());
