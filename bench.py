@@ -462,7 +462,7 @@ def run_ours(args):
                          "ms_per_launch": (enc_ms / max(enc_n, 1)) if dominant == ENC else (dec_ms / max(dec_n, 1))},
             "roofline_encode": {"kernel": ENC, "achieved": enc_gbs, "frac": enc_gbs / peak if enc_gbs else None,
                                 "ms_per_launch": enc_ms / max(enc_n, 1)},
-            "roofline_decode": {"kernel": "k_dec_tile", "achieved": dec_gbs, "frac": dec_gbs / peak if dec_gbs else None,
+            "roofline_decode": {"kernel": "k_dec_tile+k_dec_crc", "achieved": dec_gbs, "frac": dec_gbs / peak if dec_gbs else None,
                                 "ms_per_launch": dec_ms / max(dec_n, 1)},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d // e2e_steps,

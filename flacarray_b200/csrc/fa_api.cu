@@ -26,7 +26,7 @@ using namespace fa;
 // Kernels
 // =================================================================================================
 
-// persistent CTAs: each loops over (stream, frame) tickets; H = predictor history kept in registers
+// persistent CTAs: each loops over (stream, frame) units of the batch; H = predictor history kept in registers
 #ifndef FAB_ENC_CTAS
 #define FAB_ENC_CTAS 4
 #endif
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(kScanThreads) k_enc_scan(const EncParams P) {
 // frames of a batch from their slots to their final byte offsets
 __global__ void __launch_bounds__(128) k_enc_compact(const EncParams P) { compact_frame_cta(P, blockIdx.x); }
 
-// stream headers, frame-size tables, stream_starts / stream_nbytes / total from the look-back descriptors
+// stream headers, frame-size tables, stream_starts / stream_nbytes / total from the byte prefixes
 __global__ void k_enc_finalize(const EncParams P, long long* __restrict__ nbytes, long long* __restrict__ total) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < P.n_stream * P.nframes) finalize_entry(P, i / P.nframes, (int)(i % P.nframes), nbytes, total);
@@ -483,9 +483,10 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
     LevelPreset lp = level_preset((int)level);
     const int nch = dtype_channels(dtype);
     const int64_t nf = (stream_size + lp.blocksize - 1) / lp.blocksize;
-    if (n_stream * nf > 0x7fffffffLL) return ERROR_ALLOC;  // ticket counter is 32 bit
+    if (n_stream * nf > 0x7fffffffLL) return ERROR_ALLOC;  // frame indices are 32 bit
 
-    // scratch: [min/max partials of the quantise pre-pass] | desc | ends | ticket.  Sized once up front
+    // scratch: [min/max partials of the quantise pre-pass] | byte prefixes | ends | work counters | per-batch
+    // statistics, plans, frame sizes, slots.  Sized once up front
     // so that the pre-pass (queued first on the same stream) and the encoder never share bytes.
     size_t pre = 0;
     if (dtype >= FAB_F32) {
@@ -493,8 +494,8 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
         pre = 2 * align256((size_t)n_stream * nchunk * (dtype == FAB_F32 ? 4 : 8));
     }
     size_t desc_b = align256((size_t)(n_stream * nf) * 8), ends_b = align256((size_t)n_stream * 8);
-    // the three encoder kernels run over batches of (stream, frame) tickets so that the per-frame
-    // records between them stay small; one ticket counter per batch
+    // the encoder kernels run over batches of (stream, frame) units so that the per-frame records and the
+    // slot buffer between them stay small (~1 GB); one work counter per batch
     const int64_t total_frames = n_stream * nf;
     const int64_t slot_bytes = (int64_t)((16 + 2 + (int64_t)nch * (lp.blocksize * 4 + 8) + 15) & ~15ll);
     const int64_t batch = std::min<int64_t>(total_frames, std::max<int64_t>(1024, kEncBatchBytes / slot_bytes));

@@ -1,28 +1,24 @@
-// fa_encode.h -- FLAC frame encoder body: one 128-thread CTA encodes one (stream, frame) at a time
-// and loops over frames (persistent CTAs, ticket order).
+// fa_encode.h -- FLAC encoder bodies.
 //
 // Replaces the libFLAC encoder the reference drives per stream in compress.c:184-237 (serial) and
 // compress.c:337-390 (OpenMP), plus the byte bookkeeping of the write callbacks
 // (compress.c:13-104) and the final prefix-sum/concatenation (compress.c:402-429).
 //
-// Layout of the work: every thread owns 32 consecutive samples of the frame (plus the predictor
-// history before them) in registers; nothing but the packed output frame is staged in shared memory.
+// Five kernels per batch of <= 64 Ki (stream, frame) units (see "Fast path" below):
+//   analyze_frame_cta  (k_enc_analyze)  statistics of every (frame, channel)            128-thread CTA per frame
+//   design_frame       (k_enc_design)   predictor design                                one thread per (frame, channel)
+//   encode_frames_cta  (k_encode)       residual, Rice, packing, CRC-16 -> frame slot   persistent 128-thread CTAs
+//   scan_batch_cta     (k_enc_scan)     frame sizes -> byte offsets                     one CTA
+//   compact_frame_cta  (k_enc_compact)  slot -> final place                             CTA per frame
 //
-// Three kernels (see "Fast path" below): k_enc_analyze -> k_enc_design -> k_encode.
-// Two code paths per (frame, channel):
-//   * fast path  -- full 4096-sample frames whose samples fit 22 bits and have no wasted bits (the
-//     benchmark's quantised detector data): all integer work in 32-bit registers, one fused pass for
-//     the sample statistics, the five fixed-predictor error sums (VABSDIFF accumulate) and the
-//     windowed autocorrelation (FP64 FMA), REDUX warp reductions, LPC residual with 32-bit IMADs
-//     (the coefficient precision is lowered until sum|q|*max|x| provably fits, as libFLAC does for
-//     <= 16-bit input), per-thread Rice packing into a 64-bit accumulator with the CRC-16 folded
-//     into every flushed word (positions are fixed up with one GF(2) multiply per thread).
-//   * general path -- anything else (short last frames, wasted bits, wide samples, residuals that do
-//     not fit 32 bits, VERBATIM/CONSTANT subframes): the same stages with 64-bit arithmetic and
-//     per-sample bounds checks.  Slow, but only reached by frames the fast path rejects.
-//
-// Frame placement: decoupled look-back over frame sizes in ticket order gives every frame its final
-// byte offset, so the compressed bytes are written to HBM exactly once.
+// Code paths of k_encode per (frame, channel):
+//   * full path   -- 4096-sample frames: rolled 8-sample sub-blocks, 32-bit integer work for narrow samples
+//     (|x| < 2^22; the coefficient precision is lowered until sum|q|*max|x| provably fits, as libFLAC does
+//     for <= 16-bit input), 64-bit work for wide samples (the low word of an int64), wasted bits;
+//   * short path  -- 64 <= blocksize < 4096 (last frame of a stream, blocksize-1152 levels): the same stages
+//     with the thread's 32 samples resident in registers and a warp-level Rice partition search;
+//   * general path -- anything else (tiny frames, residuals that do not fit 32 bits, VERBATIM subframes):
+//     64-bit arithmetic and per-sample bounds checks.  Slow, but only reached by frames the others reject.
 #pragma once
 #include "fa_bits.h"
 #include "fa_quant.h"
@@ -113,8 +109,8 @@ struct EncParams {
     int64_t out_capacity;
     long long* starts;         // [n_stream] byte offset of every stream; must be preset to -1
     long long* ends;           // [n_stream]
-    unsigned long long* desc;  // [n_stream * nframes] look-back descriptors, zeroed
-    uint32_t* ticket;          // zeroed (one counter per launch)
+    unsigned long long* desc;  // [n_stream * nframes] inclusive byte prefix of every frame (written by k_enc_scan)
+    uint32_t* ticket;          // zeroed work counter of this batch (frames are taken in any order)
     int* err;
     int hdr_bytes;
     uint8_t* slots;            // batch scratch: frame (g - g_begin) is written at slots + (g - g_begin) * slot_bytes
@@ -123,7 +119,7 @@ struct EncParams {
     unsigned long long* base;  // running total of bytes before this batch (device scalar)
     FrameStats* stats;         // [(g - g_begin) * nch + c]
     FramePlan* plans;
-    uint32_t g_begin, g_end;   // (stream, frame) tickets covered by this batch of launches
+    uint32_t g_begin, g_end;   // (stream, frame) units covered by this batch of launches
 };
 
 // Records exchanged between the three encoder kernels, one per (frame, channel):
@@ -200,7 +196,7 @@ struct EncShared {
     // deferred tail words of the packing sessions (OR-ed in when the frame is retired)
     uint32_t tail_val[2][kEncThreads];
     int tail_word[2][kEncThreads];
-    // the frame that is packed in `out` and waits to be retired (look-back, CRC-16, copy-out)
+    // the frame that is packed in `out` and waits to be retired (CRC-16, copy to its slot)
     int prev_valid, prev_f, prev_nbytes;
     uint32_t prev_g;
     long long prev_off;
@@ -365,7 +361,7 @@ FA_D void pk_end(const Pk& pk, uint32_t& tail_val, int& tail_word) {
     tail_word = pk.word;
 }
 
-// ---- decoupled look-back descriptors: [63:62] status (0 empty, 1 aggregate, 2 inclusive prefix), [61:0] bytes
+// ---- byte-prefix words: [61:0] bytes (the two top bits were the status of the first version's look-back)
 constexpr unsigned long long kDescAgg = 1ull << 62, kDescPre = 2ull << 62, kDescMask = (1ull << 62) - 1;
 
 // Frame placement.  Every frame of a batch is first written to its own 16-byte aligned worst-case slot, so
@@ -765,7 +761,7 @@ FA_D void fixed_coefs(int order, int32_t* c, int n) {
 
 
 // ------------------------------------------------------------------------------------------------------
-// Retiring a packed frame: look-back -> byte offset, CRC-16, copy to HBM.  The frame packed during
+// Retiring a packed frame: slot address, CRC-16, copy to HBM.  The frame packed during
 // iteration n of the CTA loop is retired during iteration n + 1 (before the staged buffer is needed
 // again), which gives every predecessor a whole frame time to publish its size: no spinning.
 // ------------------------------------------------------------------------------------------------------
@@ -783,7 +779,7 @@ struct EncCtx {
 };
 
 // One warp: where the frame waiting in `out` goes (its slot) and its size.
-FA_D void retire_lookback(const EncParams& P, EncShared* sh) {
+FA_D void retire_slot(const EncParams& P, EncShared* sh) {
     if (!sh->prev_valid) return;
     if (lane() == 0) {
         const uint32_t i = sh->prev_g - P.g_begin;
@@ -792,7 +788,7 @@ FA_D void retire_lookback(const EncParams& P, EncShared* sh) {
     }
 }
 
-// All threads, after a barrier behind retire_lookback: CRC-16 partials of the staged frame (uniform
+// All threads, after a barrier behind retire_slot: CRC-16 partials of the staged frame (uniform
 // pass, one contiguous run of words per thread, positions fixed up with one GF(2) multiply) and the
 // coalesced copy to HBM.
 // skip0: thread 0 takes no share of the work (it builds the next frame's header meanwhile)
@@ -847,7 +843,7 @@ FA_D void zero_out(const EncCtx& X) {   // only used once, when the CTA starts
 // Generic (non-overlapped) retire sequence with its own barriers; leaves `out` zeroed.
 FA_D void retire_full(const EncParams& P, EncCtx& X) {
     if (X.retired) return;
-    if (warp() == 0) retire_lookback(P, X.sh);
+    if (warp() == 0) retire_slot(P, X.sh);
     sync();
     retire_copyout(P, X);
     sync();
@@ -925,7 +921,7 @@ FA_D void compact_frame_cta(const EncParams& P, uint32_t i) {
     }
 }
 
-// Stream header and frame-size table, from the finished look-back descriptors (one thread per stream
+// Stream header and frame-size table, from the finished byte prefixes (one thread per stream
 // header, one per table entry).  desc[g] holds the inclusive byte prefix of frame g.
 FA_D void finalize_entry(const EncParams& P, int64_t s, int f, long long* nbytes_out, long long* total_out) {
     const uint32_t g = (uint32_t)(s * P.nframes + f);
@@ -972,8 +968,8 @@ FA_D void finalize_entry(const EncParams& P, int64_t s, int f, long long* nbytes
 //       windowed autocorrelation -> FrameStats;
 //   design_frame (k_enc_design, one THREAD per (frame, channel)): fixed order choice, Levinson-Durbin,
 //       order choice, coefficient quantisation -> FramePlan;
-//   enc_channel_fast (k_encode, persistent CTAs in ticket order): residuals, Rice partition search,
-//       bit packing, CRC-16, look-back placement, copy-out.
+//   enc_channel_full / enc_channel_fast (k_encode, persistent CTAs): residuals, Rice parameters, bit
+//       packing, CRC-16, copy to the frame's slot.
 // The samples are read (and float input quantised) twice; the path is instruction-bound, not
 // HBM-bound, and the second read buys a design stage that runs at full machine width.
 // Eligible frames: 64 <= blocksize <= 4096 samples; anything else (and any frame whose predictive
@@ -1174,7 +1170,7 @@ FA_D void analyze_channel(const EncParams& P, AnShared* sh, const float* wsm, co
     sync();   // the partials are reused by the next channel
 }
 
-// One CTA: every channel of (stream, frame) ticket g.
+// One CTA: every channel of (stream, frame) unit g.
 // 8-byte input types only: measured on B200, parking float32 costs k_enc_analyze as much (4 GB of extra
 // stores) as the second quantisation costs k_encode, while for int64 / float64 it saves the wasted half of
 // every 16-byte load and the double-precision quantiser (cfg3 38.5 -> 35.2 ms, cfg4 300 -> 273 ms)
@@ -1306,7 +1302,7 @@ FA_D bool enc_channel_fast(const EncParams& P, EncCtx& X, const FrameSrc& S, int
     int32_t xw[H + kSpt];
     load_chunk<H, FULL>(S, c, t, xw);
     const bool retiring = !X.retired;
-    if (wp == 3 && retiring) retire_lookback(P, sh);   // previous frame: overlaps the loads above
+    if (wp == 3 && retiring) retire_slot(P, sh);   // previous frame: overlaps the loads above
 
     if (mode == 1) {
         if (retiring) {
@@ -1581,7 +1577,7 @@ FA_DNOINL int enc_channel_short(const EncParams P, EncCtx X, const FrameSrc S, i
 // shared memory (transposed: conflict-free) between the statistics, length and packing passes; the
 // Rice parameters come from shuffles inside the 2^(7 - max_porder) threads that share a finest
 // partition, and the partition order is chosen between the level's maximum and 0.  Three barriers per
-// (frame, channel): chunk statistics (B3), bit-offset scan (B5), and the ticket barrier of the CTA loop.
+// (frame, channel): chunk statistics (B3), bit-offset scan (B5), and the barrier at the top of the CTA loop.
 // ------------------------------------------------------------------------------------------------------
 // Rice parameter and estimated bits of one partition (libFLAC set_partitioned_rice_, estimate mode)
 FA_D uint32_t rice_estimate(unsigned long long sum, uint32_t n, int& k_out) {
@@ -1842,7 +1838,7 @@ FA_D bool enc_channel_full(const EncParams& P, EncCtx& X, const FrameSrc& S, int
     const bool wide1 = wide || (pa.z & 0xFFu) != 0;
     const bool retiring = !X.retired;
     FAB_TICK(1);
-    if (wp == 3 && retiring) retire_lookback(P, sh);   // previous frame
+    if (wp == 3 && retiring) retire_slot(P, sh);   // previous frame
     FAB_TICK(2);
 
     if (mode == 1) {
@@ -2343,7 +2339,7 @@ FA_DNOINL int enc_channel_general(const EncParams P, EncCtx X, const FrameSrc S,
 }
 
 // ------------------------------------------------------------------------------------------------------
-// The CTA body: loops over (stream, frame) tickets.  `smem_raw` >= enc_smem_bytes(nch).
+// The CTA body: loops over (stream, frame) units.  `smem_raw` >= enc_smem_bytes(nch).
 // ------------------------------------------------------------------------------------------------------
 template <int H>
 FA_D void encode_frames_cta(const EncParams& P, unsigned char* smem_raw) {
@@ -2437,7 +2433,7 @@ FA_D void encode_frames_cta(const EncParams& P, unsigned char* smem_raw) {
     retire_full(P, X);
 #if defined(FAB_PHASE_TIMING) && defined(__CUDACC__)
     if ((blockIdx.x == 7 || blockIdx.x == 300) && (t == 0 || t == 37 || t == 127 || t == 96))
-        printf("cta %d t %d: top %lld | plan %lld lookback %lld pass2 %lld est %lld B3 %lld copyout %lld lens %lld B5 %lld pack %lld rest %lld\n",
+        printf("cta %d t %d: top %lld | plan %lld slot %lld pass2 %lld est %lld B3 %lld copyout %lld lens %lld B5 %lld pack %lld rest %lld\n",
                (int)blockIdx.x, t, X.ph[0], X.ph[1], X.ph[2], X.ph[3], X.ph[4], X.ph[5], X.ph[6], X.ph[7], X.ph[8], X.ph[9], X.ph[10]);
 #endif
 }

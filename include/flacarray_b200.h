@@ -141,9 +141,11 @@ int fab_float_to_int(fab_ctx* ctx, const void* d_input, int dtype, int64_t n_str
 int fab_int_to_float(fab_ctx* ctx, const void* d_input, int dtype, int64_t n_stream, int64_t stream_size,
                      const void* d_offsets, const void* d_gains, void* d_output, void* stream);
 
-/* Optional per-kernel timing for roofline reports: when enabled, CUDA events are recorded on the
- * launching stream around the dominant kernel of fab_encode (which = 0) and fab_decode (which = 1).
- * fab_profile_ms returns the accumulated milliseconds and (through *count) the number of launches. */
+/* Optional kernel timing for roofline reports: when enabled, CUDA events are recorded on the launching
+ * stream around the encoder kernel sequence of one fab_encode call (which = 0: k_enc_analyze,
+ * k_enc_design, k_encode, k_enc_scan, k_enc_compact over all batches) and around the decoder kernels of
+ * one fab_decode call (which = 1: k_dec_tile, k_dec_crc).  fab_profile_ms returns the accumulated
+ * milliseconds and (through *count) the number of calls. */
 void fab_profile(fab_ctx* ctx, int enable);
 double fab_profile_ms(fab_ctx* ctx, int which, int64_t* count);
 

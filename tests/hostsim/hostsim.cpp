@@ -1,6 +1,6 @@
 // hostsim.cpp -- TEST HARNESS ONLY.  Compiles the kernel bodies of flacarray_b200/csrc for the host
 // with the OS-thread SIMT emulator of fa_simt.h so their logic can be unit-tested in the GPU-less
-// build container (bit packing, CRC, look-back bookkeeping, frame index, decode).  This file is never
+// build container (bit packing, CRC, slot placement and scan, frame index, decode).  This file is never
 // linked into libflacarray_b200.so and the Python package never loads it: the product has no CPU path.
 #include <cstdio>
 #include <cstdlib>
