@@ -390,7 +390,9 @@ def run_ours(args):
     value = 2.0 * raw * world * args.steps / (t_enc_m + t_dec_m) / 1e9
 
     # ---- e2e: public API with pinned host buffers, H2D + D2H inside the timed region ----
-    e2e_streams = min(n_stream, args.e2e_streams)
+    # pinned host memory per rank ~ 5 x the e2e array (input + two generations of results): keep the whole
+    # node below ~64 GB by shrinking the per-rank e2e array when more than two ranks share the host
+    e2e_streams = min(n_stream, args.e2e_streams if world <= 2 else max(64, (2 * args.e2e_streams) // world))
     host = torch.empty((e2e_streams, n_samp), dtype=torch.float32, pin_memory=True)
     host.copy_(data[:e2e_streams])
     torch.cuda.synchronize()
