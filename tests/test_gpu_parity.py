@@ -283,3 +283,43 @@ def test_device_resident_roundtrip(fa, oracle):
     far = fa.FlacArray.from_array(f, quanta=1e-4)
     back = far.to_array()
     assert back.is_cuda and float((back - f).abs().max()) <= 0.5e-4 * 1.001 + 1e-6
+
+
+@pytest.mark.parametrize("level", [2, 5, 8])
+def test_unaligned_streams_and_mixed_frame_kinds(fa, oracle, level):
+    """Stream lengths that are not multiples of 4 put every stream but the first at an unaligned address
+    (scalar loads instead of 16-byte vectors in every encoder path, unaligned compaction targets); each
+    stream mixes full frames, a short last frame and frame kinds the fast paths hand to one another
+    (constant, wasted bits, wide, incompressible)."""
+    rng = np.random.default_rng(77 + level)
+    L = 3 * 4096 + 1231
+    walk = np.cumsum(rng.integers(-700, 701, (5, L)), axis=1)
+    x32 = walk.astype(np.int32)
+    x32[1, 4096:8192] = 9                                   # a constant frame inside a predictive stream
+    x32[2, :4096] <<= 6                                     # wasted bits in the first frame only
+    x32[3, 8192:] = rng.integers(-2 ** 31, 2 ** 31 - 1, L - 8192, dtype=np.int64).astype(np.int32)   # VERBATIM frames
+    x32[4] = (np.cumsum(rng.integers(-2 ** 25, 2 ** 25, L)) % 2 ** 32).astype(np.uint32).astype(np.int32)  # wide + wrapping
+    x64 = (walk * 3 + 2 ** 40 * rng.integers(-4, 5, (5, 1))).astype(np.int64)
+    x64[0, :4] = [-2 ** 63, 2 ** 63 - 1, 2 ** 32, -2 ** 32]
+    for x in (x32, x64):
+        is64 = x.dtype == np.int64
+        c, s, n, _, _ = fa.array_compress(x, level=level)
+        assert np.array_equal(oracle.decode(c, s.reshape(-1), n.reshape(-1), L, is_int64=is64), x)
+        assert np.array_equal(fa.array_decompress(c, L, s, n, is_int64=is64), x)
+        got = fa.array_decompress(c, L, s, n, first_stream_sample=4090, last_stream_sample=8200, is_int64=is64)
+        assert np.array_equal(got, x[:, 4090:8200])
+        oc, _, _ = oracle.encode(x, level)
+        assert c.size <= 1.02 * oc.size, (x.dtype, level, c.size, oc.size)
+    f32 = (rng.normal(0, 1, (3, L)) + np.linspace(-2, 2, 3)[:, None]).astype(np.float32)
+    q = np.full(3, 1e-4, np.float32)
+    c, s, n, off, gain = fa.array_compress(f32, level=level, quanta=1e-4)
+    oi, oo, og = oracle.float_to_int(f32, q)
+    assert np.array_equal(oracle.decode(c, s.reshape(-1), n.reshape(-1), L), oi)
+    assert np.array_equal(off, oo) and np.array_equal(gain, og)
+    assert np.array_equal(fa.array_decompress(c, L, s, n, stream_offsets=off, stream_gains=gain), oracle.int_to_float(oi, oo, og))
+    f64 = rng.normal(0, 1, (3, L))
+    c, s, n, off, gain = fa.array_compress(f64, level=level, quanta=1e-9)
+    oi, oo, og = oracle.float_to_int(f64, np.full(3, 1e-9))
+    assert np.array_equal(oracle.decode(c, s.reshape(-1), n.reshape(-1), L, is_int64=True), oi)
+    assert np.array_equal(fa.array_decompress(c, L, s, n, stream_offsets=off, stream_gains=gain, is_int64=True),
+                          oracle.int_to_float(oi, oo, og))
