@@ -294,6 +294,10 @@ struct fab_ctx {
     int64_t launches = 0;
     std::string last_error = "";
     bool smem_configured = false;
+    // second stream for work that only fills idle SMs (CRC pass behind the tile decoder's last wave,
+    // compaction of batch b under the analysis of batch b + 1); fork / join with events
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // optional per-kernel timing (bench.py's roofline): CUDA events on the launching stream
     bool prof = false;
     struct Pending { cudaEvent_t a, b; int which; };
@@ -383,7 +387,10 @@ extern "C" int fab_create(fab_ctx** out) {
               cudaMalloc((void**)&ctx->d_window[1], 4096 * 4) == cudaSuccess &&
               cudaMemcpy(ctx->d_window[1], w1.data(), 4096 * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMalloc((void**)&ctx->d_err, 4) == cudaSuccess && cudaMemset(ctx->d_err, 0, 4) == cudaSuccess &&
-              cudaMallocHost((void**)&ctx->h_err, 4) == cudaSuccess;
+              cudaMallocHost((void**)&ctx->h_err, 4) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
     delete h;
     delete ht;
     if (!ok) {
@@ -404,6 +411,9 @@ extern "C" void fab_destroy(fab_ctx* ctx) {
     if (ctx->d_err) cudaFree(ctx->d_err);
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->aux) cudaStreamDestroy(ctx->aux);
     delete ctx;
 }
 
@@ -563,17 +573,28 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
         P.g_end = (uint32_t)std::min<int64_t>(total_frames, (bi + 1) * batch);
         P.ticket = ticket + bi;
         const int64_t nfr = (int64_t)P.g_end - (int64_t)P.g_begin;
+        // The compaction of batch b (memory-bound) runs on the second stream under the analysis of batch
+        // b + 1 (issue-bound).  The slot and frame-size buffers are reused by every batch: whoever writes
+        // them next -- k_enc_analyze when it parks samples in the slots (8-byte types), else k_encode --
+        // waits for the previous compaction.
+        const bool parked = dtype == FAB_I64 || dtype == FAB_F64;
+        if (bi > 0 && parked) FAB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
         const unsigned agrid = (unsigned)std::min<int64_t>(nfr, (int64_t)ctx->n_sm * FAB_AN_CTAS);
         if (h12) k_enc_analyze<12><<<agrid, kEncThreads, 0, st>>>(P);
         else k_enc_analyze<8><<<agrid, kEncThreads, 0, st>>>(P);
         k_enc_design<<<(unsigned)((nfr * nch + 127) / 128), 128, 0, st>>>(P, nfr * nch);
+        if (bi > 0 && !parked) FAB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
         unsigned grid = (unsigned)std::min<int64_t>(nfr, resident);
         if (h12) k_encode<12><<<grid, kEncThreads, smem, st>>>(P);
         else k_encode<8><<<grid, kEncThreads, smem, st>>>(P);
         k_enc_scan<<<1, kScanThreads, 0, st>>>(P);
-        k_enc_compact<<<(unsigned)nfr, 128, 0, st>>>(P);
+        FAB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
+        FAB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+        k_enc_compact<<<(unsigned)nfr, 128, 0, ctx->aux>>>(P);
+        FAB_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->aux));
         ctx->launches += 5;
     }
+    FAB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
     prof_end(ctx, st);
     P.g_begin = 0; P.g_end = (uint32_t)total_frames;
     k_enc_finalize<<<(unsigned)((n_stream * nf + 255) / 256), 256, 0, st>>>(P, (long long*)d_nbytes, (long long*)d_total);
@@ -662,8 +683,14 @@ extern "C" int fab_decode(fab_ctx* ctx, const unsigned char* d_bytes, const int6
         TP.restore = fuse_restore ? 1 : 0; TP.offsets = (const float*)d_offsets; TP.gains = (const float*)d_gains;
         int64_t per_cta = (int64_t)kTileWarps * 32;
         prof_begin(ctx, 1, st);
+        FAB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
         k_dec_tile<false><<<(unsigned)((total + per_cta - 1) / per_cta), kTileWarps * 32, 0, st>>>(TP);
-        k_dec_crc<<<(unsigned)((total + 3) / 4), 128, 0, st>>>(TP);
+        // the CRC pass only needs the frame table: it runs on the second stream, queued behind the tile
+        // kernel's launch so that its CTAs fill the SMs the decoder's last partial wave leaves idle
+        FAB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+        k_dec_crc<<<(unsigned)((total + 3) / 4), 128, 0, ctx->aux>>>(TP);
+        FAB_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->aux));
+        FAB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
         prof_end(ctx, st);
         ctx->launches += 2;
         // general per-thread decoder: only the frames the tile path flagged
