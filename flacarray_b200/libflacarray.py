@@ -186,6 +186,12 @@ def _scratch_out(dev, nbytes):
     return buf
 
 
+def release_scratch():
+    """Drop the per-device worst-case output buffers of the device-resident encode (they are as large as
+    the largest array encoded so far and are otherwise kept for reuse)."""
+    _enc_scratch.clear()
+
+
 def _encode_device_raw(d, n_stream, stream_size, level, quanta=None, scratch=False):
     """fab_encode into a worst-case device buffer (a fresh one, or the per-device scratch).
     Returns (buffer, starts, nbytes, total, offsets, gains)."""

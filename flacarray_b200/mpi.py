@@ -64,14 +64,56 @@ class TorchComm:
         dist.broadcast_object_list(box, src=root, group=self.group)
         return box[0]
 
+    # Point-to-point transfer of (possibly nested tuples / lists of) numpy arrays, used by the serial-writer
+    # file I/O (io_common.py).  Small objects are pickled; arrays above `_BIG` bytes travel as raw uint8
+    # tensors in bounded chunks (through device memory over NCCL, directly from host memory over gloo), so
+    # a rank's multi-GB compressed block is never pickled.
+    _BIG = 1 << 20
+    _CHUNK = 256 << 20
+
+    def _split(self, obj, big):
+        if isinstance(obj, np.ndarray) and obj.nbytes >= self._BIG:
+            big.append(np.ascontiguousarray(obj))
+            return ("__ndarray__", len(big) - 1, obj.dtype.str, obj.shape)
+        if isinstance(obj, (tuple, list)):
+            return type(obj)(self._split(o, big) for o in obj)
+        return obj
+
+    def _join(self, obj, big):
+        if isinstance(obj, tuple) and len(obj) == 4 and obj[0] == "__ndarray__":
+            return big[obj[1]].view(np.dtype(obj[2])).reshape(obj[3])
+        if isinstance(obj, (tuple, list)):
+            return type(obj)(self._join(o, big) for o in obj)
+        return obj
+
     def send(self, obj, dest):
-        """Point-to-point object transfer (used by the serial-writer file I/O, io_common.py)."""
-        dist.send_object_list([obj], dst=dest, group=self.group)
+        big = []
+        skel = self._split(obj, big)
+        dist.send_object_list([(skel, [b.nbytes for b in big])], dst=dest, group=self.group)
+        for b in big:
+            flat = torch.from_numpy(b.reshape(-1).view(np.uint8))
+            for o in range(0, flat.numel(), self._CHUNK):
+                piece = flat[o:o + self._CHUNK]
+                dist.send(piece.to(self.device) if self.device.type == "cuda" else piece, dst=dest, group=self.group)
 
     def recv(self, source):
         box = [None]
         dist.recv_object_list(box, src=source, group=self.group)
-        return box[0]
+        skel, sizes = box[0]
+        big = []
+        for nb in sizes:
+            host = np.empty(nb, dtype=np.uint8)
+            flat = torch.from_numpy(host)
+            for o in range(0, nb, self._CHUNK):
+                n = min(self._CHUNK, nb - o)
+                if self.device.type == "cuda":
+                    buf = torch.empty(n, dtype=torch.uint8, device=self.device)
+                    dist.recv(buf, src=source, group=self.group)
+                    flat[o:o + n].copy_(buf)
+                else:
+                    dist.recv(flat[o:o + n], src=source, group=self.group)
+            big.append(host)
+        return self._join(skel, big)
 
     def barrier(self):
         dist.barrier(group=self.group)

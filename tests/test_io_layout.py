@@ -111,6 +111,8 @@ def _worker(rank, world, port, q):
         from oracle import oracle as O
 
         comm = TorchComm()
+        comm._BIG = 1 << 10          # the compressed blocks of this test travel as raw tensors in chunks
+        comm._CHUNK = 3000
         rng = np.random.default_rng(5)
         n_total, L = 5, 4000
         full = np.cumsum(rng.integers(-500, 501, (n_total, L)), axis=1).astype(np.int32)
