@@ -21,6 +21,7 @@ import numpy as np
 from .utils import keep_select, select_keep_indices
 
 FORMAT_VERSION = "1"
+READ_VERSIONS = ("0", "1")
 NAMES = {
     "compressed": "compressed",
     "stream_starts": "stream_starts",
@@ -185,10 +186,8 @@ def _read_block(grp, meta, dist_range, keep_block):
             select_keep_indices(raw_gains, indices), comp, indices)
 
 
-def read_compressed(grp, keep=None, mpi_comm=None, mpi_dist=None):
-    """Load (this rank's block of) a compressed array.  Returns the reference's tuple
-    (local_shape, global_shape, compressed, n_channel, stream_starts, stream_nbytes, stream_offsets,
-    stream_gains, mpi_dist, keep_indices) -- hdf5_load_v1.py:93-246."""
+def _read_compressed_versioned(grp, keep=None, mpi_comm=None, mpi_dist=None):
+    """`read_compressed` plus the format version string as a last element."""
     from .mpi import distribute_and_verify
 
     rank, nproc = _rank_size(mpi_comm)
@@ -199,11 +198,13 @@ def read_compressed(grp, keep=None, mpi_comm=None, mpi_dist=None):
             raise RuntimeError("Group does not contain a FlacArray")
         ver = grp.attrs["flacarray_format_version"]
         ver = ver.decode() if isinstance(ver, bytes) else str(ver)
-        if ver != FORMAT_VERSION:
-            raise RuntimeError(f"Unsupported FlacArray format version {ver} (this reader handles version 1)")
+        if ver not in READ_VERSIONS:
+            raise RuntimeError(f"Unsupported FlacArray format version {ver} (this reader handles versions 0 and 1)")
         dstarts = grp[NAMES["stream_starts"]]
         meta = {
-            "n_channel": int(grp.attrs[NAMES["flac_channels"]]),
+            # version 0 predates 2-channel streams and has no channel attribute (hdf5_load_v0.py:262-270)
+            "n_channel": 1 if ver == "0" else int(grp.attrs[NAMES["flac_channels"]]),
+            "version": ver,
             "stream_size": int(dstarts.attrs[NAMES["stream_size"]]),
             "aux_shape": tuple(int(x) for x in dstarts.shape),
             "has_offsets": NAMES["stream_offsets"] in grp,
@@ -231,7 +232,35 @@ def read_compressed(grp, keep=None, mpi_comm=None, mpi_dist=None):
     else:
         blk = mpi_comm.recv(source=0)
     local_shape, starts, nbytes, offs, gains, comp, indices = blk
-    return (local_shape, global_shape, comp, meta["n_channel"], starts, nbytes, offs, gains, mpi_dist, indices)
+    return (local_shape, global_shape, comp, meta["n_channel"], starts, nbytes, offs, gains, mpi_dist, indices,
+            meta["version"])
+
+
+def read_compressed(grp, keep=None, mpi_comm=None, mpi_dist=None):
+    """Load (this rank's block of) a compressed array.  Returns the reference's tuple
+    (local_shape, global_shape, compressed, n_channel, stream_starts, stream_nbytes, stream_offsets,
+    stream_gains, mpi_dist, keep_indices) -- hdf5_load_v1.py:93-246, hdf5_load_v0.py:92-277."""
+    return _read_compressed_versioned(grp, keep=keep, mpi_comm=mpi_comm, mpi_dist=mpi_dist)[:-1]
+
+
+def _decompress_v0(compressed, stream_size, starts, nbytes, offs, gains, first, last, use_threads, no_flatten):
+    """Version-0 payloads are always 1-channel FLAC (hdf5_load_v0.py:357-411).  Offsets without gains mark
+    the legacy int64 encoding -- 32-bit samples plus one int64 offset per stream; float64 data was stored
+    as 32-bit integers with float64 offsets/gains and is restored in float32, then promoted."""
+    from .decompress import array_decompress
+
+    kw = dict(first_stream_sample=first, last_stream_sample=last, is_int64=False, use_threads=use_threads,
+              no_flatten=no_flatten)
+    if offs is not None and gains is None:
+        arr = _host(array_decompress(compressed, stream_size, starts, nbytes, **kw))
+        return arr.astype(np.int64) + np.asarray(offs).reshape(np.asarray(offs).shape + (1,))
+    if offs is None:
+        return array_decompress(compressed, stream_size, starts, nbytes, **kw)
+    want64 = np.asarray(gains).dtype == np.dtype(np.float64)
+    arr = array_decompress(compressed, stream_size, starts, nbytes,
+                           stream_offsets=np.asarray(offs, dtype=np.float32),
+                           stream_gains=np.asarray(gains, dtype=np.float32), **kw)
+    return arr.astype(np.float64) if want64 else arr
 
 
 def read_array(grp, keep=None, stream_slice=None, keep_indices=False, mpi_comm=None, mpi_dist=None, use_threads=False,
@@ -239,8 +268,8 @@ def read_array(grp, keep=None, stream_slice=None, keep_indices=False, mpi_comm=N
     """Read and decompress (hdf5_load_v1.py:249-375); the decode runs on the GPU."""
     from .decompress import array_decompress
 
-    (local_shape, global_shape, compressed, n_channel, starts, nbytes, offs, gains, mpi_dist, indices) = read_compressed(
-        grp, keep=keep, mpi_comm=mpi_comm, mpi_dist=mpi_dist)
+    (local_shape, global_shape, compressed, n_channel, starts, nbytes, offs, gains, mpi_dist, indices,
+     version) = _read_compressed_versioned(grp, keep=keep, mpi_comm=mpi_comm, mpi_dist=mpi_dist)
     first = last = None
     if stream_slice is not None:
         if stream_slice.step is not None and stream_slice.step != 1:
@@ -248,6 +277,9 @@ def read_array(grp, keep=None, stream_slice=None, keep_indices=False, mpi_comm=N
         first, last = stream_slice.start, stream_slice.stop
     if compressed is None:
         arr = None      # this rank holds no streams (empty keep selection)
+    elif version == "0":
+        arr = _decompress_v0(compressed, local_shape[-1], starts, nbytes, offs, gains, first, last, use_threads,
+                             no_flatten)
     else:
         arr = array_decompress(compressed, local_shape[-1], starts, nbytes, stream_offsets=offs, stream_gains=gains,
                                first_stream_sample=first, last_stream_sample=last, is_int64=(n_channel == 2),

@@ -233,3 +233,26 @@ def test_write_read_array_through_group_layout(fa, zarr_style):
     g3 = MemGroup(zarr_style=zarr_style)
     mod.write_array(one, g3, quanta=1e-6)
     assert g3["stream_starts"].shape == (1,) and mod.read_array(g3).shape == (6000,)
+
+
+def test_version0_group_read(oracle):
+    """hdf5_load_v0.py:357-411: legacy int64 (32-bit samples + int64 stream offsets), float32, and float64
+    stored as 32-bit integers with float64 offsets / gains."""
+    from flacarray_b200 import hdf5 as fh5
+    from test_io_layout import _v0_group
+
+    rng = np.random.default_rng(12)
+    ints = np.cumsum(rng.integers(-50, 51, (2, 3, 4000)), axis=-1).astype(np.int32)
+    offs = rng.integers(-2 ** 40, 2 ** 40, (2, 3)).astype(np.int64)
+    got = fh5.read_array(_v0_group(oracle, ints, offsets=offs))
+    assert got.dtype == np.int64 and np.array_equal(got, ints.astype(np.int64) + offs[..., None])
+    got = fh5.read_array(_v0_group(oracle, ints))
+    assert got.dtype == np.int32 and np.array_equal(got, ints)
+    part = fh5.read_array(_v0_group(oracle, ints, offsets=offs), stream_slice=slice(100, 300))
+    assert np.array_equal(part, (ints.astype(np.int64) + offs[..., None])[..., 100:300])
+    for fdt in (np.float32, np.float64):
+        foff = rng.normal(0, 1, (2, 3)).astype(fdt)
+        fgain = np.full((2, 3), 1.0e4, dtype=fdt)
+        got = fh5.read_array(_v0_group(oracle, ints, offsets=foff, gains=fgain))
+        want = oracle.int_to_float(ints, foff.astype(np.float32), fgain.astype(np.float32)).astype(fdt)
+        assert got.dtype == np.dtype(fdt) and np.array_equal(np.asarray(got), want)

@@ -90,6 +90,50 @@ def test_float_aux_datasets(oracle):
     assert back == far and back.dtype == np.float32
 
 
+def _v0_group(oracle, ints32, offsets=None, gains=None, zarr_style=False):
+    """A format-version-0 group as the first flacarray releases wrote it (hdf5_load_v0.py:22-31): same
+    dataset names as version 1, 1-channel FLAC only, and no `flac_channels` attribute."""
+    from flacarray_b200.memgroup import MemGroup
+
+    comp, starts, nbytes = oracle.encode(ints32.reshape(-1, ints32.shape[-1]), 5)
+    lead = ints32.shape[:-1]
+    grp = MemGroup(zarr_style=zarr_style)
+    grp.attrs["flacarray_format_version"] = "0"
+    grp.attrs["flacarray_software_version"] = "0.1.0"
+    ds = grp.create_dataset("stream_starts", data=starts.reshape(lead))
+    ds.attrs["stream_size"] = ints32.shape[-1]
+    grp.create_dataset("stream_bytes", data=nbytes.reshape(lead))
+    grp.create_dataset("compressed", data=comp)
+    if offsets is not None:
+        grp.create_dataset("stream_offsets", data=offsets)
+    if gains is not None:
+        grp.create_dataset("stream_gains", data=gains)
+    return grp
+
+
+def test_version0_groups_are_readable(oracle):
+    """hdf5.py:430-446 dispatches on the version attribute; version 0 has one channel and no channel attr."""
+    from flacarray_b200 import hdf5 as fh5
+    from flacarray_b200.memgroup import MemGroup
+
+    rng = np.random.default_rng(8)
+    ints = np.cumsum(rng.integers(-50, 51, (2, 3, 2000)), axis=-1).astype(np.int32)
+    offs = rng.integers(-2 ** 40, 2 ** 40, (2, 3)).astype(np.int64)
+    grp = _v0_group(oracle, ints, offsets=offs)
+    tup = fh5.read_compressed(grp)
+    assert len(tup) == 10 and tup[0] == ints.shape and tup[3] == 1
+    assert np.array_equal(tup[6], offs) and tup[7] is None
+    assert np.array_equal(oracle.decode(tup[2], tup[4].reshape(-1), tup[5].reshape(-1), 2000).reshape(ints.shape), ints)
+    keep = np.zeros((2, 3), bool)
+    keep[1, 2] = True
+    tup = fh5.read_compressed(grp, keep=keep)
+    assert tup[0] == (1, 2000) and np.array_equal(tup[6], offs[keep])
+    bad = MemGroup()
+    bad.attrs["flacarray_format_version"] = "7"
+    with pytest.raises(RuntimeError):
+        fh5.read_compressed(bad)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
