@@ -1,8 +1,8 @@
 """HDF5 front end of the FlacArray group layout: same functions and arguments as
 /root/reference/src/flacarray/hdf5.py:96-525 (`write_compressed`, `write_array`, `read_compressed`,
 `read_array`) on top of `io_common`.  Works with h5py groups when h5py is installed and with any
-object implementing the group protocol (e.g. `memgroup.MemGroup`); only format version 1 is
-supported (the version-0 reader of the reference, hdf5_load_v0.py, is not ported).
+object implementing the group protocol (e.g. `memgroup.MemGroup`); format versions 0 and 1
+are read (hdf5_load_v0.py / hdf5_load_v1.py), version 1 is written.
 
 Distributed arrays: see io_common -- rank 0 owns the file unless every rank passes a handle
 (MPI-enabled h5py), in which case every rank writes its own hyperslabs.

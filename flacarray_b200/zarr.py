@@ -1,7 +1,7 @@
 """Zarr front end of the FlacArray group layout: same functions and arguments as
 /root/reference/src/flacarray/zarr.py:145-524 on top of `io_common` (identical dataset / attribute
 names, zarr_load_v1.py:21-29; arrays are made with `create_array` and accessed by slicing because zarr
-arrays have no read_direct / write_direct).  Only format version 1 is supported.
+arrays have no read_direct / write_direct).  Format versions 0 and 1 are read, version 1 is written.
 """
 from . import io_common as _io
 from .utils import function_timer

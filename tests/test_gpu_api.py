@@ -256,3 +256,12 @@ def test_version0_group_read(oracle):
         got = fh5.read_array(_v0_group(oracle, ints, offsets=foff, gains=fgain))
         want = oracle.int_to_float(ints, foff.astype(np.float32), fgain.astype(np.float32)).astype(fdt)
         assert got.dtype == np.dtype(fdt) and np.array_equal(np.asarray(got), want)
+
+
+def test_benchmark_cli_runs(tmp_path, capsys):
+    """scripts/benchmark.py:293-354: full pass, then even streams x 100 middle samples, timer table at the end."""
+    from flacarray_b200.scripts.benchmark import cli
+    cli(["--out_dir", str(tmp_path / "bench"), "--global_shape", "(4,3,20000)"])
+    out = capsys.readouterr().out
+    assert "Full Data Tests:" in out and "Sliced Data Tests" in out
+    assert out.count("FlacArray compress in") == 4 and out.count("Direct read") == 4

@@ -207,3 +207,23 @@ def test_two_rank_serial_writer(oracle):
         p.join(timeout=60)
     for rank, msg in results:
         assert msg == "ok", f"rank {rank}: {msg}"
+
+
+def test_hdf5_utils_serial_rules():
+    """hdf5_utils.py:60-80: a group that is not open on every rank means rank 0 does the I/O."""
+    from flacarray_b200 import hdf5_utils as hu
+
+    class _Comm:
+        def __init__(self, size, have):
+            self.size, self._have, self.rank = size, have, 0
+
+        def allgather(self, v):
+            return self._have
+
+    assert hu.hdf5_use_serial(None, None) and hu.hdf5_use_serial(object(), _Comm(1, [1]))
+    assert hu.hdf5_use_serial(object(), _Comm(2, [1, 0])) and not hu.hdf5_use_serial(object(), _Comm(2, [1, 1]))
+    assert hu.have_hdf5_parallel() is False
+    hu.check_dataset_buffer_size("x", (slice(0, 4),), np.dtype(np.int64), False)
+    if not hu.have_hdf5:
+        with pytest.raises(RuntimeError):
+            hu.H5File("/nonexistent/x.h5", "r")
