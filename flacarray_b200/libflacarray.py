@@ -11,6 +11,7 @@ torch tensors (device-resident; results stay on the device as torch tensors).  `
 There is no CPU path: without the built library or without a CUDA device these functions raise.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -258,6 +259,76 @@ def _chunk_ranges(n_stream, bytes_per_stream):
     return [(edges[i], edges[i + 1]) for i in range(nchunk) if edges[i + 1] > edges[i]]
 
 
+_STAGE_MIN_BYTES = 1 << 20        # pageable pieces below this go straight to cudaMemcpy
+_NO_STAGE = os.environ.get("FLACARRAY_B200_NO_STAGE", "") == "1"     # measurement switch
+_feed_pool = None
+
+
+def _feeder_pool():
+    global _feed_pool
+    if _feed_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        _feed_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="flacarray-h2d")
+    return _feed_pool
+
+
+class _Feeder:
+    """Host -> device copies on the input side stream, issued by one helper thread a few chunks ahead of
+    the kernels.  Pinned sources are copied in place.  Pageable sources (the usual numpy array) are
+    first copied into one of two pinned staging buffers with torch's multi-threaded CPU copy -- a plain
+    cudaMemcpy from pageable memory runs at a fraction of the PCIe rate and blocks the caller -- so
+    staging chunk i+1 overlaps the transfer and the kernels of chunk i."""
+
+    def __init__(self, dev, s_in, prep, n_items, depth=2):
+        self.dev, self.s_in, self.prep, self.n, self.depth = dev, s_in, prep, n_items, depth
+        self.stage = [None, None]
+        self.stage_ev = [None, None]
+        self.k = 0
+
+    def copy(self, dst, src):
+        nbytes = src.numel() * src.element_size()
+        if nbytes < _STAGE_MIN_BYTES or _NO_STAGE or src.is_pinned():
+            dst.copy_(src, non_blocking=True)
+            return
+        k = self.k
+        self.k ^= 1
+        if self.stage_ev[k] is not None:
+            self.stage_ev[k].synchronize()          # the previous transfer out of this buffer is done
+        if self.stage[k] is None or self.stage[k].numel() < nbytes:
+            self.stage[k] = None
+            self.stage[k] = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        st = self.stage[k][:nbytes].view(src.dtype).view(src.shape)
+        st.copy_(src)
+        dst.copy_(st, non_blocking=True)
+        e = torch.cuda.Event()
+        e.record(self.s_in)
+        self.stage_ev[k] = e
+
+    def _run(self, i):
+        with torch.cuda.device(self.dev), torch.cuda.stream(self.s_in):
+            return self.prep(self, i)
+
+    def __iter__(self):
+        pool = _feeder_pool()
+        futs = []
+        nxt = 0
+        try:
+            for i in range(self.n):
+                while nxt < self.n and nxt <= i + self.depth:
+                    futs.append(pool.submit(self._run, nxt))
+                    nxt += 1
+                yield futs[i].result()
+                futs[i] = None
+        finally:
+            for f in futs:
+                if f is not None and not f.cancel():
+                    try:
+                        f.result()
+                    except Exception:  # noqa: BLE001 - the first error is already on its way up
+                        pass
+
+
 def _as_host_tensor(a):
     a = np.ascontiguousarray(a)
     if not a.flags.writeable:
@@ -286,16 +357,15 @@ def _encode_host(flat, n_stream, stream_size, level, quanta, dt):
     with torch.cuda.device(dev):
         cur = torch.cuda.current_stream(dev)
         s_in, s_out = _side_streams(dev)
-        ev_in = []
-        d_chunks = []
-        with torch.cuda.stream(s_in):
-            for a, b in ranges:
-                dc = torch.empty((b - a, stream_size), dtype=tdt, device=dev)   # owned by s_in's pool
-                dc.copy_(src[a:b], non_blocking=True)
-                e = torch.cuda.Event()
-                e.record(s_in)
-                ev_in.append(e)
-                d_chunks.append(dc)
+
+        def prep(feed, i):
+            a, b = ranges[i]
+            dc = torch.empty((b - a, stream_size), dtype=tdt, device=dev)   # owned by s_in's pool
+            feed.copy(dc, src[a:b])
+            e = torch.cuda.Event()
+            e.record(s_in)
+            return dc, e
+
         raw_total = n_stream * stream_size * isz
         host = None
         cap = 0
@@ -303,12 +373,12 @@ def _encode_host(flat, n_stream, stream_size, level, quanta, dt):
         overflow = False
         keep = []
         parts = []
-        for i, (a, b) in enumerate(ranges):
-            cur.wait_event(ev_in[i])
-            d_chunks[i].record_stream(cur)
-            out, starts, nbytes, tot, off, gain = _encode_device_raw(d_chunks[i].view(-1), b - a, stream_size, level,
+        for (a, b), (dc, ev) in zip(ranges, _Feeder(dev, s_in, prep, len(ranges))):
+            cur.wait_event(ev)
+            dc.record_stream(cur)
+            out, starts, nbytes, tot, off, gain = _encode_device_raw(dc.view(-1), b - a, stream_size, level,
                                                                      None if q is None else q[a:b])
-            d_chunks[i] = None    # input chunk can go back to the pool
+            del dc                # input chunk can go back to the pool
             if host is None:
                 # capacity from the first chunk's ratio (+3 %); a wrong guess is repaired below
                 cap = min(int(tot / ((b - a) * stream_size * isz) * raw_total * 1.03) + (1 << 20),
@@ -369,27 +439,27 @@ def _decode_host(compressed, h_starts, h_nbytes, n_stream, stream_size, first_sa
         d_off = to_device(np.asarray(offsets).reshape(-1), dev, fdt) if restore else None
         d_gain = to_device(np.asarray(gains).reshape(-1), dev, fdt) if restore else None
         out_host = torch.empty((n_stream, max(n_decode, 0)), dtype=odt, pin_memory=True)
-        staged = []
-        with torch.cuda.stream(s_in):
-            for a, b in ranges:
-                # the byte range covering this chunk's streams (keep masks select sparse subsets)
-                lo = int(h_starts[a:b].min())
-                hi = int(h_ends[a:b].max())
-                dc = torch.empty(max(hi - lo, 1), dtype=torch.uint8, device=dev)
-                dc[:hi - lo].copy_(src[lo:hi], non_blocking=True)
-                d_st = torch.from_numpy(h_starts[a:b] - lo).to(dev, non_blocking=True)
-                d_nb = torch.from_numpy(np.ascontiguousarray(h_nbytes[a:b])).to(dev, non_blocking=True)
-                e = torch.cuda.Event()
-                e.record(s_in)
-                staged.append((dc, d_st, d_nb, e, int(h_nbytes[a:b].max())))
-        for i, (a, b) in enumerate(ranges):
-            dc, d_st, d_nb, e, max_nb = staged[i]
+
+        def prep(feed, i):
+            a, b = ranges[i]
+            # the byte range covering this chunk's streams (keep masks select sparse subsets)
+            lo = int(h_starts[a:b].min())
+            hi = int(h_ends[a:b].max())
+            dc = torch.empty(max(hi - lo, 1), dtype=torch.uint8, device=dev)
+            feed.copy(dc[:hi - lo], src[lo:hi])
+            d_st = torch.from_numpy(h_starts[a:b] - lo).to(dev, non_blocking=True)
+            d_nb = torch.from_numpy(np.ascontiguousarray(h_nbytes[a:b])).to(dev, non_blocking=True)
+            e = torch.cuda.Event()
+            e.record(s_in)
+            return dc, d_st, d_nb, e, int(h_nbytes[a:b].max())
+
+        for (a, b), (dc, d_st, d_nb, e, max_nb) in zip(ranges, _Feeder(dev, s_in, prep, len(ranges))):
             cur.wait_event(e)
             for t in (dc, d_st, d_nb):
                 t.record_stream(cur)
             out = decode_device(dc, d_st, d_nb, b - a, int(stream_size), int(first_sample), int(last_sample), is_int64,
                                 max_nb, hint, None if d_off is None else d_off[a:b], None if d_gain is None else d_gain[a:b])
-            staged[i] = None
+            del dc, d_st, d_nb
             e2 = torch.cuda.Event()
             e2.record(cur)
             out.record_stream(s_out)

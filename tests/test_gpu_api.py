@@ -254,7 +254,8 @@ def test_version0_group_read(oracle):
         foff = rng.normal(0, 1, (2, 3)).astype(fdt)
         fgain = np.full((2, 3), 1.0e4, dtype=fdt)
         got = fh5.read_array(_v0_group(oracle, ints, offsets=foff, gains=fgain))
-        want = oracle.int_to_float(ints, foff.astype(np.float32), fgain.astype(np.float32)).astype(fdt)
+        want = oracle.int_to_float(ints.reshape(6, -1), foff.astype(np.float32).reshape(-1),
+                                   fgain.astype(np.float32).reshape(-1)).reshape(ints.shape).astype(fdt)
         assert got.dtype == np.dtype(fdt) and np.array_equal(np.asarray(got), want)
 
 
