@@ -12,6 +12,7 @@ There is no CPU path: without the built library or without a CUDA device these f
 """
 import ctypes as C
 import os
+import threading
 
 import numpy as np
 import torch
@@ -173,24 +174,34 @@ def wrap_int64_to_float64(idata, n_stream, stream_size, offsets, gains):
 # encode (pyx:285-594)
 # -------------------------------------------------------------------------------------------------
 
-_enc_scratch = {}   # device index -> grow-only worst-case output buffer of the device-resident encode
+_scratch_tls = threading.local()   # per thread (like the C contexts): two threads never share a scratch buffer
+
+
+def _scratch_map():
+    """device index -> grow-only worst-case output buffer of the device-resident encode (this thread's)."""
+    m = getattr(_scratch_tls, "bufs", None)
+    if m is None:
+        m = _scratch_tls.bufs = {}
+    return m
+
 
 
 def _scratch_out(dev, nbytes):
     key = dev.index if dev.index is not None else torch.cuda.current_device()
-    buf = _enc_scratch.get(key)
+    bufs = _scratch_map()
+    buf = bufs.get(key)
     if buf is None or buf.numel() < nbytes:
-        _enc_scratch[key] = None
+        bufs[key] = None
         buf = None
         buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
-        _enc_scratch[key] = buf
+        bufs[key] = buf
     return buf
 
 
 def release_scratch():
     """Drop the per-device worst-case output buffers of the device-resident encode (they are as large as
-    the largest array encoded so far and are otherwise kept for reuse)."""
-    _enc_scratch.clear()
+    the largest array encoded so far and are otherwise kept for reuse; the calling thread's)."""
+    _scratch_map().clear()
 
 
 def _encode_device_raw(d, n_stream, stream_size, level, quanta=None, scratch=False):

@@ -235,7 +235,7 @@ def test_write_read_array_through_group_layout(fa, zarr_style):
     assert g3["stream_starts"].shape == (1,) and mod.read_array(g3).shape == (6000,)
 
 
-def test_version0_group_read(oracle):
+def test_version0_group_read(fa, oracle):
     """hdf5_load_v0.py:357-411: legacy int64 (32-bit samples + int64 stream offsets), float32, and float64
     stored as 32-bit integers with float64 offsets / gains."""
     from flacarray_b200 import hdf5 as fh5
@@ -259,10 +259,41 @@ def test_version0_group_read(oracle):
         assert got.dtype == np.dtype(fdt) and np.array_equal(np.asarray(got), want)
 
 
-def test_benchmark_cli_runs(tmp_path, capsys):
+def test_benchmark_cli_runs(fa, tmp_path, capsys):
     """scripts/benchmark.py:293-354: full pass, then even streams x 100 middle samples, timer table at the end."""
     from flacarray_b200.scripts.benchmark import cli
     cli(["--out_dir", str(tmp_path / "bench"), "--global_shape", "(4,3,20000)"])
     out = capsys.readouterr().out
     assert "Full Data Tests:" in out and "Sliced Data Tests" in out
     assert out.count("FlacArray compress in") == 4 and out.count("Direct read") == 4
+
+
+def test_two_host_threads_encode_concurrently(fa):
+    """The reference's entry points are re-entrant (no global state); here every thread has its
+    own C context and scratch buffers, and ctypes drops the GIL during the calls."""
+    import threading
+
+    import torch
+
+    rng = np.random.default_rng(21)
+    arrays = [np.cumsum(rng.integers(-300, 301, (40, 50000)), axis=1).astype(np.int32) for _ in range(2)]
+    results = [None, None]
+
+    def work(i):
+        try:
+            ok = True
+            for _ in range(6):
+                d = torch.from_numpy(arrays[i]).cuda()
+                far = fa.FlacArray.from_array(d)
+                ok = ok and bool(torch.equal(far.to_array(), d))
+                ok = ok and np.array_equal(fa.FlacArray.from_array(arrays[i]).to_array(), arrays[i])
+            results[i] = ok
+        except BaseException as e:  # noqa: BLE001
+            results[i] = e
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=120)
+    assert results == [True, True], results
