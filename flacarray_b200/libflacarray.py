@@ -186,6 +186,17 @@ def _scratch_map():
 
 
 
+_GUESS_MIN_BYTES = 8 << 20        # smaller inputs always take the scratch + exact copy route
+
+
+def _ratio_history():
+    """(device, dtype, level) -> compression ratios of this thread's last device-resident encodes."""
+    m = getattr(_scratch_tls, "ratios", None)
+    if m is None:
+        m = _scratch_tls.ratios = {}
+    return m
+
+
 def _scratch_out(dev, nbytes):
     key = dev.index if dev.index is not None else torch.cuda.current_device()
     bufs = _scratch_map()
@@ -204,8 +215,13 @@ def release_scratch():
     _scratch_map().clear()
 
 
-def _encode_device_raw(d, n_stream, stream_size, level, quanta=None, scratch=False):
-    """fab_encode into a worst-case device buffer (a fresh one, or the per-device scratch).
+_ENC_OVERFLOW = 1 << 11        # ERROR_ENCODE_COLLECT: the frames did not fit the output buffer
+
+
+def _encode_device_raw(d, n_stream, stream_size, level, quanta=None, scratch=False, capacity=None):
+    """fab_encode into a worst-case device buffer (a fresh one, or the per-device scratch), or -- when
+    `capacity` is given -- into a fresh buffer of that many bytes; in that case None is returned if the
+    compressed data did not fit (the kernels stop at the capacity and flag it; nothing is written past it).
     Returns (buffer, starts, nbytes, total, offsets, gains)."""
     dev = d.device
     dt = _TORCH2NP[d.dtype]
@@ -215,7 +231,11 @@ def _encode_device_raw(d, n_stream, stream_size, level, quanta=None, scratch=Fal
         if level < 0 or level > 8:
             raise RuntimeError("Encoding failed, return code = 2")
         bound = L.fab_encode_bound(n_stream, stream_size, _FAB[dt], level)
-        out = _scratch_out(dev, bound) if scratch else torch.empty(max(bound, 1), dtype=torch.uint8, device=dev)
+        if capacity is not None:
+            bound = min(int(capacity), bound)
+            out = torch.empty(max(bound, 1), dtype=torch.uint8, device=dev)
+        else:
+            out = _scratch_out(dev, bound) if scratch else torch.empty(max(bound, 1), dtype=torch.uint8, device=dev)
         aux = torch.empty(2 * n_stream + 1, dtype=torch.int64, device=dev)
         starts, nbytes, total = aux[:n_stream], aux[n_stream:2 * n_stream], aux[2 * n_stream:]
         off = gain = None
@@ -225,6 +245,10 @@ def _encode_device_raw(d, n_stream, stream_size, level, quanta=None, scratch=Fal
         st = _stream(dev)
         rc = L.fab_encode(ctx.handle, _ptr(d), _FAB[dt], n_stream, stream_size, level, _ptr(quanta), _ptr(off),
                           _ptr(gain), _ptr(out), bound, _ptr(starts), _ptr(nbytes), _ptr(total), st)
+        if rc == 0 and capacity is not None:
+            rc = L.fab_finish(ctx.handle, st)
+            if rc == _ENC_OVERFLOW:
+                return None
         _check(rc, ctx, st, "Encoding")
         n_total = int(total.item())
     return out, starts, nbytes, n_total, off, gain
@@ -237,10 +261,26 @@ def encode_device(d, n_stream, stream_size, level, quanta=None):
     gains are None for integer input.  For float input the quantisation (utils.c:160-328) is fused in
     front of the encoder; `quanta` is None (auto) or a CUDA tensor [n_stream].
     """
-    # The encoder needs a worst-case (~ raw size) output buffer; the result handed back is an exact-size
-    # copy so that a device-resident FlacArray holds the compressed bytes only.  The worst-case buffer is
-    # a per-device scratch (stream-ordered: the copy is queued before the next encode can reuse it).
+    # The encoder needs a worst-case (~ raw size) output buffer, but a device-resident FlacArray should hold
+    # the compressed bytes only.  First call for a (device, dtype, level): encode into a per-device
+    # worst-case scratch and hand back an exact-size copy (stream-ordered: the copy is queued before the
+    # next encode can reuse the scratch).  Later calls: encode straight into a buffer sized from the largest
+    # of the recent compression ratios + 4 % and return a view of it -- no 2nd pass over the output; if the
+    # data compresses worse than that the kernels flag the overflow and the call falls back to the scratch.
+    raw = n_stream * stream_size * d.element_size()
+    key = (d.device.index, d.dtype, int(level))
+    hist = _ratio_history().setdefault(key, [])
+    if hist and raw >= _GUESS_MIN_BYTES:
+        res = _encode_device_raw(d, n_stream, stream_size, level, quanta,
+                                 capacity=int(raw * max(hist) * 1.04) + (1 << 16))
+        if res is not None:
+            out, starts, nbytes, n_total, off, gain = res
+            hist.append(n_total / raw)
+            del hist[:-4]
+            return out[:n_total], starts, nbytes, off, gain
     out, starts, nbytes, n_total, off, gain = _encode_device_raw(d, n_stream, stream_size, level, quanta, scratch=True)
+    hist.append(n_total / max(raw, 1))
+    del hist[:-4]
     return out[:n_total].clone(), starts, nbytes, off, gain
 
 

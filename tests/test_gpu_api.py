@@ -297,3 +297,27 @@ def test_two_host_threads_encode_concurrently(fa):
     for t in threads:
         t.join(timeout=120)
     assert results == [True, True], results
+
+
+def test_device_encode_capacity_guess_and_overflow_fallback(fa):
+    """Device-resident encodes size their output from recent compression ratios; data that compresses
+    worse than the guess must fall back to the worst-case buffer and still round-trip exactly."""
+    import torch
+
+    from flacarray_b200 import libflacarray as lf
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n, L = 24, 100000                                     # 9.6 MB of int32: above the guessing threshold
+    smooth = torch.cumsum(torch.randint(-3, 4, (n, L), device="cuda", generator=g), dim=1).to(torch.int32)
+    noise = torch.randint(-2 ** 31, 2 ** 31 - 1, (n, L), device="cuda", generator=g, dtype=torch.int64).to(torch.int32)
+    lf._ratio_history().clear()
+    sizes = []
+    for data in (smooth, smooth, noise, noise, smooth):
+        comp, starts, nbytes, _, _ = lf.encode_device(data.reshape(-1), n, L, 5)
+        assert int(nbytes.sum()) == comp.numel() and int(starts[-1] + nbytes[-1]) == comp.numel()
+        out = lf.decode_device(comp, starts, nbytes, n, L, -1, -1, False, int(nbytes.max()), 4096)
+        assert torch.equal(out.view(n, L), data)
+        sizes.append(comp.numel())
+    assert sizes[0] == sizes[1] == sizes[4] and sizes[2] == sizes[3] > 3 * sizes[0]
+    hist = lf._ratio_history()[(torch.cuda.current_device(), torch.int32, 5)]
+    assert len(hist) == 4 and max(hist) > 0.9
