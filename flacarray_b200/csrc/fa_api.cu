@@ -163,9 +163,61 @@ __global__ void __launch_bounds__(256) k_restore(const I* in, int64_t n_per_stre
 }
 
 // ---- decode stages ---------------------------------------------------------------------------------
-__global__ void k_dec_meta(const DecParams P) {
-    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < P.n_sel) meta_body(P, k);
+// One warp per stream.  Lane 0 walks the (short) metadata chain; the frame-size table of streams written
+// by this library is then turned into frame offsets by the whole warp (coalesced 3-byte reads, warp scan)
+// instead of a serial loop per stream -- same results as meta_body (fa_decode.h), which remains the
+// reference for the rules.
+__global__ void __launch_bounds__(128) k_dec_meta(const DecParams P) {
+    const int64_t k = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (k >= P.n_sel) return;
+    const int ln = threadIdx.x & 31;
+    const uint8_t* buf = P.bytes + P.starts[k];
+    const long long nb = P.nbytes[k];
+    StreamMeta m;
+    if (ln == 0) {
+        parse_stream_meta(buf, nb, m);
+        P.meta[k] = m;
+    }
+    m.first_frame = __shfl_sync(0xffffffffu, m.first_frame, 0);
+    m.table_off = __shfl_sync(0xffffffffu, m.table_off, 0);
+    m.blocksize = __shfl_sync(0xffffffffu, m.blocksize, 0);
+    m.channels = __shfl_sync(0xffffffffu, m.channels, 0);
+    m.bps = __shfl_sync(0xffffffffu, m.bps, 0);
+    m.table_entries = __shfl_sync(0xffffffffu, m.table_entries, 0);
+    long long* fo = P.frame_off + k * (int64_t)(P.nframes_cap + 1);
+    int flag = 0;
+    if (m.first_frame < 0 || m.channels != P.nch || m.bps != 32) {
+        if (ln == 0) atom_or_global(P.err, kErrDecodeInit);
+        flag = 4;  // undecodable
+    } else if (m.blocksize <= 0) {
+        flag = 1;  // variable blocksize: sequential walker
+    } else {
+        const int64_t nf = frames_in_stream(P.stream_size, m.blocksize);
+        if (nf > P.nframes_cap) {
+            flag = 1;
+        } else if (m.table_off >= 0 && m.table_entries == nf) {
+            const uint8_t* tb = buf + m.table_off;
+            long long pos = m.first_frame;      // offset of frame j0 (warp-uniform carry)
+            for (int64_t j0 = 0; j0 < nf; j0 += 32) {
+                const int64_t j = j0 + ln;
+                long long len = 0;
+                if (j < nf) len = ((long long)tb[3 * j] << 16) | ((long long)tb[3 * j + 1] << 8) | tb[3 * j + 2];
+                long long inc = len;
+                for (int d = 1; d < 32; d <<= 1) {
+                    long long v = __shfl_up_sync(0xffffffffu, inc, d);
+                    if (ln >= d) inc += v;
+                }
+                if (j < nf) fo[j] = pos + inc - len;
+                pos += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            if (ln == 0) fo[nf] = pos;
+            if (pos != nb) flag = 1;
+        } else {
+            for (int64_t j = ln; j < nf; j += 32) fo[j] = -1;
+            if (ln == 0) fo[nf] = nb;
+        }
+    }
+    if (ln == 0) P.stream_flag[k] = flag;
 }
 
 constexpr int kSyncThreads = 256;
@@ -174,16 +226,19 @@ constexpr int kSyncBytesPerThread = 64;
 __global__ void __launch_bounds__(kSyncThreads) k_dec_sync(const DecParams P) {
     const int64_t k = blockIdx.y;
     if (P.stream_flag[k] != 0 || P.meta[k].table_off >= 0) return;
-    const int64_t p0 = ((int64_t)blockIdx.x * kSyncThreads + threadIdx.x) * kSyncBytesPerThread;
     const int64_t nb = P.nbytes[k];
-    if (p0 >= nb) return;
     const uint8_t* buf = P.bytes + P.starts[k];
-    int64_t p1 = p0 + kSyncBytesPerThread < nb - 1 ? p0 + kSyncBytesPerThread : nb - 1;
-    uint32_t prev = buf[p0];
-    for (int64_t p = p0; p < p1; ++p) {
-        uint32_t cur = buf[p + 1];
-        if (prev == 0xFF && cur == 0xF8) sync_body(P, k, p);
-        prev = cur;
+    for (int64_t c = blockIdx.x;; c += gridDim.x) {
+        const int64_t p0 = (c * kSyncThreads + threadIdx.x) * kSyncBytesPerThread;
+        if (c * kSyncThreads * kSyncBytesPerThread >= nb) return;
+        if (p0 >= nb) continue;
+        int64_t p1 = p0 + kSyncBytesPerThread < nb - 1 ? p0 + kSyncBytesPerThread : nb - 1;
+        uint32_t prev = buf[p0];
+        for (int64_t p = p0; p < p1; ++p) {
+            uint32_t cur = buf[p + 1];
+            if (prev == 0xFF && cur == 0xF8) sync_body(P, k, p);
+            prev = cur;
+        }
     }
 }
 
@@ -250,13 +305,22 @@ __global__ void __launch_bounds__(256) k_restore_fixup(const TileParams P) {
             out[i] = restore_f32(in[i], off, coeff);
         return;
     }
-    for (int64_t jj = blockIdx.x; jj < nfr; jj += gridDim.x) {
-        int64_t j = j0 + jj;
-        if (j >= D.nframes_cap || !P.frame_flag[k * (int64_t)D.nframes_cap + j]) continue;
-        int64_t lo = j * bs - D.first, hi = lo + bs;
-        if (lo < 0) lo = 0;
-        if (hi > D.n_decode) hi = D.n_decode;
-        for (int64_t i = lo + threadIdx.x; i < hi; i += 256) out[i] = restore_f32(in[i], off, coeff);
+    __shared__ unsigned char fl[256];
+    for (int64_t base = (int64_t)blockIdx.x * 256; base < nfr; base += (int64_t)gridDim.x * 256) {
+        const int64_t jt = j0 + base + threadIdx.x;
+        const bool mine = base + threadIdx.x < nfr && jt < D.nframes_cap && P.frame_flag[k * (int64_t)D.nframes_cap + jt];
+        if (!__syncthreads_or(mine)) continue;     // the usual case: the tile path wrote floats everywhere
+        fl[threadIdx.x] = mine;
+        __syncthreads();
+        for (int q = 0; q < 256; ++q) {
+            if (!fl[q]) continue;
+            const int64_t j = j0 + base + q;
+            int64_t lo = j * bs - D.first, hi = lo + bs;
+            if (lo < 0) lo = 0;
+            if (hi > D.n_decode) hi = D.n_decode;
+            for (int64_t i = lo + threadIdx.x; i < hi; i += 256) out[i] = restore_f32(in[i], off, coeff);
+        }
+        __syncthreads();
     }
 }
 
@@ -656,11 +720,14 @@ extern "C" int fab_decode(fab_ctx* ctx, const unsigned char* d_bytes, const int6
     P.meta = (StreamMeta*)scr; P.frame_off = (long long*)(scr + meta_b); P.nframes_cap = nframes_cap;
     P.stream_flag = (int*)(scr + meta_b + fo_b); P.err = ctx->d_err; P.verify_crc16 = 1; P.frame_flag = frame_flag;
 
-    k_dec_meta<<<(unsigned)((n_stream + 127) / 128), 128, 0, st>>>(P);
+    k_dec_meta<<<(unsigned)((n_stream + 3) / 4), 128, 0, st>>>(P);
     ctx->launches++;
     {
         int64_t per_cta = (int64_t)kSyncThreads * kSyncBytesPerThread;
         int64_t gx = (max_nbytes + per_cta - 1) / per_cta;
+        // streams carrying a frame-size table leave at once: keep the grid near one wave-set of CTAs and
+        // let the CTAs of a foreign stream stride over its chunks
+        gx = std::max<int64_t>(1, std::min<int64_t>(gx, (148 * 32 + n_stream - 1) / n_stream));
         for (int64_t s0 = 0; s0 < n_stream; s0 += 65535) {
             int64_t ns = std::min<int64_t>(65535, n_stream - s0);
             DecParams Q = P;
@@ -707,7 +774,8 @@ extern "C" int fab_decode(fab_ctx* ctx, const unsigned char* d_bytes, const int6
             Q.D.starts += s0; Q.D.nbytes += s0; Q.D.meta += s0; Q.D.frame_off += s0 * (int64_t)(nframes_cap + 1);
             Q.D.stream_flag += s0; Q.D.data += s0 * n_decode; Q.D.n_sel = ns;
             Q.frame_flag += s0 * (int64_t)nframes_cap; Q.offsets += s0; Q.gains += s0;
-            dim3 grid((unsigned)std::min<int64_t>(TP.nwin, 64), (unsigned)ns);
+            // x: 256 frames per CTA pass; walker-decoded streams (rare) spread their samples over x too
+            dim3 grid((unsigned)std::min<int64_t>((TP.nwin + 255) / 256 + 3, 64), (unsigned)ns);
             k_restore_fixup<<<grid, 256, 0, st>>>(Q);
             ctx->launches++;
         }

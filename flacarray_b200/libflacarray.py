@@ -187,6 +187,8 @@ def _scratch_map():
 
 
 _GUESS_MIN_BYTES = 8 << 20        # smaller inputs always take the scratch + exact copy route
+_PROBE_MIN_BYTES = 1 << 30        # first calls at least this large probe the ratio on a subset of streams
+_PROBE_FRACTION = 64
 
 
 def _ratio_history():
@@ -270,6 +272,13 @@ def encode_device(d, n_stream, stream_size, level, quanta=None):
     raw = n_stream * stream_size * d.element_size()
     key = (d.device.index, d.dtype, int(level))
     hist = _ratio_history().setdefault(key, [])
+    if not hist and raw >= _PROBE_MIN_BYTES and n_stream >= 2 * _PROBE_FRACTION:
+        # large first call: learn the ratio from 1/64 of the streams rather than holding a worst-case
+        # buffer as large as the input (cfg4: 66 GB next to 66 GB of samples)
+        n_probe = n_stream // _PROBE_FRACTION
+        _, _, _, t_probe, _, _ = _encode_device_raw(d.reshape(-1)[:n_probe * stream_size], n_probe, stream_size, level,
+                                                    None if quanta is None else quanta[:n_probe], scratch=True)
+        hist.append(t_probe / (n_probe * stream_size * d.element_size()))
     if hist and raw >= _GUESS_MIN_BYTES:
         res = _encode_device_raw(d, n_stream, stream_size, level, quanta,
                                  capacity=int(raw * max(hist) * 1.04) + (1 << 16))

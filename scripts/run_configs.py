@@ -96,10 +96,25 @@ def cfg4(scale):
         x[i:j] += dc + sc * wave
     del wave, t
     torch.cuda.synchronize()
+    def mem(tag):
+        if os.environ.get("FAB_CFG_DEBUG"):
+            s = torch.cuda.memory_stats()
+            print(f"# cfg4 [{tag}] reserved {s['reserved_bytes.all.current'] / 1e9:.1f} GB, allocated "
+                  f"{s['allocated_bytes.all.current'] / 1e9:.1f} GB, retries {s['num_alloc_retries']}, "
+                  f"segments {s['segment.all.allocated']}", flush=True)
+
+    mem("before")
     a = ev()
     far = fa.FlacArray.from_array(x, precision=5)
     b = ev(); torch.cuda.synchronize()
     t_enc = a.elapsed_time(b)
+    mem("after from_array")
+    if os.environ.get("FAB_CFG_DEBUG"):
+        for rep in range(2):
+            a2 = ev(); far2 = fa.FlacArray.from_array(x, precision=5); b2 = ev(); torch.cuda.synchronize()
+            print(f"# cfg4 from_array again: {a2.elapsed_time(b2):.1f} ms", flush=True)
+            del far2
+        mem("after repeats")
     keep = (np.arange(n) % 2) == 0
     sl = slice(L // 2 - 50000, L // 2 + 50000)
     (part, idx), t_part = timed(lambda: far.to_array(keep=keep, stream_slice=sl, keep_indices=True), reps=2)
