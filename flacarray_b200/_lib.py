@@ -17,7 +17,7 @@ _SOURCES = [os.path.join(_HERE, "csrc", f) for f in
 _HEADER = os.path.join(os.path.dirname(_HERE), "include", "flacarray_b200.h")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared"]
 
 _lib = None
 _lock = threading.Lock()

@@ -7,10 +7,13 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -881,6 +884,294 @@ struct DevBuf {
     bool alloc(size_t n) { return cudaMalloc(&p, n ? n : 1) == cudaSuccess; }
 };
 
+// ---- large host buffers: chunks of whole streams through pinned staging buffers -------------------------
+// The caller's arrays are pageable (malloc / numpy): a cudaMemcpy straight from them runs at a fraction of
+// the link rate.  Chunk c+1 is copied into pinned memory by a few host threads and uploaded while the
+// kernels work on chunk c and chunk c-1 is copied out.  Buffers, streams and events persist between calls.
+constexpr size_t kPipeChunk = (size_t)128 << 20;   // raw bytes per chunk
+constexpr size_t kPipeMin = (size_t)64 << 20;      // smaller calls take the plain path below
+
+struct HostPipe {
+    bool ready = false;
+    void* pin_in[2] = {nullptr, nullptr};
+    void* pin_out[2] = {nullptr, nullptr};
+    size_t pin_in_b = 0, pin_out_b = 0;
+    cudaStream_t s_in = nullptr, s_k = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2], ev_k[2], ev_out[2];
+
+    bool init() {
+        if (ready) return true;
+        if (cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking) != cudaSuccess) return false;
+        if (cudaStreamCreateWithFlags(&s_k, cudaStreamNonBlocking) != cudaSuccess) return false;
+        if (cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking) != cudaSuccess) return false;
+        for (int i = 0; i < 2; ++i) {
+            if (cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming) != cudaSuccess) return false;
+            if (cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming) != cudaSuccess) return false;
+            if (cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming) != cudaSuccess) return false;
+        }
+        ready = true;
+        return true;
+    }
+    static bool grow(void* buf[2], size_t& have, size_t want) {
+        if (want <= have) return true;
+        for (int i = 0; i < 2; ++i) {
+            if (buf[i]) cudaFreeHost(buf[i]);
+            buf[i] = nullptr;
+        }
+        have = 0;
+        for (int i = 0; i < 2; ++i)
+            if (cudaHostAlloc(&buf[i], want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return false; }
+        have = want;
+        return true;
+    }
+    // device-side chunk buffers (input side, output side, per-stream tables), grow-only like the pinned ones
+    void* dev_in[2] = {nullptr, nullptr};
+    void* dev_out[2] = {nullptr, nullptr};
+    void* dev_aux[2] = {nullptr, nullptr};
+    size_t dev_in_b = 0, dev_out_b = 0, dev_aux_b = 0;
+    static bool grow_dev(void* buf[2], size_t& have, size_t want) {
+        if (want <= have) return true;
+        for (int i = 0; i < 2; ++i) {
+            if (buf[i]) cudaFree(buf[i]);
+            buf[i] = nullptr;
+        }
+        have = 0;
+        for (int i = 0; i < 2; ++i)
+            if (cudaMalloc(&buf[i], want) != cudaSuccess) { cudaGetLastError(); return false; }
+        have = want;
+        return true;
+    }
+    bool reserve(size_t in_b, size_t out_b, size_t aux_b) {
+        return init() && grow(pin_in, pin_in_b, in_b) && grow(pin_out, pin_out_b, out_b) && grow_dev(dev_in, dev_in_b, in_b) &&
+               grow_dev(dev_out, dev_out_b, out_b) && grow_dev(dev_aux, dev_aux_b, aux_b);
+    }
+    void drain() { cudaStreamSynchronize(s_in); cudaStreamSynchronize(s_k); cudaStreamSynchronize(s_out); }
+};
+HostPipe g_pipe;
+// measurement switch: FLACARRAY_B200_NO_PIPE=1 sends every call down the plain (unpipelined) path
+bool pipe_enabled() {
+    static const bool off = [] { const char* e = getenv("FLACARRAY_B200_NO_PIPE"); return e && e[0] == '1'; }();
+    return !off;
+}
+
+// memcpy split over a few threads (one core moves ~10 GB/s, the PCIe link 55)
+void par_memcpy(void* dst, const void* src, size_t n) {
+    const unsigned hw = std::thread::hardware_concurrency();
+    const size_t nt = std::min<size_t>(std::max(1u, std::min(hw, 16u)), n / ((size_t)4 << 20) + 1);
+    if (nt <= 1) { memcpy(dst, src, n); return; }
+    const size_t step = (((n + nt - 1) / nt) + 4095) & ~(size_t)4095;
+    std::vector<std::thread> th;
+    for (size_t o = step; o < n; o += step)
+        th.emplace_back([=] { memcpy((char*)dst + o, (const char*)src + o, std::min(step, n - o)); });
+    memcpy(dst, src, std::min(step, n));
+    for (auto& t : th) t.join();
+}
+
+struct PipeClock {   // FLACARRAY_B200_PIPE_DEBUG=1: phase times of the pipelined entry points on stderr
+    bool on;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    std::chrono::steady_clock::time_point t0;
+    PipeClock() : on(getenv("FLACARRAY_B200_PIPE_DEBUG") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void lap(int k) {
+        if (!on) return;
+        auto t = std::chrono::steady_clock::now();
+        acc[k] += std::chrono::duration<double, std::milli>(t - t0).count();
+        t0 = t;
+    }
+    void report(const char* what) {
+        if (on) fprintf(stderr, "%s: setup %.1f ms, stage-in %.1f, launch+finish %.1f, copy-out %.1f, tail %.1f\n", what, acc[0], acc[1], acc[2], acc[3], acc[4]);
+    }
+};
+
+#define PIPE_CUDA(expr)                                    \
+    do {                                                   \
+        if ((expr) != cudaSuccess) {                       \
+            cudaGetLastError();                            \
+            rc = FAB_ERROR_CUDA;                           \
+            goto done;                                     \
+        }                                                  \
+    } while (0)
+
+int host_encode_pipelined(fab_ctx* ctx, const void* data, int dtype, int64_t n_stream, int64_t stream_size, uint32_t level,
+                          int64_t* n_bytes, int64_t* starts, unsigned char** bytes) {
+    HostPipe& hp = g_pipe;
+    PipeClock clk;
+    const size_t stream_b = (size_t)stream_size * (dtype == FAB_I64 ? 8 : 4);
+    const int64_t per = std::max<int64_t>(1, (int64_t)(kPipeChunk / stream_b));
+    const int64_t nchunk = (n_stream + per - 1) / per;
+    const int64_t bound_c = fab_encode_bound(per, stream_size, dtype, level);
+    const int64_t bound_all = fab_encode_bound(n_stream, stream_size, dtype, level);
+    if (!hp.reserve((size_t)per * stream_b, (size_t)bound_c, (size_t)per * 16 + 64)) return ERROR_ALLOC | FAB_ERROR_CUDA;
+    struct { void* p; } d_in[2] = {{hp.dev_in[0]}, {hp.dev_in[1]}}, d_out[2] = {{hp.dev_out[0]}, {hp.dev_out[1]}},
+                        d_aux[2] = {{hp.dev_aux[0]}, {hp.dev_aux[1]}};
+    std::thread drainer;                 // copies chunk c-2 out of pinned memory while chunk c is staged
+    std::atomic<int> drain_err{0};
+    // worst-case size, untouched pages cost nothing; shrunk to the real size at the end
+    unsigned char* hb = (unsigned char*)malloc((size_t)bound_all);
+    if (!hb) return ERROR_ALLOC;
+    std::vector<int64_t> tot((size_t)nchunk, 0), pos((size_t)nchunk + 1, 0);
+    int rc = 0;
+    clk.lap(0);
+    for (int64_t c = 0; c < nchunk + 2; ++c) {
+        if (c >= 2) {                                       // chunk c-2: pinned -> caller's buffer, on a helper thread
+            const int64_t e = c - 2;
+            const int b = (int)(e & 1);
+            unsigned char* dst = hb + pos[(size_t)e];
+            const size_t nb_e = (size_t)tot[(size_t)e];
+            cudaEvent_t ev = hp.ev_out[b];
+            const void* src = hp.pin_out[b];
+            drainer = std::thread([=, &drain_err] {
+                if (cudaEventSynchronize(ev) != cudaSuccess) { drain_err = 1; return; }
+                par_memcpy(dst, src, nb_e);
+            });
+        }
+        if (c < nchunk) {                                   // stage and upload chunk c
+            const int b = (int)(c & 1);
+            const int64_t s0 = c * per, ns = std::min(per, n_stream - s0);
+            if (c >= 2) PIPE_CUDA(cudaEventSynchronize(hp.ev_in[b]));           // pinned buffer b is free again
+            par_memcpy(hp.pin_in[b], (const char*)data + (size_t)s0 * stream_b, (size_t)ns * stream_b);
+            if (c >= 2) PIPE_CUDA(cudaStreamWaitEvent(hp.s_in, hp.ev_k[b], 0));  // encode c-2 has read d_in[b]
+            PIPE_CUDA(cudaMemcpyAsync(d_in[b].p, hp.pin_in[b], (size_t)ns * stream_b, cudaMemcpyHostToDevice, hp.s_in));
+            PIPE_CUDA(cudaEventRecord(hp.ev_in[b], hp.s_in));
+            clk.lap(1);
+        }
+        if (c >= 1 && c - 1 < nchunk) {                     // encode chunk c-1, start its download
+            const int64_t e = c - 1;
+            const int b = (int)(e & 1);
+            const int64_t s0 = e * per, ns = std::min(per, n_stream - s0);
+            int64_t* d_starts = (int64_t*)d_aux[b].p;
+            int64_t* d_nb = d_starts + per;
+            int64_t* d_total = d_nb + per;
+            PIPE_CUDA(cudaStreamWaitEvent(hp.s_k, hp.ev_in[b], 0));
+            if (e >= 2) PIPE_CUDA(cudaStreamWaitEvent(hp.s_k, hp.ev_out[b], 0));  // download e-2 has read d_out[b]
+            rc = fab_encode(ctx, d_in[b].p, dtype, ns, stream_size, level, nullptr, nullptr, nullptr,
+                            (unsigned char*)d_out[b].p, bound_c, d_starts, d_nb, d_total, hp.s_k);
+            if (rc) goto done;
+            PIPE_CUDA(cudaEventRecord(hp.ev_k[b], hp.s_k));
+            rc = fab_finish(ctx, hp.s_k);
+            if (rc) goto done;
+            int64_t total = 0;
+            PIPE_CUDA(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, hp.s_k));
+            PIPE_CUDA(cudaMemcpyAsync(starts + s0, d_starts, (size_t)ns * 8, cudaMemcpyDeviceToHost, hp.s_k));
+            PIPE_CUDA(cudaStreamSynchronize(hp.s_k));
+            tot[(size_t)e] = total;
+            pos[(size_t)e + 1] = pos[(size_t)e] + total;
+            for (int64_t i = 0; i < ns; ++i) starts[s0 + i] += pos[(size_t)e];
+            // pinned buffer b was emptied by the helper thread of the previous iteration (joined below)
+            PIPE_CUDA(cudaMemcpyAsync(hp.pin_out[b], d_out[b].p, (size_t)total, cudaMemcpyDeviceToHost, hp.s_out));
+            PIPE_CUDA(cudaEventRecord(hp.ev_out[b], hp.s_out));
+            clk.lap(2);
+        }
+        if (drainer.joinable()) drainer.join();
+        if (drain_err) { rc = FAB_ERROR_CUDA; goto done; }
+        clk.lap(3);
+    }
+done:
+    if (drainer.joinable()) drainer.join();
+    if (rc) {
+        hp.drain();
+        free(hb);
+        return rc;
+    }
+    {
+        const int64_t total = pos[(size_t)nchunk];
+        unsigned char* shrunk = (unsigned char*)realloc(hb, (size_t)std::max<int64_t>(total, 1));
+        *bytes = shrunk ? shrunk : hb;
+        *n_bytes = total;
+    }
+    clk.lap(4);
+    clk.report("host_encode_pipelined");
+    return ERROR_NONE;
+}
+
+int host_decode_pipelined(fab_ctx* ctx, const unsigned char* bytes, const int64_t* starts, const int64_t* nbytes,
+                          int64_t n_stream, int64_t stream_size, int is_int64, int64_t first, int64_t last, int64_t n_decode,
+                          void* data, bool* handled) {
+    HostPipe& hp = g_pipe;
+    *handled = false;
+    const size_t row_b = (size_t)n_decode * (is_int64 ? 8 : 4);
+    const int64_t per = std::max<int64_t>(1, (int64_t)(kPipeChunk / row_b));
+    const int64_t nchunk = (n_stream + per - 1) / per;
+    // byte range covering each chunk's streams (they may be scattered when the caller selected streams)
+    std::vector<int64_t> lo((size_t)nchunk), hi((size_t)nchunk), mx((size_t)nchunk);
+    int64_t max_in = 0;
+    for (int64_t c = 0; c < nchunk; ++c) {
+        int64_t l = INT64_MAX, h = 0, m = 0;
+        for (int64_t i = c * per; i < std::min(n_stream, (c + 1) * per); ++i) {
+            l = std::min(l, starts[i]);
+            h = std::max(h, starts[i] + nbytes[i]);
+            m = std::max(m, nbytes[i]);
+        }
+        lo[(size_t)c] = l; hi[(size_t)c] = h; mx[(size_t)c] = m;
+        max_in = std::max(max_in, h - l);
+    }
+    if ((size_t)max_in > 2 * kPipeChunk) return 0;          // widely scattered selection: plain path
+    *handled = true;
+    if (!hp.reserve((size_t)std::max<int64_t>(max_in, 1), (size_t)per * row_b, (size_t)per * 16)) return ERROR_ALLOC | FAB_ERROR_CUDA;
+    struct { void* p; } d_b[2] = {{hp.dev_in[0]}, {hp.dev_in[1]}}, d_o[2] = {{hp.dev_out[0]}, {hp.dev_out[1]}},
+                        d_aux[2] = {{hp.dev_aux[0]}, {hp.dev_aux[1]}};
+    std::thread drainer;                 // copies chunk c-2 out of pinned memory while chunk c is staged
+    std::atomic<int> drain_err{0};
+    int bs_hint = 0;
+    if (nbytes[0] >= 12 && memcmp(bytes + starts[0], "fLaC", 4) == 0) bs_hint = (bytes[starts[0] + 8] << 8) | bytes[starts[0] + 9];
+    std::vector<int64_t> rel[2];
+    int rc = 0;
+    for (int64_t c = 0; c < nchunk + 2; ++c) {
+        if (c >= 2) {                                       // chunk c-2: pinned -> caller's buffer, on a helper thread
+            const int64_t e = c - 2;
+            const int b = (int)(e & 1);
+            const int64_t s0 = e * per, ns = std::min(per, n_stream - s0);
+            char* dst = (char*)data + (size_t)s0 * row_b;
+            const size_t nb_e = (size_t)ns * row_b;
+            cudaEvent_t ev = hp.ev_out[b];
+            const void* src = hp.pin_out[b];
+            drainer = std::thread([=, &drain_err] {
+                if (cudaEventSynchronize(ev) != cudaSuccess) { drain_err = 1; return; }
+                par_memcpy(dst, src, nb_e);
+            });
+        }
+        if (c < nchunk) {                                   // stage and upload chunk c
+            const int b = (int)(c & 1);
+            const int64_t s0 = c * per, ns = std::min(per, n_stream - s0);
+            const size_t in_b = (size_t)(hi[(size_t)c] - lo[(size_t)c]);
+            if (c >= 2) PIPE_CUDA(cudaEventSynchronize(hp.ev_in[b]));
+            par_memcpy(hp.pin_in[b], bytes + lo[(size_t)c], in_b);
+            rel[b].resize((size_t)ns);
+            for (int64_t i = 0; i < ns; ++i) rel[b][(size_t)i] = starts[s0 + i] - lo[(size_t)c];
+            if (c >= 2) PIPE_CUDA(cudaStreamWaitEvent(hp.s_in, hp.ev_k[b], 0));  // decode c-2 has read d_b[b] / d_aux[b]
+            // the two small pageable copies go first: the runtime waits for the stream before staging them,
+            // and behind the large upload that wait would stall this thread for the whole transfer
+            PIPE_CUDA(cudaMemcpyAsync(d_aux[b].p, rel[b].data(), (size_t)ns * 8, cudaMemcpyHostToDevice, hp.s_in));
+            PIPE_CUDA(cudaMemcpyAsync((int64_t*)d_aux[b].p + per, nbytes + s0, (size_t)ns * 8, cudaMemcpyHostToDevice, hp.s_in));
+            PIPE_CUDA(cudaMemcpyAsync(d_b[b].p, hp.pin_in[b], in_b, cudaMemcpyHostToDevice, hp.s_in));
+            PIPE_CUDA(cudaEventRecord(hp.ev_in[b], hp.s_in));
+        }
+        if (c >= 1 && c - 1 < nchunk) {                     // decode chunk c-1, start its download
+            const int64_t e = c - 1;
+            const int b = (int)(e & 1);
+            const int64_t s0 = e * per, ns = std::min(per, n_stream - s0);
+            PIPE_CUDA(cudaStreamWaitEvent(hp.s_k, hp.ev_in[b], 0));
+            if (e >= 2) PIPE_CUDA(cudaStreamWaitEvent(hp.s_k, hp.ev_out[b], 0));  // download e-2 has read d_o[b]
+            rc = fab_decode(ctx, (const unsigned char*)d_b[b].p, (const int64_t*)d_aux[b].p, (const int64_t*)d_aux[b].p + per, ns,
+                            stream_size, is_int64, first, last, d_o[b].p, nullptr, nullptr, mx[(size_t)e], bs_hint, hp.s_k);
+            if (rc) goto done;
+            PIPE_CUDA(cudaEventRecord(hp.ev_k[b], hp.s_k));
+            PIPE_CUDA(cudaStreamWaitEvent(hp.s_out, hp.ev_k[b], 0));
+            // pinned buffer b was emptied by the helper thread of the previous iteration (joined below)
+            PIPE_CUDA(cudaMemcpyAsync(hp.pin_out[b], d_o[b].p, (size_t)ns * row_b, cudaMemcpyDeviceToHost, hp.s_out));
+            PIPE_CUDA(cudaEventRecord(hp.ev_out[b], hp.s_out));
+        }
+        if (drainer.joinable()) drainer.join();
+        if (drain_err) { rc = FAB_ERROR_CUDA; goto done; }
+    }
+    rc = fab_finish(ctx, hp.s_k);
+done:
+    if (drainer.joinable()) drainer.join();
+    if (rc) hp.drain();
+    return rc;
+}
+#undef PIPE_CUDA
+
 int host_encode(const void* data, int dtype, int64_t n_stream, int64_t stream_size, uint32_t level, int64_t* n_bytes,
                 int64_t* starts, unsigned char** bytes) {
     if (level > 8) return ERROR_INVALID_LEVEL;
@@ -892,6 +1183,8 @@ int host_encode(const void* data, int dtype, int64_t n_stream, int64_t stream_si
     fab_ctx* ctx = default_ctx();
     if (!ctx) return FAB_ERROR_CUDA;
     size_t in_b = (size_t)n_stream * stream_size * (dtype == FAB_I64 ? 8 : 4);
+    if (in_b >= kPipeMin && n_stream >= 2 && pipe_enabled())
+        return host_encode_pipelined(ctx, data, dtype, n_stream, stream_size, level, n_bytes, starts, bytes);
     int64_t bound = fab_encode_bound(n_stream, stream_size, dtype, level);
     DevBuf d_in, d_out, d_aux;
     if (!d_in.alloc(in_b) || !d_out.alloc((size_t)bound) || !d_aux.alloc((size_t)n_stream * 16 + 64)) {
@@ -936,9 +1229,15 @@ int host_decode(const unsigned char* bytes, const int64_t* starts, const int64_t
         hi = std::max(hi, starts[i] + nbytes[i]);
         mx = std::max(mx, nbytes[i]);
     }
+    size_t out_b = (size_t)n_stream * n_decode * (is_int64 ? 8 : 4);
+    if (out_b >= kPipeMin && n_stream >= 2 && pipe_enabled()) {
+        bool handled = false;
+        int prc = host_decode_pipelined(ctx, bytes, starts, nbytes, n_stream, stream_size, is_int64, first, last, n_decode,
+                                        data, &handled);
+        if (handled) return prc;
+    }
     std::vector<int64_t> rel((size_t)n_stream);
     for (int64_t i = 0; i < n_stream; ++i) rel[(size_t)i] = starts[i] - lo;
-    size_t out_b = (size_t)n_stream * n_decode * (is_int64 ? 8 : 4);
     DevBuf d_b, d_aux, d_o;
     if (!d_b.alloc((size_t)(hi - lo)) || !d_aux.alloc((size_t)n_stream * 16) || !d_o.alloc(out_b)) {
         cudaGetLastError();

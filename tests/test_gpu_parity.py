@@ -253,6 +253,62 @@ def test_reference_signature_entry_points(fa, oracle):
     assert np.array_equal(back, oracle.int_to_float(oi, oo, og))
 
 
+def test_reference_signature_entry_points_large_pipelined(fa):
+    """Host arrays above 64 MB go through the chunked pinned-staging pipeline of the C entry points:
+    same bytes as the device path, exact round trip, sample windows, scattered stream selections."""
+    import time
+
+    from flacarray_b200 import _lib
+    from flacarray_b200 import libflacarray as lf
+
+    L = C.CDLL(_lib.SO_PATH)
+    libc = C.CDLL(None)
+    rng = np.random.default_rng(40)
+    for dt, n, enc, dec in ((np.int32, 150, L.encode_i32_threaded, L.decode_i32), (np.int64, 40, L.encode_i64, L.decode_i64)):
+        size = 500000
+        scale = 300 if dt == np.int32 else 2 ** 36
+        x = np.cumsum(rng.integers(-scale, scale + 1, (n, size), dtype=np.int64), axis=1).astype(dt)   # 3 / 2 chunks
+        starts = np.zeros(n, np.int64)
+        nb = C.c_int64(0)
+        buf = C.POINTER(C.c_ubyte)()
+        enc.restype = C.c_int
+        t0 = time.perf_counter()
+        rc = enc(C.c_void_p(x.ctypes.data), C.c_int64(n), C.c_int64(size), C.c_uint32(5), C.byref(nb),
+                 C.c_void_p(starts.ctypes.data), C.byref(buf))
+        t_enc = time.perf_counter() - t0
+        assert rc == 0 and nb.value > 0
+        comp = np.ctypeslib.as_array(buf, shape=(nb.value,)).copy()
+        libc.free(buf)
+        nbytes = np.empty(n, np.int64)
+        nbytes[:-1] = np.diff(starts); nbytes[-1] = nb.value - starts[-1]
+        wrap = lf.wrap_encode_i32 if dt == np.int32 else lf.wrap_encode_i64
+        c2, s2, n2 = wrap(x.reshape(-1), n, size, 5)
+        assert np.array_equal(starts, s2) and np.array_equal(nbytes, n2) and np.array_equal(comp, c2)
+        out = np.zeros((n, size), dt)
+        dec.restype = C.c_int
+        t0 = time.perf_counter()
+        rc = dec(C.c_void_p(comp.ctypes.data), C.c_void_p(starts.ctypes.data), C.c_void_p(nbytes.ctypes.data),
+                 C.c_int64(n), C.c_int64(size), C.c_int64(-1), C.c_int64(-1), C.c_void_p(out.ctypes.data), C.c_bool(True))
+        t_dec = time.perf_counter() - t0
+        assert rc == 0 and np.array_equal(out, x)
+        print(f"C host entry points, {np.dtype(dt).name} {x.nbytes / 1e6:.0f} MB: encode {x.nbytes / t_enc / 1e9:.1f} GB/s, "
+              f"decode {x.nbytes / t_dec / 1e9:.1f} GB/s")
+        # every other stream, in reverse order, samples [1000, 401000): still above the pipeline threshold
+        sel = np.arange(n - 1, -1, -2)
+        ss, sn = np.ascontiguousarray(starts[sel]), np.ascontiguousarray(nbytes[sel])
+        win = np.zeros((len(sel), 400000), dt)
+        rc = dec(C.c_void_p(comp.ctypes.data), C.c_void_p(ss.ctypes.data), C.c_void_p(sn.ctypes.data),
+                 C.c_int64(len(sel)), C.c_int64(size), C.c_int64(1000), C.c_int64(401000), C.c_void_p(win.ctypes.data),
+                 C.c_bool(True))
+        assert rc == 0 and np.array_equal(win, x[sel, 1000:401000])
+        # a corrupt byte in the last chunk is reported, not returned as data
+        bad = comp.copy()
+        bad[starts[-1] + nbytes[-1] // 2] ^= 0x10
+        rc = dec(C.c_void_p(bad.ctypes.data), C.c_void_p(starts.ctypes.data), C.c_void_p(nbytes.ctypes.data),
+                 C.c_int64(n), C.c_int64(size), C.c_int64(-1), C.c_int64(-1), C.c_void_p(out.ctypes.data), C.c_bool(True))
+        assert rc == 1 << 14
+
+
 def test_corrupt_stream_is_an_error(fa, oracle):
     rng = np.random.default_rng(39)
     x = _walk(rng, (2, 20000))
