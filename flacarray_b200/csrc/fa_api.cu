@@ -282,11 +282,14 @@ __global__ void __launch_bounds__(kTileWarps * 32, FAB_DEC_CTAS) k_dec_tile(cons
 // frame CRC-16 of every (stream, frame) item: one warp per item, see crc_frame_warp
 __global__ void __launch_bounds__(128) k_dec_crc(const TileParams P) {
     __shared__ uint16_t crc_tab[4 * 256];
+    __shared__ uint16_t s9[2 * 256];      // multiply the state by x^(8 * 512): tables of its high / low byte
     for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) crc_tab[i] = P.D.crc->crc16[i >> 8][i & 255];
+    for (int i = threadIdx.x; i < 2 * 256; i += blockDim.x)
+        s9[i] = i < 256 ? P.D.crc->shift_hi[9][i] : P.D.crc->shift_lo[9][i - 256];
     __syncthreads();
     int64_t idx = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (idx >= P.D.n_sel * P.nwin) return;
-    crc_frame_warp(P, idx, crc_tab);
+    crc_frame_warp(P, idx, crc_tab, s9, s9 + 256);
 }
 
 // int32 -> float32 for the sample ranges that were NOT written by the fused tile path (frames left to

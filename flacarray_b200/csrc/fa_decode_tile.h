@@ -601,7 +601,7 @@ FA_D void tile_warp_body(const TileParams& P, int64_t item0, TileShared* ws, con
 // with the shift tables and XOR-reduced.  A mismatch flags the stream for the sequential walker exactly
 // like a mismatch found by the fused check (tile_warp_body<true>).
 // ------------------------------------------------------------------------------------------------------
-FA_D void crc_frame_warp(const TileParams& P, int64_t idx, const uint16_t* T) {
+FA_D void crc_frame_warp(const TileParams& P, int64_t idx, const uint16_t* T, const uint16_t* S9hi, const uint16_t* S9lo) {
     const DecParams& D = P.D;
     const int ln = lane();
     const int64_t k = idx / P.nwin;
@@ -621,20 +621,45 @@ FA_D void crc_frame_warp(const TileParams& P, int64_t idx, const uint16_t* T) {
     if (len < 3 || off + len > nb) { if (ln == 0) atom_or_global(&D.stream_flag[k], 2); return; }
     const uint8_t* fp = D.bytes + D.starts[k] + off;
     const int64_t nbody = len - 2;
-    // contiguous slice of every lane, a multiple of 4 bytes long
-    const int64_t per = (((nbody + 31) / 32) + 3) & ~(int64_t)3;
-    int64_t lo = (int64_t)ln * per, hi = lo + per;
-    if (lo > nbody) lo = nbody;
-    if (hi > nbody) hi = nbody;
-    uint32_t c = 0;
-    const uint8_t* p = fp + lo;
-    const uint8_t* e = fp + hi;
-    while (p < e && ((uintptr_t)p & 3)) { c = crc16_b(T, c, *p); ++p; }
-    while (p + 4 <= e) { c = crc16_word(T, c, bswap32(ldg32((const uint32_t*)p))); p += 4; }
-    while (p < e) { c = crc16_b(T, c, *p); ++p; }
-    c = crc16_shift(D.crc, c, (uint32_t)(nbody - hi));
-    c = redux_xor(c);
     const uint32_t want = ((uint32_t)fp[len - 2] << 8) | fp[len - 1];
+    // The CRC is linear (zero initial state, no final XOR).  The frame is cut into `head` bytes up to a 16-byte
+    // boundary, n16 aligned 16-byte chunks and a `tail`; the chunks form rows of 32 that the warp loads with one
+    // coalesced 512-byte access each, RIGHT-aligned so that the last row is full.  Every lane keeps a Horner
+    // accumulator over its column (rows are 512 bytes apart: one table step), the 32 columns are then combined
+    // by a butterfly with power-of-two shifts, and the tail is appended.
+    int64_t head = (int64_t)((16 - ((uintptr_t)fp & 15)) & 15);
+    if (head > nbody) head = nbody;
+    const int64_t n16 = (nbody - head) >> 4;
+    const uint8_t* base = fp + head;
+    uint32_t c = 0;
+    if (n16 == 0) {
+        for (int64_t i = 0; i < nbody; ++i) c = crc16_b(T, c, fp[i]);
+        if (ln == 0 && c != want) atom_or_global(&D.stream_flag[k], 2);
+        return;
+    }
+    const int64_t rows = (n16 + 31) >> 5;
+    const int64_t first = (rows << 5) - n16;          // lanes below this have no chunk in row 0
+    for (int64_t r = 0; r < rows; ++r) {
+        const int64_t ci = (r << 5) + ln - first;
+        if (r > 0) c = (uint32_t)(S9hi[(c >> 8) & 0xFF] ^ S9lo[c & 0xFF]);       // 512 bytes further from the end
+        if (ci >= 0) {
+            uint32_t t = 0;
+            if (ci == 0) for (int64_t i = 0; i < head; ++i) t = crc16_b(T, t, fp[i]);   // the head runs into chunk 0
+            const U4 q = ldg128(base + (ci << 4));
+            t = crc16_word(T, t, bswap32(q.x));
+            t = crc16_word(T, t, bswap32(q.y));
+            t = crc16_word(T, t, bswap32(q.z));
+            t = crc16_word(T, t, bswap32(q.w));
+            c ^= t;
+        }
+    }
+    // lane l's column value still has to move 16 * (31 - l) bytes: combine groups of 1, 2, 4, 8, 16 lanes
+    for (int d = 0; d < 5; ++d) {
+        const uint32_t u = shfl_xor(c, 1 << d);
+        if ((ln >> d) & 1) c ^= crc16_shift_pow2(D.crc, u, 4 + d);
+    }
+    c = shfl(c, 31);
+    for (int64_t i = head + (n16 << 4); i < nbody; ++i) c = crc16_b(T, c, fp[i]);
     if (ln == 0 && c != want) atom_or_global(&D.stream_flag[k], 2);
 }
 

@@ -160,7 +160,7 @@ int hs_decode(const uint8_t* bytes, const long long* starts, const long long* nb
         fasim::launch((int)((total + 31) / 32), 32, sizeof(TileShared) + 64, [&](int b) {
             tile_warp_body<false>(TP, (int64_t)b * 32, (TileShared*)fasim::smem(), tab.data());
         });
-        fasim::launch((int)total, 32, 0, [&](int b) { crc_frame_warp(TP, (int64_t)b, tab.data()); });
+        fasim::launch((int)total, 32, 0, [&](int b) { crc_frame_warp(TP, (int64_t)b, tab.data(), crc()->shift_hi[9], crc()->shift_lo[9]); });
         int walked = 0, general = 0;
         fasim::launch(1, 1, 0, [&](int) {
             DecParams Q = P;
