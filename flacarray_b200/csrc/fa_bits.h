@@ -85,6 +85,23 @@ FA_D uint32_t crc16_word(const uint16_t* T, uint32_t c, uint32_t w) {
     return (uint32_t)(T[3 * 256 + (((c >> 8) ^ (w >> 24)) & 0xFF)] ^ T[2 * 256 + (((c & 0xFF) ^ (w >> 16)) & 0xFF)] ^
                       T[256 + ((w >> 8) & 0xFF)] ^ T[w & 0xFF]);
 }
+// The same word step without tables.  P = x^16 + x^15 + x^2 + 1 = (x + 1)(x^15 + x + 1): modulo the trinomial a
+// high part folds back with two shifts (x^15 = x + 1), modulo x + 1 a polynomial is its parity, and the two
+// residues are recombined by adding P's cofactor 0x8003 when the parities disagree.  ~20 integer instructions per
+// word and no shared-memory traffic, against four table reads whose random indices cost ~2.7 bank-conflict
+// wavefronts each.
+FA_D uint32_t crc16_word_alu(uint32_t c, uint32_t w) {
+    const uint32_t x = w ^ (c << 16);                 // x(t) * t^16 mod P is the new state
+    const uint32_t h1 = x >> 15;
+    const uint32_t v1 = (x & 0x7FFFu) ^ h1 ^ (h1 << 1);      // x mod (t^15 + t + 1), 18 bits
+    const uint32_t h2 = v1 >> 15;
+    const uint32_t m = (v1 & 0x7FFFu) ^ h2 ^ (h2 << 1);      // ... 15 bits
+    const uint32_t b = (m << 1) ^ (m << 2);                  // * t^16 = * (t^2 + t) mod the trinomial
+    const uint32_t h3 = b >> 15;
+    const uint32_t a = (b & 0x7FFFu) ^ h3 ^ (h3 << 1);
+    const uint32_t q = (uint32_t)popc32(a ^ x) & 1u;         // parity(a) != parity(x)
+    return a ^ ((0u - q) & 0x8003u);
+}
 FA_D uint32_t crc16_b(const uint16_t* T, uint32_t c, uint32_t byte) {
     return ((c << 8) & 0xFFFF) ^ T[((c >> 8) ^ byte) & 0xFF];
 }
