@@ -57,6 +57,12 @@ extern "C" {
 
 /* ------------------------------------------------------------------------------------------------
  * (1) Reference-compatible host-buffer entry points
+ *
+ * Same signatures, ownership (`*bytes` is malloc()ed, the caller frees it) and return codes as the
+ * reference.  Calls are serialised on one process-wide context.  Arrays of 64 MB or more move through
+ * persistent pinned staging buffers in 128 MB chunks of whole streams (host copies on several threads,
+ * H2D / kernels / D2H on three CUDA streams); FLACARRAY_B200_NO_PIPE=1 selects the plain
+ * cudaMemcpy path, FLACARRAY_B200_PIPE_DEBUG=1 prints the phase times of the pipelined encode.
  * ---------------------------------------------------------------------------------------------- */
 
 /* flacarray.h:209-217 (compress.c:440-459) */
