@@ -333,6 +333,32 @@ def _feeder_pool():
     return _feed_pool
 
 
+_copy_pool = None
+_NO_COPY_POOL = os.environ.get("FLACARRAY_B200_NO_COPY_POOL", "") == "1"    # measurement switch
+
+
+def _host_copy(dst, src):
+    """CPU copy into pinned memory on several cores.  torch's own copy is multi-threaded when it has
+    intra-op threads; launchers such as torchrun set OMP_NUM_THREADS=1, and then the slices are copied
+    by a small pool instead (Tensor.copy_ drops the GIL)."""
+    global _copy_pool
+    n = dst.numel()
+    if torch.get_num_threads() >= 4 or n * dst.element_size() < (32 << 20) or _NO_COPY_POOL:
+        dst.copy_(src)
+        return
+    if _copy_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        _copy_pool = ThreadPoolExecutor(max_workers=max(1, min(8, os.cpu_count() or 1)),
+                                        thread_name_prefix="flacarray-copy")
+    d1, s1 = dst.reshape(-1), src.reshape(-1)
+    parts = _copy_pool._max_workers
+    step = -(-n // parts)
+    futs = [_copy_pool.submit(d1[i:i + step].copy_, s1[i:i + step]) for i in range(0, n, step)]
+    for f in futs:
+        f.result()
+
+
 class _Feeder:
     """Host -> device copies on the input side stream, issued by one helper thread a few chunks ahead of
     the kernels.  Pinned sources are copied in place.  Pageable sources (the usual numpy array) are
@@ -359,7 +385,7 @@ class _Feeder:
             self.stage[k] = None
             self.stage[k] = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
         st = self.stage[k][:nbytes].view(src.dtype).view(src.shape)
-        st.copy_(src)
+        _host_copy(st, src)
         dst.copy_(st, non_blocking=True)
         e = torch.cuda.Event()
         e.record(self.s_in)

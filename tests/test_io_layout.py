@@ -227,3 +227,24 @@ def test_hdf5_utils_serial_rules():
     if not hu.have_hdf5:
         with pytest.raises(RuntimeError):
             hu.H5File("/nonexistent/x.h5", "r")
+
+
+def test_host_copy_pool_matches_plain_copy():
+    """libflacarray._host_copy: with one intra-op thread (torchrun's default) large staging copies are
+    split over a thread pool; the bytes must be the same as a plain copy."""
+    import torch
+
+    from flacarray_b200 import libflacarray as lf
+
+    src = torch.from_numpy(np.random.default_rng(5).integers(0, 255, (37, 1 << 20), dtype=np.uint8))   # 37 MB, odd split
+    dst = torch.zeros_like(src)
+    old = torch.get_num_threads()
+    try:
+        torch.set_num_threads(1)
+        lf._host_copy(dst, src)
+    finally:
+        torch.set_num_threads(old)
+    assert torch.equal(dst, src)
+    small = torch.zeros(1000, dtype=torch.float32)
+    lf._host_copy(small, torch.arange(1000, dtype=torch.float32))
+    assert float(small[-1]) == 999.0
