@@ -31,7 +31,7 @@ using namespace fa;
 
 // persistent CTAs: each loops over (stream, frame) units of the batch; H = predictor history kept in registers
 #ifndef FAB_ENC_CTAS
-#define FAB_ENC_CTAS 4
+#define FAB_ENC_CTAS 6
 #endif
 template <int H>
 __global__ void __launch_bounds__(kEncThreads, FAB_ENC_CTAS) k_encode(const EncParams P) {
@@ -65,8 +65,21 @@ __global__ void __launch_bounds__(kScanThreads) k_enc_scan(const EncParams P) {
     scan_batch_cta(P, part);
 }
 
-// frames of a batch from their slots to their final byte offsets
-__global__ void __launch_bounds__(128) k_enc_compact(const EncParams P) { compact_frame_cta(P, blockIdx.x); }
+// frames of a batch from their slots to their final byte offsets, CRC-16 appended (CTAs stride over the frames)
+__global__ void __launch_bounds__(128) k_enc_compact(const EncParams P) {
+    __shared__ uint16_t crc_tab[4 * 256];
+    __shared__ uint16_t s11[2 * 256];     // multiply the state by x^(8 * 2048): tables of its high / low byte
+    __shared__ CompactShared cs;
+    for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) crc_tab[i] = P.crc->crc16[i >> 8][i & 255];
+    for (int i = threadIdx.x; i < 2 * 256; i += blockDim.x)
+        s11[i] = i < 256 ? P.crc->shift_hi[11][i] : P.crc->shift_lo[11][i - 256];
+    __syncthreads();
+    const uint32_t n = P.g_end - P.g_begin;
+    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+        compact_frame_cta(P, i, crc_tab, s11, s11 + 256, &cs);
+        __syncthreads();      // cs is reused by the next frame
+    }
+}
 
 // stream headers, frame-size tables, stream_starts / stream_nbytes / total from the byte prefixes
 __global__ void k_enc_finalize(const EncParams P, long long* __restrict__ nbytes, long long* __restrict__ total) {
@@ -75,7 +88,7 @@ __global__ void k_enc_finalize(const EncParams P, long long* __restrict__ nbytes
 }
 
 // ---- float -> int: per-stream min/max (utils.c:182-193 / :267-278), chunked over the stream ------
-constexpr int64_t kEncBatchBytes = 1ll << 30;   // slot scratch of one batch of encoder launches
+constexpr int64_t kEncBatchBytes = 1ll << 29;   // slot scratch of one batch of encoder launches (two such buffers alternate)
 constexpr int kMmThreads = 256;
 constexpr int kMmChunk = 32768;  // elements per CTA
 
@@ -367,7 +380,7 @@ struct fab_ctx {
     // second stream for work that only fills idle SMs (CRC pass behind the tile decoder's last wave,
     // compaction of batch b under the analysis of batch b + 1); fork / join with events
     cudaStream_t aux = nullptr;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
     // optional per-kernel timing (bench.py's roofline): CUDA events on the launching stream
     bool prof = false;
     struct Pending { cudaEvent_t a, b; int which; };
@@ -460,7 +473,8 @@ extern "C" int fab_create(fab_ctx** out) {
               cudaMallocHost((void**)&ctx->h_err, 4) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
-              cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess;
+              cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming) == cudaSuccess;
     delete h;
     delete ht;
     if (!ok) {
@@ -483,6 +497,7 @@ extern "C" void fab_destroy(fab_ctx* ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
     delete ctx;
 }
@@ -575,18 +590,19 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
     }
     size_t desc_b = align256((size_t)(n_stream * nf) * 8), ends_b = align256((size_t)n_stream * 8);
     // the encoder kernels run over batches of (stream, frame) units so that the per-frame records and the
-    // slot buffer between them stay small (~1 GB); one work counter per batch
+    // slot buffers between them stay small (2 x 512 MB); one work counter per batch
     const int64_t total_frames = n_stream * nf;
     const int64_t slot_bytes = (int64_t)((16 + 2 + (int64_t)nch * (lp.blocksize * 4 + 8) + 15) & ~15ll);
     const int64_t batch = std::min<int64_t>(total_frames, std::max<int64_t>(1024, kEncBatchBytes / slot_bytes));
     const int64_t nbatch = (total_frames + batch - 1) / batch;
+    const int nbuf = nbatch > 1 ? 2 : 1;     // slot / frame-size buffers alternate between consecutive batches
     size_t stats_b = align256((size_t)batch * nch * sizeof(FrameStats));
     size_t plans_b = align256((size_t)batch * nch * sizeof(FramePlan));
     size_t tick_b = align256((size_t)nbatch * 4 + 16);
     size_t fsize_b = align256((size_t)batch * 4);
     size_t slots_b = align256((size_t)batch * (size_t)slot_bytes);
     unsigned char* scr;
-    int rc = ctx_scratch(ctx, pre + desc_b + ends_b + tick_b + stats_b + plans_b + fsize_b + slots_b + 256, &scr);
+    int rc = ctx_scratch(ctx, pre + desc_b + ends_b + tick_b + stats_b + plans_b + nbuf * (fsize_b + slots_b) + 256, &scr);
     if (rc) return rc;
 
     if (dtype == FAB_F32) {
@@ -603,8 +619,8 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
     uint32_t* ticket = (uint32_t*)(scr + pre + desc_b + ends_b);
     FrameStats* stats = (FrameStats*)(scr + pre + desc_b + ends_b + tick_b);
     FramePlan* plans = (FramePlan*)(scr + pre + desc_b + ends_b + tick_b + stats_b);
-    uint32_t* fsize = (uint32_t*)(scr + pre + desc_b + ends_b + tick_b + stats_b + plans_b);
-    uint8_t* slots = scr + pre + desc_b + ends_b + tick_b + stats_b + plans_b + fsize_b;
+    unsigned char* fs0 = scr + pre + desc_b + ends_b + tick_b + stats_b + plans_b;
+    unsigned char* sl0 = fs0 + nbuf * fsize_b;
     FAB_CUDA(ctx, cudaMemsetAsync(desc, 0, desc_b + ends_b + tick_b, st));
 
     EncParams P;
@@ -633,38 +649,39 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
         ctx->smem_configured = true;
     }
     P.stats = stats; P.plans = plans;
-    P.slots = slots; P.slot_bytes = slot_bytes; P.fsize = fsize;
+    P.slot_bytes = slot_bytes;
     P.base = (unsigned long long*)(ticket + ((nbatch + 3) & ~3ll));   // zeroed with the tickets (8-byte aligned)
     const int h12 = lp.max_lpc_order > 8 ? 1 : 0;
     int64_t resident = (int64_t)ctx->n_sm * std::max(1, ctx->enc_ctas_per_sm[h12][nch - 1]);
+    cudaEvent_t joins[2] = {ctx->ev_join, ctx->ev_join2};
     prof_begin(ctx, 0, st);     // slot 0: the whole encoder kernel sequence of this call (all batches)
     for (int64_t bi = 0; bi < nbatch; ++bi) {
         P.g_begin = (uint32_t)(bi * batch);
         P.g_end = (uint32_t)std::min<int64_t>(total_frames, (bi + 1) * batch);
         P.ticket = ticket + bi;
+        P.fsize = (uint32_t*)(fs0 + (bi & 1) * fsize_b);
+        P.slots = sl0 + (bi & 1) * slots_b;
         const int64_t nfr = (int64_t)P.g_end - (int64_t)P.g_begin;
-        // The compaction of batch b (memory-bound) runs on the second stream under the analysis of batch
-        // b + 1 (issue-bound).  The slot and frame-size buffers are reused by every batch: whoever writes
-        // them next -- k_enc_analyze when it parks samples in the slots (8-byte types), else k_encode --
-        // waits for the previous compaction.
-        const bool parked = dtype == FAB_I64 || dtype == FAB_F64;
-        if (bi > 0 && parked) FAB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
+        // The compaction of batch b (memory-bound, plus the frame CRCs) runs on the second stream under the
+        // kernels of batch b + 1, which use the other slot buffer; k_enc_analyze of batch b + 2 parks samples in
+        // the slots batch b compacts from, so it waits for that compaction.
+        if (bi >= 2) FAB_CUDA(ctx, cudaStreamWaitEvent(st, joins[bi & 1], 0));
         const unsigned agrid = (unsigned)std::min<int64_t>(nfr, (int64_t)ctx->n_sm * FAB_AN_CTAS);
         if (h12) k_enc_analyze<12><<<agrid, kEncThreads, 0, st>>>(P);
         else k_enc_analyze<8><<<agrid, kEncThreads, 0, st>>>(P);
         k_enc_design<<<(unsigned)((nfr * nch + 127) / 128), 128, 0, st>>>(P, nfr * nch);
-        if (bi > 0 && !parked) FAB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
         unsigned grid = (unsigned)std::min<int64_t>(nfr, resident);
         if (h12) k_encode<12><<<grid, kEncThreads, smem, st>>>(P);
         else k_encode<8><<<grid, kEncThreads, smem, st>>>(P);
         k_enc_scan<<<1, kScanThreads, 0, st>>>(P);
         FAB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
         FAB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
-        k_enc_compact<<<(unsigned)nfr, 128, 0, ctx->aux>>>(P);
-        FAB_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->aux));
+        k_enc_compact<<<(unsigned)std::min<int64_t>(nfr, (int64_t)ctx->n_sm * 16), 128, 0, ctx->aux>>>(P);
+        FAB_CUDA(ctx, cudaEventRecord(joins[bi & 1], ctx->aux));
         ctx->launches += 5;
     }
-    FAB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    FAB_CUDA(ctx, cudaStreamWaitEvent(st, joins[(nbatch - 1) & 1], 0));
+    if (nbatch > 1) FAB_CUDA(ctx, cudaStreamWaitEvent(st, joins[nbatch & 1], 0));
     prof_end(ctx, st);
     P.g_begin = 0; P.g_end = (uint32_t)total_frames;
     k_enc_finalize<<<(unsigned)((n_stream * nf + 255) / 256), 256, 0, st>>>(P, (long long*)d_nbytes, (long long*)d_total);

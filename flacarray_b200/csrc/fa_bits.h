@@ -105,6 +105,22 @@ FA_D uint32_t crc16_word_alu(uint32_t c, uint32_t w) {
 FA_D uint32_t crc16_b(const uint16_t* T, uint32_t c, uint32_t byte) {
     return ((c << 8) & 0xFFFF) ^ T[((c >> 8) ^ byte) & 0xFF];
 }
+// word steps of the CRC pass: table-free arithmetic (FAB_CRC_ALU words out of every 2) or shared-memory tables
+#ifndef FAB_CRC_ALU
+#define FAB_CRC_ALU 1
+#endif
+#define FAB_CRC_TAB_(T, c, w) crc16_word(T, c, w)
+#define FAB_CRC_ALU_(T, c, w) crc16_word_alu(c, w)
+#if FAB_CRC_ALU == 2
+#define FAB_CRC_STEP0 FAB_CRC_ALU_
+#define FAB_CRC_STEP1 FAB_CRC_ALU_
+#elif FAB_CRC_ALU == 1
+#define FAB_CRC_STEP0 FAB_CRC_ALU_
+#define FAB_CRC_STEP1 FAB_CRC_TAB_
+#else
+#define FAB_CRC_STEP0 FAB_CRC_TAB_
+#define FAB_CRC_STEP1 FAB_CRC_TAB_
+#endif
 
 // ---- Bit reader ---------------------------------------------------------------------------------
 // Reads aligned 32-bit words (coalescing-friendly, L1/L2 sector reuse) and never touches a word

@@ -601,22 +601,6 @@ FA_D void tile_warp_body(const TileParams& P, int64_t item0, TileShared* ws, con
 // with the shift tables and XOR-reduced.  A mismatch flags the stream for the sequential walker exactly
 // like a mismatch found by the fused check (tile_warp_body<true>).
 // ------------------------------------------------------------------------------------------------------
-// word steps of the CRC pass: table-free arithmetic (FAB_CRC_ALU words out of every 2) or shared-memory tables
-#ifndef FAB_CRC_ALU
-#define FAB_CRC_ALU 1
-#endif
-#define FAB_CRC_TAB_(T, c, w) crc16_word(T, c, w)
-#define FAB_CRC_ALU_(T, c, w) crc16_word_alu(c, w)
-#if FAB_CRC_ALU == 2
-#define FAB_CRC_STEP0 FAB_CRC_ALU_
-#define FAB_CRC_STEP1 FAB_CRC_ALU_
-#elif FAB_CRC_ALU == 1
-#define FAB_CRC_STEP0 FAB_CRC_ALU_
-#define FAB_CRC_STEP1 FAB_CRC_TAB_
-#else
-#define FAB_CRC_STEP0 FAB_CRC_TAB_
-#define FAB_CRC_STEP1 FAB_CRC_TAB_
-#endif
 FA_D void crc_frame_warp(const TileParams& P, int64_t idx, const uint16_t* T, const uint16_t* S9hi, const uint16_t* S9lo) {
     const DecParams& D = P.D;
     const int ln = lane();

@@ -135,7 +135,8 @@ struct FrameStats {
 struct FramePlan {             // 48 bytes, read with three 16-byte broadcast loads
     uint8_t mode, wasted, ok0, ok1, ord0, ord1, shift1, prec1, wide1, maxp0, maxp1, pad[5];
     int16_t qlp[kMaxOrd];
-    uint32_t pad2[2];
+    uint32_t fixed_bits;       // estimated size of the FIXED subframe with one Rice partition (full frames: see enc_channel_full)
+    uint32_t pad2;
 };
 
 struct Plan {
@@ -163,6 +164,9 @@ struct DesignIO {              // k_enc_design: thread-private working set of de
     double lpc_hist[kMaxOrd][kMaxOrd];
 };
 
+// Working set of the short-frame and general paths.  It lives in the 16 KB sample buffer of the full-frame
+// path (`EncCtx::res`), which those paths never use: the hot path's shared memory stays small enough for six
+// resident CTAs per SM.
 struct EncShared {
     // per-warp partials of the block reductions
     uint32_t w_or[kEncWarps];
@@ -186,30 +190,37 @@ struct EncShared {
     unsigned long long psum[2][kMaxParts];
     uint8_t kpar[2][2 * kMaxParts];            // params for porder p at offset (1 << p) - 1
     uint32_t scan[kEncWarps];
-    uint32_t crc_part[kEncWarps];
+};
+
+// State that lives across frames and paths (never aliased).
+struct EncHot {
+    unsigned long long mbar;                   // completion barrier of the TMA copy into the sample buffer
+    uint32_t scan[kEncWarps];
     uint8_t crc8[256];                         // CRC-8 table (frame headers)
     uint32_t hdr_tmp[40];                      // full-frame path: header words built by thread 0 ahead of the packing (ow-indexed)
+    int32_t warm[kMaxOrd];                     // full-frame path: the channel's first samples (>> wasted), saved before the in-place pass
     // full-frame path: per-warp partials of (estimated bits at the finest partition order, sum |residual|, flags)
+    // (two sets: the second residual pass of a channel must not overwrite what slower warps still read)
     uint32_t x_bits[2][kEncWarps];
     unsigned long long x_sum[2][kEncWarps];
     uint32_t x_flag[2][kEncWarps];             // bit 0: a residual does not fit, bit 1: some parameter >= 15
     // deferred tail words of the packing sessions (OR-ed in when the frame is retired)
     uint32_t tail_val[2][kEncThreads];
-    int tail_word[2][kEncThreads];
-    // the frame that is packed in `out` and waits to be retired (CRC-16, copy to its slot)
-    int prev_valid, prev_f, prev_nbytes;
+    uint16_t tail_word[2][kEncThreads];
+    // the frame that is packed in `out` and waits to be retired (copy to its slot)
+    int prev_valid, prev_nbytes;
     uint32_t prev_g;
-    long long prev_off;
-    uint32_t g;
     uint32_t gq[2];     // tickets, fetched one frame ahead (the atomic's latency is off the critical path)
 };
 
 FA_HD size_t enc_out_words(int nch) { return ((size_t)nch * (kMaxBs * 4 + 64) + 64) / 4; }
 FA_D int ow(int w) { return w + (w >> 4); }   // padded word index: per-thread strides of ~16 words stay off one bank
+constexpr size_t kEncHotBytes = (sizeof(EncHot) + 127) & ~(size_t)127;
+static_assert(sizeof(EncShared) <= (size_t)kMaxBs * 4, "the cold working set must fit the sample buffer");
 inline size_t enc_smem_bytes(int nch) {
     size_t words = enc_out_words(nch);
-    // EncShared | CRC slice tables | staged frame (padded) | residuals of one full frame-channel
-    return ((sizeof(EncShared) + 15) & ~(size_t)15) + 4 * 256 * 2 + (words + (words >> 4) + 8) * 4 + 16 + kMaxBs * 4;
+    // EncHot | sample / residual buffer of one full frame-channel (128-byte aligned: TMA destination) | staged frame (padded)
+    return kEncHotBytes + (size_t)kMaxBs * 4 + (words + (words >> 4) + 8) * 4 + 16;
 }
 
 // ---- small helpers -----------------------------------------------------------------------------------
@@ -285,6 +296,22 @@ FA_D int max_porder_for(int bs, int order, int level_max) {
     return p;
 }
 
+// Rice parameter and estimated bits of one partition (libFLAC set_partitioned_rice_, estimate mode)
+FA_D uint32_t rice_estimate(unsigned long long sum, uint32_t n, int& k_out) {
+    int k = 0;
+    if (sum > n) {
+        k = (64 - clz64(sum - 1)) - (32 - clz32(n));
+        if (k < 0) k = 0;
+        if (k < 30 && ((unsigned long long)n << k) < sum) k++;
+        if (k < 30 && ((unsigned long long)n << k) < sum) k++;
+        if (k > 30) k = 30;
+    }
+    k_out = k;
+    unsigned long long pb = 4ull + (unsigned long long)(1 + k) * n + (k ? (sum >> (k - 1)) : (sum << 1));
+    pb -= (n >> 1);
+    return pb > (1ull << 25) ? (1u << 25) : (uint32_t)pb;
+}
+
 FA_D int utf8_put(uint8_t* p, uint64_t v) {
     if (v < 0x80) { p[0] = (uint8_t)v; return 1; }
     int n = v < 0x800 ? 2 : v < 0x10000 ? 3 : v < 0x200000 ? 4 : v < 0x4000000 ? 5 : v < 0x80000000ull ? 6 : 7;
@@ -356,9 +383,9 @@ FA_D void pk_rice(Pk& pk, uint32_t u, int k) {
     }
 }
 // record the trailing partial word (value 0 when the session ended on a word boundary)
-FA_D void pk_end(const Pk& pk, uint32_t& tail_val, int& tail_word) {
+FA_D void pk_end(const Pk& pk, uint32_t& tail_val, uint16_t& tail_word) {
     tail_val = (uint32_t)(pk.acc >> 32);
-    tail_word = pk.word;
+    tail_word = (uint16_t)pk.word;
 }
 
 // ---- byte-prefix words: [61:0] bytes (the two top bits were the status of the first version's look-back)
@@ -371,7 +398,6 @@ constexpr unsigned long long kDescAgg = 1ull << 62, kDescPre = 2ull << 62, kDesc
 // sizes into byte offsets and k_enc_compact moves the frames to their final place: the compressed
 // bytes cross HBM three times instead of once, which costs ~1 ms at cfg2 and is far cheaper than the
 // serialisation it removes.
-FA_D void publish_aggregate(const EncParams&, uint32_t, int, int) {}
 
 // ---- sample source ------------------------------------------------------------------------------------
 struct FrameSrc {
@@ -761,93 +787,54 @@ FA_D void fixed_coefs(int order, int32_t* c, int n) {
 
 
 // ------------------------------------------------------------------------------------------------------
-// Retiring a packed frame: slot address, CRC-16, copy to HBM.  The frame packed during
-// iteration n of the CTA loop is retired during iteration n + 1 (before the staged buffer is needed
-// again), which gives every predecessor a whole frame time to publish its size: no spinning.
+// Retiring a packed frame: copy to its slot in HBM.  The frame packed during iteration n of the CTA
+// loop is retired during iteration n + 1 (before the staged buffer is needed again).  The frame's
+// CRC-16 is computed and appended by k_enc_compact, which reads every byte of the frame anyway.
 // ------------------------------------------------------------------------------------------------------
 struct EncCtx {
-    EncShared* sh;
-    const uint16_t* crcT;
+    EncHot* hot;
+    EncShared* sh;       // short-frame / general paths only: aliases `res`
     uint32_t* out;
-    int32_t* res;        // [32][128]: residual j of thread t at res[j * 128 + t]
+    int32_t* res;        // full-frame path: [8][128][4] samples of the channel (TMA destination), zigzag residuals in place
     int out_words_padded;
+    uint32_t tma_phase;  // parity of the next TMA completion (block-uniform)
 #if defined(FAB_PHASE_TIMING) && defined(__CUDACC__)
     long long ph[12];
     long long last;
 #endif
-    bool retired;   // block-uniform: the previous frame has left `out` and `out` is zeroed
+    bool retired;   // block-uniform: the previous frame has left `out`
 };
 
-// One warp: where the frame waiting in `out` goes (its slot) and its size.
-FA_D void retire_slot(const EncParams& P, EncShared* sh) {
-    if (!sh->prev_valid) return;
-    if (lane() == 0) {
-        const uint32_t i = sh->prev_g - P.g_begin;
-        P.fsize[i] = (uint32_t)(sh->prev_nbytes + 2);
-        sh->prev_off = (long long)i * P.slot_bytes;
-    }
-}
-
-// All threads, after a barrier behind retire_slot: CRC-16 partials of the staged frame (uniform
-// pass, one contiguous run of words per thread, positions fixed up with one GF(2) multiply) and the
-// coalesced copy to HBM.
+// All threads, after the barrier at the top of the CTA loop (+ one more barrier behind the tail ORs): the
+// coalesced copy of the staged frame to its slot.
 // skip0: thread 0 takes no share of the work (it builds the next frame's header meanwhile)
 FA_D void retire_copyout(const EncParams& P, const EncCtx& X, bool skip0 = false) {
-    EncShared* sh = X.sh;
-    if (!sh->prev_valid) return;
+    const EncHot* hot = X.hot;
+    if (!hot->prev_valid) return;
     const int nthr = skip0 ? kEncThreads - 1 : kEncThreads;
     const int t = skip0 ? tid() - 1 : tid();
     const uint32_t* out = X.out;
-    const int nbytes_body = sh->prev_nbytes;
-    const int wtot = (nbytes_body + 3) >> 2;
-    {
-        const int per = (wtot + nthr - 1) / nthr;
-        int w0 = t < 0 ? wtot : t * per, w1 = w0 + per < wtot ? w0 + per : wtot;
-        uint32_t crc = 0;
-        for (int w = w0; w < w1; ++w) crc = crc16_word(X.crcT, crc, out[ow(w)]);
-        uint32_t contrib = w0 < w1 ? gf16_mul(crc, P.tab->x32[wtot - w1]) : 0u;
-        contrib = redux_xor(contrib);
-        if (lane() == 0) sh->crc_part[warp()] = contrib;
-    }
-    const long long off = sh->prev_off;
-    if (off >= 0) {
-        // the slot is 16-byte aligned: four staged (big-endian) words per 16-byte store; the bytes past the
-        // frame end inside the last store are don't-care (the slot is a worst-case frame rounded up to 16)
-        uint8_t* dst = P.slots + off;
-        const int nvec = (nbytes_body + 15) >> 4;
-        for (int v = t < 0 ? nvec : t; v < nvec; v += nthr) {
-            const int w = 4 * v;          // four consecutive words never straddle a pad word (ow pads every 16)
-            const int o = ow(w);
-            U4 q;
-            q.x = bswap32(out[o]); q.y = bswap32(out[o + 1]); q.z = bswap32(out[o + 2]); q.w = bswap32(out[o + 3]);
-            sts128(dst + 16 * (size_t)v, q);
-        }
+    const int nbytes_body = hot->prev_nbytes;
+    const uint32_t i = hot->prev_g - P.g_begin;
+    if (t == 0) P.fsize[i] = (uint32_t)(nbytes_body + 2);
+    // the slot is 16-byte aligned: four staged (big-endian) words per 16-byte store; the bytes past the
+    // frame end inside the last store are don't-care (the slot is a worst-case frame rounded up to 16)
+    uint8_t* dst = P.slots + (long long)i * P.slot_bytes;
+    const int nvec = (nbytes_body + 15) >> 4;
+    for (int v = t < 0 ? nvec : t; v < nvec; v += nthr) {
+        const int w = 4 * v;          // four consecutive words never straddle a pad word (ow pads every 16)
+        const int o = ow(w);
+        U4 q;
+        q.x = bswap32(out[o]); q.y = bswap32(out[o + 1]); q.z = bswap32(out[o + 2]); q.w = bswap32(out[o + 3]);
+        sts128(dst + 16 * (size_t)v, q);
     }
 }
 
-// Thread 0, after a barrier behind retire_copyout: the two CRC-16 bytes.
-FA_D void retire_crc(const EncParams& P, EncShared* sh) {
-    if (!sh->prev_valid || sh->prev_off < 0) return;
-    const int nbytes_body = sh->prev_nbytes;
-    const int wtot = (nbytes_body + 3) >> 2;
-    uint32_t crc = sh->crc_part[0] ^ sh->crc_part[1] ^ sh->crc_part[2] ^ sh->crc_part[3];
-    crc = gf16_mul(crc, P.tab->inv8[4 * wtot - nbytes_body]);   // the staged words carry 0..3 pad bytes
-    st_global_u8x2(P.slots + sh->prev_off + nbytes_body, (crc >> 8) & 0xFFu, crc & 0xFFu);
-}
-
-FA_D void zero_out(const EncCtx& X) {   // only used once, when the CTA starts
-    U4 z; z.x = z.y = z.z = z.w = 0;
-    for (int w = 4 * tid(); w < X.out_words_padded; w += 4 * kEncThreads) sts128(X.out + w, z);
-}
-
-// Generic (non-overlapped) retire sequence with its own barriers; leaves `out` zeroed.
+// Generic (non-overlapped) retire sequence with its own barriers.
 FA_D void retire_full(const EncParams& P, EncCtx& X) {
     if (X.retired) return;
-    if (warp() == 0) retire_slot(P, X.sh);
     sync();
     retire_copyout(P, X);
-    sync();
-    if (tid() == 0) retire_crc(P, X.sh);
     sync();
     X.retired = true;
 }
@@ -892,22 +879,69 @@ FA_D void scan_batch_cta(const EncParams& P, unsigned long long* sh_part /*[kSca
     if (t == 0) *P.base = sh_part[kW];
 }
 
-// One CTA: frame i of the batch from its slot to its final place (any byte alignment).
-FA_D void compact_frame_cta(const EncParams& P, uint32_t i) {
+// One CTA (128 threads): frame i of the batch from its slot to its final place (any byte alignment), plus
+// the frame's CRC-16, which is appended here: the compaction reads every byte of the frame anyway and is
+// memory-bound, so the ~15 instructions per word ride along instead of sitting on k_encode's chain.
+// The CRC is linear (zero initial state, no final XOR): the body is cut into 16-byte chunks, rows of 128
+// chunks are loaded with one coalesced access each and RIGHT-aligned so that the last row is full; every
+// thread keeps a Horner accumulator over its column (rows are 2048 bytes apart: one step with the
+// shift tables S11), the 128 columns are combined by a butterfly of power-of-two shifts and the
+// (< 16) trailing bytes are appended.  T: [4][256] slice tables, S11hi / S11lo: state * x^(8 * 2048).
+struct CompactShared { uint32_t wcrc[4]; };
+FA_D void compact_frame_cta(const EncParams& P, uint32_t i, const uint16_t* T, const uint16_t* S11hi, const uint16_t* S11lo,
+                            CompactShared* cs) {
     const uint32_t g = P.g_begin + i;
-    const uint32_t len = P.fsize[i];
+    const uint32_t len = P.fsize[i];              // body + the two CRC bytes
     const unsigned long long end = P.desc[g];
     if ((long long)end > P.out_capacity) {
         if (tid() == 0) atom_or_global(P.err, kErrEncodeCollect);
         return;
     }
+    const uint32_t body = len - 2u;
     uint8_t* dst = P.out + (end - len);
     const uint32_t* src = (const uint32_t*)(P.slots + (long long)i * P.slot_bytes);   // 16-byte aligned
-    const int t = tid(), nt = nthreads();
+    const int t = tid(), ln = lane(), wp = warp();
+    // ---- CRC-16 of the body
+    {
+        const uint32_t n16 = body >> 4;
+        const uint32_t rows = (n16 + 127u) >> 7;
+        const uint32_t first = (rows << 7) - n16;     // threads below this have no chunk in row 0
+        uint32_t c = 0;
+        for (uint32_t r = 0; r < rows; ++r) {
+            const int64_t ci = (int64_t)(r << 7) + t - (int64_t)first;
+            if (r > 0) c = (uint32_t)(S11hi[(c >> 8) & 0xFF] ^ S11lo[c & 0xFF]);
+            if (ci >= 0) {
+                const U4 q = ldg128(src + (ci << 2));
+                uint32_t x = 0;
+                x = FAB_CRC_STEP0(T, x, bswap32(q.x));
+                x = FAB_CRC_STEP1(T, x, bswap32(q.y));
+                x = FAB_CRC_STEP0(T, x, bswap32(q.z));
+                x = FAB_CRC_STEP1(T, x, bswap32(q.w));
+                c ^= x;
+            }
+        }
+        // thread t's column value still has to move 16 * (127 - t) bytes: lanes first (groups of 1 .. 16), then warps
+        for (int d = 0; d < 5; ++d) {
+            const uint32_t u = shfl_xor(c, 1 << d);
+            if ((ln >> d) & 1) c ^= crc16_shift_pow2(P.crc, u, 4 + d);
+        }
+        if (ln == 31) cs->wcrc[wp] = c;
+        sync();
+        if (t == 0) {
+            uint32_t v = 0;
+            for (int w = 0; w < 4; ++w) v = crc16_shift_pow2(P.crc, v, 9) ^ cs->wcrc[w];     // warps are 512 bytes apart
+            const uint8_t* sb = (const uint8_t*)src;
+            for (uint32_t k = n16 << 4; k < body; ++k) v = crc16_b(T, v, sb[k]);
+            dst[body] = (uint8_t)(v >> 8);
+            dst[body + 1] = (uint8_t)v;
+        }
+    }
+    // ---- the body bytes
+    const int nt = nthreads();
     int head = (int)((4 - ((uintptr_t)dst & 3)) & 3);
-    if ((uint32_t)head > len) head = (int)len;
+    if ((uint32_t)head > body) head = (int)body;
     if (t < head) dst[t] = (uint8_t)(src[0] >> (8 * t));
-    const uint32_t nwords = (len - (uint32_t)head) >> 2;
+    const uint32_t nwords = (body - (uint32_t)head) >> 2;
     uint32_t* dw = (uint32_t*)(dst + head);
     const uint32_t sh8 = 8u * (uint32_t)head;     // source byte offset of dw[0] is `head` (0..3)
     for (uint32_t w = (uint32_t)t; w < nwords; w += (uint32_t)nt) {
@@ -915,7 +949,7 @@ FA_D void compact_frame_cta(const EncParams& P, uint32_t i) {
         dw[w] = head ? ((a >> sh8) | (b << (32u - sh8))) : a;
     }
     const uint32_t tail0 = (uint32_t)head + 4u * nwords;
-    if ((uint32_t)t < len - tail0) {
+    if ((uint32_t)t < body - tail0) {
         uint32_t k = tail0 + (uint32_t)t;
         dst[k] = (uint8_t)(src[k >> 2] >> (8 * (k & 3)));
     }
@@ -994,13 +1028,15 @@ FA_D void analyze_channel(const EncParams& P, AnShared* sh, const float* wsm, co
     int32_t xw[H + kSpt];
     load_chunk<H, FULL>(S, c, t, xw);
     if (FULL && park != nullptr) {
-        // park the channel's int32 samples (quantised / split once, here) for k_encode: 128 B per thread
+        // park the channel's int32 samples (quantised / split once, here) for k_encode in the order its threads
+        // consume them: [quad q][thread t][4] -- every store and every later load is one coalesced 512-byte
+        // access per warp, and the whole 16 KB block is what k_encode's TMA copy brings into shared memory
 #pragma unroll
         for (int q = 0; q < kSpt / 4; ++q) {
             U4 v;
             v.x = (uint32_t)xw[H + 4 * q]; v.y = (uint32_t)xw[H + 4 * q + 1];
             v.z = (uint32_t)xw[H + 4 * q + 2]; v.w = (uint32_t)xw[H + 4 * q + 3];
-            sts128(park + t * kSpt + 4 * q, v);
+            sts128(park + ((q * kEncThreads + t) << 2), v);
         }
     }
 
@@ -1170,11 +1206,8 @@ FA_D void analyze_channel(const EncParams& P, AnShared* sh, const float* wsm, co
     sync();   // the partials are reused by the next channel
 }
 
-// One CTA: every channel of (stream, frame) unit g.
-// 8-byte input types only: measured on B200, parking float32 costs k_enc_analyze as much (4 GB of extra
-// stores) as the second quantisation costs k_encode, while for int64 / float64 it saves the wasted half of
-// every 16-byte load and the double-precision quantiser (cfg3 38.5 -> 35.2 ms, cfg4 300 -> 273 ms)
-FA_D bool frame_parked(const EncParams& P) { return P.dtype == kI64 || P.dtype == kF64; }
+// Word index of in-frame sample i inside the parked [8][128][4] block of a full frame-channel.
+FA_HD int park_word(int i) { return ((((i >> 2) & 7) * kEncThreads + (i >> 5)) << 2) + (i & 3); }
 
 // window values of thread t: samples 32 t - H .. 32 t + 31 (zeros outside the window)
 template <int H>
@@ -1212,11 +1245,11 @@ FA_D void analyze_frame_cta(const EncParams& P, uint32_t g, AnShared* sh, const 
     const int esize = (P.dtype == kI32 || P.dtype == kF32) ? 4 : 8;
     S.base = (const unsigned char*)P.data + (s * P.stream_size + samp0) * esize;
     S.vec = (((uintptr_t)S.base) & 15) == 0;
-    // full frames of the 8-byte types are parked as planar int32 in the frame's (still unused) output
-    // slot: k_encode then reads plain integers instead of converting / splitting the input a second time
-    int32_t* slot = frame_parked(P) ? (int32_t*)(P.slots + (int64_t)(g - P.g_begin) * P.slot_bytes) : nullptr;
+    // full frames are parked as planar int32 in the frame's (still unused) output slot: k_encode then reads
+    // plain integers (quantised / split exactly once) through one TMA copy per channel
+    int32_t* slot = (int32_t*)(P.slots + (int64_t)(g - P.g_begin) * P.slot_bytes);
     for (int c = 0; c < P.nch; ++c) {
-        if (bs == kMaxBs) analyze_channel<H, true>(P, sh, wsm, S, c, st + c, slot ? slot + c * kMaxBs : nullptr);
+        if (bs == kMaxBs) analyze_channel<H, true>(P, sh, wsm, S, c, st + c, slot + c * kMaxBs);
         else analyze_channel<H, false>(P, sh, wsm, S, c, st + c, nullptr);
     }
 }
@@ -1243,6 +1276,15 @@ FA_D void design_frame(const EncParams& P, int64_t i) {
         design_fixed(&d, bs, bps, st.bad, level_maxp);
         design_lpc(&d, bs, bps, P.max_lpc_order, P.qlp_precision, level_maxp, maxabs);
         pl.wasted = (uint8_t)st.wasted;
+        if (d.cand_ok[0]) {
+            // size of the FIXED subframe with a single Rice partition, from the analysis pass's sum |e| (the first four
+            // samples are not in that sum; at most `order` of them are warm-up): what k_encode compares the LPC
+            // candidate's like-for-like estimate with before it spends a second residual pass on the fixed predictor
+            int k0 = 0;
+            const uint32_t o = (uint32_t)d.cand[0].order;
+            uint32_t rb = rice_estimate(d.t_fe[o], (uint32_t)bs - o, k0);
+            pl.fixed_bits = o * (uint32_t)bps + rb + 6u + (k0 >= 15 ? 1u : 0u);
+        }
         pl.ok0 = (uint8_t)d.cand_ok[0];
         pl.ok1 = (uint8_t)d.cand_ok[1];
         pl.ord0 = (uint8_t)d.cand[0].order;
@@ -1281,6 +1323,7 @@ template <int H, bool FULL>
 FA_D bool enc_channel_fast(const EncParams& P, EncCtx& X, const FrameSrc& S, int c, int f, uint32_t g, int bitpos0,
                            int& bitpos_end) {
     EncShared* sh = X.sh;
+    EncHot* hot = X.hot;
     uint32_t* out = X.out;
     const int t = tid();
     const int ln = lane(), wp = warp();
@@ -1302,25 +1345,22 @@ FA_D bool enc_channel_fast(const EncParams& P, EncCtx& X, const FrameSrc& S, int
     int32_t xw[H + kSpt];
     load_chunk<H, FULL>(S, c, t, xw);
     const bool retiring = !X.retired;
-    if (wp == 3 && retiring) retire_slot(P, sh);   // previous frame: overlaps the loads above
 
     if (mode == 1) {
         if (retiring) {
             sync();
             retire_copyout(P, X);
             sync();
-            if (t == 0) retire_crc(P, sh);
             X.retired = true;
         }
         bitpos_end = bitpos0 + (c == 0 ? 8 * frame_header_bytes(bs, f) : 0) + subframe_header_bits(0, 0, 0, 32, 0);
         if (t == 0) {
-            if (c == P.nch - 1) publish_aggregate(P, g, f, bitpos_end);
             Pk pk;
             pk_begin(pk, out, bitpos0);
-            if (c == 0) emit_frame_header(pk, sh->crc8, bs, f, P.nch);
+            if (c == 0) emit_frame_header(pk, hot->crc8, bs, f, P.nch);
             emit_subframe_header(pk, 0, 0, 0);
             emit_sample(pk, xw[H], 32);
-            pk_end(pk, sh->tail_val[c][0], sh->tail_word[c][0]);
+            pk_end(pk, hot->tail_val[c][0], hot->tail_word[c][0]);
         }
         return true;
     }
@@ -1409,10 +1449,7 @@ FA_D bool enc_channel_fast(const EncParams& P, EncCtx& X, const FrameSrc& S, int
         }
     }
     sync();   // B4
-    if (retiring) {
-        if (t == 0) retire_crc(P, sh);
-        X.retired = true;    // the copy-out (before B4) is ordered before the packing below by B5
-    }
+    if (retiring) X.retired = true;    // the copy-out (before B4) is ordered before the packing below by B5
     // ---- every thread: pick the winner (stream_encoder.c process_subframe_: smallest estimate wins)
     const uint32_t verbatim_bits = (uint32_t)bps * (uint32_t)bs;
     int win = -1;
@@ -1493,9 +1530,8 @@ FA_D bool enc_channel_fast(const EncParams& P, EncCtx& X, const FrameSrc& S, int
     bitpos_end = body0 + (int)total;
     Pk pk;
     if (t == 0) {
-        if (c == P.nch - 1) publish_aggregate(P, g, f, bitpos_end);
         pk_begin(pk, out, bitpos0);
-        if (c == 0) emit_frame_header(pk, sh->crc8, bs, f, P.nch);
+        if (c == 0) emit_frame_header(pk, hot->crc8, bs, f, P.nch);
         emit_subframe_header(pk, ptype, order, wasted);
         for (int j = 0; j < order; ++j) emit_sample(pk, xw[H + j], bps);
         if (ptype == 3) {
@@ -1550,7 +1586,7 @@ FA_D bool enc_channel_fast(const EncParams& P, EncCtx& X, const FrameSrc& S, int
                 }
             }
         }
-        pk_end(pk, sh->tail_val[c][t], sh->tail_word[c][t]);
+        pk_end(pk, hot->tail_val[c][t], hot->tail_word[c][t]);
     }
     return true;
 }
@@ -1570,243 +1606,120 @@ FA_DNOINL int enc_channel_short(const EncParams P, EncCtx X, const FrameSrc S, i
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Full 4096-sample frames: the hot path.  Written as ROLLED loops over sub-blocks of 8 samples so that
-// the instruction stream of a frame fits the instruction caches (the fully unrolled predecessor was
-// instruction-fetch bound: 39 k SASS instructions, 18 % of the stall samples "no instruction"), which
-// also keeps the register count low enough for 5-6 resident CTAs per SM.  Residuals are parked in
-// shared memory (transposed: conflict-free) between the statistics, length and packing passes; the
-// Rice parameters come from shuffles inside the 2^(7 - max_porder) threads that share a finest
-// partition, and the partition order is chosen between the level's maximum and 0.  Three barriers per
-// (frame, channel): chunk statistics (B3), bit-offset scan (B5), and the barrier at the top of the CTA loop.
+// Full 4096-sample frames: the hot path.
+//
+// Input: the channel's int32 samples as k_enc_analyze parked them ([quad][thread][4], 16 KB).  One TMA bulk
+// copy (cp.async.bulk -> UBLKCP, completion on an mbarrier) brings the block into shared memory while the
+// threads fetch the plan and their predictor history; every later access is a conflict-free LDS.128 / STS.128
+// of the thread's own quads.  Per (frame, channel):
+//   residual pass   ONE candidate (the LPC plan if there is one, else the fixed predictor): residuals of the
+//                   thread's 32 samples in two rolled trips of 16, zigzag-coded IN PLACE over the samples,
+//                   sum |r|.  The fixed predictor is only evaluated (second pass, samples re-fetched by TMA)
+//                   when the LPC residual does not fit or when the analysis pass's exact sum |e| says the fixed
+//                   subframe is smaller, both compared as single-partition estimates.
+//   estimate        Rice parameter and estimated bits of the finest partitions by shuffles inside the
+//                   2^(7 - max_porder) threads that share one; partition order = the level's maximum or 0.
+//   lengths + scan  exact code lengths of the chunk -> warp / block exclusive scan (barrier B5)
+//   pack            right-aligned 64-bit accumulator in two registers, one predicated store per completed
+//                   word; the trailing partial word is OR-ed in when the frame is retired.
+// Three barriers per (frame, channel): top of the CTA loop, partials (B3), scan (B5).  The previous frame is
+// copied to its slot between B3 and B5 while thread 0 builds this channel's header.
 // ------------------------------------------------------------------------------------------------------
-// Rice parameter and estimated bits of one partition (libFLAC set_partitioned_rice_, estimate mode)
-FA_D uint32_t rice_estimate(unsigned long long sum, uint32_t n, int& k_out) {
-    int k = 0;
-    if (sum > n) {
-        k = (64 - clz64(sum - 1)) - (32 - clz32(n));
-        if (k < 0) k = 0;
-        if (k < 30 && ((unsigned long long)n << k) < sum) k++;
-        if (k < 30 && ((unsigned long long)n << k) < sum) k++;
-        if (k > 30) k = 30;
-    }
-    k_out = k;
-    unsigned long long pb = 4ull + (unsigned long long)(1 + k) * n + (k ? (sum >> (k - 1)) : (sum << 1));
-    pb -= (n >> 1);
-    return pb > (1ull << 25) ? (1u << 25) : (uint32_t)pb;
-}
+FA_D uint32_t zigzag32(int32_t r) { return ((uint32_t)r << 1) ^ (uint32_t)(r >> 31); }
 
-// 8 consecutive samples of channel c starting at in-frame sample i (a multiple of 8, inside the frame)
-FA_D void load8(const FrameSrc& S, int c, int i, int32_t* x) {
-    if (S.dtype == kI32 || S.dtype == kF32) {
-        const uint32_t* p = (const uint32_t*)S.base + i;
-        U4 a, b;
-        if (S.vec) { a = ldg128(p); b = ldg128(p + 4); }
-        else {
-            a.x = ldg32(p); a.y = ldg32(p + 1); a.z = ldg32(p + 2); a.w = ldg32(p + 3);
-            b.x = ldg32(p + 4); b.y = ldg32(p + 5); b.z = ldg32(p + 6); b.w = ldg32(p + 7);
-        }
-        uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        if (S.dtype == kF32) {
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                float fv;
-                memcpy(&fv, &v[q], 4);
-                v[q] = (uint32_t)quant_f32(fv, S.off32, S.gain32);
-            }
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) x[q] = (int32_t)v[q];
-    } else {
-        const unsigned long long* p = (const unsigned long long*)S.base + i;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            unsigned long long e0, e1;
-            if (S.vec) {
-                U4 v = ldg128(p + 2 * q);
-                e0 = ((unsigned long long)v.y << 32) | v.x;
-                e1 = ((unsigned long long)v.w << 32) | v.z;
-            } else {
-                e0 = p[2 * q];
-                e1 = p[2 * q + 1];
-            }
-            if (S.dtype == kF64) {
-                double d0, d1;
-                memcpy(&d0, &e0, 8); memcpy(&d1, &e1, 8);
-                e0 = (unsigned long long)quant_f64(d0, S.off64, S.gain64);
-                e1 = (unsigned long long)quant_f64(d1, S.off64, S.gain64);
-            }
-            x[2 * q] = c == 0 ? (int32_t)(uint32_t)e0 : (int32_t)(uint32_t)(e0 >> 32);
-            x[2 * q + 1] = c == 0 ? (int32_t)(uint32_t)e1 : (int32_t)(uint32_t)(e1 >> 32);
-        }
-    }
-}
-
-// LPC residuals of 8 samples: w[0 .. H) = history, w[H .. H + 8) = the samples
-template <int H, int ORD>
-FA_D void lpc8(const int32_t* w, const int32_t* coef, int shift, int32_t* r) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        int32_t sum = 0;
-#pragma unroll
-        for (int m = 0; m < ORD; ++m) sum += coef[m] * w[H + i - 1 - m];
-        r[i] = w[H + i] - (sum >> shift);
-    }
-}
-template <int H>
-FA_D void lpc8_dispatch(int order, const int32_t* w, const int32_t* coef, int shift, int32_t* r) {
-    switch (order) {
-    case 0: lpc8<H, 0>(w, coef, shift, r); break;
-    case 1: lpc8<H, 1>(w, coef, shift, r); break;
-    case 2: lpc8<H, 2>(w, coef, shift, r); break;
-    case 3: lpc8<H, 3>(w, coef, shift, r); break;
-    case 4: lpc8<H, 4>(w, coef, shift, r); break;
-    case 5: lpc8<H, 5>(w, coef, shift, r); break;
-    case 6: lpc8<H, 6>(w, coef, shift, r); break;
-    case 7: lpc8<H, 7>(w, coef, shift, r); break;
-    case 8: lpc8<H, 8>(w, coef, shift, r); break;
-    default:
-        if constexpr (H > 8) {
-            switch (order) {
-            case 9: lpc8<H, 9>(w, coef, shift, r); break;
-            case 10: lpc8<H, 10>(w, coef, shift, r); break;
-            case 11: lpc8<H, 11>(w, coef, shift, r); break;
-            default: lpc8<H, 12>(w, coef, shift, r); break;
-            }
-        } else {
-            lpc8<H, 0>(w, coef, shift, r);
-        }
-        break;
-    }
-}
-// 64-bit accumulation; bit i of the result is CLEAR when residual i does not fit the Rice coder
-template <int H>
-FA_D uint32_t lpc8_wide(const int32_t* w, const int32_t* coef, int shift, int32_t* r) {
-    uint32_t ok = 0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        int64_t sum = 0;
-#pragma unroll
-        for (int m = 0; m < H; ++m) sum += (int64_t)coef[m] * (int64_t)w[H + i - 1 - m];   // coef[m] = 0 beyond the order
-        int64_t v = (int64_t)w[H + i] - (sum >> shift);
-        if (fits_res(v)) ok |= 1u << i;
-        r[i] = (int32_t)v;
-    }
-    return ok;
-}
-
-// Pass 2 of a full frame: the thread's 32 samples in 4 rolled sub-blocks of 8.  do0 / do1: accumulate the
-// sum |residual| of the fixed / LPC candidate into s0 / s1; the LPC residual (do1) or else the fixed one
-// is parked in res[j * 128 + t].  Thread 0 leaves its warm-up samples out of the sums.
-template <int H>
-FA_D void full_pass2(const FrameSrc& S, int c, int t, int wasted, bool wide, bool do0, int ord0, bool do1, int ord1,
-                     const int32_t* coef, int shift1, bool wide1, int32_t* res, unsigned long long& s0_out,
-                     unsigned long long& s1_out, bool& fit0, bool& fit1) {
-    int32_t w[H + 8];
-    // history: the H samples before the chunk (zeros for thread 0)
+// Residuals of the thread's 32 samples for a predictor of at most NC coefficients (coef[m] = 0 beyond the
+// order; a fixed predictor is passed as its literal coefficients with shift 0).  buf: the channel's samples,
+// replaced by the zigzag-coded residuals.  WIDE: 64-bit accumulation, and residuals that do not fit the Rice
+// coder clear `fit_out`.  Thread 0's first `order` samples are warm-up: left out of the sum and of the check.
+template <int NC, bool WIDE>
+FA_D void residual_pass(int32_t* buf, EncHot* hot, const int32_t* park, int t, int wasted, const int32_t* coef, int shift,
+                        int order, unsigned long long& sum_out, bool& fit_out) {
+    int32_t w[NC + 16];
     if (t == 0) {
 #pragma unroll
-        for (int i = 0; i < H; ++i) w[i] = 0;
+        for (int i = 0; i < NC; ++i) w[i] = 0;
     } else {
-        if (H == 8) {
-            load8(S, c, t * kSpt - 8, w);
-        } else {
-            int32_t tmp[16];
-            load8(S, c, t * kSpt - 16, tmp);
-            load8(S, c, t * kSpt - 8, tmp + 8);
+        // the NC samples before the chunk = the last quads of thread t - 1 (L2 hits: the TMA copy has just read them)
 #pragma unroll
-            for (int i = 0; i < H; ++i) w[i] = tmp[16 - H + i];
+        for (int qq = 0; qq < NC / 4; ++qq) {
+            const U4 v = ldg128(park + (((8 - NC / 4 + qq) * kEncThreads + (t - 1)) << 2));
+            w[4 * qq] = (int32_t)v.x; w[4 * qq + 1] = (int32_t)v.y; w[4 * qq + 2] = (int32_t)v.z; w[4 * qq + 3] = (int32_t)v.w;
         }
         if (wasted) {
 #pragma unroll
-            for (int i = 0; i < H; ++i) w[i] >>= wasted;
+            for (int i = 0; i < NC; ++i) w[i] >>= wasted;
         }
     }
-    int32_t cf[H];
-    fixed_coefs(ord0, cf, H);
-    const int skip0 = t == 0 ? ord0 : 0, skip1 = t == 0 ? ord1 : 0;
-    uint32_t a0 = 0, a1 = 0;                 // narrow sums
-    unsigned long long b0 = 0, b1 = 0;       // wide sums
-    uint32_t bad0 = 0, bad1 = 0;
-    int32_t nx[8];                            // next sub-block, in flight while the current one is processed
-    load8(S, c, t * kSpt, nx);
+    uint32_t a = 0;
+    unsigned long long b = 0;
+    uint32_t bad = 0;
 #pragma unroll 1
-    for (int it = 0; it < kSpt / 8; ++it) {
+    for (int h = 0; h < 2; ++h) {
+        int32_t* p = buf + ((h * 4 * kEncThreads + t) << 2);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) w[H + i] = nx[i];
-        if (it + 1 < kSpt / 8) load8(S, c, t * kSpt + (it + 1) * 8, nx);
+        for (int qq = 0; qq < 4; ++qq) {
+            const U4 v = lds128(p + qq * (kEncThreads * 4));
+            w[NC + 4 * qq] = (int32_t)v.x; w[NC + 4 * qq + 1] = (int32_t)v.y;
+            w[NC + 4 * qq + 2] = (int32_t)v.z; w[NC + 4 * qq + 3] = (int32_t)v.w;
+        }
         if (wasted) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) w[H + i] >>= wasted;
+            for (int i = 0; i < 16; ++i) w[NC + i] >>= wasted;
         }
-        const int sk0 = skip0 - it * 8, sk1 = skip1 - it * 8;
-        const bool plain = sk0 <= 0 && sk1 <= 0;     // no warm-up sample in this sub-block (all but thread 0's first)
-        int32_t r[8];
-        if (do0) {
-            if (!wide) {
-                // fixed predictor = LPC with the literal coefficients (1), (2,-1), (3,-3,1), (4,-6,4,-1), shift 0
-                lpc8_dispatch<H>(ord0, w, cf, 0, r);
-                if (plain) {
+        if (h == 0 && t == 0) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) a0 = sad_acc(r[i], 0, a0);
-                } else {
+            for (int i = 0; i < kMaxOrd; ++i) hot->warm[i] = w[NC + i];
+        }
+        uint32_t u[16];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        if (i >= sk0) a0 = sad_acc(r[i], 0, a0);
-                }
+        for (int i = 0; i < 16; ++i) {
+            if (!WIDE) {
+                int32_t sum = 0;
+#pragma unroll
+                for (int m = 0; m < NC; ++m) sum += coef[m] * w[NC + i - 1 - m];
+                const int32_t r = w[NC + i] - (sum >> shift);
+                a = sad_acc(r, 0, a);
+                u[i] = zigzag32(r);
             } else {
-                uint32_t ok = lpc8_wide<H>(w, cf, 0, r);
+                int64_t sum = 0;
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (i >= sk0) {
-                        b0 += (unsigned long long)(r[i] < 0 ? -(int64_t)r[i] : (int64_t)r[i]);
-                        if (!((ok >> i) & 1u)) bad0 = 1;
-                    }
-            }
-            if (!do1) {
-                if (plain) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) res[(it * 8 + i) * kEncThreads + t] = r[i];
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) res[(it * 8 + i) * kEncThreads + t] = i >= sk0 ? r[i] : w[H + i];   // warm-up: the sample
-                }
+                for (int m = 0; m < NC; ++m) sum += (int64_t)coef[m] * (int64_t)w[NC + i - 1 - m];
+                const int64_t v = (int64_t)w[NC + i] - (sum >> shift);
+                if (!fits_res(v)) bad |= 1u << i;
+                const int32_t r = (int32_t)v;
+                u[i] = zigzag32(r);
+                b += ((unsigned long long)u[i] + 1ull) >> 1;     // |r|
             }
         }
-        if (do1) {
-            if (!wide1) {
-                lpc8_dispatch<H>(ord1, w, coef, shift1, r);
-                if (plain) {
+        if (h == 0 && t == 0) {
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) a1 = sad_acc(r[i], 0, a1);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        if (i >= sk1) a1 = sad_acc(r[i], 0, a1);
+            for (int i = 0; i < NC; ++i) {
+                if (i < order) {
+                    const unsigned long long ar = ((unsigned long long)u[i] + 1ull) >> 1;
+                    if (WIDE) b -= ar; else a -= (uint32_t)ar;
+                    bad &= ~(1u << i);
                 }
-            } else {
-                uint32_t ok = lpc8_wide<H>(w, coef, shift1, r);
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (i >= sk1) {
-                        b1 += (unsigned long long)(r[i] < 0 ? -(int64_t)r[i] : (int64_t)r[i]);
-                        if (!((ok >> i) & 1u)) bad1 = 1;
-                    }
-            }
-            if (plain) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) res[(it * 8 + i) * kEncThreads + t] = r[i];
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) res[(it * 8 + i) * kEncThreads + t] = i >= sk1 ? r[i] : w[H + i];   // warm-up: the sample
             }
         }
 #pragma unroll
-        for (int i = 0; i < H; ++i) w[i] = w[8 + i];
+        for (int qq = 0; qq < 4; ++qq) {
+            U4 v;
+            v.x = u[4 * qq]; v.y = u[4 * qq + 1]; v.z = u[4 * qq + 2]; v.w = u[4 * qq + 3];
+            sts128(p + qq * (kEncThreads * 4), v);
+        }
+#pragma unroll
+        for (int i = 0; i < NC; ++i) w[i] = w[16 + i];
     }
-    s0_out = wide ? b0 : (unsigned long long)a0;
-    s1_out = wide1 ? b1 : (unsigned long long)a1;
-    fit0 = bad0 == 0;
-    fit1 = bad1 == 0;
+    sum_out = WIDE ? b : (unsigned long long)a;
+    fit_out = bad == 0;
+}
+
+template <int H, bool WIDE>
+FA_D void residual_dispatch(int32_t* buf, EncHot* hot, const int32_t* park, int t, int wasted, const int32_t* coef, int shift,
+                            int order, unsigned long long& sum_out, bool& fit_out) {
+    if (order <= 4) residual_pass<4, WIDE>(buf, hot, park, t, wasted, coef, shift, order, sum_out, fit_out);
+    else if (H <= 8 || order <= 8) residual_pass<8, WIDE>(buf, hot, park, t, wasted, coef, shift, order, sum_out, fit_out);
+    else residual_pass<H, WIDE>(buf, hot, park, t, wasted, coef, shift, order, sum_out, fit_out);
 }
 
 #if defined(FAB_PHASE_TIMING) && defined(__CUDACC__)
@@ -1815,20 +1728,27 @@ FA_D void full_pass2(const FrameSrc& S, int c, int t, int wasted, bool wide, boo
 #define FAB_TICK(k) do { } while (0)
 #endif
 
+// park: the channel's parked samples in HBM (16-byte aligned)
 template <int H>
-FA_D bool enc_channel_full(const EncParams& P, EncCtx& X, const FrameSrc& S, int c, int f, uint32_t g, int bitpos0,
+FA_D bool enc_channel_full(const EncParams& P, EncCtx& X, const int32_t* park, int c, int f, uint32_t g, int bitpos0,
                            int& bitpos_end) {
-    EncShared* sh = X.sh;
+    EncHot* hot = X.hot;
     uint32_t* out = X.out;
     int32_t* res = X.res;
     const int t = tid();
     const int ln = lane(), wp = warp();
     constexpr int bs = kMaxBs;
+    // ---- the channel's samples: one TMA copy into the sample buffer.  Every thread is done with the buffer's
+    //      previous contents: channel 0 starts behind the barrier at the top of the CTA loop
+    if (c > 0) sync();
+    if (t == 0) {
+        fence_proxy_async();
+        bulk_load(res, park, (uint32_t)(kMaxBs * 4), &hot->mbar);
+    }
     // ---- the plan of this (frame, channel): three broadcast loads, decoded in registers
     const unsigned char* pp = (const unsigned char*)(P.plans + ((size_t)(g - P.g_begin) * P.nch + c));
     const U4 pa = ldg128(pp), pb = ldg128(pp + 16), pc = ldg128(pp + 32);
     const int mode = (int)(pa.x & 0xFFu);
-    if (mode == 0) return false;
     const int wasted = (int)((pa.x >> 8) & 0xFFu);
     const int bps = 32 - wasted;
     const int ok0 = (int)((pa.x >> 16) & 0xFFu), ok1 = (int)(pa.x >> 24);
@@ -1836,139 +1756,130 @@ FA_D bool enc_channel_full(const EncParams& P, EncCtx& X, const FrameSrc& S, int
     const int shift1 = (int)((pa.y >> 16) & 0xFFu), prec1 = (int)(pa.y >> 24);
     const bool wide = mode == 3;
     const bool wide1 = wide || (pa.z & 0xFFu) != 0;
+    const uint32_t fixed_bits = pc.z;
     const bool retiring = !X.retired;
     FAB_TICK(1);
-    if (wp == 3 && retiring) retire_slot(P, sh);   // previous frame
+    mbar_wait(&hot->mbar, X.tma_phase);
+    X.tma_phase ^= 1u;
     FAB_TICK(2);
+    if (mode == 0) return false;     // (the copy has landed: the general path may reuse the buffer)
 
     if (mode == 1) {
         if (retiring) {
             sync();
             retire_copyout(P, X);
             sync();
-            if (t == 0) retire_crc(P, sh);
             X.retired = true;
         }
         bitpos_end = bitpos0 + (c == 0 ? 8 * frame_header_bytes(bs, f) : 0) + subframe_header_bits(0, 0, 0, 32, 0);
         if (t == 0) {
-            if (c == P.nch - 1) publish_aggregate(P, g, f, bitpos_end);
             Pk pk;
             pk_begin(pk, out, bitpos0);
-            if (c == 0) emit_frame_header(pk, sh->crc8, bs, f, P.nch);
+            if (c == 0) emit_frame_header(pk, hot->crc8, bs, f, P.nch);
             emit_subframe_header(pk, 0, 0, 0);
-            emit_sample(pk, src_sample(S, c, 0), 32);
-            pk_end(pk, sh->tail_val[c][0], sh->tail_word[c][0]);
+            emit_sample(pk, res[0], 32);
+            pk_end(pk, hot->tail_val[c][0], hot->tail_word[c][0]);
         }
         return true;
     }
-    int32_t coef[H];
+    int32_t coef1[H];
     {
-        const uint32_t qw[8] = {pb.x, pb.y, pb.z, pb.w, pc.x, pc.y, pc.z, pc.w};
+        const uint32_t qw[6] = {pb.x, pb.y, pb.z, pb.w, pc.x, pc.y};
 #pragma unroll
-        for (int m = 0; m < H; ++m) coef[m] = (int32_t)(int16_t)(uint16_t)(qw[m >> 1] >> (16 * (m & 1)));
+        for (int m = 0; m < H; ++m) coef1[m] = (int32_t)(int16_t)(uint16_t)(qw[m >> 1] >> (16 * (m & 1)));
     }
 
-    // ---- pass 2: sum |residual| of the chunk for both candidates; the LPC residual (or the fixed one when
-    //      there is no LPC candidate) is parked in shared memory
-    unsigned long long s0 = 0, s1 = 0;
-    bool fit0 = true, fit1 = true;
-    full_pass2<H>(S, c, t, wasted, wide, ok0 != 0, ord0, ok1 != 0, ord1, coef, shift1, wide1, res, s0, s1, fit0, fit1);
-    FAB_TICK(3);
-
-    // ---- finest partitions: 2^gsh consecutive threads each; sums by butterfly, parameters and estimated
-    //      bits computed redundantly by every thread of the group
+    // ---- residual pass + estimate, for the LPC candidate first; the fixed predictor only on demand
     const int maxp = P.max_porder;
     const int gsh = 7 - maxp;
-    unsigned long long g0 = s0, g1 = s1;
-    for (int m = 1; m < (1 << gsh); m <<= 1) {
-        g0 += shfl_xor_u64(g0, m);
-        g1 += shfl_xor_u64(g1, m);
-    }
     const int part = t >> gsh;
     const bool leader = (t & ((1 << gsh) - 1)) == 0;
-    const uint32_t npart0 = (uint32_t)(bs >> maxp) - (part == 0 ? (uint32_t)ord0 : 0u);
-    const uint32_t npart1 = (uint32_t)(bs >> maxp) - (part == 0 ? (uint32_t)ord1 : 0u);
-    int kf0 = 0, kf1 = 0;
-    const uint32_t e0 = rice_estimate(g0, npart0, kf0), e1 = rice_estimate(g1, npart1, kf1);
-    {
-        const uint32_t b0 = redux_add(leader ? e0 : 0u), b1 = redux_add(leader ? e1 : 0u);
-        const unsigned long long t0s = warp_sum_u64(s0), t1s = warp_sum_u64(s1);
-        const uint32_t f0 = (ballot(!fit0) ? 1u : 0u) | (ballot(kf0 >= 15) ? 2u : 0u);
-        const uint32_t f1 = (ballot(!fit1) ? 1u : 0u) | (ballot(kf1 >= 15) ? 2u : 0u);
-        if (ln == 0) {
-            sh->x_bits[0][wp] = b0; sh->x_bits[1][wp] = b1;
-            sh->x_sum[0][wp] = t0s; sh->x_sum[1][wp] = t1s;
-            sh->x_flag[0][wp] = f0; sh->x_flag[1][wp] = f1;
-        }
-    }
-    FAB_TICK(4);
-    sync();   // B3: the partials and (retiring) the byte offset of the previous frame are visible
-    FAB_TICK(5);
-
-    // ---- every thread: partition order (maximum or 0) and winner (smallest estimate, stream_encoder.c
-    //      process_subframe_); all inputs are block-uniform
     const uint32_t verbatim_bits = (uint32_t)bps * (uint32_t)bs;
-    int win = -1, porder = 0, kwin = 0, rice2 = 0;
-    {
-        uint32_t best = verbatim_bits;
+    int cand = ok1 ? 1 : (ok0 ? 0 : -1);
+    if (cand < 0) return false;
+    int order = 0, porder = 0, k = 0, rice2 = 0;
+    int32_t cf[H];
+    for (int pass = 0;; ++pass) {
+        order = cand ? ord1 : ord0;
+        const int shift = cand ? shift1 : 0;
+        if (cand) {
 #pragma unroll
-        for (int cd = 0; cd < 2; ++cd) {
-            if (!(cd == 0 ? ok0 : ok1)) continue;
-            uint32_t bits_hi = 0, flag = 0;
-            unsigned long long tot = 0;
-#pragma unroll
-            for (int w = 0; w < kEncWarps; ++w) { bits_hi += sh->x_bits[cd][w]; tot += sh->x_sum[cd][w]; flag |= sh->x_flag[cd][w]; }
-            if (flag & 1u) continue;                       // a residual does not fit the Rice coder
-            const uint32_t ord = (uint32_t)(cd == 0 ? ord0 : ord1);
-            int k0 = 0;
-            uint32_t bits_lo = rice_estimate(tot, (uint32_t)bs - ord, k0);
-            bits_lo += 6u + (k0 >= 15 ? 1u : 0u);
-            bits_hi += 6u + ((flag & 2u) ? (1u << maxp) : 0u);
-            const bool use_hi = bits_hi < bits_lo;
-            const uint32_t res_bits = use_hi ? bits_hi : bits_lo;
-            const uint32_t bits = ord * (uint32_t)bps + res_bits + (cd == 1 ? 9u + ord * (uint32_t)prec1 : 0u);
-            if (bits < best) {
-                best = bits; win = cd;
-                porder = use_hi ? maxp : 0;
-                kwin = use_hi ? (cd == 0 ? kf0 : kf1) : k0;
-                rice2 = use_hi ? ((flag & 2u) ? 1 : 0) : (k0 >= 15 ? 1 : 0);
-            }
+            for (int m = 0; m < H; ++m) cf[m] = coef1[m];
+        } else {
+            fixed_coefs(ord0, cf, H);
         }
+        unsigned long long s = 0;
+        bool fit = true;
+        if (cand ? wide1 : wide) residual_dispatch<H, true>(res, hot, park, t, wasted, cf, shift, order, s, fit);
+        else residual_dispatch<H, false>(res, hot, park, t, wasted, cf, shift, order, s, fit);
+        FAB_TICK(3);
+        // finest partitions: 2^gsh consecutive threads each; parameters and estimated bits computed redundantly by
+        // every thread of the group
+        unsigned long long gs = s;
+        for (int m = 1; m < (1 << gsh); m <<= 1) gs += shfl_xor_u64(gs, m);
+        const uint32_t npart = (uint32_t)(bs >> maxp) - (part == 0 ? (uint32_t)order : 0u);
+        int kf = 0;
+        const uint32_t e = rice_estimate(gs, npart, kf);
+        {
+            const uint32_t bsum = redux_add(leader ? e : 0u);
+            const unsigned long long ts = warp_sum_u64(s);
+            const uint32_t fl = (ballot(!fit) ? 1u : 0u) | (ballot(kf >= 15) ? 2u : 0u);
+            if (ln == 0) { hot->x_bits[pass & 1][wp] = bsum; hot->x_sum[pass & 1][wp] = ts; hot->x_flag[pass & 1][wp] = fl; }
+        }
+        FAB_TICK(4);
+        sync();   // B3: the partials are visible (and the tail ORs of the previous frame are ordered before its copy-out)
+        FAB_TICK(5);
+        // every thread: partition order (maximum or 0) and size of the subframe; all inputs are block-uniform
+        uint32_t bits_hi = 0, flag = 0;
+        unsigned long long tot = 0;
+#pragma unroll
+        for (int w = 0; w < kEncWarps; ++w) { bits_hi += hot->x_bits[pass & 1][w]; tot += hot->x_sum[pass & 1][w]; flag |= hot->x_flag[pass & 1][w]; }
+        int k0 = 0;
+        uint32_t bits_lo = rice_estimate(tot, (uint32_t)(bs - order), k0);
+        bits_lo += 6u + (k0 >= 15 ? 1u : 0u);
+        bits_hi += 6u + ((flag & 2u) ? (1u << maxp) : 0u);
+        const bool use_hi = bits_hi < bits_lo;
+        const uint32_t side = (uint32_t)order * (uint32_t)bps + (cand ? 9u + (uint32_t)order * (uint32_t)prec1 : 0u);
+        const bool unfit = (flag & 1u) != 0;
+        if (cand == 1 && ok0 && (unfit || fixed_bits < side + bits_lo)) {
+            // the fixed predictor looks smaller (or the LPC residual does not fit): fetch the samples again and redo
+            cand = 0;
+            if (t == 0) {
+                fence_proxy_async();
+                bulk_load(res, park, (uint32_t)(kMaxBs * 4), &hot->mbar);
+            }
+            mbar_wait(&hot->mbar, X.tma_phase);
+            X.tma_phase ^= 1u;
+            continue;
+        }
+        if (unfit || side + (use_hi ? bits_hi : bits_lo) >= verbatim_bits) return false;   // (block-uniform) general path
+        porder = use_hi ? maxp : 0;
+        k = use_hi ? kf : k0;
+        rice2 = use_hi ? ((flag & 2u) ? 1 : 0) : (k0 >= 15 ? 1 : 0);
+        break;
     }
-    if (win < 0) {            // (block-uniform) nothing beats VERBATIM: general path
-        if (retiring) retire_copyout(P, X);
-        sync();
-        if (retiring) { if (t == 0) retire_crc(P, sh); X.retired = true; }
-        return false;
-    }
-    const int order = win == 0 ? ord0 : ord1;
     const int plen = rice2 ? 5 : 4;
-    const int k = kwin;
     const int skip = t == 0 ? order : 0;
-    const int ptype = win == 0 ? 2 : 3;
-    const int prec = win == 0 ? 0 : prec1;
-    // ---- previous frame: CRC partials + copy to its slot, by threads 1..127; thread 0 meanwhile builds the
-    //      frame / subframe header of this channel into hdr_tmp (a serial job that used to sit behind the
-    //      scan barrier and made the other 127 threads wait)
+    const int ptype = cand == 0 ? 2 : 3;
+    const int prec = cand == 0 ? 0 : prec1;
+    // ---- previous frame: copy to its slot, by threads 1..127; thread 0 meanwhile builds the frame / subframe
+    //      header of this channel into hdr_tmp
     if (retiring) retire_copyout(P, X, true);
     Pk pk;
     int hdr_words = 0;
     if (t == 0) {
         // same accumulator protocol as Pk, words go to hdr_tmp[0 ..); bit offset of the first word kept
-        pk_begin(pk, sh->hdr_tmp, bitpos0 & 31);          // word index 0 = frame word (bitpos0 >> 5)
-        if (c == 0) emit_frame_header(pk, sh->crc8, bs, f, P.nch);
+        pk_begin(pk, hot->hdr_tmp, bitpos0 & 31);          // word index 0 = frame word (bitpos0 >> 5)
+        if (c == 0) emit_frame_header(pk, hot->crc8, bs, f, P.nch);
         emit_subframe_header(pk, ptype, order, wasted);
-        // warm-up samples: parked in res by the LPC pass; if the fixed predictor won after an LPC pass they
-        // are re-parked by the redo below, which has not run yet -> read them from the source
-        for (int j = 0; j < order; ++j)
-            emit_sample(pk, (win == 0 && ok1) ? (src_sample(S, c, j) >> wasted) : res[j * kEncThreads], bps);
+        for (int j = 0; j < order; ++j) emit_sample(pk, hot->warm[j], bps);
         if (ptype == 3) {
             pk_emit(pk, (uint32_t)(prec1 - 1), 4);
             pk_emit(pk, (uint32_t)shift1 & 31u, 5);
             for (int j = 0; j < order; ++j) {
-                int32_t cj = coef[0];
+                int32_t cj = cf[0];
 #pragma unroll
-                for (int q = 1; q < H; ++q) cj = (q == j) ? coef[q] : cj;
+                for (int q = 1; q < H; ++q) cj = (q == j) ? cf[q] : cj;
                 pk_emit(pk, (uint32_t)cj & ((1u << prec1) - 1u), prec1);
             }
         }
@@ -1977,23 +1888,21 @@ FA_D bool enc_channel_full(const EncParams& P, EncCtx& X, const FrameSrc& S, int
         hdr_words = pk.word;
     }
     FAB_TICK(6);
-    if (win == 0 && ok1) {
-        // the fixed predictor won but the parked residual is the LPC one: redo the fixed pass (L1/L2 hits)
-        unsigned long long d0, d1;
-        bool q0, q1;
-        full_pass2<H>(S, c, t, wasted, wide, true, ord0, false, 0, coef, 0, false, res, d0, d1, q0, q1);
-    }
     // ---- exact code lengths of the chunk, block scan
     const bool part_start = porder == 0 ? t == 0 : leader;
     uint32_t lens = part_start ? (uint32_t)plen : 0u;
-    uint32_t qmax = 0;
-#pragma unroll 8
-    for (int j = 0; j < kSpt; ++j) {
-        int32_t rv = res[j * kEncThreads + t];
-        uint32_t u = ((uint32_t)rv << 1) ^ (uint32_t)(rv >> 31);
-        uint32_t q = j >= skip ? (u >> k) : 0u;
-        lens += q;
-        qmax = q > qmax ? q : qmax;
+    uint32_t qor = 0;
+    const int32_t* rp = res + (t << 2);
+#pragma unroll
+    for (int q = 0; q < kSpt / 4; ++q) {
+        const U4 v = lds128(rp + q * (kEncThreads * 4));
+        uint32_t q0 = v.x >> k, q1 = v.y >> k, q2 = v.z >> k, q3 = v.w >> k;
+        if (4 * q < H) {      // only the first quads can hold warm-up samples
+            q0 = 4 * q + 0 < skip ? 0u : q0; q1 = 4 * q + 1 < skip ? 0u : q1;
+            q2 = 4 * q + 2 < skip ? 0u : q2; q3 = 4 * q + 3 < skip ? 0u : q3;
+        }
+        lens += (q0 + q1) + (q2 + q3);
+        qor |= (q0 | q1) | (q2 | q3);
     }
     lens += (uint32_t)(kSpt - skip) * (uint32_t)(k + 1);
     uint32_t inc = lens;
@@ -2002,18 +1911,15 @@ FA_D bool enc_channel_full(const EncParams& P, EncCtx& X, const FrameSrc& S, int
         uint32_t n = shfl_up(inc, d);
         if (ln >= d) inc += n;
     }
-    if (ln == 31) sh->scan[wp] = inc;
+    if (ln == 31) hot->scan[wp] = inc;
     FAB_TICK(7);
     sync();   // B5: also orders the copy-out of the previous frame before the packing stores below
     FAB_TICK(8);
-    if (retiring) {
-        if (t == 0) retire_crc(P, sh);
-        X.retired = true;
-    }
+    if (retiring) X.retired = true;
     uint32_t wbase = 0, total = 0;
 #pragma unroll
     for (int w = 0; w < kEncWarps; ++w) {
-        uint32_t x = sh->scan[w];
+        uint32_t x = hot->scan[w];
         if (w < wp) wbase += x;
         total += x;
     }
@@ -2023,56 +1929,74 @@ FA_D bool enc_channel_full(const EncParams& P, EncCtx& X, const FrameSrc& S, int
     const int sub0 = bitpos0 + (c == 0 ? 8 * frame_header_bytes(bs, f) : 0);
     const int body0 = sub0 + hdr_bits;
 
-    // ---- pack
+    // ---- pack: the pending bits sit right-aligned in `lo` (fill < 32 of them between codes; older bits above
+    //      them are stale and never read again)
     bitpos_end = body0 + (int)total;
+    uint32_t lo = 0, hi = 0;
+    int fill, word;
     if (t == 0) {
-        // move the finished header words into the staged frame and continue the same packing session there
+        // move the finished header words into the staged frame and continue the same bit stream there
         const int w0 = bitpos0 >> 5;
-        for (int i = 0; i < hdr_words; ++i) out[ow(w0 + i)] = sh->hdr_tmp[ow(i)];
-        pk.out = out;
-        pk.word = w0 + hdr_words;
+        for (int i = 0; i < hdr_words; ++i) out[ow(w0 + i)] = hot->hdr_tmp[ow(i)];
+        fill = pk.fill;
+        word = w0 + hdr_words;
+        lo = fill ? (uint32_t)(pk.acc >> (64 - fill)) : 0u;
     } else {
-        pk_begin(pk, out, body0 + (int)excl);
+        const int pos = body0 + (int)excl;
+        fill = pos & 31;
+        word = pos >> 5;
     }
-    if (part_start) pk_emit(pk, (uint32_t)k, plen);
-    if (qmax + (uint32_t)k + 1u <= 32u) {
-        // every code of the chunk fits one emit: branch-free loop on a (hi, lo) register pair
-        uint32_t hi = (uint32_t)(pk.acc >> 32), lo = 0;
-        int fill = pk.fill, word = pk.word;
+    if (part_start) {
+        hi = funnel_lc(lo, hi, (uint32_t)plen);
+        lo = (lo << plen) | (uint32_t)k;
+        fill += plen;
+        if (fill >= 32) { fill -= 32; out[ow(word)] = funnel_r(lo, hi, (uint32_t)fill); word++; }
+    }
+    if (qor + (uint32_t)k + 1u <= 32u) {
+        // every code of the chunk fits 32 bits: branch-free appends
         const uint32_t kbit = 1u << k, kmask = kbit - 1u;
-        const int k1 = k + 1;
-#pragma unroll 4
-        for (int j = 0; j < kSpt; ++j) {
-            int32_t rv = res[j * kEncThreads + t];
-            if (j >= skip) {
-                uint32_t u = ((uint32_t)rv << 1) ^ (uint32_t)(rv >> 31);
-                uint32_t low = (u & kmask) | kbit;
-                int len = (int)(u >> k) + k1;
-                uint64_t v = (uint64_t)low << (64 - fill - len);
-                hi |= (uint32_t)(v >> 32);
-                lo |= (uint32_t)v;
-                fill += len;
-                if (fill >= 32) {
-                    out[ow(word)] = hi;
-                    word++;
-                    hi = lo;
-                    lo = 0;
-                    fill -= 32;
-                }
-            }
+        const uint32_t k1 = (uint32_t)k + 1u;
+        // (a code of length 0 and value 0 is a no-op: that is how thread 0 passes over its warm-up samples)
+#define FAB_APPEND_M(uv, msk)                                                          \
+        do {                                                                           \
+            const uint32_t u_ = (uv);                                                  \
+            const uint32_t len_ = ((u_ >> k) + k1) & (msk);                            \
+            hi = funnel_lc(lo, hi, len_);                                              \
+            lo = funnel_lc(0u, lo, len_) | (((u_ & kmask) | kbit) & (msk));            \
+            fill += (int)len_;                                                         \
+            if (fill >= 32) { fill -= 32; out[ow(word)] = funnel_r(lo, hi, (uint32_t)fill); word++; } \
+        } while (0)
+#define FAB_APPEND(uv) FAB_APPEND_M(uv, 0xFFFFFFFFu)
+#pragma unroll
+        for (int q = 0; q < H / 4; ++q) {       // quads that may hold warm-up samples (thread 0)
+            const U4 v = lds128(rp + q * (kEncThreads * 4));
+            FAB_APPEND_M(v.x, 4 * q + 0 >= skip ? 0xFFFFFFFFu : 0u);
+            FAB_APPEND_M(v.y, 4 * q + 1 >= skip ? 0xFFFFFFFFu : 0u);
+            FAB_APPEND_M(v.z, 4 * q + 2 >= skip ? 0xFFFFFFFFu : 0u);
+            FAB_APPEND_M(v.w, 4 * q + 3 >= skip ? 0xFFFFFFFFu : 0u);
         }
-        pk.acc = (uint64_t)hi << 32;
-        pk.fill = fill;
-        pk.word = word;
+#pragma unroll 2
+        for (int q = H / 4; q < kSpt / 4; ++q) {
+            const U4 v = lds128(rp + q * (kEncThreads * 4));
+            FAB_APPEND(v.x);
+            FAB_APPEND(v.y);
+            FAB_APPEND(v.z);
+            FAB_APPEND(v.w);
+        }
+#undef FAB_APPEND
+#undef FAB_APPEND_M
+        hot->tail_val[c][t] = fill ? (lo << (32 - fill)) : 0u;
+        hot->tail_word[c][t] = (uint16_t)word;
     } else {
+        Pk pq;
+        pq.out = out;
+        pq.acc = fill ? ((uint64_t)lo << (64 - fill)) : 0ull;
+        pq.fill = fill;
+        pq.word = word;
 #pragma unroll 1
-        for (int j = skip; j < kSpt; ++j) {
-            int32_t rv = res[j * kEncThreads + t];
-            uint32_t u = ((uint32_t)rv << 1) ^ (uint32_t)(rv >> 31);
-            pk_rice(pk, u, k);
-        }
+        for (int j = skip; j < kSpt; ++j) pk_rice(pq, (uint32_t)res[(((j >> 2) * kEncThreads + t) << 2) + (j & 3)], k);
+        pk_end(pq, hot->tail_val[c][t], hot->tail_word[c][t]);
     }
-    pk_end(pk, sh->tail_val[c][t], sh->tail_word[c][t]);
     FAB_TICK(9);
     return true;
 }
@@ -2292,10 +2216,9 @@ FA_D void enc_channel_general_body(const EncParams& P, EncCtx& X, const FrameSrc
     Pk pk;
     bool open = false;
     if (t == 0) {
-        if (c == P.nch - 1) publish_aggregate(P, g, f, bitpos_end);
         pk_begin(pk, out, bitpos0);
         open = true;
-        if (c == 0) emit_frame_header(pk, sh->crc8, bs, f, P.nch);
+        if (c == 0) emit_frame_header(pk, X.hot->crc8, bs, f, P.nch);
         emit_subframe_header(pk, ptype, order, wasted);
         if (ptype == 0) {
             emit_sample(pk, G.x[kMaxOrd], bps);
@@ -2329,7 +2252,7 @@ FA_D void enc_channel_general_body(const EncParams& P, EncCtx& X, const FrameSrc
             }
         }
     }
-    if (open) pk_end(pk, sh->tail_val[c][t], sh->tail_word[c][t]);
+    if (open) pk_end(pk, X.hot->tail_val[c][t], X.hot->tail_word[c][t]);
 }
 
 FA_DNOINL int enc_channel_general(const EncParams P, EncCtx X, const FrameSrc S, int c, int f, uint32_t g, int bitpos0) {
@@ -2343,38 +2266,42 @@ FA_DNOINL int enc_channel_general(const EncParams P, EncCtx X, const FrameSrc S,
 // ------------------------------------------------------------------------------------------------------
 template <int H>
 FA_D void encode_frames_cta(const EncParams& P, unsigned char* smem_raw) {
-    EncShared* sh = (EncShared*)smem_raw;
-    uint16_t* crcT = (uint16_t*)(smem_raw + ((sizeof(EncShared) + 15) & ~(size_t)15));
+    EncHot* hot = (EncHot*)smem_raw;
     const int t = tid();
     const int nch = P.nch;
     const uint32_t total_frames = P.g_end;
     EncCtx X;
-    X.sh = sh; X.crcT = crcT; X.out = (uint32_t*)(crcT + 4 * 256);
+    X.hot = hot;
+    X.res = (int32_t*)(smem_raw + kEncHotBytes);       // 128-byte aligned: TMA destination
+    X.sh = (EncShared*)X.res;
+    X.out = (uint32_t*)(X.res + kMaxBs);
     X.out_words_padded = (int)(enc_out_words(nch) + (enc_out_words(nch) >> 4) + 8);
-    X.res = (int32_t*)(X.out + ((X.out_words_padded + 3) & ~3));
     X.retired = false;
+    X.tma_phase = 0;
 #if defined(FAB_PHASE_TIMING) && defined(__CUDACC__)
     for (int k = 0; k < 12; ++k) X.ph[k] = 0;
     X.last = clock64();
 #endif
 
-    for (int i = t; i < 4 * 256; i += kEncThreads) crcT[i] = P.crc->crc16[i >> 8][i & 255];
-    for (int i = t; i < 256; i += kEncThreads) sh->crc8[i] = P.crc->crc8[i];
-    if (t == 0) { sh->prev_valid = 0; sh->gq[0] = P.g_begin + atom_add_global(P.ticket, 1u); }
-    sh->tail_val[0][t] = 0; sh->tail_val[1][t] = 0;
-    zero_out(X);
+    for (int i = t; i < 256; i += kEncThreads) hot->crc8[i] = P.crc->crc8[i];
+    if (t == 0) {
+        mbar_init(&hot->mbar, 1);
+        hot->prev_valid = 0;
+        hot->gq[0] = P.g_begin + atom_add_global(P.ticket, 1u);
+    }
+    hot->tail_val[0][t] = 0; hot->tail_val[1][t] = 0;
 
     for (int iter = 0;; ++iter) {
         // ---- work assignment: dynamic tickets (any order: every frame has its own output slot)
         FAB_TICK(10);
         sync();   // also: every thread has finished packing the previous frame (all plain stores done)
         FAB_TICK(0);
-        const uint32_t g = sh->gq[iter & 1];
-        if (t == 0) sh->gq[(iter + 1) & 1] = P.g_begin + atom_add_global(P.ticket, 1u);   // for the next iteration
+        const uint32_t g = hot->gq[iter & 1];
+        if (t == 0) hot->gq[(iter + 1) & 1] = P.g_begin + atom_add_global(P.ticket, 1u);   // for the next iteration
         // trailing partial words of the previous frame's packing sessions
         for (int c = 0; c < nch; ++c) {
-            uint32_t tv = sh->tail_val[c][t];
-            if (tv) { atom_or_shared(&X.out[ow(sh->tail_word[c][t])], tv); sh->tail_val[c][t] = 0; }
+            uint32_t tv = hot->tail_val[c][t];
+            if (tv) { atom_or_shared(&X.out[ow(hot->tail_word[c][t])], tv); hot->tail_val[c][t] = 0; }
         }
         X.retired = false;
         if (g >= total_frames) break;
@@ -2386,8 +2313,10 @@ FA_D void encode_frames_cta(const EncParams& P, unsigned char* smem_raw) {
         FrameSrc S;
         S.dtype = P.dtype; S.bs = bs;
         S.off32 = 0.f; S.gain32 = 0.f; S.off64 = 0.; S.gain64 = 0.;
-        if (P.dtype == kF32) { S.off32 = ((const float*)P.offsets)[s]; S.gain32 = ((const float*)P.gains)[s]; }
-        if (P.dtype == kF64) { S.off64 = ((const double*)P.offsets)[s]; S.gain64 = ((const double*)P.gains)[s]; }
+        if (bs != kMaxBs) {      // (full frames read the integers k_enc_analyze parked; the source is only needed if they fall back)
+            if (P.dtype == kF32) { S.off32 = ((const float*)P.offsets)[s]; S.gain32 = ((const float*)P.gains)[s]; }
+            if (P.dtype == kF64) { S.off64 = ((const double*)P.offsets)[s]; S.gain64 = ((const double*)P.gains)[s]; }
+        }
         const int esize = (P.dtype == kI32 || P.dtype == kF32) ? 4 : 8;
         S.base = (const unsigned char*)P.data + (s * P.stream_size + samp0) * esize;
         S.vec = (((uintptr_t)S.base) & 15) == 0;
@@ -2397,16 +2326,13 @@ FA_D void encode_frames_cta(const EncParams& P, unsigned char* smem_raw) {
             int bend = 0;
             bool done = false;
             if (bs == kMaxBs) {
-                if (frame_parked(P)) {
-                    // planar int32 samples parked by k_enc_analyze in this frame's slot (the compressed frame
-                    // only replaces them when the frame is retired, one iteration from now)
-                    FrameSrc Sp;
-                    Sp.dtype = kI32; Sp.bs = bs; Sp.vec = true;
-                    Sp.off32 = 0.f; Sp.gain32 = 0.f; Sp.off64 = 0.; Sp.gain64 = 0.;
-                    Sp.base = P.slots + (int64_t)(g - P.g_begin) * P.slot_bytes + (int64_t)c * kMaxBs * 4;
-                    done = enc_channel_full<H>(P, X, Sp, c, f, g, bitpos, bend);
-                } else {
-                    done = enc_channel_full<H>(P, X, S, c, f, g, bitpos, bend);
+                // planar int32 samples parked by k_enc_analyze in this frame's slot (the compressed frame only
+                // replaces them when the frame is retired, one iteration from now)
+                const int32_t* park = (const int32_t*)(P.slots + (int64_t)(g - P.g_begin) * P.slot_bytes) + (int64_t)c * kMaxBs;
+                done = enc_channel_full<H>(P, X, park, c, f, g, bitpos, bend);
+                if (!done && (P.dtype == kF32 || P.dtype == kF64)) {
+                    if (P.dtype == kF32) { S.off32 = ((const float*)P.offsets)[s]; S.gain32 = ((const float*)P.gains)[s]; }
+                    else { S.off64 = ((const double*)P.offsets)[s]; S.gain64 = ((const double*)P.gains)[s]; }
                 }
             }
             else if (bs >= 64) {
@@ -2425,15 +2351,14 @@ FA_D void encode_frames_cta(const EncParams& P, unsigned char* smem_raw) {
         // The writes below are ordered before their readers by the barrier at the top of the loop.
         if (t == 0) {
             if (bitpos & 31) X.out[ow(bitpos >> 5)] = 0;   // final partial word: nobody plain-stores it, tails are OR-ed in
-            sh->prev_valid = 1; sh->prev_g = g; sh->prev_f = f; sh->prev_nbytes = (bitpos + 7) >> 3;
+            hot->prev_valid = 1; hot->prev_g = g; hot->prev_nbytes = (bitpos + 7) >> 3;
         }
     }
     // ---- drain: the last frame of this CTA (its tails were OR-ed in above)
-    sync();
     retire_full(P, X);
 #if defined(FAB_PHASE_TIMING) && defined(__CUDACC__)
     if ((blockIdx.x == 7 || blockIdx.x == 300) && (t == 0 || t == 37 || t == 127 || t == 96))
-        printf("cta %d t %d: top %lld | plan %lld slot %lld pass2 %lld est %lld B3 %lld copyout %lld lens %lld B5 %lld pack %lld rest %lld\n",
+        printf("cta %d t %d: top %lld | plan %lld tma %lld resid %lld est %lld B3 %lld hdr/copy %lld lens %lld B5 %lld pack %lld rest %lld\n",
                (int)blockIdx.x, t, X.ph[0], X.ph[1], X.ph[2], X.ph[3], X.ph[4], X.ph[5], X.ph[6], X.ph[7], X.ph[8], X.ph[9], X.ph[10]);
 #endif
 }

@@ -40,6 +40,8 @@ FA_D uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
 FA_D uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_l(lo, hi, s); }
 // upper word of (hi:lo) << min(s, 32)
 FA_D uint32_t funnel_lc(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_lc(lo, hi, s); }
+// lower word of (hi:lo) >> (s & 31)
+FA_D uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_r(lo, hi, s); }
 FA_D void atom_or_shared(uint32_t* p, uint32_t v) { atomicOr(p, v); }
 FA_D void atom_add_shared64(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }
 FA_D void atom_or_shared_u32(uint32_t* p, uint32_t v) { atomicOr(p, v); }
@@ -73,6 +75,28 @@ FA_D void cp_async16(void* smem_dst, const void* gsrc) {
 }
 FA_D void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 FA_D void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// ---- TMA bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP / SYNCS) -------------------
+FA_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+FA_D void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// orders this thread's earlier generic-proxy accesses of shared memory before its later async-proxy (TMA) writes
+FA_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// one thread: arm the barrier with the byte count and start the copy (16-byte aligned addresses, bytes % 16 == 0)
+FA_D void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// every consumer: block until the phase with this parity has completed
+FA_D void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
 FA_D uint32_t ldg32(const uint32_t* p) { return __ldg(p); }
 struct U4 { uint32_t x, y, z, w; };
 FA_D U4 ldg128(const void* p) {  // 16-byte aligned, read-only path
@@ -210,6 +234,10 @@ inline uint32_t funnel_lc(uint32_t lo, uint32_t hi, uint32_t s) {
     if (s >= 32) return lo;
     return s ? (hi << s) | (lo >> (32 - s)) : hi;
 }
+inline uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {
+    s &= 31;
+    return s ? (lo >> s) | (hi << (32 - s)) : lo;
+}
 inline void atom_or_shared(uint32_t* p, uint32_t v) { __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 inline void atom_add_shared64(unsigned long long* p, unsigned long long v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline uint32_t atom_add_global(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
@@ -230,6 +258,16 @@ inline void spin_pause() { std::this_thread::yield(); }
 inline void cp_async16(void* smem_dst, const void* gsrc) { memcpy(smem_dst, gsrc, 16); }
 inline void cp_async_commit() {}
 inline void cp_async_wait_all() {}
+inline void mbar_init(unsigned long long* bar, uint32_t) { *bar = 0; }
+inline void fence_proxy_async() {}
+// emulated barrier word = number of completed phases; the phase with parity p has completed when the count's parity differs
+inline void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, unsigned long long* bar) {
+    memcpy(smem_dst, gsrc, bytes);
+    __atomic_fetch_add(bar, 1ull, __ATOMIC_RELEASE);
+}
+inline void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    while ((__atomic_load_n(bar, __ATOMIC_ACQUIRE) & 1ull) == (unsigned long long)parity) std::this_thread::yield();
+}
 inline uint32_t ldg32(const uint32_t* p) { return *p; }
 struct U4 { uint32_t x, y, z, w; };
 inline U4 ldg128(const void* p) { U4 r; memcpy(&r, p, 16); return r; }

@@ -108,7 +108,12 @@ int hs_encode(const void* data, int dtype, int64_t n_stream, int64_t stream_size
         else encode_frames_cta<8>(P, fasim::smem());
     });
     fasim::launch(1, kScanThreads, (kScanThreads / 32 + 1) * 8, [&](int) { scan_batch_cta(P, (unsigned long long*)fasim::smem()); });
-    fasim::launch((int)total_frames, 128, 0, [&](int b) { compact_frame_cta(P, (uint32_t)b); });
+    std::vector<uint16_t> ctab(4 * 256), s11(2 * 256);
+    for (int i = 0; i < 4 * 256; ++i) ctab[(size_t)i] = crc()->crc16[i >> 8][i & 255];
+    for (int i = 0; i < 256; ++i) { s11[(size_t)i] = crc()->shift_hi[11][i]; s11[(size_t)(256 + i)] = crc()->shift_lo[11][i]; }
+    fasim::launch((int)total_frames, 128, sizeof(CompactShared), [&](int b) {
+        compact_frame_cta(P, (uint32_t)b, ctab.data(), s11.data(), s11.data() + 256, (CompactShared*)fasim::smem());
+    });
     fasim::launch(1, 1, 0, [&](int) {
         for (int64_t s = 0; s < n_stream; ++s)
             for (int f = 0; f < nf; ++f) finalize_entry(P, s, f, nbytes, total);
