@@ -662,9 +662,9 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
         P.fsize = (uint32_t*)(fs0 + (bi & 1) * fsize_b);
         P.slots = sl0 + (bi & 1) * slots_b;
         const int64_t nfr = (int64_t)P.g_end - (int64_t)P.g_begin;
-        // The compaction of batch b (memory-bound, plus the frame CRCs) runs on the second stream under the
-        // kernels of batch b + 1, which use the other slot buffer; k_enc_analyze of batch b + 2 parks samples in
-        // the slots batch b compacts from, so it waits for that compaction.
+        // The size scan and the compaction of batch b (memory-bound, plus the frame CRCs) run on the second stream
+        // under the kernels of batch b + 1, which use the other slot / frame-size buffers; k_enc_analyze of batch
+        // b + 2 parks samples in the slots batch b compacts from, so it waits for that compaction.
         if (bi >= 2) FAB_CUDA(ctx, cudaStreamWaitEvent(st, joins[bi & 1], 0));
         const unsigned agrid = (unsigned)std::min<int64_t>(nfr, (int64_t)ctx->n_sm * FAB_AN_CTAS);
         if (h12) k_enc_analyze<12><<<agrid, kEncThreads, 0, st>>>(P);
@@ -673,9 +673,9 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
         unsigned grid = (unsigned)std::min<int64_t>(nfr, resident);
         if (h12) k_encode<12><<<grid, kEncThreads, smem, st>>>(P);
         else k_encode<8><<<grid, kEncThreads, smem, st>>>(P);
-        k_enc_scan<<<1, kScanThreads, 0, st>>>(P);
         FAB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
         FAB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+        k_enc_scan<<<1, kScanThreads, 0, ctx->aux>>>(P);      // (the running byte total is carried from scan to scan: all on aux)
         k_enc_compact<<<(unsigned)std::min<int64_t>(nfr, (int64_t)ctx->n_sm * 16), 128, 0, ctx->aux>>>(P);
         FAB_CUDA(ctx, cudaEventRecord(joins[bi & 1], ctx->aux));
         ctx->launches += 5;

@@ -153,6 +153,7 @@ struct AnShared {              // k_enc_analyze: per-warp partials of the block 
     uint32_t w_bad[kEncWarps];
     unsigned long long w_fe[kEncWarps][5];
     double w_ac[kEncWarps][kMaxOrd + 1];
+    int32_t stage[kEncThreads * kSpt];   // full frames: the channel's int32 samples, [quad][thread][4]
 };
 
 struct DesignIO {              // k_enc_design: thread-private working set of design_fixed / design_lpc
@@ -198,7 +199,7 @@ struct EncHot {
     uint32_t scan[kEncWarps];
     uint8_t crc8[256];                         // CRC-8 table (frame headers)
     uint32_t hdr_tmp[40];                      // full-frame path: header words built by thread 0 ahead of the packing (ow-indexed)
-    int32_t warm[kMaxOrd];                     // full-frame path: the channel's first samples (>> wasted), saved before the in-place pass
+    alignas(16) int32_t warm[kMaxOrd];         // full-frame path: the channel's first samples (>> wasted), saved before the in-place pass
     // full-frame path: per-warp partials of (estimated bits at the finest partition order, sum |residual|, flags)
     // (two sets: the second residual pass of a channel must not overwrite what slower warps still read)
     uint32_t x_bits[2][kEncWarps];
@@ -211,6 +212,7 @@ struct EncHot {
     int prev_valid, prev_nbytes;
     uint32_t prev_g;
     uint32_t gq[2];     // tickets, fetched one frame ahead (the atomic's latency is off the critical path)
+    int gq_f[2], gq_bs[2];   // ... with their frame number and blocksize (thread 0 does the divisions, also ahead)
 };
 
 FA_HD size_t enc_out_words(int nch) { return ((size_t)nch * (kMaxBs * 4 + 64) + 64) / 4; }
@@ -1209,6 +1211,302 @@ FA_D void analyze_channel(const EncParams& P, AnShared* sh, const float* wsm, co
 // Word index of in-frame sample i inside the parked [8][128][4] block of a full frame-channel.
 FA_HD int park_word(int i) { return ((((i >> 2) & 7) * kEncThreads + (i >> 5)) << 2) + (i & 3); }
 
+// ------------------------------------------------------------------------------------------------------
+// Full frames (4096 samples), two phases per (frame, channel):
+//   stage   convert the thread's 32 input samples to int32 exactly once (float -> quantise, int64 -> low /
+//           high word), PARK them for k_encode ([quad][thread][4] in the frame's slot, both channels of an
+//           8-byte type in one go) and stage the channel in shared memory in the same layout;
+//   stats   from shared memory (conflict-free LDS.128, rolled trips of B samples): OR / min / max, the five
+//           fixed-predictor error sums, the windowed autocorrelation -> block reduction -> FrameStats.
+// The predictor history of a chunk is the end of its left neighbour's chunk, read from the staged channel:
+// nothing is converted twice.
+// ------------------------------------------------------------------------------------------------------
+FA_D uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+FA_D float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+FA_D float fabs32(float f) { return u2f(f2u(f) & 0x7FFFFFFFu); }
+
+// utils.c:232-240 for one sample without the double-precision detour: for gain > 0 and |y| < 2^22,
+// (int)((double)y +- 0.5) is round-half-away-from-zero of the float y = gain * (x - off); adding 1.5 * 2^23
+// rounds y to the nearest integer (ties to even) in the mantissa, which is the same number except on exact
+// ties -- those, wide values, NaN and non-positive gains take the reference's operation sequence.
+FA_D int32_t quant_f32_fast(float x, float off, float gain, bool gain_pos) {
+    const float st = fsub(x, off);
+    const float y = fmul(gain, st);
+    const float r = fadd(y, 12582912.0f);
+    const float d = fsub(y, fsub(r, 12582912.0f));
+    if (gain_pos && fabs32(y) < 4194304.0f && fabs32(d) != 0.5f) return (int32_t)(f2u(r) - 0x4B400000u);
+    return quant_f32(x, off, gain);
+}
+
+FA_D U4 ld128(const void* p) { return lds128(p); }    // plain (coherent) 16-byte load, any address space
+
+// Stage channel c of the frame; c == 0 converts the input (and parks every channel), c == 1 re-reads the high
+// words this thread parked a moment ago.
+FA_D void analyze_stage(const FrameSrc& S, int c, int t, int32_t* park_frame, int32_t* stage) {
+    if (c > 0) {
+#pragma unroll
+        for (int q = 0; q < kSpt / 4; ++q) {
+            const int o = (q * kEncThreads + t) << 2;
+            sts128(stage + o, ld128(park_frame + c * kMaxBs + o));
+        }
+        return;
+    }
+    if (S.dtype == kI32 || S.dtype == kF32) {
+        const uint32_t* p = (const uint32_t*)S.base + t * kSpt;
+        const bool gain_pos = S.gain32 > 0.0f;
+        U4 v[kSpt / 4];
+#pragma unroll
+        for (int q = 0; q < kSpt / 4; ++q) {
+            if (S.vec) v[q] = ldg128(p + 4 * q);
+            else { v[q].x = ldg32(p + 4 * q); v[q].y = ldg32(p + 4 * q + 1); v[q].z = ldg32(p + 4 * q + 2); v[q].w = ldg32(p + 4 * q + 3); }
+        }
+#pragma unroll
+        for (int q = 0; q < kSpt / 4; ++q) {
+            U4 w = v[q];
+            if (S.dtype == kF32) {
+                w.x = (uint32_t)quant_f32_fast(u2f(w.x), S.off32, S.gain32, gain_pos);
+                w.y = (uint32_t)quant_f32_fast(u2f(w.y), S.off32, S.gain32, gain_pos);
+                w.z = (uint32_t)quant_f32_fast(u2f(w.z), S.off32, S.gain32, gain_pos);
+                w.w = (uint32_t)quant_f32_fast(u2f(w.w), S.off32, S.gain32, gain_pos);
+            }
+            const int o = (q * kEncThreads + t) << 2;
+            sts128(park_frame + o, w);
+            sts128(stage + o, w);
+        }
+    } else {
+        const unsigned long long* p = (const unsigned long long*)S.base + t * kSpt;
+#pragma unroll 2
+        for (int q = 0; q < kSpt / 4; ++q) {
+            unsigned long long e[4];
+            if (S.vec) {
+                const U4 a = ldg128(p + 4 * q), b = ldg128(p + 4 * q + 2);
+                e[0] = ((unsigned long long)a.y << 32) | a.x; e[1] = ((unsigned long long)a.w << 32) | a.z;
+                e[2] = ((unsigned long long)b.y << 32) | b.x; e[3] = ((unsigned long long)b.w << 32) | b.z;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) e[i] = p[4 * q + i];
+            }
+            if (S.dtype == kF64) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    double d;
+                    memcpy(&d, &e[i], 8);
+                    e[i] = (unsigned long long)quant_f64(d, S.off64, S.gain64);
+                }
+            }
+            U4 lo, hi;
+            lo.x = (uint32_t)e[0]; lo.y = (uint32_t)e[1]; lo.z = (uint32_t)e[2]; lo.w = (uint32_t)e[3];
+            hi.x = (uint32_t)(e[0] >> 32); hi.y = (uint32_t)(e[1] >> 32); hi.z = (uint32_t)(e[2] >> 32); hi.w = (uint32_t)(e[3] >> 32);
+            const int o = (q * kEncThreads + t) << 2;
+            sts128(park_frame + o, lo);
+            sts128(park_frame + kMaxBs + o, hi);
+            sts128(stage + o, lo);
+        }
+    }
+}
+
+template <int H>
+FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const float* wsm, const FrameSrc& S, int c, FrameStats* st,
+                               int32_t* park_frame) {
+    constexpr int B = H <= 8 ? 8 : 16;          // samples per rolled trip (>= H: the history of a trip is the trip before)
+    const int t = tid();
+    const int ln = lane(), wp = warp();
+    int32_t* stage = sh->stage;
+    analyze_stage(S, c, t, park_frame, stage);
+    sync();
+    const bool do_lpc = P.max_lpc_order > 0;
+    // ---- history: the H samples before the chunk (zeros before the frame)
+    int32_t hx[H];
+    double hw[H];         // hw[l - 1] = windowed sample (32 t - l)
+#pragma unroll
+    for (int i = 0; i < H; ++i) { hx[i] = 0; hw[i] = 0.0; }
+    if (t != 0) {
+#pragma unroll
+        for (int qq = 0; qq < H / 4; ++qq) {
+            const U4 v = lds128(stage + (((8 - H / 4 + qq) * kEncThreads + (t - 1)) << 2));
+            hx[4 * qq] = (int32_t)v.x; hx[4 * qq + 1] = (int32_t)v.y; hx[4 * qq + 2] = (int32_t)v.z; hx[4 * qq + 3] = (int32_t)v.w;
+        }
+        if (do_lpc) {
+#pragma unroll
+            for (int qq = 0; qq < H / 4; ++qq) {
+                const U4 w4 = lds128(wsm + (qq * kEncThreads + t) * 4);
+                hw[H - 1 - 4 * qq] = (double)fmul((float)hx[4 * qq], u2f(w4.x));
+                hw[H - 2 - 4 * qq] = (double)fmul((float)hx[4 * qq + 1], u2f(w4.y));
+                hw[H - 3 - 4 * qq] = (double)fmul((float)hx[4 * qq + 2], u2f(w4.z));
+                hw[H - 4 - 4 * qq] = (double)fmul((float)hx[4 * qq + 3], u2f(w4.w));
+            }
+        }
+    }
+    // ---- statistics, fixed-predictor error sums (libFLAC fixed.c: sum |e_k| over i >= 4), windowed
+    //      autocorrelation (lpc.c: float data * float window, double accumulation)
+    uint32_t orv = 0;
+    int32_t mn = 0x7fffffff, mx = (int32_t)0x80000000u;
+    uint32_t fe0 = 0, fe1 = 0, fe2 = 0, fe3 = 0, fe4 = 0;
+    uint32_t p1 = (uint32_t)hx[H - 1] - (uint32_t)hx[H - 2];
+    uint32_t p2, p3;
+    int32_t xprev = hx[H - 1];
+    {
+        const uint32_t p1b = (uint32_t)hx[H - 2] - (uint32_t)hx[H - 3];
+        const uint32_t p1c = (uint32_t)hx[H - 3] - (uint32_t)hx[H - 4];
+        const uint32_t p2b = p1b - p1c;
+        p2 = p1 - p1b;
+        p3 = p2 - p2b;
+    }
+    double ac[H + 1];
+#pragma unroll
+    for (int l = 0; l <= H; ++l) ac[l] = 0.0;
+#pragma unroll 1
+    for (int it = 0; it < kSpt / B; ++it) {
+        int32_t x[B];
+#pragma unroll
+        for (int qq = 0; qq < B / 4; ++qq) {
+            const U4 v = lds128(stage + (((it * (B / 4) + qq) * kEncThreads + t) << 2));
+            x[4 * qq] = (int32_t)v.x; x[4 * qq + 1] = (int32_t)v.y; x[4 * qq + 2] = (int32_t)v.z; x[4 * qq + 3] = (int32_t)v.w;
+        }
+        const bool head = it == 0 && t == 0;     // the frame's first four samples stay out of the fixed-predictor sums
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            const int32_t a0 = x[j];
+            orv |= (uint32_t)a0;
+            mn = a0 < mn ? a0 : mn;
+            mx = a0 > mx ? a0 : mx;
+            const uint32_t d1 = (uint32_t)a0 - (uint32_t)xprev;
+            const uint32_t d2 = d1 - p1, d3 = d2 - p2, d4 = d3 - p3;
+            p1 = d1; p2 = d2; p3 = d3;
+            xprev = a0;
+            if (j >= 4 || !head) {
+                fe0 = sad_acc(a0, 0, fe0);
+                fe1 = sad_acc((int32_t)d1, 0, fe1);
+                fe2 = sad_acc((int32_t)d2, 0, fe2);
+                fe3 = sad_acc((int32_t)d3, 0, fe3);
+                fe4 = sad_acc((int32_t)d4, 0, fe4);
+            }
+        }
+        if (do_lpc) {
+            double cw[B];      // windowed samples of this trip
+#pragma unroll
+            for (int qq = 0; qq < B / 4; ++qq) {
+                const U4 w4 = lds128(wsm + ((H / 4 + it * (B / 4) + qq) * kEncThreads + t) * 4);
+                cw[4 * qq] = (double)fmul((float)x[4 * qq], u2f(w4.x));
+                cw[4 * qq + 1] = (double)fmul((float)x[4 * qq + 1], u2f(w4.y));
+                cw[4 * qq + 2] = (double)fmul((float)x[4 * qq + 2], u2f(w4.z));
+                cw[4 * qq + 3] = (double)fmul((float)x[4 * qq + 3], u2f(w4.w));
+            }
+#pragma unroll
+            for (int j = 0; j < B; ++j) {
+#pragma unroll
+                for (int l = 0; l <= H; ++l) {
+                    const double other = l <= j ? cw[j - l] : hw[l - j - 1];
+                    ac[l] = dfma(cw[j], other, ac[l]);
+                }
+            }
+#pragma unroll
+            for (int l = 1; l <= H; ++l) hw[l - 1] = cw[B - l];
+        }
+    }
+
+    // ---- block reduction: REDUX for the integers, transposing butterfly for the doubles
+    {
+        uint32_t wor = redux_or(orv);
+        int32_t wmn = redux_min(mn), wmx = redux_max(mx);
+        unsigned long long s0 = warp_sum_u32_wide(fe0), s1 = warp_sum_u32_wide(fe1), s2 = warp_sum_u32_wide(fe2),
+                           s3 = warp_sum_u32_wide(fe3), s4 = warp_sum_u32_wide(fe4);
+        if (ln == 0) {
+            sh->w_or[wp] = wor; sh->w_mn[wp] = wmn; sh->w_mx[wp] = wmx;
+            sh->w_fe[wp][0] = s0; sh->w_fe[wp][1] = s1; sh->w_fe[wp][2] = s2; sh->w_fe[wp][3] = s3; sh->w_fe[wp][4] = s4;
+        }
+        if (do_lpc) {
+            double v8 = warp_sum8_d(ac);
+            if ((ln & 3) == 0) sh->w_ac[wp][((ln >> 4) & 1) * 4 + ((ln >> 3) & 1) * 2 + ((ln >> 2) & 1)] = v8;
+#pragma unroll
+            for (int l = 8; l <= H; ++l) {
+                double v = warp_sum_d(ac[l]);
+                if (ln == 0) sh->w_ac[wp][l] = v;
+            }
+        } else if (ln <= H) {
+            sh->w_ac[wp][ln] = 0.0;
+        }
+    }
+    sync();
+    // ---- every thread: frame totals of the sample statistics -> mode (block-uniform)
+    uint32_t t_or = 0;
+    int32_t a = 0x7fffffff, b = (int32_t)0x80000000u;
+#pragma unroll
+    for (int w = 0; w < kEncWarps; ++w) {
+        t_or |= sh->w_or[w];
+        a = sh->w_mn[w] < a ? sh->w_mn[w] : a;
+        b = sh->w_mx[w] > b ? sh->w_mx[w] : b;
+    }
+    int mode = 2, wasted = 0;
+    if (a == b) mode = 1;                                           // CONSTANT
+    else {
+        wasted = ctz32(t_or);                                       // t_or != 0: the samples differ
+        // the 32-bit sums above are only valid for narrow (unshifted) samples
+        if (a < -(1 << kNarrowBits) || b >= (1 << kNarrowBits)) mode = 3;
+    }
+    if (mode == 3) {
+        // wide samples (up to the full int32 range, e.g. the low word of an int64): the fixed-predictor
+        // statistics are redone with 64-bit differences on the samples >> wasted (libFLAC:
+        // FLAC__fixed_compute_best_predictor_wide); orders whose residual leaves the int32 range are excluded.
+        // The autocorrelation stays valid.
+        unsigned long long we[5] = {0, 0, 0, 0, 0};
+        uint32_t bad = 0;
+        int64_t q1 = (int64_t)(hx[H - 1] >> wasted) - (int64_t)(hx[H - 2] >> wasted);
+        int64_t q1b = (int64_t)(hx[H - 2] >> wasted) - (int64_t)(hx[H - 3] >> wasted);
+        int64_t q1c = (int64_t)(hx[H - 3] >> wasted) - (int64_t)(hx[H - 4] >> wasted);
+        int64_t q2 = q1 - q1b, q2b = q1b - q1c;
+        int64_t q3 = q2 - q2b;
+        int64_t prev = (int64_t)(hx[H - 1] >> wasted);
+#pragma unroll 1
+        for (int q = 0; q < kSpt / 4; ++q) {
+            const U4 v = lds128(stage + ((q * kEncThreads + t) << 2));
+            const int32_t xs[4] = {(int32_t)v.x >> wasted, (int32_t)v.y >> wasted, (int32_t)v.z >> wasted, (int32_t)v.w >> wasted};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int64_t e[5];
+                e[0] = (int64_t)xs[j];
+                e[1] = e[0] - prev;
+                e[2] = e[1] - q1; e[3] = e[2] - q2; e[4] = e[3] - q3;
+                q1 = e[1]; q2 = e[2]; q3 = e[3];
+                prev = e[0];
+                if (q > 0 || t != 0) {
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) {
+                        if (!fits_res(e[k])) bad |= 1u << k;
+                        we[k] += (unsigned long long)(e[k] < 0 ? -e[k] : e[k]);
+                    }
+                }
+            }
+        }
+        uint32_t wbad = redux_or(bad);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            unsigned long long v = warp_sum_u64(we[k]);
+            if (ln == 0) sh->w_fe[wp][k] = v;
+        }
+        if (ln == 0) sh->w_bad[wp] = wbad;
+        sync();
+    }
+    // ---- writers: statistics of the samples >> wasted.  Every difference is a multiple of 2^wasted and
+    //      float(x) * w scales exactly, so shifting / scaling the narrow sums is exact.
+    if (t < 5) {
+        unsigned long long v = 0;
+        for (int w = 0; w < kEncWarps; ++w) v += sh->w_fe[w][t];
+        if (mode == 2) v >>= wasted;
+        st->fe[t] = v;
+    } else if (t >= 8 && t < 8 + H + 1) {
+        int l = t - 8;
+        double v = dadd(dadd(sh->w_ac[0][l], sh->w_ac[1][l]), dadd(sh->w_ac[2][l], sh->w_ac[3][l]));
+        if (wasted) v *= 1.0 / (double)(1ull << (2 * wasted));
+        st->ac[l] = v;
+    } else if (t == 31) {
+        uint32_t tb = 0;
+        if (mode == 3) for (int w = 0; w < kEncWarps; ++w) tb |= sh->w_bad[w];
+        st->mode = mode; st->wasted = wasted; st->mn = a >> wasted; st->mx = b >> wasted; st->bad = tb; st->pad = 0;
+    }
+    sync();   // the partials and the staged channel are reused by the next channel / frame
+}
+
 // window values of thread t: samples 32 t - H .. 32 t + 31 (zeros outside the window)
 template <int H>
 FA_D void analyze_fill_window(const EncParams& P, float* wsm) {
@@ -1249,7 +1547,7 @@ FA_D void analyze_frame_cta(const EncParams& P, uint32_t g, AnShared* sh, const 
     // plain integers (quantised / split exactly once) through one TMA copy per channel
     int32_t* slot = (int32_t*)(P.slots + (int64_t)(g - P.g_begin) * P.slot_bytes);
     for (int c = 0; c < P.nch; ++c) {
-        if (bs == kMaxBs) analyze_channel<H, true>(P, sh, wsm, S, c, st + c, slot + c * kMaxBs);
+        if (bs == kMaxBs) analyze_channel_full<H>(P, sh, wsm, S, c, st + c, slot);
         else analyze_channel<H, false>(P, sh, wsm, S, c, st + c, nullptr);
     }
 }
@@ -1668,7 +1966,12 @@ FA_D void residual_pass(int32_t* buf, EncHot* hot, const int32_t* park, int t, i
         }
         if (h == 0 && t == 0) {
 #pragma unroll
-            for (int i = 0; i < kMaxOrd; ++i) hot->warm[i] = w[NC + i];
+            for (int qq = 0; qq < kMaxOrd / 4; ++qq) {
+                U4 v;
+                v.x = (uint32_t)w[NC + 4 * qq]; v.y = (uint32_t)w[NC + 4 * qq + 1];
+                v.z = (uint32_t)w[NC + 4 * qq + 2]; v.w = (uint32_t)w[NC + 4 * qq + 3];
+                sts128(&hot->warm[4 * qq], v);
+            }
         }
         uint32_t u[16];
 #pragma unroll
@@ -2264,6 +2567,31 @@ FA_DNOINL int enc_channel_general(const EncParams P, EncCtx X, const FrameSrc S,
 // ------------------------------------------------------------------------------------------------------
 // The CTA body: loops over (stream, frame) units.  `smem_raw` >= enc_smem_bytes(nch).
 // ------------------------------------------------------------------------------------------------------
+// Thread 0: take the next (stream, frame) ticket of the batch and do its index arithmetic one frame ahead.
+FA_D void enc_fetch_ticket(const EncParams& P, EncHot* hot, int slot) {
+    const uint32_t g = P.g_begin + atom_add_global(P.ticket, 1u);
+    const int f = (int)(g % (uint32_t)P.nframes);
+    const int64_t left = P.stream_size - (int64_t)f * P.blocksize;
+    hot->gq[slot] = g;
+    hot->gq_f[slot] = f;
+    hot->gq_bs[slot] = (int)(left < P.blocksize ? left : P.blocksize);
+}
+
+// Where the samples of (stream, frame) unit g come from (short-frame and general paths; full frames read the
+// integers k_enc_analyze parked).
+FA_D FrameSrc enc_frame_src(const EncParams& P, uint32_t g, int f, int bs) {
+    const int64_t s = (int64_t)(g / (uint32_t)P.nframes);
+    FrameSrc S;
+    S.dtype = P.dtype; S.bs = bs;
+    S.off32 = 0.f; S.gain32 = 0.f; S.off64 = 0.; S.gain64 = 0.;
+    if (P.dtype == kF32) { S.off32 = ((const float*)P.offsets)[s]; S.gain32 = ((const float*)P.gains)[s]; }
+    if (P.dtype == kF64) { S.off64 = ((const double*)P.offsets)[s]; S.gain64 = ((const double*)P.gains)[s]; }
+    const int esize = (P.dtype == kI32 || P.dtype == kF32) ? 4 : 8;
+    S.base = (const unsigned char*)P.data + (s * P.stream_size + (int64_t)f * P.blocksize) * esize;
+    S.vec = (((uintptr_t)S.base) & 15) == 0;
+    return S;
+}
+
 template <int H>
 FA_D void encode_frames_cta(const EncParams& P, unsigned char* smem_raw) {
     EncHot* hot = (EncHot*)smem_raw;
@@ -2287,7 +2615,7 @@ FA_D void encode_frames_cta(const EncParams& P, unsigned char* smem_raw) {
     if (t == 0) {
         mbar_init(&hot->mbar, 1);
         hot->prev_valid = 0;
-        hot->gq[0] = P.g_begin + atom_add_global(P.ticket, 1u);
+        enc_fetch_ticket(P, hot, 0);
     }
     hot->tail_val[0][t] = 0; hot->tail_val[1][t] = 0;
 
@@ -2297,7 +2625,8 @@ FA_D void encode_frames_cta(const EncParams& P, unsigned char* smem_raw) {
         sync();   // also: every thread has finished packing the previous frame (all plain stores done)
         FAB_TICK(0);
         const uint32_t g = hot->gq[iter & 1];
-        if (t == 0) hot->gq[(iter + 1) & 1] = P.g_begin + atom_add_global(P.ticket, 1u);   // for the next iteration
+        const int f = hot->gq_f[iter & 1], bs = hot->gq_bs[iter & 1];
+        if (t == 0) enc_fetch_ticket(P, hot, (iter + 1) & 1);   // for the next iteration
         // trailing partial words of the previous frame's packing sessions
         for (int c = 0; c < nch; ++c) {
             uint32_t tv = hot->tail_val[c][t];
@@ -2305,21 +2634,6 @@ FA_D void encode_frames_cta(const EncParams& P, unsigned char* smem_raw) {
         }
         X.retired = false;
         if (g >= total_frames) break;
-        const int64_t s = (int64_t)(g / (uint32_t)P.nframes);
-        const int f = (int)(g % (uint32_t)P.nframes);
-        const int64_t samp0 = (int64_t)f * P.blocksize;
-        const int bs = (int)((P.stream_size - samp0) < P.blocksize ? (P.stream_size - samp0) : P.blocksize);
-
-        FrameSrc S;
-        S.dtype = P.dtype; S.bs = bs;
-        S.off32 = 0.f; S.gain32 = 0.f; S.off64 = 0.; S.gain64 = 0.;
-        if (bs != kMaxBs) {      // (full frames read the integers k_enc_analyze parked; the source is only needed if they fall back)
-            if (P.dtype == kF32) { S.off32 = ((const float*)P.offsets)[s]; S.gain32 = ((const float*)P.gains)[s]; }
-            if (P.dtype == kF64) { S.off64 = ((const double*)P.offsets)[s]; S.gain64 = ((const double*)P.gains)[s]; }
-        }
-        const int esize = (P.dtype == kI32 || P.dtype == kF32) ? 4 : 8;
-        S.base = (const unsigned char*)P.data + (s * P.stream_size + samp0) * esize;
-        S.vec = (((uintptr_t)S.base) & 15) == 0;
 
         int bitpos = 0;
         for (int c = 0; c < nch; ++c) {
@@ -2330,19 +2644,15 @@ FA_D void encode_frames_cta(const EncParams& P, unsigned char* smem_raw) {
                 // replaces them when the frame is retired, one iteration from now)
                 const int32_t* park = (const int32_t*)(P.slots + (int64_t)(g - P.g_begin) * P.slot_bytes) + (int64_t)c * kMaxBs;
                 done = enc_channel_full<H>(P, X, park, c, f, g, bitpos, bend);
-                if (!done && (P.dtype == kF32 || P.dtype == kF64)) {
-                    if (P.dtype == kF32) { S.off32 = ((const float*)P.offsets)[s]; S.gain32 = ((const float*)P.gains)[s]; }
-                    else { S.off64 = ((const double*)P.offsets)[s]; S.gain64 = ((const double*)P.gains)[s]; }
-                }
             }
             else if (bs >= 64) {
                 // (the short path retires the previous frame on every return: its plans never have mode 0)
-                bend = enc_channel_short<H>(P, X, S, c, f, g, bitpos);
+                bend = enc_channel_short<H>(P, X, enc_frame_src(P, g, f, bs), c, f, g, bitpos);
                 done = bend >= 0;
                 X.retired = true;
             }
             if (!done) {
-                bend = enc_channel_general(P, X, S, c, f, g, bitpos);
+                bend = enc_channel_general(P, X, enc_frame_src(P, g, f, bs), c, f, g, bitpos);
                 X.retired = true;
             }
             bitpos = bend;

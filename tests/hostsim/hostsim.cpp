@@ -241,4 +241,12 @@ void hs_int_to_float(const void* data, int is64, int64_t n_stream, int64_t strea
 }
 
 uint32_t hs_crc16(const uint8_t* p, int64_t n) { return crc16_bytes(crc(), p, n); }
+
+// the analysis pass's single-precision quantiser against the reference operation sequence (fa_quant.h)
+int64_t hs_quant_fast_mismatches(const float* x, int64_t n, float off, float gain) {
+    int64_t bad = 0;
+    for (int64_t i = 0; i < n; ++i)
+        if (quant_f32_fast(x[i], off, gain, gain > 0.0f) != quant_f32(x[i], off, gain)) bad++;
+    return bad;
+}
 }

@@ -136,3 +136,25 @@ def test_corrupt_frame_is_caught_by_the_crc_pass(H):
     for mode in (0, 2):
         with pytest.raises(RuntimeError, match="16384"):
             H.decode(bad, s, n, 9000, mode=mode)
+
+
+def test_fast_quantiser_matches_reference_sequence(H):
+    """quant_f32_fast (k_enc_analyze) == quant_f32 (utils.c:232-240 restated) on ties, wide values, NaN, odd gains."""
+    import ctypes as C
+
+    L = H.lib()
+    L.hs_quant_fast_mismatches.restype = C.c_int64
+    L.hs_quant_fast_mismatches.argtypes = [C.c_void_p, C.c_int64, C.c_float, C.c_float]
+    rng = np.random.default_rng(31)
+    for off, gain in ((0.0, 1.0), (0.0, 1e4), (1.2345, 1e4), (-3.3, 1e7), (0.5, 2.0), (0.0, -1e4), (0.0, 0.0), (7.0, 3.4e38)):
+        parts = [
+            rng.normal(0, 1, 200000), rng.normal(0, 1e3, 50000), rng.uniform(-500, 500, 50000),
+            np.arange(-4000, 4000) * 0.5, np.arange(-4000, 4000) * 0.5 / 1e4, np.arange(-4000, 4000) * 0.25 + off,
+            (np.arange(-2000, 2000) + 0.5) / max(abs(gain), 1e-30) + off,
+            np.array([0.0, -0.0, np.nan, np.inf, -np.inf, 1e-45, -1e-45, 3.4e38, -3.4e38, 4194303.5, 4194304.0, -4194304.5,
+                      8388607.5, 8388608.0, 2147483520.0, 2147483648.0, -2147483648.0, -2147483904.0, 0.49999997, -0.49999997]),
+            np.float32(2.0) ** rng.integers(-30, 40, 2000) * rng.choice([-1, 1], 2000),
+        ]
+        x = np.ascontiguousarray(np.concatenate(parts), np.float32)
+        bad = L.hs_quant_fast_mismatches(x.ctypes.data, x.size, C.c_float(off), C.c_float(gain))
+        assert bad == 0, (off, gain, bad)
