@@ -597,7 +597,7 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
     const int64_t nbatch = (total_frames + batch - 1) / batch;
     const int nbuf = nbatch > 1 ? 2 : 1;     // slot / frame-size buffers alternate between consecutive batches
     size_t stats_b = align256((size_t)batch * nch * sizeof(FrameStats));
-    size_t plans_b = align256((size_t)batch * nch * sizeof(FramePlan));
+    size_t plans_b = align256((size_t)batch * nch * sizeof(FramePlan)) + align256((size_t)batch * nch * sizeof(PlanHeader));
     size_t tick_b = align256((size_t)nbatch * 4 + 16);
     size_t fsize_b = align256((size_t)batch * 4);
     size_t slots_b = align256((size_t)batch * (size_t)slot_bytes);
@@ -605,6 +605,7 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
     int rc = ctx_scratch(ctx, pre + desc_b + ends_b + tick_b + stats_b + plans_b + nbuf * (fsize_b + slots_b) + 256, &scr);
     if (rc) return rc;
 
+    prof_begin(ctx, 0, st);     // slot 0: every kernel of this call: min/max pre-pass, all encoder batches
     if (dtype == FAB_F32) {
         rc = launch_quant_params<float>(ctx, (const float*)d_data, n_stream, stream_size, (const float*)d_quanta,
                                         (float*)d_offsets, (float*)d_gains, st);
@@ -649,12 +650,12 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
         ctx->smem_configured = true;
     }
     P.stats = stats; P.plans = plans;
+    P.hdrs = (PlanHeader*)((unsigned char*)plans + align256((size_t)batch * nch * sizeof(FramePlan)));
     P.slot_bytes = slot_bytes;
     P.base = (unsigned long long*)(ticket + ((nbatch + 3) & ~3ll));   // zeroed with the tickets (8-byte aligned)
     const int h12 = lp.max_lpc_order > 8 ? 1 : 0;
     int64_t resident = (int64_t)ctx->n_sm * std::max(1, ctx->enc_ctas_per_sm[h12][nch - 1]);
     cudaEvent_t joins[2] = {ctx->ev_join, ctx->ev_join2};
-    prof_begin(ctx, 0, st);     // slot 0: the whole encoder kernel sequence of this call (all batches)
     for (int64_t bi = 0; bi < nbatch; ++bi) {
         P.g_begin = (uint32_t)(bi * batch);
         P.g_end = (uint32_t)std::min<int64_t>(total_frames, (bi + 1) * batch);
@@ -682,10 +683,10 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
     }
     FAB_CUDA(ctx, cudaStreamWaitEvent(st, joins[(nbatch - 1) & 1], 0));
     if (nbatch > 1) FAB_CUDA(ctx, cudaStreamWaitEvent(st, joins[nbatch & 1], 0));
-    prof_end(ctx, st);
     P.g_begin = 0; P.g_end = (uint32_t)total_frames;
     k_enc_finalize<<<(unsigned)((n_stream * nf + 255) / 256), 256, 0, st>>>(P, (long long*)d_nbytes, (long long*)d_total);
     ctx->launches++;
+    prof_end(ctx, st);
     FAB_CUDA(ctx, cudaGetLastError());
     return 0;
 }

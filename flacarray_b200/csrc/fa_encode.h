@@ -92,6 +92,7 @@ inline int stream_header_bytes(int nframes) { return 4 + 4 + 34 + 4 + 8 + 3 * nf
 
 struct FrameStats;
 struct FramePlan;
+struct PlanHeader;
 
 struct EncParams {
     const void* data;
@@ -119,6 +120,7 @@ struct EncParams {
     unsigned long long* base;  // running total of bytes before this batch (device scalar)
     FrameStats* stats;         // [(g - g_begin) * nch + c]
     FramePlan* plans;
+    PlanHeader* hdrs;          // [(g - g_begin) * nch + c] subframe preambles built by k_enc_design
     uint32_t g_begin, g_end;   // (stream, frame) units covered by this batch of launches
 };
 
@@ -139,6 +141,17 @@ struct FramePlan {             // 48 bytes, read with three 16-byte broadcast lo
     uint32_t pad2;
 };
 
+// Everything of a full frame's subframe that is known before its residual is computed, as a ready-made MSB-first bit
+// string per candidate: [frame header (channel 0 only)] subframe header byte, warm-up samples, and for LPC the
+// precision, shift and coefficients.  Built by the design thread (which runs serial code anyway), so that no
+// thread of k_encode has to emit ~50 fields one after the other while its 127 neighbours wait.  nbits == 0:
+// not built (wasted bits, no such candidate): k_encode's thread 0 then emits the header itself.
+struct PlanHeader {            // 128 bytes
+    uint32_t nbits_lpc, nbits_fix;
+    uint32_t lpc[22];          // <= 88 + 8 + 12 * 32 + 9 + 12 * 15 = 669 bits
+    uint32_t fix[8];           // <= 88 + 8 + 4 * 32 = 224 bits
+};
+
 struct Plan {
     int type;      // 0 constant, 1 verbatim, 2 fixed, 3 lpc
     int order, wasted, shift, prec, porder, rice2;
@@ -154,7 +167,9 @@ struct AnShared {              // k_enc_analyze: per-warp partials of the block 
     unsigned long long w_fe[kEncWarps][5];
     double w_ac[kEncWarps][kMaxOrd + 1];
     int32_t stage[kEncThreads * kSpt];   // full frames: the channel's int32 samples, [quad][thread][4]
+    double red[kEncWarps][(kMaxOrd + 1) * 33];   // full frames: per-lane autocorrelation partials, [lag][lane] padded
 };
+constexpr int kRedStride = 33;
 
 struct DesignIO {              // k_enc_design: thread-private working set of design_fixed / design_lpc
     unsigned long long t_fe[5];
@@ -288,6 +303,9 @@ FA_D uint32_t gf16_mul(uint32_t a, uint32_t b) {  // a * b mod x^16 + x^15 + x^2
     }
     return r & 0xFFFFu;
 }
+
+// Word index of in-frame sample i inside the parked [8][128][4] block of a full frame-channel.
+FA_HD int park_word(int i) { return ((((i >> 2) & 7) * kEncThreads + (i >> 5)) << 2) + (i & 3); }
 
 FA_D bool fits_res(int64_t v) { return v >= -2147483647LL && v <= 2147483647LL; }
 
@@ -484,8 +502,7 @@ FA_D void load_chunk(const FrameSrc& S, int c, int t, int32_t* xw) {
 }
 
 // ---- frame / subframe headers (thread 0, through its packing session) ----------------------------------
-FA_D void emit_frame_header(Pk& pk, const uint8_t* crc8, int bs, int f, int nch) {
-    uint8_t h[16];
+FA_D int build_frame_header(uint8_t* h, const uint8_t* crc8, int bs, int f, int nch) {   // h[16]; returns the byte count
     int n = 0;
     int bc = blocksize_code(bs);
     h[n++] = 0xFF; h[n++] = 0xF8;
@@ -497,7 +514,20 @@ FA_D void emit_frame_header(Pk& pk, const uint8_t* crc8, int bs, int f, int nch)
     uint32_t c = 0;
     for (int i = 0; i < n; ++i) c = crc8[c ^ h[i]];
     h[n++] = (uint8_t)c;
+    return n;
+}
+FA_D void emit_frame_header(Pk& pk, const uint8_t* crc8, int bs, int f, int nch) {
+    uint8_t h[16];
+    const int n = build_frame_header(h, crc8, bs, f, nch);
     for (int i = 0; i < n; ++i) pk_emit(pk, h[i], 8);
+}
+// append nb (1..32) bits of v (< 2^nb) to a zero-initialised MSB-first bit string of *n bits
+FA_D void hdr_put(uint32_t* w, uint32_t& n, uint32_t v, int nb) {
+    const int word = (int)(n >> 5), off = (int)(n & 31);
+    const uint64_t x = (uint64_t)v << (64 - off - nb);
+    w[word] |= (uint32_t)(x >> 32);
+    if (off + nb > 32) w[word + 1] |= (uint32_t)x;
+    n += (uint32_t)nb;
 }
 
 // subframe header byte (+ wasted-bits unary), warm-up samples are emitted by the caller
@@ -1208,8 +1238,6 @@ FA_D void analyze_channel(const EncParams& P, AnShared* sh, const float* wsm, co
     sync();   // the partials are reused by the next channel
 }
 
-// Word index of in-frame sample i inside the parked [8][128][4] block of a full frame-channel.
-FA_HD int park_word(int i) { return ((((i >> 2) & 7) * kEncThreads + (i >> 5)) << 2) + (i & 3); }
 
 // ------------------------------------------------------------------------------------------------------
 // Full frames (4096 samples), two phases per (frame, channel):
@@ -1225,16 +1253,20 @@ FA_D uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 FA_D float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 FA_D float fabs32(float f) { return u2f(f2u(f) & 0x7FFFFFFFu); }
 
-// utils.c:232-240 for one sample without the double-precision detour: for gain > 0 and |y| < 2^22,
-// (int)((double)y +- 0.5) is round-half-away-from-zero of the float y = gain * (x - off); adding 1.5 * 2^23
-// rounds y to the nearest integer (ties to even) in the mantissa, which is the same number except on exact
-// ties -- those, wide values, NaN and non-positive gains take the reference's operation sequence.
+// utils.c:232-240 for one sample without the double-precision detour.  For gain > 0 the reference's
+// (int)((double)y +- 0.5), y = gain * (x - off), is round-half-away-from-zero of the float y.  In single
+// precision y +- 0.5 is exact or rounds without crossing an integer for every |y| < 2^22 except
+// |y| = 0.5 - 2^-25 (checked over all 1.25e9 such floats), so a truncating conversion of that sum plus a guard
+// for |y| < 0.5 gives the same integer.  Wide values, NaN and non-positive gains take the reference's sequence.
 FA_D int32_t quant_f32_fast(float x, float off, float gain, bool gain_pos) {
     const float st = fsub(x, off);
     const float y = fmul(gain, st);
-    const float r = fadd(y, 12582912.0f);
-    const float d = fsub(y, fsub(r, 12582912.0f));
-    if (gain_pos && fabs32(y) < 4194304.0f && fabs32(d) != 0.5f) return (int32_t)(f2u(r) - 0x4B400000u);
+    const float ay = fabs32(y);
+    if (gain_pos && ay < 4194304.0f) {
+        const float z = fadd(y, u2f((f2u(y) & 0x80000000u) | 0x3F000000u));
+        const int32_t i = (int32_t)z;
+        return ay < 0.5f ? 0 : i;
+    }
     return quant_f32(x, off, gain);
 }
 
@@ -1255,10 +1287,17 @@ FA_D void analyze_stage(const FrameSrc& S, int c, int t, int32_t* park_frame, in
         const uint32_t* p = (const uint32_t*)S.base + t * kSpt;
         const bool gain_pos = S.gain32 > 0.0f;
         U4 v[kSpt / 4];
+        if (S.vec) {
 #pragma unroll
-        for (int q = 0; q < kSpt / 4; ++q) {
-            if (S.vec) v[q] = ldg128(p + 4 * q);
-            else { v[q].x = ldg32(p + 4 * q); v[q].y = ldg32(p + 4 * q + 1); v[q].z = ldg32(p + 4 * q + 2); v[q].w = ldg32(p + 4 * q + 3); }
+            for (int q = 0; q < kSpt / 4; ++q) v[q] = ldg128(p + 4 * q);
+        } else {
+#pragma unroll 1
+            for (int q = 0; q < kSpt / 4; ++q) {      // (rolled: keeps ptxas from predicating 32 scalar loads into the aligned path)
+                U4 w;
+                w.x = ldg32(p + 4 * q); w.y = ldg32(p + 4 * q + 1); w.z = ldg32(p + 4 * q + 2); w.w = ldg32(p + 4 * q + 3);
+#pragma unroll
+                for (int k = 0; k < kSpt / 4; ++k) if (k == q) v[k] = w;
+            }
         }
 #pragma unroll
         for (int q = 0; q < kSpt / 4; ++q) {
@@ -1355,8 +1394,8 @@ FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const float* ws
     double ac[H + 1];
 #pragma unroll
     for (int l = 0; l <= H; ++l) ac[l] = 0.0;
-#pragma unroll 1
-    for (int it = 0; it < kSpt / B; ++it) {
+#pragma unroll
+    for (int it = 0; it < kSpt / B; ++it) {     // (unrolled: the windowed-sample history moves by renaming)
         int32_t x[B];
 #pragma unroll
         for (int qq = 0; qq < B / 4; ++qq) {
@@ -1416,12 +1455,18 @@ FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const float* ws
             sh->w_fe[wp][0] = s0; sh->w_fe[wp][1] = s1; sh->w_fe[wp][2] = s2; sh->w_fe[wp][3] = s3; sh->w_fe[wp][4] = s4;
         }
         if (do_lpc) {
-            double v8 = warp_sum8_d(ac);
-            if ((ln & 3) == 0) sh->w_ac[wp][((ln >> 4) & 1) * 4 + ((ln >> 3) & 1) * 2 + ((ln >> 2) & 1)] = v8;
+            // every lane parks its partials, then lane l sums lag l over the warp in lane order (two chains): a fixed
+            // order (deterministic bytes) at a fraction of the instructions of a register butterfly over doubles
+            double* red = sh->red[wp];
 #pragma unroll
-            for (int l = 8; l <= H; ++l) {
-                double v = warp_sum_d(ac[l]);
-                if (ln == 0) sh->w_ac[wp][l] = v;
+            for (int l = 0; l <= H; ++l) red[l * kRedStride + ln] = ac[l];
+            syncwarp();
+            if (ln <= H) {
+                const double* r = red + ln * kRedStride;
+                double e = 0.0, o = 0.0;
+#pragma unroll 8
+                for (int i = 0; i < 32; i += 2) { e = dadd(e, r[i]); o = dadd(o, r[i + 1]); }
+                sh->w_ac[wp][ln] = dadd(e, o);
             }
         } else if (ln <= H) {
             sh->w_ac[wp][ln] = 0.0;
@@ -1597,6 +1642,34 @@ FA_D void design_frame(const EncParams& P, int64_t i) {
         }
     }
     P.plans[i] = pl;
+    if (P.hdrs != nullptr) {
+        PlanHeader ph;
+        memset(&ph, 0, sizeof(ph));
+        if (bs == kMaxBs && pl.mode >= 2 && pl.wasted == 0) {
+            const int c = (int)(i % P.nch);
+            const int32_t* park = (const int32_t*)(P.slots + (int64_t)(g - P.g_begin) * P.slot_bytes) + (int64_t)c * kMaxBs;
+            uint8_t fh[16];
+            const int nfh = c == 0 ? build_frame_header(fh, P.crc->crc8, bs, f, P.nch) : 0;
+            if (pl.ok1) {
+                uint32_t n = 0;
+                for (int b = 0; b < nfh; ++b) hdr_put(ph.lpc, n, fh[b], 8);
+                hdr_put(ph.lpc, n, (uint32_t)(32 + pl.ord1 - 1) << 1, 8);
+                for (int j = 0; j < pl.ord1; ++j) hdr_put(ph.lpc, n, (uint32_t)park[park_word(j)], 32);
+                hdr_put(ph.lpc, n, (uint32_t)(pl.prec1 - 1), 4);
+                hdr_put(ph.lpc, n, (uint32_t)pl.shift1 & 31u, 5);
+                for (int j = 0; j < pl.ord1; ++j) hdr_put(ph.lpc, n, (uint32_t)(int32_t)pl.qlp[j] & ((1u << pl.prec1) - 1u), pl.prec1);
+                ph.nbits_lpc = n;
+            }
+            if (pl.ok0) {
+                uint32_t n = 0;
+                for (int b = 0; b < nfh; ++b) hdr_put(ph.fix, n, fh[b], 8);
+                hdr_put(ph.fix, n, (uint32_t)(8 + pl.ord0) << 1, 8);
+                for (int j = 0; j < pl.ord0; ++j) hdr_put(ph.fix, n, (uint32_t)park[park_word(j)], 32);
+                ph.nbits_fix = n;
+            }
+        }
+        P.hdrs[i] = ph;
+    }
 }
 
 // residuals of a fixed predictor by repeated differences (order <= 4 subtractions per sample)
@@ -2165,12 +2238,24 @@ FA_D bool enc_channel_full(const EncParams& P, EncCtx& X, const int32_t* park, i
     const int skip = t == 0 ? order : 0;
     const int ptype = cand == 0 ? 2 : 3;
     const int prec = cand == 0 ? 0 : prec1;
-    // ---- previous frame: copy to its slot, by threads 1..127; thread 0 meanwhile builds the frame / subframe
-    //      header of this channel into hdr_tmp
-    if (retiring) retire_copyout(P, X, true);
+    // ---- previous frame: copy to its slot.  This channel's header: the bit string k_enc_design prepared (every
+    //      thread fetches "its" word of it now and stores it behind B5); without one, thread 0 emits the fields into
+    //      hdr_tmp while threads 1..127 do the copying
+    const PlanHeader* ph = P.hdrs + ((size_t)(g - P.g_begin) * P.nch + c);
+    const uint32_t hn = P.hdrs != nullptr ? ldg32(cand ? &ph->nbits_lpc : &ph->nbits_fix) : 0u;     // (block-uniform)
+    const bool pre = hn != 0;
+    const uint32_t* hwords = cand ? ph->lpc : ph->fix;
+    const uint32_t hs = (uint32_t)bitpos0 & 31u;
+    const int hfull = (int)((hs + hn) >> 5);          // frame words that are complete once the header is in
+    uint32_t hval = 0;
+    if (pre && t < hfull) {
+        const uint32_t b = ldg32(hwords + t), a = t > 0 ? ldg32(hwords + t - 1) : 0u;
+        hval = hs ? funnel_r(b, a, hs) : b;
+    }
+    if (retiring) retire_copyout(P, X, !pre);
     Pk pk;
     int hdr_words = 0;
-    if (t == 0) {
+    if (t == 0 && !pre) {
         // same accumulator protocol as Pk, words go to hdr_tmp[0 ..); bit offset of the first word kept
         pk_begin(pk, hot->hdr_tmp, bitpos0 & 31);          // word index 0 = frame word (bitpos0 >> 5)
         if (c == 0) emit_frame_header(pk, hot->crc8, bs, f, P.nch);
@@ -2237,7 +2322,23 @@ FA_D bool enc_channel_full(const EncParams& P, EncCtx& X, const int32_t* park, i
     bitpos_end = body0 + (int)total;
     uint32_t lo = 0, hi = 0;
     int fill, word;
-    if (t == 0) {
+    if (pre) {
+        if (t < hfull) out[ow((bitpos0 >> 5) + t)] = hval;
+    }
+    if (t == 0 && pre) {
+        // the header bits behind the last complete word, then the residual coding method and partition order
+        fill = (int)((hs + hn) & 31u);
+        word = (bitpos0 >> 5) + hfull;
+        if (fill) {
+            const int kw = (int)((hn - 1u) >> 5), r = (int)((hn - 1u) & 31u) + 1;     // last header word, bits used in it
+            const uint64_t x = (((uint64_t)(kw > 0 ? ldg32(hwords + kw - 1) : 0u) << 32) | ldg32(hwords + kw)) >> (32 - r);
+            lo = (uint32_t)x & ((1u << fill) - 1u);
+        }
+        hi = funnel_lc(lo, hi, 6u);
+        lo = (lo << 6) | ((uint32_t)rice2 << 4) | (uint32_t)porder;
+        fill += 6;
+        if (fill >= 32) { fill -= 32; out[ow(word)] = funnel_r(lo, hi, (uint32_t)fill); word++; }
+    } else if (t == 0) {
         // move the finished header words into the staged frame and continue the same bit stream there
         const int w0 = bitpos0 >> 5;
         for (int i = 0; i < hdr_words; ++i) out[ow(w0 + i)] = hot->hdr_tmp[ow(i)];

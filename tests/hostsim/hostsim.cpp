@@ -81,7 +81,8 @@ int hs_encode(const void* data, int dtype, int64_t n_stream, int64_t stream_size
     FramePlan* plan_base = (FramePlan*)(((uintptr_t)plans.data() + 15) & ~(uintptr_t)15);
     if ((uintptr_t)plan_base + (size_t)(total_frames * nch) * sizeof(FramePlan) > (uintptr_t)(plans.data() + plans.size()))
         return kErrAlloc;
-    P.stats = stats.data(); P.plans = plan_base; P.g_begin = 0; P.g_end = (uint32_t)total_frames;
+    std::vector<PlanHeader> hdrs((size_t)(total_frames * nch));
+    P.stats = stats.data(); P.plans = plan_base; P.hdrs = hdrs.data(); P.g_begin = 0; P.g_end = (uint32_t)total_frames;
     // slots for the frames of the (single) batch (analyze parks samples there, encode writes frames)
     const int64_t slot_bytes = (int64_t)((16 + 2 + (int64_t)nch * (lp.blocksize * 4 + 8) + 15) & ~15ll);
     std::vector<uint32_t> slots_w((size_t)(total_frames * slot_bytes / 4) + 8);
