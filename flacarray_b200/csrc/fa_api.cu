@@ -47,10 +47,7 @@ __global__ void __launch_bounds__(kEncThreads, FAB_ENC_CTAS) k_encode(const EncP
 template <int H>
 __global__ void __launch_bounds__(kEncThreads, FAB_AN_CTAS) k_enc_analyze(const EncParams P) {
     __shared__ AnShared sh;
-    __shared__ __align__(16) float wsm[an_window_bytes(H) / 4];
-    analyze_fill_window<H>(P, wsm);
-    __syncthreads();
-    for (uint32_t g = P.g_begin + blockIdx.x; g < P.g_end; g += gridDim.x) analyze_frame_cta<H>(P, g, &sh, wsm);
+    for (uint32_t g = P.g_begin + blockIdx.x; g < P.g_end; g += gridDim.x) analyze_frame_cta<H>(P, g, &sh);
 }
 
 // predictor design: one thread per (frame, channel)
@@ -369,7 +366,7 @@ struct fab_ctx {
     EncTables* d_tab = nullptr;
     int n_sm = 0;
     int enc_ctas_per_sm[2][2] = {{0, 0}, {0, 0}};   // [H == 12][nch - 1]
-    float* d_window[2] = {nullptr, nullptr};  // [0] 1152, [1] 4096
+    float* d_window[3] = {nullptr, nullptr, nullptr};  // [0] 1152, [1] 4096 (both zero-padded to 4096 floats), [2] 4096 in [quad][thread][4] order
     int* d_err = nullptr;
     int* h_err = nullptr;  // pinned
     unsigned char* scratch = nullptr;
@@ -458,15 +455,18 @@ extern "C" int fab_create(fab_ctx** out) {
     EncTables* ht = new EncTables();
     enc_tables_init(ht);
     cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, dev);
-    std::vector<float> w0(1152), w1(4096);
+    std::vector<float> w0(4096, 0.f), w1(4096), w2(4096);
     make_tukey_window(w0.data(), 1152);
     make_tukey_window(w1.data(), 4096);
+    permute_window_qt(w1.data(), w2.data());
     bool ok = cudaMalloc((void**)&ctx->d_crc, sizeof(CrcTables)) == cudaSuccess &&
               cudaMemcpy(ctx->d_crc, h, sizeof(CrcTables), cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMalloc((void**)&ctx->d_tab, sizeof(EncTables)) == cudaSuccess &&
               cudaMemcpy(ctx->d_tab, ht, sizeof(EncTables), cudaMemcpyHostToDevice) == cudaSuccess &&
-              cudaMalloc((void**)&ctx->d_window[0], 1152 * 4) == cudaSuccess &&
-              cudaMemcpy(ctx->d_window[0], w0.data(), 1152 * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMalloc((void**)&ctx->d_window[0], 4096 * 4) == cudaSuccess &&
+              cudaMemcpy(ctx->d_window[0], w0.data(), 4096 * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMalloc((void**)&ctx->d_window[2], 4096 * 4) == cudaSuccess &&
+              cudaMemcpy(ctx->d_window[2], w2.data(), 4096 * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMalloc((void**)&ctx->d_window[1], 4096 * 4) == cudaSuccess &&
               cudaMemcpy(ctx->d_window[1], w1.data(), 4096 * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMalloc((void**)&ctx->d_err, 4) == cudaSuccess && cudaMemset(ctx->d_err, 0, 4) == cudaSuccess &&
@@ -492,6 +492,7 @@ extern "C" void fab_destroy(fab_ctx* ctx) {
     if (ctx->d_tab) cudaFree(ctx->d_tab);
     if (ctx->d_window[0]) cudaFree(ctx->d_window[0]);
     if (ctx->d_window[1]) cudaFree(ctx->d_window[1]);
+    if (ctx->d_window[2]) cudaFree(ctx->d_window[2]);
     if (ctx->d_err) cudaFree(ctx->d_err);
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
     if (ctx->scratch) cudaFree(ctx->scratch);
@@ -631,6 +632,7 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
     P.max_lpc_order = lp.max_lpc_order; P.max_porder = lp.max_porder;
     P.qlp_precision = lp.blocksize <= 384 ? 13 : (lp.blocksize <= 1152 ? 14 : 15);
     P.window = ctx->d_window[lp.blocksize == 1152 ? 0 : 1];
+    P.window_qt = ctx->d_window[2];
     P.crc = ctx->d_crc; P.tab = ctx->d_tab;
     P.out = d_out; P.out_capacity = out_capacity;
     P.starts = (long long*)d_starts; P.ends = ends; P.desc = desc; P.ticket = ticket; P.err = ctx->d_err;

@@ -60,6 +60,11 @@ inline void make_tukey_window(float* w, int L) {
     }
 }
 
+// the window in the order the full-frame analysis reads it: element (quad q, thread t, e) = w[32 t + 4 q + e]
+inline void permute_window_qt(const float* w, float* out) {
+    for (int i = 0; i < kMaxBs; ++i) out[((((i >> 2) & 7) * kEncThreads + (i >> 5)) << 2) + (i & 3)] = w[i];
+}
+
 // CRC-16 position tables (host-initialised): x32[m] = x^(32 m) mod P, inv8[k] = x^(-8 k) mod P.
 struct EncTables {
     uint16_t x32[kX32Len];
@@ -103,7 +108,8 @@ struct EncParams {
     int nch;
     int blocksize, nframes;    // per stream
     int max_lpc_order, max_porder, qlp_precision;
-    const float* window;       // tukey(0.5) of length blocksize
+    const float* window;       // tukey(0.5) of length blocksize, zero-padded to kMaxBs floats
+    const float* window_qt;    // the same window for blocksize kMaxBs in the parked [quad][thread][4] order
     const CrcTables* crc;
     const EncTables* tab;
     uint8_t* out;
@@ -1050,7 +1056,7 @@ FA_D int fast_level_maxp(int bs, int level_max) {
 }
 
 template <int H, bool FULL>
-FA_D void analyze_channel(const EncParams& P, AnShared* sh, const float* wsm, const FrameSrc& S, int c, FrameStats* st,
+FA_D void analyze_channel(const EncParams& P, AnShared* sh, const FrameSrc& S, int c, FrameStats* st,
                           int32_t* park) {
     const int t = tid();
     const int ln = lane(), wp = warp();
@@ -1116,7 +1122,7 @@ FA_D void analyze_channel(const EncParams& P, AnShared* sh, const float* wsm, co
 #pragma unroll
         for (int q = 0; q < H / 4; ++q) {
             if (t != 0) {
-                U4 w4 = lds128(wsm + (q * kEncThreads + t) * 4);
+                U4 w4 = ldg128(P.window + t * kSpt - H + 4 * q);
                 float w0, w1, w2, w3;
                 memcpy(&w0, &w4.x, 4); memcpy(&w1, &w4.y, 4); memcpy(&w2, &w4.z, 4); memcpy(&w3, &w4.w, 4);
                 wv[H - 4 * q] = (double)fmul((float)xw[4 * q], w0);
@@ -1129,7 +1135,7 @@ FA_D void analyze_channel(const EncParams& P, AnShared* sh, const float* wsm, co
 #pragma unroll
         for (int j = 0; j < kSpt; ++j) {
             if ((j & 3) == 0) {
-                U4 w4 = lds128(wsm + (((H + j) >> 2) * kEncThreads + t) * 4);
+                U4 w4 = ldg128(P.window + t * kSpt + j);
                 memcpy(&wq[0], &w4.x, 4); memcpy(&wq[1], &w4.y, 4); memcpy(&wq[2], &w4.z, 4); memcpy(&wq[3], &w4.w, 4);
             }
             wv[0] = (double)fmul((float)xw[H + j], wq[j & 3]);
@@ -1345,7 +1351,7 @@ FA_D void analyze_stage(const FrameSrc& S, int c, int t, int32_t* park_frame, in
 }
 
 template <int H>
-FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const float* wsm, const FrameSrc& S, int c, FrameStats* st,
+FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const FrameSrc& S, int c, FrameStats* st,
                                int32_t* park_frame) {
     constexpr int B = H <= 8 ? 8 : 16;          // samples per rolled trip (>= H: the history of a trip is the trip before)
     const int t = tid();
@@ -1368,7 +1374,7 @@ FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const float* ws
         if (do_lpc) {
 #pragma unroll
             for (int qq = 0; qq < H / 4; ++qq) {
-                const U4 w4 = lds128(wsm + (qq * kEncThreads + t) * 4);
+                const U4 w4 = ldg128(P.window_qt + (((8 - H / 4 + qq) * kEncThreads + (t - 1)) << 2));
                 hw[H - 1 - 4 * qq] = (double)fmul((float)hx[4 * qq], u2f(w4.x));
                 hw[H - 2 - 4 * qq] = (double)fmul((float)hx[4 * qq + 1], u2f(w4.y));
                 hw[H - 3 - 4 * qq] = (double)fmul((float)hx[4 * qq + 2], u2f(w4.z));
@@ -1394,8 +1400,8 @@ FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const float* ws
     double ac[H + 1];
 #pragma unroll
     for (int l = 0; l <= H; ++l) ac[l] = 0.0;
-#pragma unroll
-    for (int it = 0; it < kSpt / B; ++it) {     // (unrolled: the windowed-sample history moves by renaming)
+#pragma unroll 1
+    for (int it = 0; it < kSpt / B; ++it) {     // (rolled: unrolling the trips makes ptxas hoist every load and spill)
         int32_t x[B];
 #pragma unroll
         for (int qq = 0; qq < B / 4; ++qq) {
@@ -1425,7 +1431,7 @@ FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const float* ws
             double cw[B];      // windowed samples of this trip
 #pragma unroll
             for (int qq = 0; qq < B / 4; ++qq) {
-                const U4 w4 = lds128(wsm + ((H / 4 + it * (B / 4) + qq) * kEncThreads + t) * 4);
+                const U4 w4 = ldg128(P.window_qt + (((it * (B / 4) + qq) * kEncThreads + t) << 2));
                 cw[4 * qq] = (double)fmul((float)x[4 * qq], u2f(w4.x));
                 cw[4 * qq + 1] = (double)fmul((float)x[4 * qq + 1], u2f(w4.y));
                 cw[4 * qq + 2] = (double)fmul((float)x[4 * qq + 2], u2f(w4.z));
@@ -1552,25 +1558,8 @@ FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const float* ws
     sync();   // the partials and the staged channel are reused by the next channel / frame
 }
 
-// window values of thread t: samples 32 t - H .. 32 t + 31 (zeros outside the window)
 template <int H>
-FA_D void analyze_fill_window(const EncParams& P, float* wsm) {
-    const int t = tid();
-    for (int q = 0; q < (H + kSpt) / 4; ++q) {
-        float v[4];
-        for (int e = 0; e < 4; ++e) {
-            int i = t * kSpt - H + 4 * q + e;
-            v[e] = (i >= 0 && i < P.blocksize) ? P.window[i] : 0.f;
-        }
-        U4 u;
-        memcpy(&u.x, &v[0], 4); memcpy(&u.y, &v[1], 4); memcpy(&u.z, &v[2], 4); memcpy(&u.w, &v[3], 4);
-        sts128(wsm + (q * kEncThreads + t) * 4, u);
-    }
-}
-FA_HD constexpr size_t an_window_bytes(int H) { return (size_t)((H + kSpt) / 4) * kEncThreads * 16; }
-
-template <int H>
-FA_D void analyze_frame_cta(const EncParams& P, uint32_t g, AnShared* sh, const float* wsm) {
+FA_D void analyze_frame_cta(const EncParams& P, uint32_t g, AnShared* sh) {
     const int64_t s = (int64_t)(g / (uint32_t)P.nframes);
     const int f = (int)(g % (uint32_t)P.nframes);
     const int64_t samp0 = (int64_t)f * P.blocksize;
@@ -1592,8 +1581,8 @@ FA_D void analyze_frame_cta(const EncParams& P, uint32_t g, AnShared* sh, const 
     // plain integers (quantised / split exactly once) through one TMA copy per channel
     int32_t* slot = (int32_t*)(P.slots + (int64_t)(g - P.g_begin) * P.slot_bytes);
     for (int c = 0; c < P.nch; ++c) {
-        if (bs == kMaxBs) analyze_channel_full<H>(P, sh, wsm, S, c, st + c, slot);
-        else analyze_channel<H, false>(P, sh, wsm, S, c, st + c, nullptr);
+        if (bs == kMaxBs) analyze_channel_full<H>(P, sh, S, c, st + c, slot);
+        else analyze_channel<H, false>(P, sh, S, c, st + c, nullptr);
     }
 }
 

@@ -39,8 +39,11 @@ int hs_encode(const void* data, int dtype, int64_t n_stream, int64_t stream_size
     LevelPreset lp = level_preset(level);
     int nch = (dtype == kI64 || dtype == kF64) ? 2 : 1;
     int nf = (int)((stream_size + lp.blocksize - 1) / lp.blocksize);
-    std::vector<float> window((size_t)lp.blocksize);
-    make_tukey_window(window.data(), lp.blocksize);
+    std::vector<float> window_v(4096 + 4, 0.f), window_qt_v(4096 + 4, 0.f);   // 16-byte aligned views below
+    float* window = (float*)(((uintptr_t)window_v.data() + 15) & ~(uintptr_t)15);
+    float* window_qt = (float*)(((uintptr_t)window_qt_v.data() + 15) & ~(uintptr_t)15);
+    make_tukey_window(window, lp.blocksize);
+    if (lp.blocksize == 4096) permute_window_qt(window, window_qt);
     if (dtype == kF32) {
         const float* d = (const float*)data;
         for (int64_t s = 0; s < n_stream; ++s) {
@@ -70,7 +73,7 @@ int hs_encode(const void* data, int dtype, int64_t n_stream, int64_t stream_size
     P.blocksize = lp.blocksize; P.nframes = nf;
     P.max_lpc_order = lp.max_lpc_order; P.max_porder = lp.max_porder;
     P.qlp_precision = lp.blocksize <= 384 ? 13 : (lp.blocksize <= 1152 ? 14 : 15);
-    P.window = window.data(); P.crc = crc(); P.tab = &tab;
+    P.window = window; P.window_qt = window_qt; P.crc = crc(); P.tab = &tab;
     P.out = out; P.out_capacity = cap; P.starts = starts; P.ends = ends.data(); P.desc = desc.data();
     P.ticket = &ticket; P.err = &err; P.hdr_bytes = stream_header_bytes(nf);
     // the three encoder kernels: analyze (one CTA per frame) -> design (one thread per record) -> encode
@@ -90,14 +93,11 @@ int hs_encode(const void* data, int dtype, int64_t n_stream, int64_t stream_size
     unsigned long long base = 0;
     P.slots = (uint8_t*)(((uintptr_t)slots_w.data() + 15) & ~(uintptr_t)15); P.slot_bytes = slot_bytes;
     P.fsize = fsize.data(); P.base = &base;
-    fasim::launch(1, kEncThreads, sizeof(AnShared) + 16 + an_window_bytes(12), [&](int) {
+    fasim::launch(1, kEncThreads, sizeof(AnShared) + 16, [&](int) {
         AnShared* ash = (AnShared*)fasim::smem();
-        float* wsm = (float*)(fasim::smem() + ((sizeof(AnShared) + 15) & ~(size_t)15));
-        if (lp.max_lpc_order > 8) analyze_fill_window<12>(P, wsm); else analyze_fill_window<8>(P, wsm);
-        fa::sync();
         for (uint32_t g = 0; g < (uint32_t)total_frames; ++g) {
-            if (lp.max_lpc_order > 8) analyze_frame_cta<12>(P, g, ash, wsm);
-            else analyze_frame_cta<8>(P, g, ash, wsm);
+            if (lp.max_lpc_order > 8) analyze_frame_cta<12>(P, g, ash);
+            else analyze_frame_cta<8>(P, g, ash);
         }
     });
     fasim::launch(1, 1, 0, [&](int) {
