@@ -47,6 +47,8 @@ __global__ void __launch_bounds__(kEncThreads, FAB_ENC_CTAS) k_encode(const EncP
 template <int H>
 __global__ void __launch_bounds__(kEncThreads, FAB_AN_CTAS) k_enc_analyze(const EncParams P) {
     __shared__ AnShared sh;
+    if (P.blocksize == kMaxBs) analyze_fill_window(P, &sh);
+    __syncthreads();
     for (uint32_t g = P.g_begin + blockIdx.x; g < P.g_end; g += gridDim.x) analyze_frame_cta<H>(P, g, &sh);
 }
 

@@ -172,10 +172,10 @@ struct AnShared {              // k_enc_analyze: per-warp partials of the block 
     uint32_t w_bad[kEncWarps];
     unsigned long long w_fe[kEncWarps][5];
     double w_ac[kEncWarps][kMaxOrd + 1];
-    int32_t stage[kEncThreads * kSpt];   // full frames: the channel's int32 samples, [quad][thread][4]
-    double red[kEncWarps][(kMaxOrd + 1) * 33];   // full frames: per-lane autocorrelation partials, [lag][lane] padded
+    int32_t stage[kEncThreads * kSpt];   // full frames: the channel's int32 samples, [quad][thread][4]; afterwards every
+                                         // warp's own quads hold its per-lane autocorrelation partials
+    float wqt[kEncThreads * kSpt];       // the window in the same [quad][thread][4] order (filled once per CTA)
 };
-constexpr int kRedStride = 33;
 
 struct DesignIO {              // k_enc_design: thread-private working set of design_fixed / design_lpc
     unsigned long long t_fe[5];
@@ -1350,6 +1350,10 @@ FA_D void analyze_stage(const FrameSrc& S, int c, int t, int32_t* park_frame, in
     }
 }
 
+FA_D void analyze_fill_window(const EncParams& P, AnShared* sh) {      // once per CTA (blocksize-4096 levels)
+    for (int i = tid(); i < kEncThreads * kSpt / 4; i += kEncThreads) sts128(sh->wqt + 4 * i, ldg128(P.window_qt + 4 * i));
+}
+
 template <int H>
 FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const FrameSrc& S, int c, FrameStats* st,
                                int32_t* park_frame) {
@@ -1374,7 +1378,7 @@ FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const FrameSrc&
         if (do_lpc) {
 #pragma unroll
             for (int qq = 0; qq < H / 4; ++qq) {
-                const U4 w4 = ldg128(P.window_qt + (((8 - H / 4 + qq) * kEncThreads + (t - 1)) << 2));
+                const U4 w4 = lds128(sh->wqt + (((8 - H / 4 + qq) * kEncThreads + (t - 1)) << 2));
                 hw[H - 1 - 4 * qq] = (double)fmul((float)hx[4 * qq], u2f(w4.x));
                 hw[H - 2 - 4 * qq] = (double)fmul((float)hx[4 * qq + 1], u2f(w4.y));
                 hw[H - 3 - 4 * qq] = (double)fmul((float)hx[4 * qq + 2], u2f(w4.z));
@@ -1382,6 +1386,7 @@ FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const FrameSrc&
             }
         }
     }
+    sync();    // every history read is done: from here on a warp only touches its own quads of the staged channel
     // ---- statistics, fixed-predictor error sums (libFLAC fixed.c: sum |e_k| over i >= 4), windowed
     //      autocorrelation (lpc.c: float data * float window, double accumulation)
     uint32_t orv = 0;
@@ -1431,7 +1436,7 @@ FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const FrameSrc&
             double cw[B];      // windowed samples of this trip
 #pragma unroll
             for (int qq = 0; qq < B / 4; ++qq) {
-                const U4 w4 = ldg128(P.window_qt + (((it * (B / 4) + qq) * kEncThreads + t) << 2));
+                const U4 w4 = lds128(sh->wqt + (((it * (B / 4) + qq) * kEncThreads + t) << 2));
                 cw[4 * qq] = (double)fmul((float)x[4 * qq], u2f(w4.x));
                 cw[4 * qq + 1] = (double)fmul((float)x[4 * qq + 1], u2f(w4.y));
                 cw[4 * qq + 2] = (double)fmul((float)x[4 * qq + 2], u2f(w4.z));
@@ -1463,15 +1468,18 @@ FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const FrameSrc&
         if (do_lpc) {
             // every lane parks its partials, then lane l sums lag l over the warp in lane order (two chains): a fixed
             // order (deterministic bytes) at a fraction of the instructions of a register butterfly over doubles
-            double* red = sh->red[wp];
+            // (the partials overwrite the warp's own, consumed quads of the staged channel: lag l goes to half (l & 1) of
+            // quad (l >> 1), rotated by l columns so that the column reads below are conflict-free)
+            syncwarp();
 #pragma unroll
-            for (int l = 0; l <= H; ++l) red[l * kRedStride + ln] = ac[l];
+            for (int l = 0; l <= H; ++l)
+                ((double*)(stage + (((l >> 1) * kEncThreads + 32 * wp) << 2) + (l & 1) * 64))[(ln + l) & 31] = ac[l];
             syncwarp();
             if (ln <= H) {
-                const double* r = red + ln * kRedStride;
+                const double* r = (const double*)(stage + (((ln >> 1) * kEncThreads + 32 * wp) << 2) + (ln & 1) * 64);
                 double e = 0.0, o = 0.0;
 #pragma unroll 8
-                for (int i = 0; i < 32; i += 2) { e = dadd(e, r[i]); o = dadd(o, r[i + 1]); }
+                for (int i = 0; i < 32; i += 2) { e = dadd(e, r[(i + ln) & 31]); o = dadd(o, r[(i + 1 + ln) & 31]); }
                 sh->w_ac[wp][ln] = dadd(e, o);
             }
         } else if (ln <= H) {
@@ -1510,7 +1518,7 @@ FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const FrameSrc&
         int64_t prev = (int64_t)(hx[H - 1] >> wasted);
 #pragma unroll 1
         for (int q = 0; q < kSpt / 4; ++q) {
-            const U4 v = lds128(stage + ((q * kEncThreads + t) << 2));
+            const U4 v = ld128(park_frame + c * kMaxBs + ((q * kEncThreads + t) << 2));   // (this thread parked them itself)
             const int32_t xs[4] = {(int32_t)v.x >> wasted, (int32_t)v.y >> wasted, (int32_t)v.z >> wasted, (int32_t)v.w >> wasted};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {

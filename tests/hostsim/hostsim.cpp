@@ -95,6 +95,8 @@ int hs_encode(const void* data, int dtype, int64_t n_stream, int64_t stream_size
     P.fsize = fsize.data(); P.base = &base;
     fasim::launch(1, kEncThreads, sizeof(AnShared) + 16, [&](int) {
         AnShared* ash = (AnShared*)fasim::smem();
+        if (lp.blocksize == kMaxBs) analyze_fill_window(P, ash);
+        fa::sync();
         for (uint32_t g = 0; g < (uint32_t)total_frames; ++g) {
             if (lp.max_lpc_order > 8) analyze_frame_cta<12>(P, g, ash);
             else analyze_frame_cta<8>(P, g, ash);
