@@ -280,15 +280,11 @@ __global__ void __launch_bounds__(kDecThreads) k_dec_frames(const DecParams P, i
 #ifndef FAB_DEC_CTAS
 #define FAB_DEC_CTAS 6
 #endif
-template <bool CRC>
 __global__ void __launch_bounds__(kTileWarps * 32, FAB_DEC_CTAS) k_dec_tile(const TileParams P) {
-    __shared__ uint16_t crc_tab[4 * 256];
     __shared__ TileShared ws[kTileWarps];
-    for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) crc_tab[i] = P.D.crc->crc16[i >> 8][i & 255];
-    __syncthreads();
     int64_t item0 = ((int64_t)blockIdx.x * kTileWarps + (threadIdx.x >> 5)) * 32;
     if (item0 >= P.D.n_sel * P.nwin) return;
-    tile_warp_body<CRC>(P, item0, &ws[threadIdx.x >> 5], crc_tab);
+    tile_warp_body(P, item0, &ws[threadIdx.x >> 5]);
 }
 
 // frame CRC-16 of every (stream, frame) item: one warp per item, see crc_frame_warp
@@ -779,7 +775,7 @@ extern "C" int fab_decode(fab_ctx* ctx, const unsigned char* d_bytes, const int6
         int64_t per_cta = (int64_t)kTileWarps * 32;
         prof_begin(ctx, 1, st);
         FAB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
-        k_dec_tile<false><<<(unsigned)((total + per_cta - 1) / per_cta), kTileWarps * 32, 0, st>>>(TP);
+        k_dec_tile<<<(unsigned)((total + per_cta - 1) / per_cta), kTileWarps * 32, 0, st>>>(TP);
         // the CRC pass only needs the frame table: it runs on the second stream, queued behind the tile
         // kernel's launch so that its CTAs fill the SMs the decoder's last partial wave leaves idle
         FAB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));

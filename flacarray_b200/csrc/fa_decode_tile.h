@@ -3,13 +3,17 @@
 // Same role as frame_body() in fa_decode.h (libFLAC frame decode + the write callback
 // decompress.c:66-101), restructured for the machine:
 //   * compressed bytes stream through a per-lane shared-memory ring filled by cp.async at one
-//     warp-uniform point per group of 4 samples (see BitRdC: register prefetch stalls the whole warp);
+//     warp-uniform point per group of samples (see BitRdC: register prefetch stalls the whole warp);
+//   * the bit reader is a CURSOR into that ring: every code is decoded from a 32-bit window fetched at
+//     the cursor (two ring words + one funnel shift), so the steady-state loop has no refill branch and
+//     no buffer state -- with 32 lanes at 32 different bit positions a "refill if low" test is taken by
+//     some lane on almost every sample, i.e. the whole warp pays the refill every time;
 //   * predictor history and coefficients live in registers (order <= 12, 32-bit samples), four
 //     samples per loop trip so the history "shift" is register renaming;
 //   * every lane appends its samples to a [32 lanes][32 samples] shared-memory tile; after 32 samples
 //     the warp transposes the tile so that each store instruction writes 128 contiguous bytes of one
 //     frame (fully coalesced), optionally restoring int32 -> float32 on the way (utils.c:350-368);
-//   * CRC-16 is folded into the bit reader (slice-by-4 per fetched word, tables in shared memory);
+//   * the frame CRC-16 is checked by its own frame-parallel pass (crc_frame_warp, k_dec_crc);
 //   * frames this path does not handle (33-bit side channel, order > 12, ...) are flagged and left to
 //     the general per-thread decoder.
 #pragma once
@@ -26,7 +30,8 @@ constexpr int kTileStride = 33;
 constexpr int kTileWarps = FAB_TILE_WARPS;  // warps per CTA
 
 constexpr int kRingChunks = 4;                 // 16-byte chunks per lane in the shared-memory ring
-constexpr int kRingStride = kRingChunks * 4 + 4;   // words per lane row (16-byte aligned, spreads the banks)
+constexpr int kRingWords = kRingChunks * 4;
+constexpr int kRingStride = kRingWords + 4;    // words per lane row (16-byte aligned, spreads the banks)
 
 struct TileRow {          // per-lane output description, read by all lanes during the flush
     int32_t* out;         // address of (frame sample 0, channel 0)
@@ -44,22 +49,16 @@ struct TileShared {       // per warp
 // that is topped up with asynchronous 16-byte copies (cp.async) at ONE warp-uniform point per group of
 // samples (brc_service).  A register prefetch queue does not work here: register scoreboards are per
 // warp, so whenever one lane consumed its prefetched chunk the whole warp waited for the most recent
-// load of ANY lane -- the DRAM/L2 latency was exposed at almost every refill (30 % of the stall samples
-// of the previous version).  With the ring, loads never target a register; the 64-bit MSB-aligned
-// buffer is refilled with (short-latency) shared-memory reads.  The CRC-16 lags two words behind so
-// that the frame end, only known after the last sample, is handled exactly.
+// load of ANY lane.  With the ring, loads never target a register.  `pos` is the bit cursor, counted
+// from the first byte of the first chunk; ring word (pos >> 5) & 15 holds the bit under the cursor.
 struct BitRdC {
     const U4* gp;      // next chunk to copy
     const U4* gend;    // first chunk holding no valid byte
-    uint32_t* ring;    // this lane's ring
-    uint32_t rd;       // words taken so far (absolute, counted from the first chunk)
+    uint32_t* ring;    // this lane's ring (nullptr: inactive lane)
+    uint32_t pos;      // bit cursor
+    uint32_t pos0;     // cursor at brc_init
     uint32_t wr;       // chunks issued so far
     uint32_t landed;   // chunks known to be complete in the ring
-    uint64_t buf;
-    int n;
-    int nwords;        // words taken after word 0
-    uint32_t crc;      // CRC state before word (nwords - 1) [absolute numbering, see brc_finish_crc]
-    uint32_t w1, w2;   // last taken word (w1) and the one before (w2)
     int err;
 };
 
@@ -69,11 +68,11 @@ FA_D U4 u4_zero() { U4 z; z.x = z.y = z.z = z.w = 0; return z; }
 FA_D void brc_service(BitRdC& br) {
     cp_async_wait_all();          // copies issued at the previous service point: a whole sample group old
     br.landed = br.wr;
-    // at most two chunks per service point: 4 samples rarely consume more than 32 bytes (a lane that does
-    // runs into the underflow path of brc_take, which services again)
+    // at most two chunks per service point: 8 samples rarely consume more than 32 bytes (a lane that does
+    // runs into the wait of brc_ensure, which services again)
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-        if (br.ring != nullptr && br.wr - (br.rd >> 2) < (uint32_t)kRingChunks) {
+        if (br.ring != nullptr && br.wr - (br.pos >> 7) < (uint32_t)kRingChunks) {
             uint32_t* slot = br.ring + (br.wr & (kRingChunks - 1)) * 4;
             if (br.gp < br.gend) cp_async16(slot, br.gp);
             else sts128(slot, u4_zero());     // past the end of the stream: zeros
@@ -84,148 +83,91 @@ FA_D void brc_service(BitRdC& br) {
     cp_async_commit();
 }
 
-FA_D uint32_t brc_take(BitRdC& br) {
-    if ((br.rd >> 2) >= br.landed) {
-        // ran ahead of the copies (long codes, or the first words of a frame): wait for what is in
-        // flight; if the ring is empty, fetch now
+// Make bits [pos, pos + nbits) readable (nbits <= 224: they fit the ring next to the cursor's chunk).
+FA_D void brc_ensure(BitRdC& br, uint32_t nbits) {
+    const uint32_t need = ((br.pos + nbits - 1u) >> 7) + 1u;     // chunks that must have landed
+    if (need > br.landed) {
+        // ran ahead of the copies (long codes, or the first words of a frame): wait for what is in flight; if that
+        // is not enough, fetch now
         cp_async_wait_all();
         br.landed = br.wr;
-        if ((br.rd >> 2) >= br.landed) {
+        while (need > br.landed) {
             brc_service(br);
             cp_async_wait_all();
             br.landed = br.wr;
         }
     }
-    uint32_t w = br.ring[((br.rd >> 2) & (kRingChunks - 1)) * 4 + (br.rd & 3)];
-    br.rd++;
-    return bswap32(w);
 }
 
-template <bool CRC>
-FA_D void brc_fetch(BitRdC& br, const uint16_t* T) {
-    uint32_t w = brc_take(br);
-    if (CRC) {
-        if (br.nwords >= 2) br.crc = crc16_word(T, br.crc, br.w2);
-        br.w2 = br.w1;
-        br.w1 = w;
-    }
-    br.nwords++;
-    br.buf |= (uint64_t)w << (32 - br.n);
-    br.n += 32;
+// the 32 bits under the cursor (the caller has ensured them)
+FA_D uint32_t brc_peek(const BitRdC& br) {
+    const uint32_t wi = br.pos >> 5;
+    const uint32_t w0 = bswap32(br.ring[wi & (kRingWords - 1)]), w1 = bswap32(br.ring[(wi + 1) & (kRingWords - 1)]);
+    return funnel_l(w1, w0, br.pos & 31u);
 }
 
-// Start reading at byte `start` (crc0 = CRC state over the frame bytes before `start`).
-template <bool CRC>
-FA_D void brc_init(BitRdC& br, uint32_t* ring, const uint8_t* start, const uint8_t* end, uint32_t crc0, const uint16_t* T) {
+// Start reading at byte `start`.
+FA_D void brc_init(BitRdC& br, uint32_t* ring, const uint8_t* start, const uint8_t* end) {
     uintptr_t s = (uintptr_t)start;
     br.gp = (const U4*)(s & ~(uintptr_t)15);
     br.gend = (const U4*)(((uintptr_t)end + 15) & ~(uintptr_t)15);
     br.ring = ring;
-    br.rd = (uint32_t)((s & 15) >> 2);      // words of the first chunk that precede `start`
+    br.pos = (uint32_t)(s & 15) * 8u;
+    br.pos0 = br.pos;
     br.wr = 0;
     br.landed = 0;
-    int a = (int)(s & 3);
-    br.buf = 0; br.n = 0; br.nwords = 0; br.err = 0; br.w1 = br.w2 = 0;
-    br.crc = crc0;
+    br.err = 0;
     brc_service(br);
-    uint32_t w = brc_take(br);
-    // word 0 is consumed byte-wise by the CRC (its leading `a` bytes precede `start`), so it does not
-    // enter the lagging word queue
-    if (CRC) for (int b = a; b < 4; ++b) br.crc = crc16_b(T, br.crc, (w >> (24 - 8 * b)) & 0xFF);
-    br.buf = ((uint64_t)w << 32) << (8 * a);
-    br.n = 32 - 8 * a;
 }
 
-template <bool CRC>
-FA_D void brc_refill(BitRdC& br, const uint16_t* T) {
-    if (br.n <= 32) brc_fetch<CRC>(br, T);
-}
-
-template <bool CRC>
-FA_D uint32_t brc_read(BitRdC& br, int nb, const uint16_t* T) {  // nb in [0, 32]
-    brc_refill<CRC>(br, T);
-    uint32_t v = nb ? (uint32_t)(br.buf >> (64 - nb)) : 0u;
-    br.buf = nb ? (br.buf << nb) : br.buf;
-    br.n -= nb;
+FA_D uint32_t brc_read(BitRdC& br, int nb) {  // nb in [0, 32]
+    if (nb == 0) return 0u;
+    brc_ensure(br, 64u);
+    const uint32_t v = brc_peek(br) >> (32 - nb);
+    br.pos += (uint32_t)nb;
     return v;
 }
-template <bool CRC>
-FA_D int32_t brc_read_signed(BitRdC& br, int nb, const uint16_t* T) {  // nb in [0, 32]
+FA_D int32_t brc_read_signed(BitRdC& br, int nb) {  // nb in [0, 32]
     if (nb == 0) return 0;
-    uint32_t v = brc_read<CRC>(br, nb, T);
+    uint32_t v = brc_read(br, nb);
     uint32_t sign = 1u << (nb - 1);
     return (int32_t)((v ^ sign) - sign);
 }
-template <bool CRC>
-FA_D uint32_t brc_unary(BitRdC& br, const uint16_t* T) {
+FA_D uint32_t brc_unary(BitRdC& br) {
     uint32_t q = 0;
     for (;;) {
-        brc_refill<CRC>(br, T);
-        if (br.buf != 0) {
-            int z = clz64(br.buf);
-            q += (uint32_t)z;
-            br.buf = (br.buf << z) << 1;
-            br.n -= z + 1;
-            return q;
+        brc_ensure(br, 64u);
+        const uint32_t w = brc_peek(br);
+        if (w != 0) {
+            const int z = clz32(w);
+            br.pos += (uint32_t)z + 1u;
+            return q + (uint32_t)z;
         }
-        q += (uint32_t)br.n;
-        br.n = 0;
+        q += 32u;
+        br.pos += 32u;
         if (br.gp > br.gend + 4 + kRingChunks) { br.err = 1; return q; }  // ran off the end of the stream
     }
 }
-// Rice code with parameter k (< 32): fast path when the whole code sits in the buffer.
-template <bool CRC>
-FA_D int32_t brc_rice(BitRdC& br, int k, const uint16_t* T) {
-    brc_refill<CRC>(br, T);
+FA_D int32_t unzigzag32(uint32_t u) { return (int32_t)(u >> 1) ^ -(int32_t)(u & 1); }
+// Rice code with parameter k (< 32): any length.
+FA_D int32_t brc_rice(BitRdC& br, int k) {
+    brc_ensure(br, 64u);
+    const uint32_t w = brc_peek(br);
+    const int z = clz32(w);                    // 32 when w == 0
     uint32_t q, low;
-    // fast path on 32-bit halves: the whole code (z zeros, the 1, k low bits) lies in the upper word
-    const uint32_t hi = (uint32_t)(br.buf >> 32), lo = (uint32_t)br.buf;
-    const int z = clz32(hi);                   // 32 when hi == 0
-    const int used = z + 1 + k;
-    if (used <= 32 && used <= br.n) {
+    if (z + 1 + k <= 32) {
         q = (uint32_t)z;
-        const uint32_t t = funnel_lc(lo, hi, (uint32_t)(z + 1));     // bits behind the unary part
-        low = k ? t >> (32 - k) : 0u;
-        const uint32_t nhi = funnel_lc(lo, hi, (uint32_t)used), nlo = funnel_lc(0u, lo, (uint32_t)used);
-        br.buf = ((uint64_t)nhi << 32) | nlo;
-        br.n -= used;
-    } else if (br.buf != 0 && clz64(br.buf) + 1 + k <= br.n) {
-        const int z64 = clz64(br.buf);
-        q = (uint32_t)z64;
-        uint64_t t = (br.buf << z64) << 1;
-        low = k ? (uint32_t)(t >> (64 - k)) : 0u;
-        br.buf = k ? (t << k) : t;
-        br.n -= z64 + 1 + k;
+        low = k ? ((w << (z + 1)) >> (32 - k)) : 0u;     // (k >= 1 here implies z + 1 <= 31)
+        br.pos += (uint32_t)(z + 1 + k);
     } else {
-        q = brc_unary<CRC>(br, T);
-        low = brc_read<CRC>(br, k, T);
+        q = brc_unary(br);
+        low = brc_read(br, k);
     }
-    uint32_t u = (q << k) | low;
-    return (int32_t)(u >> 1) ^ -(int32_t)(u & 1);
+    return unzigzag32((q << k) | low);
 }
 
-// Bits consumed since brc_init (a = start byte offset inside word 0).
-FA_D int64_t brc_pos_bits(const BitRdC& br, int a) { return (int64_t)(br.nwords + 1) * 32 - br.n - 8 * a; }
-
-// CRC-16 over [frame start, first CRC byte).  E = byte index of the first CRC byte counted from the
-// start of word 0.  Words are numbered absolutely: word 0 (brc_init), then takes 1..nwords.  With
-// F = nwords takes, br.crc covers words 0..F-2 (F >= 2) or word 0 only (F == 1); the queue holds the
-// rest.  Because at most 64 unread bits remain, E lies in word F-1, F or right after F.
-FA_D uint32_t brc_finish_crc(const BitRdC& br, const uint16_t* T, int64_t E) {
-    uint32_t c16 = br.crc;
-    int64_t covered = (br.nwords >= 2) ? (int64_t)br.nwords - 1 : 1;
-    uint32_t q[2] = {br.w2, br.w1};
-    int qn = br.nwords >= 2 ? 2 : br.nwords;
-    if (br.nwords == 1) q[0] = br.w1;
-    int64_t wE = E >> 2;
-    for (int t = 0; t < qn; ++t) {
-        int64_t wabs = covered + t;
-        if (wabs > wE) break;
-        int nb = wabs < wE ? 4 : (int)(E & 3);
-        for (int b = 0; b < nb; ++b) c16 = crc16_b(T, c16, (q[t] >> (24 - 8 * b)) & 0xFF);
-    }
-    return c16;
-}
+// Bits consumed since brc_init.
+FA_D int64_t brc_pos_bits(const BitRdC& br) { return (int64_t)(br.pos - br.pos0); }
 
 struct TileLane {
     int mode;       // 0 const, 1 verbatim, 2 predictive
@@ -240,12 +182,11 @@ struct TileLane {
 };
 
 // Subframe header.  false => this path cannot decode it (br.err tells a bad stream from "unsupported").
-template <bool CRC>
-FA_D bool tile_subframe_begin(BitRdC& br, const uint16_t* T, int bs, int bps, TileLane& L) {
-    if (brc_read<CRC>(br, 1, T) != 0) return false;
-    int type = (int)brc_read<CRC>(br, 6, T);
+FA_D bool tile_subframe_begin(BitRdC& br, int bs, int bps, TileLane& L) {
+    if (brc_read(br, 1) != 0) return false;
+    int type = (int)brc_read(br, 6);
     int wasted = 0;
-    if (brc_read<CRC>(br, 1, T)) wasted = (int)brc_unary<CRC>(br, T) + 1;
+    if (brc_read(br, 1)) wasted = (int)brc_unary(br) + 1;
     bps -= wasted;
     if (bps <= 0 || bps > 32 || br.err) return false;
     L.wasted = wasted;
@@ -263,7 +204,7 @@ FA_D bool tile_subframe_begin(BitRdC& br, const uint16_t* T, int bs, int bps, Ti
     if (type == 0) {
         L.mode = 0;
         L.raw_left = 0;
-        L.cval = brc_read_signed<CRC>(br, bps, T);
+        L.cval = brc_read_signed(br, bps);
         return true;
     }
     if (type == 1) {
@@ -286,29 +227,28 @@ FA_D bool tile_subframe_begin(BitRdC& br, const uint16_t* T, int bs, int bps, Ti
 }
 
 // After the warm-up samples: LPC parameters + residual header.
-template <bool CRC>
-FA_D bool tile_subframe_params(BitRdC& br, const uint16_t* T, int bs, TileLane& L) {
+FA_D bool tile_subframe_params(BitRdC& br, int bs, TileLane& L) {
     const int order = L.order;
     L.need_params = 0;
     if (L.lpc) {
-        int prec = (int)brc_read<CRC>(br, 4, T) + 1;
+        int prec = (int)brc_read(br, 4) + 1;
         if (prec == 16) return false;
-        int sh = (int)brc_read<CRC>(br, 5, T);
+        int sh = (int)brc_read(br, 5);
         if (sh & 16) return false;  // negative shift
         L.shift = sh;
 #pragma unroll
         for (int j = 0; j < kTileOrd; ++j)
-            if (j < order) L.c[j] = brc_read_signed<CRC>(br, prec, T);
+            if (j < order) L.c[j] = brc_read_signed(br, prec);
     } else {
         const int32_t fx[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};
 #pragma unroll
         for (int j = 0; j < 4; ++j) L.c[j] = fx[order][j];
     }
-    uint32_t method = brc_read<CRC>(br, 2, T);
+    uint32_t method = brc_read(br, 2);
     if (method > 1) return false;
     L.plen = method == 0 ? 4 : 5;
     L.esc = method == 0 ? 15 : 31;
-    int porder = (int)brc_read<CRC>(br, 4, T);
+    int porder = (int)brc_read(br, 4);
     L.psize = bs >> porder;
     L.nparts = 1 << porder;
     if (porder > 0 && (L.psize << porder) != bs) return false;
@@ -318,31 +258,30 @@ FA_D bool tile_subframe_params(BitRdC& br, const uint16_t* T, int bs, TileLane& 
     return !br.err;
 }
 
-template <bool CRC>
-FA_D void tile_open_partition(BitRdC& br, const uint16_t* T, TileLane& L) {
+FA_D void tile_open_partition(BitRdC& br, TileLane& L) {
     while (L.left == 0) {
         L.part++;
         if (L.part >= L.nparts) { br.err = 1; L.left = 1 << 30; L.k = 0; return; }
         L.left = L.psize - (L.part == 0 ? L.order : 0);
-        int k = (int)brc_read<CRC>(br, L.plen, T);
-        if (k == L.esc) { L.k = -1; L.rawbits = (int)brc_read<CRC>(br, 5, T); }
+        int k = (int)brc_read(br, L.plen);
+        if (k == L.esc) { L.k = -1; L.rawbits = (int)brc_read(br, 5); }
         else L.k = k;
     }
 }
 
 // One sample, any mode (slow path: warm-up, verbatim, constant, partition edges, escapes).
-template <bool CRC, int ORD>
-FA_D int32_t tile_next_sample(BitRdC& br, const uint16_t* T, TileLane& L) {
+template <int ORD>
+FA_D int32_t tile_next_sample(BitRdC& br, TileLane& L) {
     int32_t v;
     if (L.mode == 0) {
         v = L.cval;
     } else if (L.raw_left > 0) {
-        v = brc_read_signed<CRC>(br, L.bps, T);
+        v = brc_read_signed(br, L.bps);
         L.raw_left--;
     } else {
-        if (L.left == 0) tile_open_partition<CRC>(br, T, L);
+        if (L.left == 0) tile_open_partition(br, L);
         L.left--;
-        int32_t r = (L.k >= 0) ? brc_rice<CRC>(br, L.k, T) : brc_read_signed<CRC>(br, L.rawbits, T);
+        int32_t r = (L.k >= 0) ? brc_rice(br, L.k) : brc_read_signed(br, L.rawbits);
         int64_t sum = 0;
 #pragma unroll
         for (int j = 0; j < ORD; ++j) sum += (int64_t)L.c[j] * (int64_t)L.h[j];
@@ -354,12 +293,26 @@ FA_D int32_t tile_next_sample(BitRdC& br, const uint16_t* T, TileLane& L) {
     return (int32_t)((uint32_t)v << L.wasted);
 }
 
-// Four residual samples of one partition (k >= 0): the steady-state inner loop.
-template <bool CRC, int ORD>
-FA_D void tile_next4(BitRdC& br, const uint16_t* T, TileLane& L, int32_t* out4) {
+// Four residual samples of one partition (k >= 0): the steady-state inner loop.  Codes of at most 32 bits are
+// taken straight from the window under the cursor; a longer one goes through the general routine.
+template <int ORD>
+FA_D void tile_next4(BitRdC& br, TileLane& L, int32_t* out4) {
     int32_t r[4];
+    const int k = L.k;
+    brc_ensure(br, 4u * 32u + 32u);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) r[q] = brc_rice<CRC>(br, L.k, T);
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t w = brc_peek(br);
+        const int z = clz32(w);
+        if (z + 1 + k <= 32) {
+            const uint32_t low = k ? ((w << (z + 1)) >> (32 - k)) : 0u;
+            br.pos += (uint32_t)(z + 1 + k);
+            r[q] = unzigzag32(((uint32_t)z << k) | low);
+        } else {
+            r[q] = brc_rice(br, k);
+            brc_ensure(br, 4u * 32u + 32u);
+        }
+    }
     L.left -= 4;
     int32_t s[4];
 #pragma unroll
@@ -392,8 +345,8 @@ struct TileParams {
 };
 
 // Decode + flush all tiles of one channel pass with a compile-time upper bound on the predictor order.
-template <bool CRC, int ORD>
-FA_D void tile_channel_pass(const TileParams& P, TileShared* ws, const uint16_t* T, BitRdC& br, TileLane& L, bool& run,
+template <int ORD>
+FA_D void tile_channel_pass(const TileParams& P, TileShared* ws, BitRdC& br, TileLane& L, bool& run,
                             bool& fail, bool& punt, int bs, uint32_t bsmax, int c, int nch) {
     const int ln = lane();
     int32_t* trow = ws->tile + ln * kTileStride;
@@ -405,18 +358,18 @@ FA_D void tile_channel_pass(const TileParams& P, TileShared* ws, const uint16_t*
             if (run && i < bs) {
                 bool fast = L.mode == 2 && L.raw_left == 0 && !L.need_params && L.left >= 4 && L.k >= 0 && i + 4 <= bs;
                 if (fast) {
-                    tile_next4<CRC, ORD>(br, T, L, trow + s);
+                    tile_next4<ORD>(br, L, trow + s);
                 } else {
                     for (int q = 0; q < 4; ++q) {
                         int32_t v = 0;
                         if (run && i + q < bs) {
                             if (L.need_params && L.raw_left == 0) {
-                                if (!tile_subframe_params<CRC>(br, T, bs, L)) {
+                                if (!tile_subframe_params(br, bs, L)) {
                                     run = false;
                                     if (br.err) fail = true; else punt = true;
                                 }
                             }
-                            if (run) v = tile_next_sample<CRC, ORD>(br, T, L);
+                            if (run) v = tile_next_sample<ORD>(br, L);
                         }
                         trow[s + q] = v;
                     }
@@ -474,8 +427,7 @@ FA_D void tile_channel_pass(const TileParams& P, TileShared* ws, const uint16_t*
 
 // One warp: 32 consecutive (stream, frame) work items.  `ws` = this warp's shared storage, `T` = CRC
 // slice tables in shared memory.
-template <bool CRC>
-FA_D void tile_warp_body(const TileParams& P, int64_t item0, TileShared* ws, const uint16_t* T) {
+FA_D void tile_warp_body(const TileParams& P, int64_t item0, TileShared* ws) {
     const DecParams& D = P.D;
     const int ln = lane();
     const int nch = D.nch;
@@ -503,7 +455,6 @@ FA_D void tile_warp_body(const TileParams& P, int64_t item0, TileShared* ws, con
         }
     }
     FrameHdr fh;
-    uint32_t crc0 = 0;
     if (active) {
         const long long* fo = D.frame_off + k * (int64_t)(D.nframes_cap + 1);
         off = fo[j];
@@ -524,7 +475,6 @@ FA_D void tile_warp_body(const TileParams& P, int64_t item0, TileShared* ws, con
             active = false;
         } else {
             bs = fh.blocksize;
-            if (CRC) for (int b = 0; b < fh.hdr_bytes; ++b) crc0 = crc16_b(T, crc0, fp[b]);
         }
     }
     // publish the row description
@@ -546,14 +496,10 @@ FA_D void tile_warp_body(const TileParams& P, int64_t item0, TileShared* ws, con
     for (int m = 16; m >= 1; m >>= 1) { uint32_t o = shfl_xor(bsmax, m); bsmax = o > bsmax ? o : bsmax; }
 
     BitRdC br;
-    int a = 0;
     if (active) {
-        const uint8_t* body = fp + fh.hdr_bytes;
-        a = (int)((uintptr_t)body & 3);
-        brc_init<CRC>(br, ws->ring + ln * kRingStride, body, end, crc0, T);
+        brc_init(br, ws->ring + ln * kRingStride, fp + fh.hdr_bytes, end);
     } else {
-        br.gp = br.gend = nullptr; br.ring = nullptr; br.rd = 0; br.wr = 0; br.landed = 0;
-        br.buf = 0; br.n = 64; br.nwords = 0; br.crc = 0; br.w1 = br.w2 = 0; br.err = 0;
+        br.gp = br.gend = nullptr; br.ring = nullptr; br.pos = br.pos0 = 0; br.wr = 0; br.landed = 0; br.err = 0;
     }
     bool fail = false;      // stream problem -> walker
     bool punt = false;      // unsupported subframe -> general decoder
@@ -561,7 +507,7 @@ FA_D void tile_warp_body(const TileParams& P, int64_t item0, TileShared* ws, con
     L.mode = 0; L.order = 0; L.raw_left = 0; L.need_params = 0; L.left = 0; L.k = 0; L.wasted = 0; L.shift = 0; L.cval = 0;
     for (int c = 0; c < nch; ++c) {
         if (active && !fail && !punt) {
-            if (!tile_subframe_begin<CRC>(br, T, bs, 32, L)) {
+            if (!tile_subframe_begin(br, bs, 32, L)) {
                 if (br.err) fail = true; else punt = true;
             }
         }
@@ -569,25 +515,21 @@ FA_D void tile_warp_body(const TileParams& P, int64_t item0, TileShared* ws, con
         // warp-uniform bound on the predictor order picks the instantiation of the sample loop
         uint32_t omax = (uint32_t)((run && L.mode == 2) ? L.order : 0);
         for (int m = 16; m >= 1; m >>= 1) { uint32_t o = shfl_xor(omax, m); omax = o > omax ? o : omax; }
-        if (omax <= 4) tile_channel_pass<CRC, 4>(P, ws, T, br, L, run, fail, punt, bs, bsmax, c, nch);
-        else if (omax <= 8) tile_channel_pass<CRC, 8>(P, ws, T, br, L, run, fail, punt, bs, bsmax, c, nch);
-        else tile_channel_pass<CRC, kTileOrd>(P, ws, T, br, L, run, fail, punt, bs, bsmax, c, nch);
+        if (omax <= 4) tile_channel_pass<4>(P, ws, br, L, run, fail, punt, bs, bsmax, c, nch);
+        else if (omax <= 8) tile_channel_pass<8>(P, ws, br, L, run, fail, punt, bs, bsmax, c, nch);
+        else tile_channel_pass<kTileOrd>(P, ws, br, L, run, fail, punt, bs, bsmax, c, nch);
         if (run && br.err) fail = true;
     }
     if (active) {
         if (punt && !fail) {
             P.frame_flag[k * (int64_t)D.nframes_cap + j] = 1;
         } else if (!fail) {
-            // frame end: pad to a byte, CRC-16, chain check against the next frame's start
-            int64_t bits = brc_pos_bits(br, a);            // relative to the body start
+            // frame end: pad to a byte, chain check against the next frame's start (the CRC-16 is k_dec_crc's job)
+            int64_t bits = brc_pos_bits(br);               // relative to the body start
             int64_t body_bytes = (bits + 7) >> 3;
             int64_t len = fh.hdr_bytes + body_bytes + 2;
             if (fp + len > end) fail = true;
             if (!fail && next >= 0 && off + len != next) fail = true;
-            if (!fail && CRC) {
-                uint32_t want = ((uint32_t)fp[len - 2] << 8) | fp[len - 1];
-                if (brc_finish_crc(br, T, a + body_bytes) != want) fail = true;
-            }
         }
         if (fail) atom_or_global(&D.stream_flag[k], 2);
     }

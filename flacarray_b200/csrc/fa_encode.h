@@ -255,6 +255,14 @@ FA_D double shfl_xor_d(double v, int m) {
     memcpy(&v, &u, 8);
     return v;
 }
+FA_D double shfl_down_d(double v, int d) {
+    unsigned long long u;
+    memcpy(&u, &v, 8);
+    uint32_t lo = shfl_down((uint32_t)u, d), hi = shfl_down((uint32_t)(u >> 32), d);
+    u = ((unsigned long long)hi << 32) | lo;
+    memcpy(&v, &u, 8);
+    return v;
+}
 FA_D unsigned long long shfl_xor_u64(unsigned long long u, int m) {
     uint32_t lo = shfl_xor((uint32_t)u, m), hi = shfl_xor((uint32_t)(u >> 32), m);
     return ((unsigned long long)hi << 32) | lo;
@@ -1432,7 +1440,18 @@ FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const FrameSrc&
                 fe4 = sad_acc((int32_t)d4, 0, fe4);
             }
         }
-        if (do_lpc) {
+    }
+    // (a second pass over the staged samples: one loop with both the integer statistics and the double-precision
+    // products needs more than the 80 registers six resident CTAs leave per thread, and ptxas spills in the loop)
+    if (do_lpc) {
+#pragma unroll 1
+        for (int it = 0; it < kSpt / B; ++it) {
+            int32_t x[B];
+#pragma unroll
+            for (int qq = 0; qq < B / 4; ++qq) {
+                const U4 v = lds128(stage + (((it * (B / 4) + qq) * kEncThreads + t) << 2));
+                x[4 * qq] = (int32_t)v.x; x[4 * qq + 1] = (int32_t)v.y; x[4 * qq + 2] = (int32_t)v.z; x[4 * qq + 3] = (int32_t)v.w;
+            }
             double cw[B];      // windowed samples of this trip
 #pragma unroll
             for (int qq = 0; qq < B / 4; ++qq) {
@@ -1475,13 +1494,17 @@ FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const FrameSrc&
             for (int l = 0; l <= H; ++l)
                 ((double*)(stage + (((l >> 1) * kEncThreads + 32 * wp) << 2) + (l & 1) * 64))[(ln + l) & 31] = ac[l];
             syncwarp();
-            if (ln <= H) {
-                const double* r = (const double*)(stage + (((ln >> 1) * kEncThreads + 32 * wp) << 2) + (ln & 1) * 64);
-                double e = 0.0, o = 0.0;
-#pragma unroll 8
-                for (int i = 0; i < 32; i += 2) { e = dadd(e, r[(i + ln) & 31]); o = dadd(o, r[(i + 1 + ln) & 31]); }
-                sh->w_ac[wp][ln] = dadd(e, o);
+            // NP lanes per lag, each sums a contiguous third (half) of the 32 columns; the parts meet in the first one
+            constexpr int NP = (H + 1) * 3 <= 32 ? 3 : 2;
+            const int l = ln / NP, part = ln - l * NP;
+            double acc = 0.0;
+            if (l <= H) {
+                const double* r = (const double*)(stage + (((l >> 1) * kEncThreads + 32 * wp) << 2) + (l & 1) * 64);
+                const int c0 = (part * 32) / NP, c1 = ((part + 1) * 32) / NP;
+                for (int i = c0; i < c1; ++i) acc = dadd(acc, r[(i + l) & 31]);
             }
+            const double a1 = shfl_down_d(acc, 1), a2 = shfl_down_d(acc, 2);
+            if (part == 0 && l <= H) sh->w_ac[wp][l] = NP == 3 ? dadd(dadd(acc, a1), a2) : dadd(acc, a1);
         } else if (ln <= H) {
             sh->w_ac[wp][ln] = 0.0;
         }

@@ -453,11 +453,10 @@ def _encode_host(flat, n_stream, stream_size, level, quanta, dt):
             return dc, e
 
         raw_total = n_stream * stream_size * isz
+        bound = int(_lib.lib().fab_encode_bound(n_stream, stream_size, _FAB[dt], level))
         host = None
         cap = 0
         pos = 0
-        overflow = False
-        keep = []
         parts = []
         for (a, b), (dc, ev) in zip(ranges, _Feeder(dev, s_in, prep, len(ranges))):
             cur.wait_event(ev)
@@ -466,28 +465,28 @@ def _encode_host(flat, n_stream, stream_size, level, quanta, dt):
                                                                      None if q is None else q[a:b])
             del dc                # input chunk can go back to the pool
             if host is None:
-                # capacity from the first chunk's ratio (+3 %); a wrong guess is repaired below
-                cap = min(int(tot / ((b - a) * stream_size * isz) * raw_total * 1.03) + (1 << 20),
-                          int(_lib.lib().fab_encode_bound(n_stream, stream_size, _FAB[dt], level)))
+                # capacity from the first chunk's ratio (+3 %); a wrong guess grows the buffer below
+                cap = min(int(tot / ((b - a) * stream_size * isz) * raw_total * 1.03) + (1 << 20), bound)
                 host = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+            if pos + tot > cap:
+                # the guess was too small: move what has arrived into a buffer sized from the ratio seen so far for the
+                # remaining streams (+10 %), never more than the worst case.  No device buffer is kept alive for this:
+                # device memory stays bounded by the chunk pipeline whatever the size of the input
+                s_out.synchronize()
+                done = b * stream_size * isz
+                cap = min(max(int((pos + tot) / done * raw_total * 1.10) + (1 << 20), pos + tot), bound)
+                bigger = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+                bigger[:pos].copy_(host[:pos])
+                host = bigger
             e = torch.cuda.Event()
             e.record(cur)
-            if pos + tot > cap:
-                overflow = True
-            if not overflow:
-                out.record_stream(s_out)
-                s_out.wait_event(e)
-                with torch.cuda.stream(s_out):
-                    host[pos:pos + tot].copy_(out[:tot], non_blocking=True)
-            keep.append((out, tot, pos))
+            out.record_stream(s_out)
+            s_out.wait_event(e)
+            with torch.cuda.stream(s_out):
+                host[pos:pos + tot].copy_(out[:tot], non_blocking=True)
+            del out               # (record_stream keeps it valid until the copy has run)
             parts.append((starts + pos, nbytes, off, gain))
             pos += tot
-        if overflow:
-            s_out.synchronize()
-            host = torch.empty(pos, dtype=torch.uint8, pin_memory=True)
-            for out, tot, p0 in keep:
-                host[p0:p0 + tot].copy_(out[:tot], non_blocking=True)
-            cur.synchronize()
         starts = to_host(torch.cat([p[0] for p in parts]))
         nbytes = to_host(torch.cat([p[1] for p in parts]))
         off = gain = None
@@ -495,7 +494,6 @@ def _encode_host(flat, n_stream, stream_size, level, quanta, dt):
             off = to_host(torch.cat([p[2] for p in parts]))
             gain = to_host(torch.cat([p[3] for p in parts]))
         s_out.synchronize()
-        del keep
     return host[:pos].numpy(), starts, nbytes, off, gain
 
 

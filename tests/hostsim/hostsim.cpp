@@ -166,7 +166,7 @@ int hs_decode(const uint8_t* bytes, const long long* starts, const long long* nb
         for (int i = 0; i < 4 * 256; ++i) tab[(size_t)i] = crc()->crc16[i >> 8][i & 255];
         // the product launches the tile decoder without the fused CRC and checks it in k_dec_crc
         fasim::launch((int)((total + 31) / 32), 32, sizeof(TileShared) + 64, [&](int b) {
-            tile_warp_body<false>(TP, (int64_t)b * 32, (TileShared*)fasim::smem(), tab.data());
+            tile_warp_body(TP, (int64_t)b * 32, (TileShared*)fasim::smem());
         });
         fasim::launch((int)total, 32, 0, [&](int b) { crc_frame_warp(TP, (int64_t)b, tab.data(), crc()->shift_hi[9], crc()->shift_lo[9]); });
         int walked = 0, general = 0;
