@@ -187,92 +187,74 @@ class FlacArray:
     def typestr(self):
         return self._typestr
 
-    # ---- __getitem__ helpers (array.py:279-407) ----
-    def _slice_nelem(self, slc, dim):
-        start, stop, step = slc.indices(dim)
-        nslc = (stop - start) // step
-        return max(nslc, 0)
+    # ---- indexing: one resolver turns any key into (keep mask, sample window, result shape) ----
+    def _resolve_key(self, raw_key):
+        """Normalise an indexing key.
 
-    def _keep_view(self, key):
-        if len(key) != len(self._leading_shape):
-            msg = f"keep_view {key} does not match leading "
-            msg += f"dimensions {len(self._leading_shape)}"
-            raise ValueError(msg)
-        view = np.zeros(self._leading_shape, dtype=bool)
-        view[key] = True
-        return view
-
-    def _get_full_key(self, key):
+        Same selection rules as the reference's __getitem__ (array.py:279-449): integers and slices (any step) on the
+        leading axes, an integer or a contiguous slice on the sample axis, missing axes mean "everything", a 1-D array
+        is addressed by its sample axis alone.  Returns (keep, first, last, shape): `keep` is a boolean mask over the
+        leading axes (None when nothing is selected), [first, last) the sample window and `shape` the shape of the
+        result.  Streams always come back in storage order (a negative step does not reverse them -- array.py:287).
+        Supersets: negative integers count from the end, an out-of-range integer selects nothing instead of raising.
+        """
+        key = raw_key if isinstance(raw_key, tuple) else (raw_key,)
+        if self._flatten_single:
+            if len(key) != 1:
+                raise ValueError(f"Slice key {raw_key} is not valid for single, flattened stream.")
+            key = (0,) + key
         ndim = len(self._local_shape)
-        full_key = list()
-        if self._flatten_single:
-            if isinstance(key, tuple):
-                if len(key) != 1:
-                    msg = f"Slice key {key} is not valid for single, "
-                    msg += "flattened stream."
-                    raise ValueError(msg)
-                full_key = [0, key[0]]
-            else:
-                full_key = [0, key]
-        else:
-            if isinstance(key, tuple):
-                full_key.extend(key)
-            else:
-                full_key.append(key)
-        if len(full_key) > ndim:
-            raise ValueError(f"Invalid slice key {key}, too many dimensions")
-        full_key.extend([slice(None) for _ in range(ndim - len(full_key))])
-        return full_key
+        if len(key) > ndim:
+            raise ValueError(f"Invalid slice key {raw_key}, too many dimensions")
+        key = key + (slice(None),) * (ndim - len(key))
 
-    def _get_leading_axes(self, full_key):
-        leading_shape = list()
-        keep_slice = list()
+        picked = []          # per leading axis: the indices it keeps
+        shape = []           # axes of the result (integer keys drop theirs)
+        for n, k in zip(self._leading_shape, key[:-1]):
+            if isinstance(k, (int, np.integer)):
+                i = int(k) + (n if k < 0 else 0)
+                inside = 0 <= i < n
+                picked.append(np.array([i] if inside else [], dtype=np.int64))
+                if not inside:
+                    shape.append(0)
+            elif isinstance(k, slice):
+                idx = np.arange(n, dtype=np.int64)[k]
+                picked.append(idx)
+                shape.append(idx.size)
+            else:
+                raise ValueError("Leading dimensions support integer indices and slices.")
         if self._flatten_single:
-            keep_slice = [0]
-        else:
-            for axis, axkey in enumerate(full_key[:-1]):
-                if not isinstance(axkey, (int, np.integer)):
-                    leading_shape.append(self._slice_nelem(axkey, self._local_shape[axis]))
-                else:
-                    if axkey < 0 or axkey >= self._local_shape[axis]:
-                        leading_shape.append(0)
-                keep_slice.append(axkey)
-        leading_shape = tuple(leading_shape)
-        keep_slice = tuple(keep_slice)
-        if len(keep_slice) == 0 or 0 in leading_shape:
-            # (an out-of-range integer index gives a zero-length result; the reference's _keep_view
-            # would raise IndexError here before reaching its own empty-array branch)
-            keep = None
-        else:
-            keep = self._keep_view(keep_slice)
-        return leading_shape, keep
+            shape = []
 
-    def _get_sample_axis(self, full_key):
-        sample_key = full_key[-1]
-        if sample_key is None:
-            return (0, self._stream_size, (self._stream_size,))
-        if isinstance(sample_key, slice):
-            start, stop, step = sample_key.indices(self._stream_size)
+        size = self._stream_size
+        k = key[-1]
+        if k is None:
+            k = slice(None)
+        if isinstance(k, slice):
+            first, last, step = k.indices(size)
             if step != 1:
                 raise ValueError("Only stride==1 supported on stream slices")
-            if stop - start <= 0:
-                return (0, 0, (0,))
-            return (start, stop, (stop - start,))
-        elif isinstance(sample_key, (int, np.integer)):
-            return (sample_key, sample_key + 1, ())
-        raise ValueError("Stream dimension supports contiguous slices or single indices.")
+            last = max(last, first)
+            shape.append(last - first)
+        elif isinstance(k, (int, np.integer)):
+            first = int(k) + (size if k < 0 else 0)
+            last = first + 1
+            if not 0 <= first < size:
+                first = last = 0          # nothing to decode: the result is zeros of the leading shape
+        else:
+            raise ValueError("Stream dimension supports contiguous slices or single indices.")
+
+        keep = None
+        if last > first and all(ix.size for ix in picked):
+            keep = np.zeros(self._leading_shape, dtype=bool)
+            keep[np.ix_(*picked)] = True
+        return keep, first, last, tuple(shape)
 
     def __getitem__(self, raw_key):
         """Decompress a slice of data on the fly (array.py:409-449)."""
-        key = self._get_full_key(raw_key)
-        leading_shape, keep = self._get_leading_axes(key)
-        first, last, sample_shape = self._get_sample_axis(key)
-        full_shape = leading_shape + sample_shape
-        n_total = 1 if len(full_shape) == 0 else int(np.prod(full_shape))
-        if n_total == 0:
-            return np.zeros(full_shape, dtype=self._dtype)
-        if len(full_shape) == 0 and (first < 0 or first >= self._stream_size):
-            return np.zeros(full_shape, dtype=self._dtype)
+        keep, first, last, shape = self._resolve_key(raw_key)
+        if keep is None:
+            return np.zeros(shape, dtype=self._dtype)
         arr, _ = array_decompress_slice(
             self._compressed,
             self._stream_size,
@@ -285,7 +267,7 @@ class FlacArray:
             last_stream_sample=last,
             is_int64=self._is_int64,
         )
-        return arr.reshape(full_shape)
+        return arr.reshape(shape)
 
     def __delitem__(self, key):
         raise RuntimeError("Cannot delete individual streams")
@@ -294,43 +276,30 @@ class FlacArray:
         raise RuntimeError("Cannot modify individual byte streams")
 
     def __repr__(self):
-        mpistr = ""
+        where = ""
         if self._mpi_comm is not None:
-            rank = self._mpi_comm.rank
-            mpistr = f" | Rank {rank:04d} "
-            mpistr += f"{self._mpi_dist[rank][0]}-"
-            mpistr += f"{self._mpi_dist[rank][1] - 1} |"
-        rep = f"<FlacArray{mpistr} {self._typestr} "
-        rep += f"shape={self._shape} bytes={self._local_nbytes}>"
-        return rep
+            lo, hi = self._mpi_dist[self._mpi_comm.rank]
+            where = f" | Rank {self._mpi_comm.rank:04d} {lo}-{hi - 1} |"
+        return f"<FlacArray{where} {self._typestr} shape={self._shape} bytes={self._local_nbytes}>"
 
     def __eq__(self, other):
-        """array.py:469-516: shapes, dtype, starts and compressed BYTES equal; offsets/gains allclose."""
+        """Same data in the same layout (array.py:469-516): shapes, dtype, stream starts and the compressed BYTES must
+        be identical, offsets / gains equal to floating-point tolerance."""
         def host(x):
             return x.cpu().numpy() if is_torch(x) else x
 
-        if self._shape != other._shape:
-            log.debug(f"other shape {other._shape} != {self._shape}")
-            return False
-        if self._dtype != other._dtype:
-            log.debug(f"other dtype {other._dtype} != {self._dtype}")
-            return False
-        if self._global_shape != other._global_shape:
-            log.debug(f"other global_shape {other._global_shape} != {self._global_shape}")
-            return False
-        if not np.array_equal(host(self._stream_starts), host(other._stream_starts)):
-            log.debug("other starts != starts")
-            return False
-        if not np.array_equal(host(self._compressed), host(other._compressed)):
-            log.debug("other compressed != compressed")
-            return False
-        for a, b, nm in ((self._stream_offsets, other._stream_offsets, "offsets"),
-                         (self._stream_gains, other._stream_gains, "gains")):
-            if (a is None) != (b is None):
-                log.debug(f"stream_{nm}: one is None")
+        for name in ("_shape", "_dtype", "_global_shape"):
+            if getattr(self, name) != getattr(other, name):
+                log.debug(f"FlacArray.__eq__: {name[1:]} differs")
                 return False
-            if a is not None and not np.allclose(host(a), host(b)):
-                log.debug(f"other stream_{nm} != stream_{nm}")
+        for name in ("_stream_starts", "_compressed"):
+            if not np.array_equal(host(getattr(self, name)), host(getattr(other, name))):
+                log.debug(f"FlacArray.__eq__: {name[1:]} differs")
+                return False
+        for name in ("_stream_offsets", "_stream_gains"):
+            mine, theirs = getattr(self, name), getattr(other, name)
+            if (mine is None) != (theirs is None) or (mine is not None and not np.allclose(host(mine), host(theirs))):
+                log.debug(f"FlacArray.__eq__: {name[1:]} differs")
                 return False
         return True
 

@@ -578,6 +578,12 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
     const int nch = dtype_channels(dtype);
     const int64_t nf = (stream_size + lp.blocksize - 1) / lp.blocksize;
     if (n_stream * nf > 0x7fffffffLL) return ERROR_ALLOC;  // frame indices are 32 bit
+    if (8 + 3 * nf > 0xFFFFFFLL) {
+        // the per-stream frame-size table (APPLICATION block "faB2") carries a 24-bit length: a stream of more than
+        // ~5.59 M frames (6.4e9 samples at blocksize 1152, 22.9e9 at 4096) cannot be described
+        ctx->last_error = "stream too long for the frame-size table (more than 5592402 frames)";
+        return ERROR_ENCODE_INIT;
+    }
 
     // scratch: [min/max partials of the quantise pre-pass] | byte prefixes | ends | work counters | per-batch
     // statistics, plans, frame sizes, slots.  Sized once up front

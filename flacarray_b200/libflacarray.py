@@ -200,7 +200,10 @@ def _ratio_history():
 
 
 def _scratch_out(dev, nbytes):
-    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    # one buffer per (device, CUDA stream): the exact-size copy handed back to the caller is queued on the stream
+    # the encode ran on, so only work on that same stream may reuse the scratch
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    key = (idx, torch.cuda.current_stream(dev).cuda_stream)
     bufs = _scratch_map()
     buf = bufs.get(key)
     if buf is None or buf.numel() < nbytes:
@@ -655,10 +658,33 @@ def decode_device(comp, starts, nbytes, n_stream, stream_size, first_sample, las
     return out
 
 
+def _check_sample_range(stream_size, first_sample, last_sample):
+    """decompress.c:207-222 / pyx:769-777: the window [first, last) must lie inside the stream."""
+    if first_sample >= 0 and last_sample >= 0:
+        if last_sample > stream_size:
+            raise RuntimeError("last_sample is beyond end of stream")
+        if first_sample > stream_size - 1:
+            raise RuntimeError("first_sample is beyond last element of stream")
+        if first_sample >= last_sample:
+            raise RuntimeError("first_sample is larger than last_sample")
+
+
+def _check_byte_windows(h_starts, h_nbytes, n_compressed):
+    """Every (start, nbytes) window must lie inside the compressed buffer: the kernels index it directly (a stale
+    index array would otherwise turn into out-of-bounds device reads instead of an error)."""
+    if h_starts.size == 0:
+        return
+    if h_starts.size != h_nbytes.size:
+        raise RuntimeError("starts and nbytes should have the same number of elements")
+    if int(h_starts.min()) < 0 or int(h_nbytes.min()) < 0 or int((h_starts + h_nbytes).max()) > int(n_compressed):
+        raise RuntimeError("stream starts / nbytes point outside the compressed buffer")
+
+
 def _wrap_decode(compressed, starts, nbytes, n_stream, stream_size, first_sample, last_sample, is_int64):
     on_dev = is_torch(compressed) and compressed.is_cuda
     h_starts = starts.cpu().numpy() if is_torch(starts) else np.asarray(starts)
     h_nbytes = nbytes.cpu().numpy() if is_torch(nbytes) else np.asarray(nbytes)
+    _check_byte_windows(h_starts.reshape(-1), h_nbytes.reshape(-1), compressed.numel() if is_torch(compressed) else compressed.size)
     if not on_dev:
         if is_torch(compressed):
             compressed = compressed.numpy()
@@ -703,13 +729,8 @@ def decode_flac(compressed, starts, nbytes, stream_size, first_sample=-1, last_s
         raise RuntimeError("Compressed byte array should be one dimensional")
 
     n_decode = stream_size
+    _check_sample_range(stream_size, first_sample, last_sample)
     if first_sample >= 0 and last_sample >= 0:
-        if last_sample > stream_size:
-            raise RuntimeError("last_sample is beyond end of stream")
-        if first_sample > stream_size - 1:
-            raise RuntimeError("first_sample is beyond last element of stream")
-        if first_sample >= last_sample:
-            raise RuntimeError("first_sample is larger than last_sample")
         n_decode = last_sample - first_sample
 
     output_shape = tuple(starts.shape) + (n_decode,)
@@ -763,6 +784,7 @@ def decode_flac_float(compressed, starts, nbytes, stream_size, offsets, gains, f
                       is_int64=False):
     """decode_flac followed by utils.int_to_float (utils.c:330-368) without leaving the device."""
     n_decode = stream_size
+    _check_sample_range(stream_size, first_sample, last_sample)
     if first_sample >= 0 and last_sample >= 0:
         n_decode = last_sample - first_sample
     output_shape = tuple(starts.shape) + (n_decode,)
@@ -770,6 +792,7 @@ def decode_flac_float(compressed, starts, nbytes, stream_size, offsets, gains, f
     on_dev = is_torch(compressed) and compressed.is_cuda
     h_starts = (starts.cpu().numpy() if is_torch(starts) else np.asarray(starts)).reshape(-1)
     h_nbytes = (nbytes.cpu().numpy() if is_torch(nbytes) else np.asarray(nbytes)).reshape(-1)
+    _check_byte_windows(h_starts, h_nbytes, compressed.numel() if is_torch(compressed) else compressed.size)
     if not on_dev:
         if is_torch(compressed):
             compressed = compressed.numpy()

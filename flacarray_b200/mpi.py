@@ -119,94 +119,52 @@ class TorchComm:
         dist.barrier(group=self.group)
 
 
+def _even_split(n_elem, parts):
+    """Contiguous [first, last) ranges of `n_elem` items over `parts` owners, the first n % parts one longer (the
+    np.array_split rule the reference uses, mpi.py:84-90)."""
+    base, extra = divmod(int(n_elem), parts)
+    edges = [p * base + min(p, extra) for p in range(parts + 1)]
+    return [(edges[p], edges[p + 1]) for p in range(parts)]
+
+
 def distribute_and_verify(mpi_comm, n_elem, mpi_dist=None):
-    """Compute or verify the distribution of `n_elem` leading-axis elements (mpi.py:33-90)."""
-    if mpi_dist is not None:
+    """The leading-axis distribution [(first, last), ...] over the communicator's ranks: computed when `mpi_dist` is
+    None, otherwise checked (one non-empty range per rank, contiguous, covering [0, n_elem)) -- mpi.py:33-90."""
+    nproc = 1 if mpi_comm is None else mpi_comm.size
+    if mpi_dist is None:
+        if n_elem < nproc:
+            raise RuntimeError(f"Cannot distribute {n_elem} streams among {nproc} processes.")
+        return _even_split(n_elem, nproc)
+    if len(mpi_dist) != nproc:
         if mpi_comm is None:
-            if len(mpi_dist) != 1 or mpi_dist[0][0] != 0 or mpi_dist[0][1] != n_elem:
-                msg = "mpi_comm is None and mpi_dist does not contain single range "
-                msg += "of all elements"
-                raise RuntimeError(msg)
-            return mpi_dist
-        if mpi_comm.size != len(mpi_dist):
-            msg = f"If specified, mpi_dist (len={len(mpi_dist)}) should have same "
-            msg += f"length as comm size ({mpi_comm.size})"
-            raise RuntimeError(msg)
-        if mpi_dist[0][0] != 0 or mpi_dist[-1][1] != n_elem:
-            msg = f"If specified, mpi_dist ({mpi_dist[0][0]} ... {mpi_dist[-1][1]})"
-            msg += f" should span the full range of elements ({n_elem})"
-            raise RuntimeError(msg)
-        for proc in range(1, mpi_comm.size):
-            if mpi_dist[proc][0] != mpi_dist[proc - 1][1]:
-                raise RuntimeError("mpi_dist must have contiguous ranges of first, last (exclusive)")
-            if mpi_dist[proc][1] <= mpi_dist[proc][0]:
-                raise RuntimeError(f"mpi_dist has no data for process {proc}")
-        return mpi_dist
-    if mpi_comm is None:
-        return [(0, n_elem)]
-    # uniform split, first n % size ranks get one extra (np.array_split rule, mpi.py:84-90)
-    size = mpi_comm.size
-    base, extra = divmod(int(n_elem), size)
-    if base == 0:
-        msg = f"Cannot distribute {n_elem} streams among {size}"
-        msg += " processes."
-        raise RuntimeError(msg)
-    dist_out = []
-    off = 0
-    for proc in range(size):
-        n = base + (1 if proc < extra else 0)
-        dist_out.append((off, off + n))
-        off += n
-    return dist_out
+            raise RuntimeError("mpi_comm is None and mpi_dist does not contain single range of all elements")
+        raise RuntimeError(f"If specified, mpi_dist (len={len(mpi_dist)}) should have same length as comm size ({nproc})")
+    if mpi_dist[0][0] != 0 or mpi_dist[-1][1] != n_elem:
+        if mpi_comm is None:
+            raise RuntimeError("mpi_comm is None and mpi_dist does not contain single range of all elements")
+        raise RuntimeError(f"If specified, mpi_dist ({mpi_dist[0][0]} ... {mpi_dist[-1][1]}) should span the full "
+                           f"range of elements ({n_elem})")
+    for proc, (lo, hi) in enumerate(mpi_dist):
+        if proc > 0 and lo != mpi_dist[proc - 1][1]:
+            raise RuntimeError("mpi_dist must have contiguous ranges of first, last (exclusive)")
+        if hi <= lo and nproc > 1:
+            raise RuntimeError(f"mpi_dist has no data for process {proc}")
+    return mpi_dist
 
 
 def global_array_properties(local_shape, mpi_comm):
-    """Global shape and per-rank leading-axis ranges (mpi.py:93-153)."""
-    props = dict()
-    local_shape = tuple(int(x) for x in local_shape)
-    if mpi_comm is None:
-        if len(local_shape) == 1:
-            props["shape"] = (1, local_shape[0])
-            props["dist"] = [(0, 1)]
-        else:
-            props["shape"] = local_shape
-            props["dist"] = [(0, local_shape[0])]
-        return props
-    all_shapes = mpi_comm.gather(local_shape, root=0)
-    err = False
-    if mpi_comm.rank == 0:
-        dist_l = list()
-        shp = all_shapes[0]
-        if len(shp) == 1:
-            lda = 1
-            trl = shp
-        else:
-            lda = shp[0]
-            trl = shp[1:]
-        dist_l.append((0, lda))
-        ldoff = lda
-        for s in all_shapes[1:]:
-            if len(s) == 1:
-                lda += 1
-                dist_l.append((ldoff, ldoff + 1))
-                ldoff += 1
-                if s != trl:
-                    err = True
-                    break
-            else:
-                lda += s[0]
-                dist_l.append((ldoff, ldoff + s[0]))
-                ldoff += s[0]
-                if s[1:] != trl:
-                    err = True
-                    break
-        props["shape"] = (lda,) + tuple(trl)
-        props["dist"] = dist_l
-    err = mpi_comm.bcast(err, root=0)
-    props = mpi_comm.bcast(props, root=0)
-    if err:
+    """{"shape": global shape, "dist": [(first, last) per rank]} from every rank's local shape (mpi.py:93-153).  The
+    ranks hold consecutive blocks of the leading axis; a 1-D local array counts as one stream.  Trailing dimensions
+    must agree everywhere."""
+    mine = tuple(int(x) for x in local_shape)
+    if len(mine) == 1:
+        mine = (1,) + mine
+    shapes = [mine] if mpi_comm is None else [tuple(s) for s in mpi_comm.allgather(mine)]
+    if any(s[1:] != shapes[0][1:] for s in shapes):
         raise RuntimeError("Inconsistent array dimensions across processes")
-    return props
+    edges = np.concatenate([[0], np.cumsum([s[0] for s in shapes])])
+    return {"shape": (int(edges[-1]),) + shapes[0][1:],
+            "dist": [(int(edges[p]), int(edges[p + 1])) for p in range(len(shapes))]}
 
 
 def global_bytes(local_nbytes, stream_starts, mpi_comm):

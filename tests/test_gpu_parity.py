@@ -379,3 +379,22 @@ def test_unaligned_streams_and_mixed_frame_kinds(fa, oracle, level):
     assert np.array_equal(oracle.decode(c, s.reshape(-1), n.reshape(-1), L, is_int64=True), oi)
     assert np.array_equal(fa.array_decompress(c, L, s, n, stream_offsets=off, stream_gains=gain, is_int64=True),
                           oracle.int_to_float(oi, oo, og))
+
+
+def test_encoded_bytes_match_frozen_sha256(fa, golden_dir):
+    """Byte determinism across builds: SHA-256 of the encoder's output for small versions of the five BASELINE
+    configs, frozen on a B200 by scripts/freeze_gpu_sha.py (re-freeze only for a deliberate encoder change)."""
+    import hashlib
+    import json
+
+    from oracle.small_configs import small_configs as _inputs
+
+    path = os.path.join(golden_dir, "gpu_encoded_sha256.json")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/gpu_encoded_sha256.json not frozen yet")
+    want = json.load(open(path))
+    for name, x in _inputs().items():
+        for level in (0, 5, 8):
+            comp, _, _, _, _ = fa.array_compress(x, level=level)
+            got = hashlib.sha256(np.asarray(comp).tobytes()).hexdigest()
+            assert got == want[f"{name}/L{level}"]["sha256"], (name, level, int(np.asarray(comp).size), want[f"{name}/L{level}"]["nbytes"])
