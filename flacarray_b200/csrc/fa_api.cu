@@ -35,8 +35,14 @@ using namespace fa;
 #endif
 template <int H>
 __global__ void __launch_bounds__(kEncThreads, FAB_ENC_CTAS) k_encode(const EncParams P) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    encode_frames_cta<H>(P, smem);
+    extern __shared__ __align__(128) unsigned char smem[];
+    encode_frames_cta<H, true>(P, smem);
+}
+// the frames that are not full 4096-sample frames (see k_enc_analyze_short)
+template <int H>
+__global__ void __launch_bounds__(kEncThreads, 4) k_encode_short(const EncParams P, uint32_t first, uint32_t stride) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    encode_frames_cta<H, false>(P, smem, first, stride);
 }
 
 // sample statistics, fixed-predictor error sums and windowed autocorrelation of every (frame, channel)
@@ -47,9 +53,17 @@ __global__ void __launch_bounds__(kEncThreads, FAB_ENC_CTAS) k_encode(const EncP
 template <int H>
 __global__ void __launch_bounds__(kEncThreads, FAB_AN_CTAS) k_enc_analyze(const EncParams P) {
     __shared__ AnShared sh;
-    if (P.blocksize == kMaxBs) analyze_fill_window(P, &sh);
+    analyze_fill_window(P, &sh);
     __syncthreads();
-    for (uint32_t g = P.g_begin + blockIdx.x; g < P.g_end; g += gridDim.x) analyze_frame_cta<H>(P, g, &sh);
+    for (uint32_t g = P.g_begin + blockIdx.x; g < P.g_end; g += gridDim.x) analyze_frame_cta<H, true>(P, g, &sh);
+}
+// ... and of the frames that are not full 4096-sample frames: the last frame of every stream (CTA i takes the
+// i-th such frame of the batch), or every frame of a blocksize-1152 level
+template <int H>
+__global__ void __launch_bounds__(kEncThreads) k_enc_analyze_short(const EncParams P, uint32_t first, uint32_t stride) {
+    __shared__ AnShared sh;
+    for (uint64_t g = (uint64_t)first + (uint64_t)blockIdx.x * stride; g < P.g_end; g += (uint64_t)gridDim.x * stride)
+        analyze_frame_cta<H, false>(P, (uint32_t)g, &sh);
 }
 
 // predictor design: one thread per (frame, channel)
@@ -649,6 +663,8 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
     if (!ctx->smem_configured) {
         FAB_CUDA(ctx, cudaFuncSetAttribute(k_encode<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_smem_bytes(2) + FAB_SMEM_PAD));
         FAB_CUDA(ctx, cudaFuncSetAttribute(k_encode<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_smem_bytes(2)));
+        FAB_CUDA(ctx, cudaFuncSetAttribute(k_encode_short<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_smem_bytes(2)));
+        FAB_CUDA(ctx, cudaFuncSetAttribute(k_encode_short<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_smem_bytes(2)));
         for (int c = 0; c < 2; ++c) {
             FAB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->enc_ctas_per_sm[0][c], k_encode<8>, kEncThreads, enc_smem_bytes(c + 1) + FAB_SMEM_PAD));
             FAB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->enc_ctas_per_sm[1][c], k_encode<12>, kEncThreads, enc_smem_bytes(c + 1)));
@@ -673,19 +689,52 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
         // under the kernels of batch b + 1, which use the other slot / frame-size buffers; k_enc_analyze of batch
         // b + 2 parks samples in the slots batch b compacts from, so it waits for that compaction.
         if (bi >= 2) FAB_CUDA(ctx, cudaStreamWaitEvent(st, joins[bi & 1], 0));
-        const unsigned agrid = (unsigned)std::min<int64_t>(nfr, (int64_t)ctx->n_sm * FAB_AN_CTAS);
-        if (h12) k_enc_analyze<12><<<agrid, kEncThreads, 0, st>>>(P);
-        else k_enc_analyze<8><<<agrid, kEncThreads, 0, st>>>(P);
+        if (lp.blocksize == kMaxBs) {
+            const unsigned agrid = (unsigned)std::min<int64_t>(nfr, (int64_t)ctx->n_sm * FAB_AN_CTAS);
+            if (h12) k_enc_analyze<12><<<agrid, kEncThreads, 0, st>>>(P);
+            else k_enc_analyze<8><<<agrid, kEncThreads, 0, st>>>(P);
+            ctx->launches++;
+        }
+        // frames that are not full: every frame (blocksize 1152), or the last frame of each stream when the stream
+        // length is not a multiple of the blocksize
+        uint32_t first = P.g_begin, stride = 1;
+        int64_t cnt = nfr;
+        {
+            if (lp.blocksize == kMaxBs) {
+                cnt = 0;
+                if (stream_size % lp.blocksize != 0) {
+                    stride = (uint32_t)nf;
+                    const int64_t g_last = ((int64_t)P.g_begin / nf) * nf + (nf - 1);     // last frame of the batch's first stream
+                    first = (uint32_t)g_last;
+                    cnt = g_last < (int64_t)P.g_end ? ((int64_t)P.g_end - 1 - g_last) / nf + 1 : 0;
+                }
+            }
+            if (cnt > 0) {
+                const unsigned sgrid = (unsigned)std::min<int64_t>(cnt, (int64_t)ctx->n_sm * 8);
+                if (h12) k_enc_analyze_short<12><<<sgrid, kEncThreads, 0, st>>>(P, first, stride);
+                else k_enc_analyze_short<8><<<sgrid, kEncThreads, 0, st>>>(P, first, stride);
+                ctx->launches++;
+            }
+        }
         k_enc_design<<<(unsigned)((nfr * nch + 127) / 128), 128, 0, st>>>(P, nfr * nch);
-        unsigned grid = (unsigned)std::min<int64_t>(nfr, resident);
-        if (h12) k_encode<12><<<grid, kEncThreads, smem, st>>>(P);
-        else k_encode<8><<<grid, kEncThreads, smem, st>>>(P);
+        if (lp.blocksize == kMaxBs) {
+            unsigned grid = (unsigned)std::min<int64_t>(nfr, resident);
+            if (h12) k_encode<12><<<grid, kEncThreads, smem, st>>>(P);
+            else k_encode<8><<<grid, kEncThreads, smem, st>>>(P);
+            ctx->launches++;
+        }
+        if (cnt > 0) {
+            const unsigned sgrid = (unsigned)std::min<int64_t>(cnt, (int64_t)ctx->n_sm * 4);
+            if (h12) k_encode_short<12><<<sgrid, kEncThreads, smem, st>>>(P, first, stride);
+            else k_encode_short<8><<<sgrid, kEncThreads, smem, st>>>(P, first, stride);
+            ctx->launches++;
+        }
         FAB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
         FAB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
         k_enc_scan<<<1, kScanThreads, 0, ctx->aux>>>(P);      // (the running byte total is carried from scan to scan: all on aux)
         k_enc_compact<<<(unsigned)std::min<int64_t>(nfr, (int64_t)ctx->n_sm * 16), 128, 0, ctx->aux>>>(P);
         FAB_CUDA(ctx, cudaEventRecord(joins[bi & 1], ctx->aux));
-        ctx->launches += 5;
+        ctx->launches += 3;
     }
     FAB_CUDA(ctx, cudaStreamWaitEvent(st, joins[(nbatch - 1) & 1], 0));
     if (nbatch > 1) FAB_CUDA(ctx, cudaStreamWaitEvent(st, joins[nbatch & 1], 0));

@@ -1285,6 +1285,7 @@ FA_D int32_t quant_f32_fast(float x, float off, float gain, bool gain_pos) {
 }
 
 FA_D U4 ld128(const void* p) { return lds128(p); }    // plain (coherent) 16-byte load, any address space
+FA_D U4 u4_zero_enc() { U4 z; z.x = z.y = z.z = z.w = 0; return z; }
 
 // Stage channel c of the frame; c == 0 converts the input (and parks every channel), c == 1 re-reads the high
 // words this thread parked a moment ago.
@@ -1441,6 +1442,17 @@ FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const FrameSrc&
             }
         }
     }
+    // ---- the integer statistics go to the per-warp partials now (REDUX): their registers are free for the second pass
+    {
+        uint32_t wor = redux_or(orv);
+        int32_t wmn = redux_min(mn), wmx = redux_max(mx);
+        unsigned long long s0 = warp_sum_u32_wide(fe0), s1 = warp_sum_u32_wide(fe1), s2 = warp_sum_u32_wide(fe2),
+                           s3 = warp_sum_u32_wide(fe3), s4 = warp_sum_u32_wide(fe4);
+        if (ln == 0) {
+            sh->w_or[wp] = wor; sh->w_mn[wp] = wmn; sh->w_mx[wp] = wmx;
+            sh->w_fe[wp][0] = s0; sh->w_fe[wp][1] = s1; sh->w_fe[wp][2] = s2; sh->w_fe[wp][3] = s3; sh->w_fe[wp][4] = s4;
+        }
+    }
     // (a second pass over the staged samples: one loop with both the integer statistics and the double-precision
     // products needs more than the 80 registers six resident CTAs leave per thread, and ptxas spills in the loop)
     if (do_lpc) {
@@ -1474,18 +1486,10 @@ FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const FrameSrc&
         }
     }
 
-    // ---- block reduction: REDUX for the integers, transposing butterfly for the doubles
+    // ---- the autocorrelation partials: through the warp's own, consumed quads of the staged channel
     {
-        uint32_t wor = redux_or(orv);
-        int32_t wmn = redux_min(mn), wmx = redux_max(mx);
-        unsigned long long s0 = warp_sum_u32_wide(fe0), s1 = warp_sum_u32_wide(fe1), s2 = warp_sum_u32_wide(fe2),
-                           s3 = warp_sum_u32_wide(fe3), s4 = warp_sum_u32_wide(fe4);
-        if (ln == 0) {
-            sh->w_or[wp] = wor; sh->w_mn[wp] = wmn; sh->w_mx[wp] = wmx;
-            sh->w_fe[wp][0] = s0; sh->w_fe[wp][1] = s1; sh->w_fe[wp][2] = s2; sh->w_fe[wp][3] = s3; sh->w_fe[wp][4] = s4;
-        }
         if (do_lpc) {
-            // every lane parks its partials, then lane l sums lag l over the warp in lane order (two chains): a fixed
+            // every lane parks its partials, then a few lanes per lag sum them in lane order: a fixed
             // order (deterministic bytes) at a fraction of the instructions of a register butterfly over doubles
             // (the partials overwrite the warp's own, consumed quads of the staged channel: lag l goes to half (l & 1) of
             // quad (l >> 1), rotated by l columns so that the column reads below are conflict-free)
@@ -1533,12 +1537,17 @@ FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const FrameSrc&
         // The autocorrelation stays valid.
         unsigned long long we[5] = {0, 0, 0, 0, 0};
         uint32_t bad = 0;
-        int64_t q1 = (int64_t)(hx[H - 1] >> wasted) - (int64_t)(hx[H - 2] >> wasted);
-        int64_t q1b = (int64_t)(hx[H - 2] >> wasted) - (int64_t)(hx[H - 3] >> wasted);
-        int64_t q1c = (int64_t)(hx[H - 3] >> wasted) - (int64_t)(hx[H - 4] >> wasted);
+        // (the four samples before the chunk are fetched again -- the last quad thread t - 1 parked -- rather than kept
+        // in registers across the loops above, which are short of registers as it is)
+        U4 hq = u4_zero_enc();
+        if (t != 0) hq = ld128(park_frame + c * kMaxBs + ((7 * kEncThreads + (t - 1)) << 2));
+        const int32_t h4[4] = {(int32_t)hq.x >> wasted, (int32_t)hq.y >> wasted, (int32_t)hq.z >> wasted, (int32_t)hq.w >> wasted};
+        int64_t q1 = (int64_t)h4[3] - (int64_t)h4[2];
+        int64_t q1b = (int64_t)h4[2] - (int64_t)h4[1];
+        int64_t q1c = (int64_t)h4[1] - (int64_t)h4[0];
         int64_t q2 = q1 - q1b, q2b = q1b - q1c;
         int64_t q3 = q2 - q2b;
-        int64_t prev = (int64_t)(hx[H - 1] >> wasted);
+        int64_t prev = (int64_t)h4[3];
 #pragma unroll 1
         for (int q = 0; q < kSpt / 4; ++q) {
             const U4 v = ld128(park_frame + c * kMaxBs + ((q * kEncThreads + t) << 2));   // (this thread parked them itself)
@@ -1589,13 +1598,17 @@ FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const FrameSrc&
     sync();   // the partials and the staged channel are reused by the next channel / frame
 }
 
-template <int H>
+// FULL: the caller is the kernel for full (4096-sample) frames and skips every other frame; !FULL: the kernel for the
+// rest (last frame of a stream, blocksize-1152 levels).  Two kernels because inlining both bodies into one makes
+// ptxas spill inside the full-frame loops (3.8 KB of spill stores against 84 bytes).
+template <int H, bool FULL>
 FA_D void analyze_frame_cta(const EncParams& P, uint32_t g, AnShared* sh) {
     const int64_t s = (int64_t)(g / (uint32_t)P.nframes);
     const int f = (int)(g % (uint32_t)P.nframes);
     const int64_t samp0 = (int64_t)f * P.blocksize;
     const int bs = (int)((P.stream_size - samp0) < P.blocksize ? (P.stream_size - samp0) : P.blocksize);
     FrameStats* st = P.stats + (size_t)(g - P.g_begin) * P.nch;
+    if ((bs == kMaxBs) != FULL) return;
     if (bs < 64) {
         if (tid() < P.nch) st[tid()].mode = 0;
         return;
@@ -1612,7 +1625,7 @@ FA_D void analyze_frame_cta(const EncParams& P, uint32_t g, AnShared* sh) {
     // plain integers (quantised / split exactly once) through one TMA copy per channel
     int32_t* slot = (int32_t*)(P.slots + (int64_t)(g - P.g_begin) * P.slot_bytes);
     for (int c = 0; c < P.nch; ++c) {
-        if (bs == kMaxBs) analyze_channel_full<H>(P, sh, S, c, st + c, slot);
+        if constexpr (FULL) analyze_channel_full<H>(P, sh, S, c, st + c, slot);
         else analyze_channel<H, false>(P, sh, S, c, st + c, nullptr);
     }
 }
@@ -2698,6 +2711,15 @@ FA_D void enc_fetch_ticket(const EncParams& P, EncHot* hot, int slot) {
     hot->gq_bs[slot] = (int)(left < P.blocksize ? left : P.blocksize);
 }
 
+FA_D void enc_set_ticket(const EncParams& P, EncHot* hot, int slot, uint64_t g64) {
+    const uint32_t g = g64 < (uint64_t)P.g_end ? (uint32_t)g64 : P.g_end;
+    const int f = (int)(g % (uint32_t)P.nframes);
+    const int64_t left = P.stream_size - (int64_t)f * P.blocksize;
+    hot->gq[slot] = g;
+    hot->gq_f[slot] = f;
+    hot->gq_bs[slot] = (int)(left < P.blocksize ? left : P.blocksize);
+}
+
 // Where the samples of (stream, frame) unit g come from (short-frame and general paths; full frames read the
 // integers k_enc_analyze parked).
 FA_D FrameSrc enc_frame_src(const EncParams& P, uint32_t g, int f, int bs) {
@@ -2713,8 +2735,12 @@ FA_D FrameSrc enc_frame_src(const EncParams& P, uint32_t g, int f, int bs) {
     return S;
 }
 
-template <int H>
-FA_D void encode_frames_cta(const EncParams& P, unsigned char* smem_raw) {
+// FULLK: the kernel of the full (4096-sample) frames -- persistent CTAs taking tickets over the whole batch and
+// passing over the other frames; !FULLK: the kernel of those other frames (last frame of a stream, blocksize-1152
+// levels), CTA i starting at frame `first + i * stride`.  Two kernels so that the register-hungry short path does
+// not share a register budget (and an instruction cache) with the full-frame path.
+template <int H, bool FULLK>
+FA_D void encode_frames_cta(const EncParams& P, unsigned char* smem_raw, uint32_t first = 0, uint32_t stride = 1) {
     EncHot* hot = (EncHot*)smem_raw;
     const int t = tid();
     const int nch = P.nch;
@@ -2733,10 +2759,12 @@ FA_D void encode_frames_cta(const EncParams& P, unsigned char* smem_raw) {
 #endif
 
     for (int i = t; i < 256; i += kEncThreads) hot->crc8[i] = P.crc->crc8[i];
+    uint64_t g_mine = (uint64_t)first + (uint64_t)blockIdx_x() * stride;      // (!FULLK)
     if (t == 0) {
         mbar_init(&hot->mbar, 1);
         hot->prev_valid = 0;
-        enc_fetch_ticket(P, hot, 0);
+        if (FULLK) enc_fetch_ticket(P, hot, 0);
+        else enc_set_ticket(P, hot, 0, g_mine);
     }
     hot->tail_val[0][t] = 0; hot->tail_val[1][t] = 0;
 
@@ -2747,7 +2775,12 @@ FA_D void encode_frames_cta(const EncParams& P, unsigned char* smem_raw) {
         FAB_TICK(0);
         const uint32_t g = hot->gq[iter & 1];
         const int f = hot->gq_f[iter & 1], bs = hot->gq_bs[iter & 1];
-        if (t == 0) enc_fetch_ticket(P, hot, (iter + 1) & 1);   // for the next iteration
+        if (FULLK) {
+            if (t == 0) enc_fetch_ticket(P, hot, (iter + 1) & 1);   // for the next iteration
+        } else {
+            g_mine += (uint64_t)gridDim_x() * stride;
+            if (t == 0) enc_set_ticket(P, hot, (iter + 1) & 1, g_mine);
+        }
         // trailing partial words of the previous frame's packing sessions
         for (int c = 0; c < nch; ++c) {
             uint32_t tv = hot->tail_val[c][t];
@@ -2755,18 +2788,18 @@ FA_D void encode_frames_cta(const EncParams& P, unsigned char* smem_raw) {
         }
         X.retired = false;
         if (g >= total_frames) break;
+        if ((bs == kMaxBs) != FULLK) continue;      // the other kernel's frame (the pending frame, if any, stays pending)
 
         int bitpos = 0;
         for (int c = 0; c < nch; ++c) {
             int bend = 0;
             bool done = false;
-            if (bs == kMaxBs) {
+            if constexpr (FULLK) {
                 // planar int32 samples parked by k_enc_analyze in this frame's slot (the compressed frame only
                 // replaces them when the frame is retired, one iteration from now)
                 const int32_t* park = (const int32_t*)(P.slots + (int64_t)(g - P.g_begin) * P.slot_bytes) + (int64_t)c * kMaxBs;
                 done = enc_channel_full<H>(P, X, park, c, f, g, bitpos, bend);
-            }
-            else if (bs >= 64) {
+            } else if (bs >= 64) {
                 // (the short path retires the previous frame on every return: its plans never have mode 0)
                 bend = enc_channel_short<H>(P, X, enc_frame_src(P, g, f, bs), c, f, g, bitpos);
                 done = bend >= 0;

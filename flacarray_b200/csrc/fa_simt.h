@@ -23,6 +23,8 @@
 namespace fa {
 FA_D int tid() { return (int)threadIdx.x; }
 FA_D int nthreads() { return (int)blockDim.x; }
+FA_D uint32_t blockIdx_x() { return blockIdx.x; }
+FA_D uint32_t gridDim_x() { return gridDim.x; }
 FA_D int lane() { return (int)(threadIdx.x & 31); }
 FA_D int warp() { return (int)(threadIdx.x >> 5); }
 FA_D void sync() { __syncthreads(); }
@@ -147,6 +149,7 @@ FA_D double dfma(double a, double b, double c) { return __fma_rn(a, b, c); }
 namespace fasim {
 struct Block {
     int nthreads;
+    uint32_t nblocks = 1;
     std::barrier<> bar;
     std::vector<std::unique_ptr<std::barrier<>>> wbar;
     std::vector<uint64_t> xchg;  // one slot per thread
@@ -170,6 +173,7 @@ template <class F>
 void launch(int nblocks, int nthreads, size_t smem_bytes, F body) {
     for (int b = 0; b < nblocks; ++b) {
         Block blk(nthreads, smem_bytes);
+        blk.nblocks = (uint32_t)nblocks;
         std::vector<std::thread> th;
         for (int t = 0; t < nthreads; ++t) {
             th.emplace_back([&, t] {
@@ -193,6 +197,8 @@ inline unsigned char* smem() {
 namespace fa {
 inline int tid() { return fasim::tls.tid; }
 inline int nthreads() { return fasim::tls.blk->nthreads; }
+inline uint32_t blockIdx_x() { return (uint32_t)fasim::tls.bid; }
+inline uint32_t gridDim_x() { return fasim::tls.blk->nblocks; }
 inline int lane() { return fasim::tls.tid & 31; }
 inline int warp() { return fasim::tls.tid >> 5; }
 inline void sync() { fasim::tls.blk->bar.arrive_and_wait(); }

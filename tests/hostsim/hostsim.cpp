@@ -98,8 +98,8 @@ int hs_encode(const void* data, int dtype, int64_t n_stream, int64_t stream_size
         if (lp.blocksize == kMaxBs) analyze_fill_window(P, ash);
         fa::sync();
         for (uint32_t g = 0; g < (uint32_t)total_frames; ++g) {
-            if (lp.max_lpc_order > 8) analyze_frame_cta<12>(P, g, ash);
-            else analyze_frame_cta<8>(P, g, ash);
+            if (lp.max_lpc_order > 8) { analyze_frame_cta<12, true>(P, g, ash); analyze_frame_cta<12, false>(P, g, ash); }
+            else { analyze_frame_cta<8, true>(P, g, ash); analyze_frame_cta<8, false>(P, g, ash); }
         }
     });
     fasim::launch(1, 1, 0, [&](int) {
@@ -107,8 +107,13 @@ int hs_encode(const void* data, int dtype, int64_t n_stream, int64_t stream_size
     });
     // persistent CTAs: the emulator runs blocks one after the other, so one block drains every ticket
     fasim::launch(1, kEncThreads, enc_smem_bytes(nch), [&](int) {
-        if (lp.max_lpc_order > 8) encode_frames_cta<12>(P, fasim::smem());
-        else encode_frames_cta<8>(P, fasim::smem());
+        if (lp.max_lpc_order > 8) encode_frames_cta<12, true>(P, fasim::smem());
+        else encode_frames_cta<8, true>(P, fasim::smem());
+    });
+    // the frames that are not full (one block striding over every frame, like the ticket kernel: it passes over the full ones)
+    fasim::launch(1, kEncThreads, enc_smem_bytes(nch), [&](int) {
+        if (lp.max_lpc_order > 8) encode_frames_cta<12, false>(P, fasim::smem(), 0, 1);
+        else encode_frames_cta<8, false>(P, fasim::smem(), 0, 1);
     });
     fasim::launch(1, kScanThreads, (kScanThreads / 32 + 1) * 8, [&](int) { scan_batch_cta(P, (unsigned long long*)fasim::smem()); });
     std::vector<uint16_t> ctab(4 * 256), s11(2 * 256);
