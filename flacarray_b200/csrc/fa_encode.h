@@ -1452,6 +1452,9 @@ FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const FrameSrc&
             sh->w_or[wp] = wor; sh->w_mn[wp] = wmn; sh->w_mx[wp] = wmx;
             sh->w_fe[wp][0] = s0; sh->w_fe[wp][1] = s1; sh->w_fe[wp][2] = s2; sh->w_fe[wp][3] = s3; sh->w_fe[wp][4] = s4;
         }
+        // (reconverge HERE: without it ptxas lets lane 0 run the whole loop below on its own, apart from lanes 1..31 --
+        // every instruction of the second pass was issued twice per warp)
+        syncwarp();
     }
     // (a second pass over the staged samples: one loop with both the integer statistics and the double-precision
     // products needs more than the 80 registers six resident CTAs leave per thread, and ptxas spills in the loop)
