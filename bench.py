@@ -408,20 +408,85 @@ def run_ours(args):
     t_enc_m, t_dec_m, wall_m = [float(x) for x in tt.cpu()]
     value = 2.0 * raw * world * args.steps / (t_enc_m + t_dec_m) / 1e9
 
+    # ---- extra legs on one GPU: the other compression levels, and streams WITHOUT this library's frame-size table ----
+    extras = {}
+    if world == 1:
+        ns_x = min(n_stream, 250)
+        sub = data[:ns_x].reshape(-1)
+        qx = quanta[:ns_x]
+        lv = {}
+        for level in (0, 2, 5, 8):
+            best = 1e30
+            for rep in range(3):
+                a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+                a.record()
+                c_, s_, nb_, off_, gain_ = lf.encode_device(sub, ns_x, n_samp, level, qx)
+                b.record(); torch.cuda.synchronize()
+                if rep:
+                    best = min(best, a.elapsed_time(b))
+            lv[str(level)] = {"encode_gbs": ns_x * n_samp * 4 / best / 1e6, "ratio": c_.numel() / (ns_x * n_samp * 4)}
+            if level == 5:
+                keep5 = (c_, s_, nb_, off_, gain_)
+            del c_
+        extras["levels"] = {"streams": ns_x, "by_level": lv}
+        # foreign streams: the same level-5 bytes with the APPLICATION block (frame-size table "faB2") cut out, which is what
+        # libFLAC would have written: fLaC + STREAMINFO (now the last metadata block) + frames.  The decoder then finds
+        # the frames with its sync scan (k_dec_sync: FF F8 + header checks + CRC-8, decompress.c:274-299's job).
+        c5, s5, nb5, off5, gain5 = keep5
+        hs, hn = s5.cpu().numpy().reshape(-1), nb5.cpu().numpy().reshape(-1)
+        nf = -(-n_samp // 4096)
+        cut = 4 + 8 + 3 * nf                     # block header + "faB2" + frame count + 3 bytes per frame
+        fstarts = np.zeros(ns_x, np.int64); fn = hn - cut
+        fstarts[1:] = np.cumsum(fn)[:-1]
+        fcomp = torch.empty(int(fn.sum()), dtype=torch.uint8, device=dev)
+        for i in range(ns_x):
+            a0, o0 = int(hs[i]), int(fstarts[i])
+            fcomp[o0:o0 + 42] = c5[a0:a0 + 42]
+            fcomp[o0 + 4] |= 0x80            # STREAMINFO is the last metadata block now
+            fcomp[o0 + 42:o0 + int(fn[i])] = c5[a0 + 42 + cut:a0 + int(hn[i])]
+        fs_t = torch.from_numpy(fstarts).to(dev); fn_t = torch.from_numpy(fn).to(dev)
+        mxf, mx5 = int(fn.max()), int(hn.max())
+        res = {}
+        for name, (cc, ss, nn, mm) in {"table": (c5, s5, nb5, mx5), "foreign": (fcomp, fs_t, fn_t, mxf)}.items():
+            best = 1e30
+            for rep in range(3):
+                a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+                a.record()
+                o_ = lf.decode_device(cc, ss, nn, ns_x, n_samp, -1, -1, False, mm, 4096, off5, gain5)
+                b.record(); torch.cuda.synchronize()
+                if rep:
+                    best = min(best, a.elapsed_time(b))
+            res[name] = (best, o_)
+        if not torch.equal(res["table"][1], res["foreign"][1]):
+            raise SystemExit("bench: decode of the table-less streams differs from the table-indexed decode")
+        extras["decode_foreign_gbs"] = ns_x * n_samp * 4 / res["foreign"][0] / 1e6
+        extras["decode_table_gbs_same_sample"] = ns_x * n_samp * 4 / res["table"][0] / 1e6
+        del res, fcomp, keep5, c5
+
     # ---- e2e: public API with pinned host buffers, H2D + D2H inside the timed region ----
-    # pinned host memory per rank ~ 5 x the e2e array (input + two generations of results): keep the whole
-    # node below ~64 GB by shrinking the per-rank e2e array when more than two ranks share the host
-    e2e_streams = min(n_stream, args.e2e_streams if world <= 2 else max(64, (2 * args.e2e_streams) // world))
+    # pinned host memory per rank ~ 2.6 x the e2e array (input, compressed bytes, decoded output; the previous step's results
+    # are released before the next step so the pinned pool recycles them).  The array keeps its full size at every rank
+    # count as long as all ranks together stay below half of the host's available memory.
+    avail = 0
+    try:
+        with open("/proc/meminfo") as f:
+            for ln in f:
+                if ln.startswith("MemAvailable:"):
+                    avail = int(ln.split()[1]) * 1024
+    except OSError:
+        pass
+    per_stream = 2.6 * n_samp * 4
+    fit = int(0.5 * avail / world / per_stream) if avail else args.e2e_streams
+    e2e_streams = max(16, min(n_stream, args.e2e_streams, fit))
     host = torch.empty((e2e_streams, n_samp), dtype=torch.float32, pin_memory=True)
     host.copy_(data[:e2e_streams])
     torch.cuda.synchronize()
     host_np = host.numpy()
     e2e_raw = host_np.nbytes
-    # warm-up: two generations of result buffers, because a user's previous FlacArray / array is still
-    # alive while the next one is produced (the pinned host pool reaches its steady state)
-    far = fa.FlacArray.from_array(host_np, quanta=QUANTA)
-    back = far.to_array()
-    for _ in range(2):
+    # warm-up (the pinned host pool and the device pools reach their steady state)
+    far = back = None
+    for _ in range(3):
+        del far, back
         far = fa.FlacArray.from_array(host_np, quanta=QUANTA)
         back = far.to_array()
     barrier()
@@ -429,6 +494,7 @@ def run_ours(args):
     e2e_steps = max(1, min(args.steps, 3))
     h2d = d2h = 0
     for _ in range(e2e_steps):
+        del far, back
         far = fa.FlacArray.from_array(host_np, quanta=QUANTA)
         back = far.to_array()
         h2d += e2e_raw + far.nbytes
@@ -439,6 +505,34 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = 2.0 * e2e_raw * world * e2e_steps / float(te.item()) / 1e9
+    # ---- the copy ceiling of this box: every rank moves the same bytes per step over PCIe (pinned memory, both directions
+    #      at once, nothing else running) -- what e2e would be if the kernels and the host-side staging were free
+    far_nbytes = int(far.nbytes)
+    del far
+    dsrc = data[:e2e_streams]
+    back_t = torch.from_numpy(back) if isinstance(back, np.ndarray) else back
+    pinned_out = back_t if (not back_t.is_cuda and back_t.is_pinned()) else torch.empty_like(host)
+    s_up, s_dn = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    frac = far_nbytes / e2e_raw
+    rows_c = max(1, int(e2e_streams * frac))          # the compressed bytes, as rows of the same buffers
+    def copy_step():
+        with torch.cuda.stream(s_up):
+            dsrc.copy_(host, non_blocking=True)
+            dsrc[:rows_c].copy_(host[:rows_c], non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            pinned_out.view(-1)[:host.numel()].view_as(host).copy_(dsrc, non_blocking=True)
+            pinned_out.view(-1)[:rows_c * n_samp].view(rows_c, n_samp).copy_(dsrc[:rows_c], non_blocking=True)
+    copy_step(); barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        copy_step()
+    torch.cuda.synchronize()
+    t_copy = time.perf_counter() - t0
+    tc = torch.tensor([t_copy], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+    copy_ceiling = 2.0 * e2e_raw * world * e2e_steps / float(tc.item()) / 1e9
+    del back, back_t, pinned_out
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -488,9 +582,13 @@ def run_ours(args):
                                 "ms_per_launch": dec_ms / max(dec_n, 1)},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "GB/s", "h2d_bytes_per_step": h2d // e2e_steps,
-                    "d2h_bytes_per_step": d2h // e2e_steps, "streams": e2e_streams, "steps": e2e_steps},
+                    "d2h_bytes_per_step": d2h // e2e_steps, "streams": e2e_streams, "steps": e2e_steps,
+                    "copy_ceiling": copy_ceiling, "frac_of_copy_ceiling": e2e_value / copy_ceiling,
+                    "copy_ceiling_how": "same H2D + D2H bytes per step from / to pinned memory on two streams, all ranks at once, "
+                                        "no kernels, no staging"},
             "gpu_launches": launches, "clocks": clocks,
         }
+        line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

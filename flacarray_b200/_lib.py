@@ -88,6 +88,8 @@ def lib():
         L.fab_decode.argtypes = [_vp, _vp, _vp, _vp, _i64, _i64, _i32, _i64, _i64, _vp, _vp, _vp, _i64, _i32, _vp]
         L.fab_float_to_int.restype = _i32
         L.fab_float_to_int.argtypes = [_vp, _vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp, _vp]
+        L.fab_stream_std.restype = _i32
+        L.fab_stream_std.argtypes = [_vp, _vp, _i32, _i64, _i64, _vp, _vp]
         L.fab_int_to_float.restype = _i32
         L.fab_int_to_float.argtypes = [_vp, _vp, _i32, _i64, _i64, _vp, _vp, _vp, _vp]
         L.fab_profile.argtypes = [_vp, _i32]
@@ -104,7 +106,7 @@ EXPORTED = [
     "encode_i32", "encode_i32_threaded", "encode_i64", "encode_i64_threaded", "decode_i32", "decode_i64",
     "float32_to_int32", "float64_to_int64", "int64_to_float64", "int32_to_float32",
     "fab_create", "fab_destroy", "fab_last_error", "fab_launch_count", "fab_encode_bound", "fab_encode",
-    "fab_decode", "fab_float_to_int", "fab_int_to_float", "fab_finish", "fab_profile", "fab_profile_ms",
+    "fab_decode", "fab_stream_std", "fab_float_to_int", "fab_int_to_float", "fab_finish", "fab_profile", "fab_profile_ms",
 ]
 
 

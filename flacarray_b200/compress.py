@@ -8,7 +8,7 @@ a superset: an array of the leading shape is accepted.
 import numpy as np
 
 from .libflacarray import encode_flac, encode_flac_float, is_torch, np_dtype
-from .utils import function_timer, quanta_from_precision
+from .utils import function_timer
 
 
 @function_timer
@@ -43,10 +43,22 @@ def array_compress(arr, level=5, quanta=None, precision=None, use_threads=False)
             except TypeError:
                 dquanta = quanta * np.ones(leading_shape, dtype=dt)
         else:
-            dquanta = np.asarray(quanta_from_precision(arr, precision, leading_shape)).astype(dt)
+            # utils.py:282-296: the standard deviations are reduced on the device, inside the encode call (a host
+            # array crosses the bus once: every chunk of streams gets its quanta right before it is encoded)
+            dquanta = None
+            try:
+                len(precision)
+                if tuple(precision.shape) != leading_shape:
+                    msg = f"precision array ({precision}) has shape that does not "
+                    msg += f"match leading shape of data ({precision.shape} != "
+                    msg += f"{leading_shape})"
+                    raise RuntimeError(msg)
+            except TypeError:
+                pass
         if level < 0 or level > 8:
             raise RuntimeError("FLAC only supports compression levels 0-8")
-        compressed, starts, nbytes, foff, gains = encode_flac_float(arr, level, dquanta)
+        compressed, starts, nbytes, foff, gains = encode_flac_float(arr, level, dquanta,
+                                                                    precision=None if quanta is not None else precision)
         if len(leading_shape) == 0:
             foff, gains = foff.reshape((-1,)), gains.reshape((-1,))
         else:

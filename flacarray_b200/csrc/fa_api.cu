@@ -48,14 +48,19 @@ __global__ void __launch_bounds__(kEncThreads, 4) k_encode_short(const EncParams
 // sample statistics, fixed-predictor error sums and windowed autocorrelation of every (frame, channel)
 // (persistent CTAs: the thread's slice of the tukey window is loaded into shared memory once)
 #ifndef FAB_AN_CTAS
-#define FAB_AN_CTAS 6
+#define FAB_AN_CTAS 5     // (96 registers: no spills in the autocorrelation loop; 5 CTAs beat 6 with spills and 6 with 4-sample trips)
 #endif
 template <int H>
 __global__ void __launch_bounds__(kEncThreads, FAB_AN_CTAS) k_enc_analyze(const EncParams P) {
     __shared__ AnShared sh;
     analyze_fill_window(P, &sh);
     __syncthreads();
-    for (uint32_t g = P.g_begin + blockIdx.x; g < P.g_end; g += gridDim.x) analyze_frame_cta<H, true>(P, g, &sh);
+    for (uint32_t g = P.g_begin + blockIdx.x; g < P.g_end; g += gridDim.x) {
+#ifdef FAB_AN_PREFETCH    // (measured: pulling the next frame into the L2 costs 0.5 ms per 10^9 samples instead of saving any)
+        if (threadIdx.x == 0 && (uint64_t)g + gridDim.x < P.g_end) analyze_prefetch(P, g + gridDim.x);
+#endif
+        analyze_frame_cta<H, true>(P, g, &sh);
+    }
 }
 // ... and of the frames that are not full 4096-sample frames: the last frame of every stream (CTA i takes the
 // i-th such frame of the batch), or every frame of a blocksize-1152 level
@@ -82,14 +87,19 @@ __global__ void __launch_bounds__(kScanThreads) k_enc_scan(const EncParams P) {
 __global__ void __launch_bounds__(128) k_enc_compact(const EncParams P) {
     __shared__ uint16_t crc_tab[4 * 256];
     __shared__ uint16_t s11[2 * 256];     // multiply the state by x^(8 * 2048): tables of its high / low byte
+    __shared__ uint16_t shd[5 * 2 * 256]; // ... by x^(8 * 2^(4 + d)), d = 0 .. 4: [d][hi / lo][256]
     __shared__ CompactShared cs;
     for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) crc_tab[i] = P.crc->crc16[i >> 8][i & 255];
     for (int i = threadIdx.x; i < 2 * 256; i += blockDim.x)
         s11[i] = i < 256 ? P.crc->shift_hi[11][i] : P.crc->shift_lo[11][i - 256];
+    for (int i = threadIdx.x; i < 5 * 2 * 256; i += blockDim.x) {
+        const int d = i >> 9, lo = (i >> 8) & 1, b = i & 255;
+        shd[i] = lo ? P.crc->shift_lo[4 + d][b] : P.crc->shift_hi[4 + d][b];
+    }
     __syncthreads();
     const uint32_t n = P.g_end - P.g_begin;
     for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
-        compact_frame_cta(P, i, crc_tab, s11, s11 + 256, &cs);
+        compact_frame_cta(P, i, crc_tab, s11, s11 + 256, shd, &cs);
         __syncthreads();      // cs is reused by the next frame
     }
 }
@@ -101,7 +111,10 @@ __global__ void k_enc_finalize(const EncParams P, long long* __restrict__ nbytes
 }
 
 // ---- float -> int: per-stream min/max (utils.c:182-193 / :267-278), chunked over the stream ------
-constexpr int64_t kEncBatchBytes = 1ll << 29;   // slot scratch of one batch of encoder launches (two such buffers alternate)
+#ifndef FAB_ENC_BATCH_LOG2
+#define FAB_ENC_BATCH_LOG2 30
+#endif
+constexpr int64_t kEncBatchBytes = 1ll << FAB_ENC_BATCH_LOG2;   // slot scratch of one batch of encoder launches (two such buffers alternate)
 constexpr int kMmThreads = 256;
 constexpr int kMmChunk = 32768;  // elements per CTA
 
@@ -153,6 +166,58 @@ __global__ void k_quant_params(const T* __restrict__ pmin, const T* __restrict__
     }
     if constexpr (sizeof(T) == 4) quant_params_f32(mn, mx, quanta != nullptr, quanta ? quanta[s] : 0.f, &offsets[s], &gains[s]);
     else quant_params_f64(mn, mx, quanta != nullptr, quanta ? quanta[s] : 0., &offsets[s], &gains[s]);
+}
+
+// ---- `precision` -> quanta: per-stream population standard deviation (reference utils.py:282-296 calls
+// np.std(data, axis=-1)).  One read of the input: every CTA reduces a chunk to (mean, M2 = sum (x - mean)^2) in
+// double precision around a local shift (the chunk's first element), one thread per stream then merges the chunk
+// moments in chunk order (Chan et al.) -> sqrt(M2 / n), rounded to the storage type.
+template <typename T>
+__global__ void __launch_bounds__(kMmThreads) k_moments(const T* __restrict__ data, int64_t stream_size, int nchunk,
+                                                        double* __restrict__ pmean, double* __restrict__ pm2) {
+    const int64_t s = blockIdx.y;
+    const int c = blockIdx.x;
+    const int64_t lo = (int64_t)c * kMmChunk;
+    const int64_t hi = lo + kMmChunk < stream_size ? lo + kMmChunk : stream_size;
+    const T* p = data + s * stream_size;
+    const double K = (double)p[lo];
+    double s1 = 0.0, s2 = 0.0;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += kMmThreads) {
+        const double d = (double)p[i] - K;
+        s1 += d;
+        s2 = fma(d, d, s2);
+    }
+    __shared__ double sh1[kMmThreads / 32], sh2[kMmThreads / 32];
+    for (int m = 16; m >= 1; m >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, m);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, m);
+    }
+    if ((threadIdx.x & 31) == 0) { sh1[threadIdx.x >> 5] = s1; sh2[threadIdx.x >> 5] = s2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kMmThreads / 32; ++w) { s1 += sh1[w]; s2 += sh2[w]; }
+        const double n = (double)(hi - lo);
+        pmean[s * nchunk + c] = K + s1 / n;
+        pm2[s * nchunk + c] = s2 - s1 * s1 / n;
+    }
+}
+
+template <typename T>
+__global__ void k_std_final(const double* __restrict__ pmean, const double* __restrict__ pm2, int nchunk, int64_t stream_size,
+                            int64_t n_stream, T* __restrict__ out) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_stream) return;
+    double n = 0.0, mean = 0.0, m2 = 0.0;
+    for (int c = 0; c < nchunk; ++c) {
+        const int64_t lo = (int64_t)c * kMmChunk;
+        const double nb = (double)((lo + kMmChunk < stream_size ? lo + kMmChunk : stream_size) - lo);
+        const double mb = pmean[s * nchunk + c], qb = pm2[s * nchunk + c];
+        const double d = mb - mean, nt = n + nb;
+        mean += d * (nb / nt);
+        m2 += qb + d * d * (n * nb / nt);
+        n = nt;
+    }
+    out[s] = (T)sqrt(m2 > 0.0 ? m2 / n : 0.0);
 }
 
 template <typename T, typename I>
@@ -390,6 +455,10 @@ struct fab_ctx {
     // compaction of batch b under the analysis of batch b + 1); fork / join with events
     cudaStream_t aux = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
+    // third stream: the few frames that are not full (last frame of every stream) are analysed / encoded by their own
+    // small kernels next to the full-frame kernels of the same batch instead of behind them
+    cudaStream_t aux2 = nullptr;
+    cudaEvent_t ev_sfork = nullptr, ev_sjoin = nullptr;
     // optional per-kernel timing (bench.py's roofline): CUDA events on the launching stream
     bool prof = false;
     struct Pending { cudaEvent_t a, b; int which; };
@@ -486,7 +555,10 @@ extern "C" int fab_create(fab_ctx** out) {
               cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
               cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess &&
-              cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming) == cudaSuccess;
+              cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->aux2, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_sfork, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&ctx->ev_sjoin, cudaEventDisableTiming) == cudaSuccess;
     delete h;
     delete ht;
     if (!ok) {
@@ -512,6 +584,9 @@ extern "C" void fab_destroy(fab_ctx* ctx) {
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
     if (ctx->aux) cudaStreamDestroy(ctx->aux);
+    if (ctx->ev_sfork) cudaEventDestroy(ctx->ev_sfork);
+    if (ctx->ev_sjoin) cudaEventDestroy(ctx->ev_sjoin);
+    if (ctx->aux2) cudaStreamDestroy(ctx->aux2);
     delete ctx;
 }
 
@@ -609,7 +684,7 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
     }
     size_t desc_b = align256((size_t)(n_stream * nf) * 8), ends_b = align256((size_t)n_stream * 8);
     // the encoder kernels run over batches of (stream, frame) units so that the per-frame records and the
-    // slot buffers between them stay small (2 x 512 MB); one work counter per batch
+    // slot buffers between them stay bounded (2 x 1 GB); one work counter per batch
     const int64_t total_frames = n_stream * nf;
     const int64_t slot_bytes = (int64_t)((16 + 2 + (int64_t)nch * (lp.blocksize * 4 + 8) + 15) & ~15ll);
     const int64_t batch = std::min<int64_t>(total_frames, std::max<int64_t>(1024, kEncBatchBytes / slot_bytes));
@@ -689,45 +764,66 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
         // under the kernels of batch b + 1, which use the other slot / frame-size buffers; k_enc_analyze of batch
         // b + 2 parks samples in the slots batch b compacts from, so it waits for that compaction.
         if (bi >= 2) FAB_CUDA(ctx, cudaStreamWaitEvent(st, joins[bi & 1], 0));
+        // frames that are not full: every frame (blocksize 1152), or the last frame of each stream when the stream
+        // length is not a multiple of the blocksize
+        uint32_t first = P.g_begin, stride = 1;
+        int64_t cnt = nfr;
+        if (lp.blocksize == kMaxBs) {
+            cnt = 0;
+            if (stream_size % lp.blocksize != 0) {
+                stride = (uint32_t)nf;
+                const int64_t g_last = ((int64_t)P.g_begin / nf) * nf + (nf - 1);     // last frame of the batch's first stream
+                first = (uint32_t)g_last;
+                cnt = g_last < (int64_t)P.g_end ? ((int64_t)P.g_end - 1 - g_last) / nf + 1 : 0;
+            }
+        }
+        // (with full frames around, the short-frame kernels go to the third stream: latency-bound, a CTA per SM)
+#ifdef FAB_NO_SIDE
+        const bool side = false;
+#else
+        const bool side = lp.blocksize == kMaxBs && cnt > 0;
+#endif
+        cudaStream_t sst = side ? ctx->aux2 : st;
+        if (side) {
+            FAB_CUDA(ctx, cudaEventRecord(ctx->ev_sfork, st));
+            FAB_CUDA(ctx, cudaStreamWaitEvent(sst, ctx->ev_sfork, 0));
+        }
+        if (cnt > 0) {
+            const unsigned sgrid = (unsigned)std::min<int64_t>(cnt, (int64_t)ctx->n_sm * 8);
+            if (h12) k_enc_analyze_short<12><<<sgrid, kEncThreads, 0, sst>>>(P, first, stride);
+            else k_enc_analyze_short<8><<<sgrid, kEncThreads, 0, sst>>>(P, first, stride);
+            ctx->launches++;
+        }
         if (lp.blocksize == kMaxBs) {
             const unsigned agrid = (unsigned)std::min<int64_t>(nfr, (int64_t)ctx->n_sm * FAB_AN_CTAS);
             if (h12) k_enc_analyze<12><<<agrid, kEncThreads, 0, st>>>(P);
             else k_enc_analyze<8><<<agrid, kEncThreads, 0, st>>>(P);
             ctx->launches++;
         }
-        // frames that are not full: every frame (blocksize 1152), or the last frame of each stream when the stream
-        // length is not a multiple of the blocksize
-        uint32_t first = P.g_begin, stride = 1;
-        int64_t cnt = nfr;
-        {
-            if (lp.blocksize == kMaxBs) {
-                cnt = 0;
-                if (stream_size % lp.blocksize != 0) {
-                    stride = (uint32_t)nf;
-                    const int64_t g_last = ((int64_t)P.g_begin / nf) * nf + (nf - 1);     // last frame of the batch's first stream
-                    first = (uint32_t)g_last;
-                    cnt = g_last < (int64_t)P.g_end ? ((int64_t)P.g_end - 1 - g_last) / nf + 1 : 0;
-                }
-            }
-            if (cnt > 0) {
-                const unsigned sgrid = (unsigned)std::min<int64_t>(cnt, (int64_t)ctx->n_sm * 8);
-                if (h12) k_enc_analyze_short<12><<<sgrid, kEncThreads, 0, st>>>(P, first, stride);
-                else k_enc_analyze_short<8><<<sgrid, kEncThreads, 0, st>>>(P, first, stride);
-                ctx->launches++;
-            }
+        if (side) {
+            FAB_CUDA(ctx, cudaEventRecord(ctx->ev_sjoin, sst));
+            FAB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_sjoin, 0));
         }
         k_enc_design<<<(unsigned)((nfr * nch + 127) / 128), 128, 0, st>>>(P, nfr * nch);
+        if (side) {
+            FAB_CUDA(ctx, cudaEventRecord(ctx->ev_sfork, st));
+            FAB_CUDA(ctx, cudaStreamWaitEvent(sst, ctx->ev_sfork, 0));
+        }
+        if (cnt > 0) {
+            const unsigned sgrid = (unsigned)std::min<int64_t>(cnt, (int64_t)ctx->n_sm * 4);
+            if (h12) k_encode_short<12><<<sgrid, kEncThreads, smem, sst>>>(P, first, stride);
+            else k_encode_short<8><<<sgrid, kEncThreads, smem, sst>>>(P, first, stride);
+            ctx->launches++;
+        }
         if (lp.blocksize == kMaxBs) {
             unsigned grid = (unsigned)std::min<int64_t>(nfr, resident);
             if (h12) k_encode<12><<<grid, kEncThreads, smem, st>>>(P);
             else k_encode<8><<<grid, kEncThreads, smem, st>>>(P);
             ctx->launches++;
         }
-        if (cnt > 0) {
-            const unsigned sgrid = (unsigned)std::min<int64_t>(cnt, (int64_t)ctx->n_sm * 4);
-            if (h12) k_encode_short<12><<<sgrid, kEncThreads, smem, st>>>(P, first, stride);
-            else k_encode_short<8><<<sgrid, kEncThreads, smem, st>>>(P, first, stride);
-            ctx->launches++;
+        if (side) {
+            FAB_CUDA(ctx, cudaEventRecord(ctx->ev_sjoin, sst));
+            FAB_CUDA(ctx, cudaStreamWaitEvent(st, ctx->ev_sjoin, 0));
         }
         FAB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
         FAB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
@@ -877,6 +973,38 @@ extern "C" int fab_decode(fab_ctx* ctx, const unsigned char* d_bytes, const int6
 // =================================================================================================
 // Converters
 // =================================================================================================
+template <typename T>
+static int launch_stream_std(fab_ctx* ctx, const T* d_in, int64_t n_stream, int64_t stream_size, T* d_std, cudaStream_t st) {
+    int nchunk = (int)((stream_size + kMmChunk - 1) / kMmChunk);
+    unsigned char* scr;
+    const size_t part = align256((size_t)n_stream * nchunk * sizeof(double));
+    int rc = ctx_scratch(ctx, 2 * part, &scr);
+    if (rc) return rc;
+    double* pmean = (double*)scr;
+    double* pm2 = (double*)(scr + part);
+    for (int64_t s0 = 0; s0 < n_stream; s0 += 65535) {
+        int64_t ns = std::min<int64_t>(65535, n_stream - s0);
+        dim3 grid((unsigned)nchunk, (unsigned)ns);
+        k_moments<T><<<grid, kMmThreads, 0, st>>>(d_in + s0 * stream_size, stream_size, nchunk, pmean + s0 * nchunk, pm2 + s0 * nchunk);
+        ctx->launches++;
+    }
+    k_std_final<T><<<(unsigned)((n_stream + 127) / 128), 128, 0, st>>>(pmean, pm2, nchunk, stream_size, n_stream, d_std);
+    ctx->launches++;
+    FAB_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
+extern "C" int fab_stream_std(fab_ctx* ctx, const void* d_input, int dtype, int64_t n_stream, int64_t stream_size,
+                              void* d_std, void* stream) {
+    if (!ctx) return FAB_ERROR_CUDA;
+    if (n_stream == 0) return ERROR_ZERO_NSTREAM;
+    if (stream_size == 0) return ERROR_ZERO_STREAMSIZE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == FAB_F32) return launch_stream_std<float>(ctx, (const float*)d_input, n_stream, stream_size, (float*)d_std, st);
+    if (dtype == FAB_F64) return launch_stream_std<double>(ctx, (const double*)d_input, n_stream, stream_size, (double*)d_std, st);
+    return ERROR_CONVERT_TYPE;
+}
+
 extern "C" int fab_float_to_int(fab_ctx* ctx, const void* d_input, int dtype, int64_t n_stream, int64_t stream_size,
                                 const void* d_quanta, void* d_output, void* d_offsets, void* d_gains, void* stream) {
     if (!ctx) return FAB_ERROR_CUDA;

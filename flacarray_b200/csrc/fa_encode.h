@@ -230,10 +230,16 @@ struct EncHot {
     uint32_t tail_val[2][kEncThreads];
     uint16_t tail_word[2][kEncThreads];
     // the frame that is packed in `out` and waits to be retired (copy to its slot)
-    int prev_valid, prev_nbytes;
+    int prev_nbytes;
     uint32_t prev_g;
     uint32_t gq[2];     // tickets, fetched one frame ahead (the atomic's latency is off the critical path)
     int gq_f[2], gq_bs[2];   // ... with their frame number and blocksize (thread 0 does the divisions, also ahead)
+    // ... and with the frame's plans and the first 16 bytes of its prebuilt headers (both channels), copied in by
+    // thread 0 with cp.async one frame ahead: the ticket -> plan -> header chain of dependent global loads (three L2
+    // round trips in a row at the start of every frame) is off the critical path
+    alignas(16) U4 pf_plan[2][2][3];
+    alignas(16) U4 pf_hdr[2][2];
+    int prev_valid2[2];  // (frame pending in `out`, by iteration parity)
 };
 
 FA_HD size_t enc_out_words(int nch) { return ((size_t)nch * (kMaxBs * 4 + 64) + 64) / 4; }
@@ -856,7 +862,6 @@ struct EncCtx {
 // skip0: thread 0 takes no share of the work (it builds the next frame's header meanwhile)
 FA_D void retire_copyout(const EncParams& P, const EncCtx& X, bool skip0 = false) {
     const EncHot* hot = X.hot;
-    if (!hot->prev_valid) return;
     const int nthr = skip0 ? kEncThreads - 1 : kEncThreads;
     const int t = skip0 ? tid() - 1 : tid();
     const uint32_t* out = X.out;
@@ -932,10 +937,68 @@ FA_D void scan_batch_cta(const EncParams& P, unsigned long long* sh_part /*[kSca
 // chunks are loaded with one coalesced access each and RIGHT-aligned so that the last row is full; every
 // thread keeps a Horner accumulator over its column (rows are 2048 bytes apart: one step with the
 // shift tables S11), the 128 columns are combined by a butterfly of power-of-two shifts and the
-// (< 16) trailing bytes are appended.  T: [4][256] slice tables, S11hi / S11lo: state * x^(8 * 2048).
+// (< 16) trailing bytes are appended.  The same registers feed the copy: the destination is cut into ALIGNED
+// 16-byte blocks, block k = the last `a` bytes of chunk k - 1 (from the left neighbour lane) and the first 16 - a
+// bytes of chunk k, a = destination address mod 16, assembled with funnel shifts (AW = a / 4 selects the words at
+// compile time) and written with one 16-byte store; the (< 16) bytes before the first and the (< 32) bytes
+// behind the last aligned block are stored bytewise.
+// T: [4][256] slice tables, S11hi / S11lo: state * x^(8 * 2048), SH: [5][2][256] = state * x^(8 * 2^(4 + d)), hi / lo byte.
 struct CompactShared { uint32_t wcrc[4]; };
+FA_D U4 u4_zero_enc() { U4 z; z.x = z.y = z.z = z.w = 0; return z; }
+
+template <int AW>
+FA_D uint32_t compact_rows(const uint32_t* src, uint8_t* dst_al, uint32_t a, uint32_t n16, const uint16_t* T,
+                           const uint16_t* S11hi, const uint16_t* S11lo) {
+    const int t = tid(), ln = lane();
+    const uint32_t rows = (n16 + 127u) >> 7;
+    const uint32_t first = (rows << 7) - n16;     // threads below this have no chunk in row 0
+    const uint32_t sh = (a & 3u) ? 8u * (4u - (a & 3u)) : 32u;
+    const int64_t kb0 = a ? 1 : 0;                // first destination block that lies inside the frame
+    uint32_t c = 0;
+    int64_t ci = (int64_t)t - (int64_t)first;
+    U4 q = u4_zero_enc(), pq = u4_zero_enc();
+    if (ci >= 0) q = ldg128(src + (ci << 2));
+    if (ln == 0 && ci >= 1) pq = ldg128(src + ((ci - 1) << 2));     // lane 0's left neighbour sits in another warp
+#pragma unroll 2
+    for (uint32_t r = 0; r < rows; ++r) {
+        const int64_t cn = ci + 128;
+        U4 qn = u4_zero_enc(), pn = u4_zero_enc();
+        if (r + 1 < rows) {
+            qn = ldg128(src + (cn << 2));
+            if (ln == 0) pn = ldg128(src + ((cn - 1) << 2));
+        }
+        if (r > 0) c = (uint32_t)(S11hi[(c >> 8) & 0xFF] ^ S11lo[c & 0xFF]);
+        // words 3 - AW .. 3 of the chunk on the left
+        U4 p;
+        p.w = shfl_up(q.w, 1);
+        p.z = AW >= 1 ? shfl_up(q.z, 1) : 0u;
+        p.y = AW >= 2 ? shfl_up(q.y, 1) : 0u;
+        p.x = AW >= 3 ? shfl_up(q.x, 1) : 0u;
+        if (ln == 0) p = pq;
+        if (ci >= 0) {
+            uint32_t x = 0;
+            x = FAB_CRC_STEP0(T, x, bswap32(q.x));
+            x = FAB_CRC_STEP1(T, x, bswap32(q.y));
+            x = FAB_CRC_STEP0(T, x, bswap32(q.z));
+            x = FAB_CRC_STEP1(T, x, bswap32(q.w));
+            c ^= x;
+            if (ci >= kb0) {
+                const uint32_t W[8] = {p.x, p.y, p.z, p.w, q.x, q.y, q.z, q.w};
+                U4 o;
+                o.x = funnel_rc(W[3 - AW], W[4 - AW], sh);
+                o.y = funnel_rc(W[4 - AW], W[5 - AW], sh);
+                o.z = funnel_rc(W[5 - AW], W[6 - AW], sh);
+                o.w = funnel_rc(W[6 - AW], W[7 - AW], sh);
+                sts128(dst_al + 16 * ci, o);
+            }
+        }
+        q = qn; pq = pn; ci = cn;
+    }
+    return c;
+}
+
 FA_D void compact_frame_cta(const EncParams& P, uint32_t i, const uint16_t* T, const uint16_t* S11hi, const uint16_t* S11lo,
-                            CompactShared* cs) {
+                            const uint16_t* SH, CompactShared* cs) {
     const uint32_t g = P.g_begin + i;
     const uint32_t len = P.fsize[i];              // body + the two CRC bytes
     const unsigned long long end = P.desc[g];
@@ -945,59 +1008,41 @@ FA_D void compact_frame_cta(const EncParams& P, uint32_t i, const uint16_t* T, c
     }
     const uint32_t body = len - 2u;
     uint8_t* dst = P.out + (end - len);
-    const uint32_t* src = (const uint32_t*)(P.slots + (long long)i * P.slot_bytes);   // 16-byte aligned
+    const uint8_t* sb = P.slots + (long long)i * P.slot_bytes;      // 16-byte aligned
+    const uint32_t* src = (const uint32_t*)sb;
     const int t = tid(), ln = lane(), wp = warp();
-    // ---- CRC-16 of the body
-    {
-        const uint32_t n16 = body >> 4;
-        const uint32_t rows = (n16 + 127u) >> 7;
-        const uint32_t first = (rows << 7) - n16;     // threads below this have no chunk in row 0
-        uint32_t c = 0;
-        for (uint32_t r = 0; r < rows; ++r) {
-            const int64_t ci = (int64_t)(r << 7) + t - (int64_t)first;
-            if (r > 0) c = (uint32_t)(S11hi[(c >> 8) & 0xFF] ^ S11lo[c & 0xFF]);
-            if (ci >= 0) {
-                const U4 q = ldg128(src + (ci << 2));
-                uint32_t x = 0;
-                x = FAB_CRC_STEP0(T, x, bswap32(q.x));
-                x = FAB_CRC_STEP1(T, x, bswap32(q.y));
-                x = FAB_CRC_STEP0(T, x, bswap32(q.z));
-                x = FAB_CRC_STEP1(T, x, bswap32(q.w));
-                c ^= x;
-            }
-        }
-        // thread t's column value still has to move 16 * (127 - t) bytes: lanes first (groups of 1 .. 16), then warps
-        for (int d = 0; d < 5; ++d) {
-            const uint32_t u = shfl_xor(c, 1 << d);
-            if ((ln >> d) & 1) c ^= crc16_shift_pow2(P.crc, u, 4 + d);
-        }
-        if (ln == 31) cs->wcrc[wp] = c;
-        sync();
-        if (t == 0) {
-            uint32_t v = 0;
-            for (int w = 0; w < 4; ++w) v = crc16_shift_pow2(P.crc, v, 9) ^ cs->wcrc[w];     // warps are 512 bytes apart
-            const uint8_t* sb = (const uint8_t*)src;
-            for (uint32_t k = n16 << 4; k < body; ++k) v = crc16_b(T, v, sb[k]);
-            dst[body] = (uint8_t)(v >> 8);
-            dst[body + 1] = (uint8_t)v;
-        }
+    const uint32_t a = (uint32_t)((uintptr_t)dst & 15u);
+    uint8_t* dst_al = dst - a;
+    const uint32_t n16 = body >> 4;
+    uint32_t c;
+    switch (a >> 2) {
+        case 0: c = compact_rows<0>(src, dst_al, a, n16, T, S11hi, S11lo); break;
+        case 1: c = compact_rows<1>(src, dst_al, a, n16, T, S11hi, S11lo); break;
+        case 2: c = compact_rows<2>(src, dst_al, a, n16, T, S11hi, S11lo); break;
+        default: c = compact_rows<3>(src, dst_al, a, n16, T, S11hi, S11lo); break;
     }
-    // ---- the body bytes
-    const int nt = nthreads();
-    int head = (int)((4 - ((uintptr_t)dst & 3)) & 3);
-    if ((uint32_t)head > body) head = (int)body;
-    if (t < head) dst[t] = (uint8_t)(src[0] >> (8 * t));
-    const uint32_t nwords = (body - (uint32_t)head) >> 2;
-    uint32_t* dw = (uint32_t*)(dst + head);
-    const uint32_t sh8 = 8u * (uint32_t)head;     // source byte offset of dw[0] is `head` (0..3)
-    for (uint32_t w = (uint32_t)t; w < nwords; w += (uint32_t)nt) {
-        uint32_t a = src[w], b = head ? src[w + 1] : 0u;
-        dw[w] = head ? ((a >> sh8) | (b << (32u - sh8))) : a;
+    // thread t's column value still has to move 16 * (127 - t) bytes: lanes first (groups of 1 .. 16), then warps
+    for (int d = 0; d < 5; ++d) {
+        const uint32_t u = shfl_xor(c, 1 << d);
+        if ((ln >> d) & 1) c ^= (uint32_t)(SH[(2 * d) * 256 + ((u >> 8) & 0xFF)] ^ SH[(2 * d + 1) * 256 + (u & 0xFF)]);
     }
-    const uint32_t tail0 = (uint32_t)head + 4u * nwords;
-    if ((uint32_t)t < body - tail0) {
-        uint32_t k = tail0 + (uint32_t)t;
-        dst[k] = (uint8_t)(src[k >> 2] >> (8 * (k & 3)));
+    if (ln == 31) cs->wcrc[wp] = c;
+    // the bytes outside the aligned blocks: src [0, hb) in front, src [done, body) behind
+    const uint32_t h = a ? 16u - a : 0u;
+    const uint32_t hb = h < body ? h : body;
+    const uint32_t done = n16 > (a ? 1u : 0u) ? 16u * n16 - a : hb;
+    if ((uint32_t)t < hb) dst[t] = sb[t];
+    if (t >= 32 && t < 96) {
+        const uint32_t k = done + (uint32_t)(t - 32);
+        if (k < body) dst[k] = sb[k];
+    }
+    sync();
+    if (t == 0) {
+        uint32_t v = 0;
+        for (int w = 0; w < 4; ++w) v = crc16_shift_pow2(P.crc, v, 9) ^ cs->wcrc[w];     // warps are 512 bytes apart
+        for (uint32_t k = n16 << 4; k < body; ++k) v = crc16_b(T, v, sb[k]);
+        dst[body] = (uint8_t)(v >> 8);
+        dst[body + 1] = (uint8_t)v;
     }
 }
 
@@ -1268,24 +1313,20 @@ FA_D float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 FA_D float fabs32(float f) { return u2f(f2u(f) & 0x7FFFFFFFu); }
 
 // utils.c:232-240 for one sample without the double-precision detour.  For gain > 0 the reference's
-// (int)((double)y +- 0.5), y = gain * (x - off), is round-half-away-from-zero of the float y.  In single
-// precision y +- 0.5 is exact or rounds without crossing an integer for every |y| < 2^22 except
-// |y| = 0.5 - 2^-25 (checked over all 1.25e9 such floats), so a truncating conversion of that sum plus a guard
-// for |y| < 0.5 gives the same integer.  Wide values, NaN and non-positive gains take the reference's sequence.
+// (int)((double)y +- 0.5), y = gain * (x - off), is trunc(y +- 0.5) of the EXACT sum (the double add is exact for
+// 1 <= |y| < 2^22, and below 1 it is exact or nowhere near an integer).  A single-precision add that rounds towards
+// zero never crosses an integer on the way (an integer between the rounded and the exact sum would itself be a
+// float closer to the exact sum), so its truncation is the same integer (checked over all 2.5e9 floats |y| < 2^22);
+// the sign of y is the sign of x - off, and y = +-0 gives 0 either way.  Wide values, NaN and non-positive gains
+// take the reference's sequence.
 FA_D int32_t quant_f32_fast(float x, float off, float gain, bool gain_pos) {
     const float st = fsub(x, off);
     const float y = fmul(gain, st);
-    const float ay = fabs32(y);
-    if (gain_pos && ay < 4194304.0f) {
-        const float z = fadd(y, u2f((f2u(y) & 0x80000000u) | 0x3F000000u));
-        const int32_t i = (int32_t)z;
-        return ay < 0.5f ? 0 : i;
-    }
+    if (gain_pos && fabs32(y) < 4194304.0f) return trunc_fadd(y, u2f((f2u(y) & 0x80000000u) | 0x3F000000u));
     return quant_f32(x, off, gain);
 }
 
 FA_D U4 ld128(const void* p) { return lds128(p); }    // plain (coherent) 16-byte load, any address space
-FA_D U4 u4_zero_enc() { U4 z; z.x = z.y = z.z = z.w = 0; return z; }
 
 // Stage channel c of the frame; c == 0 converts the input (and parks every channel), c == 1 re-reads the high
 // words this thread parked a moment ago.
@@ -1459,33 +1500,48 @@ FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const FrameSrc&
     // (a second pass over the staged samples: one loop with both the integer statistics and the double-precision
     // products needs more than the 80 registers six resident CTAs leave per thread, and ptxas spills in the loop)
     if (do_lpc) {
+        // tukey(0.5) over 4096 samples is exactly 1.0f on samples 1023 .. 3072: warps 1 and 2 skip the table
+        const bool flat = wp == 1 || wp == 2;
+        // (nine accumulators, eight history values and the trip's eight samples as doubles need ~96 registers: at 80
+        // ptxas kept three accumulators in local memory, one spill access per sample.  Measured per 10^9 samples:
+        // 6 CTAs/SM with spills 7.98 ms, 6 CTAs with 4-sample trips 7.75, 5 CTAs with 8-sample trips 7.40)
+#ifndef FAB_AN_B2
+#define FAB_AN_B2 8
+#endif
+        constexpr int B2 = FAB_AN_B2;
 #pragma unroll 1
-        for (int it = 0; it < kSpt / B; ++it) {
-            int32_t x[B];
+        for (int it = 0; it < kSpt / B2; ++it) {
+            int32_t x[B2];
 #pragma unroll
-            for (int qq = 0; qq < B / 4; ++qq) {
-                const U4 v = lds128(stage + (((it * (B / 4) + qq) * kEncThreads + t) << 2));
+            for (int qq = 0; qq < B2 / 4; ++qq) {
+                const U4 v = lds128(stage + (((it * (B2 / 4) + qq) * kEncThreads + t) << 2));
                 x[4 * qq] = (int32_t)v.x; x[4 * qq + 1] = (int32_t)v.y; x[4 * qq + 2] = (int32_t)v.z; x[4 * qq + 3] = (int32_t)v.w;
             }
-            double cw[B];      // windowed samples of this trip
+            double cw[B2];      // windowed samples of this trip
+            if (flat) {
 #pragma unroll
-            for (int qq = 0; qq < B / 4; ++qq) {
-                const U4 w4 = lds128(sh->wqt + (((it * (B / 4) + qq) * kEncThreads + t) << 2));
-                cw[4 * qq] = (double)fmul((float)x[4 * qq], u2f(w4.x));
-                cw[4 * qq + 1] = (double)fmul((float)x[4 * qq + 1], u2f(w4.y));
-                cw[4 * qq + 2] = (double)fmul((float)x[4 * qq + 2], u2f(w4.z));
-                cw[4 * qq + 3] = (double)fmul((float)x[4 * qq + 3], u2f(w4.w));
+                for (int j = 0; j < B2; ++j) cw[j] = (double)(float)x[j];
+            } else {
+#pragma unroll
+                for (int qq = 0; qq < B2 / 4; ++qq) {
+                    const U4 w4 = lds128(sh->wqt + (((it * (B2 / 4) + qq) * kEncThreads + t) << 2));
+                    cw[4 * qq] = (double)fmul((float)x[4 * qq], u2f(w4.x));
+                    cw[4 * qq + 1] = (double)fmul((float)x[4 * qq + 1], u2f(w4.y));
+                    cw[4 * qq + 2] = (double)fmul((float)x[4 * qq + 2], u2f(w4.z));
+                    cw[4 * qq + 3] = (double)fmul((float)x[4 * qq + 3], u2f(w4.w));
+                }
             }
 #pragma unroll
-            for (int j = 0; j < B; ++j) {
+            for (int j = 0; j < B2; ++j) {
 #pragma unroll
                 for (int l = 0; l <= H; ++l) {
                     const double other = l <= j ? cw[j - l] : hw[l - j - 1];
                     ac[l] = dfma(cw[j], other, ac[l]);
                 }
             }
+            // history of the next trip: the trip's samples, then what remains of the old history
 #pragma unroll
-            for (int l = 1; l <= H; ++l) hw[l - 1] = cw[B - l];
+            for (int l = H; l >= 1; --l) hw[l - 1] = l <= B2 ? cw[B2 - l] : hw[l - 1 - B2];
         }
     }
 
@@ -1599,6 +1655,17 @@ FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const FrameSrc&
         st->mode = mode; st->wasted = wasted; st->mn = a >> wasted; st->mx = b >> wasted; st->bad = tb; st->pad = 0;
     }
     sync();   // the partials and the staged channel are reused by the next channel / frame
+}
+
+// One thread: pull full frame g of the input towards the L2 (the CTA that will analyse it is busy with another frame).
+FA_D void analyze_prefetch(const EncParams& P, uint32_t g) {
+    const int64_t s = (int64_t)(g / (uint32_t)P.nframes);
+    const int f = (int)(g % (uint32_t)P.nframes);
+    const int64_t samp0 = (int64_t)f * P.blocksize;
+    if (P.stream_size - samp0 < P.blocksize) return;
+    const int esize = (P.dtype == kI32 || P.dtype == kF32) ? 4 : 8;
+    const unsigned char* base = (const unsigned char*)P.data + (s * P.stream_size + samp0) * esize;
+    if (((uintptr_t)base & 15) == 0) prefetch_l2_bulk(base, (uint32_t)(P.blocksize * esize));
 }
 
 // FULL: the caller is the kernel for full (4096-sample) frames and skips every other frame; !FULL: the kernel for the
@@ -2143,7 +2210,7 @@ FA_D void residual_dispatch(int32_t* buf, EncHot* hot, const int32_t* park, int 
 // park: the channel's parked samples in HBM (16-byte aligned)
 template <int H>
 FA_D bool enc_channel_full(const EncParams& P, EncCtx& X, const int32_t* park, int c, int f, uint32_t g, int bitpos0,
-                           int& bitpos_end) {
+                           int& bitpos_end, int slot) {
     EncHot* hot = X.hot;
     uint32_t* out = X.out;
     int32_t* res = X.res;
@@ -2152,14 +2219,16 @@ FA_D bool enc_channel_full(const EncParams& P, EncCtx& X, const int32_t* park, i
     constexpr int bs = kMaxBs;
     // ---- the channel's samples: one TMA copy into the sample buffer.  Every thread is done with the buffer's
     //      previous contents: channel 0 starts behind the barrier at the top of the CTA loop
-    if (c > 0) sync();
-    if (t == 0) {
-        fence_proxy_async();
-        bulk_load(res, park, (uint32_t)(kMaxBs * 4), &hot->mbar);
+    //      (channel 0's copy was started by the caller, ahead of the copy-out of the previous frame)
+    if (c > 0) {
+        sync();
+        if (t == 0) {
+            fence_proxy_async();
+            bulk_load(res, park, (uint32_t)(kMaxBs * 4), &hot->mbar);
+        }
     }
-    // ---- the plan of this (frame, channel): three broadcast loads, decoded in registers
-    const unsigned char* pp = (const unsigned char*)(P.plans + ((size_t)(g - P.g_begin) * P.nch + c));
-    const U4 pa = ldg128(pp), pb = ldg128(pp + 16), pc = ldg128(pp + 32);
+    // ---- the plan of this (frame, channel): prefetched into shared memory one frame ahead, decoded in registers
+    const U4 pa = lds128(&hot->pf_plan[slot][c][0]), pb = lds128(&hot->pf_plan[slot][c][1]), pc = lds128(&hot->pf_plan[slot][c][2]);
     const int mode = (int)(pa.x & 0xFFu);
     const int wasted = (int)((pa.x >> 8) & 0xFFu);
     const int bps = 32 - wasted;
@@ -2169,7 +2238,6 @@ FA_D bool enc_channel_full(const EncParams& P, EncCtx& X, const int32_t* park, i
     const bool wide = mode == 3;
     const bool wide1 = wide || (pa.z & 0xFFu) != 0;
     const uint32_t fixed_bits = pc.z;
-    const bool retiring = !X.retired;
     FAB_TICK(1);
     mbar_wait(&hot->mbar, X.tma_phase);
     X.tma_phase ^= 1u;
@@ -2177,12 +2245,6 @@ FA_D bool enc_channel_full(const EncParams& P, EncCtx& X, const int32_t* park, i
     if (mode == 0) return false;     // (the copy has landed: the general path may reuse the buffer)
 
     if (mode == 1) {
-        if (retiring) {
-            sync();
-            retire_copyout(P, X);
-            sync();
-            X.retired = true;
-        }
         bitpos_end = bitpos0 + (c == 0 ? 8 * frame_header_bytes(bs, f) : 0) + subframe_header_bits(0, 0, 0, 32, 0);
         if (t == 0) {
             Pk pk;
@@ -2239,7 +2301,7 @@ FA_D bool enc_channel_full(const EncParams& P, EncCtx& X, const int32_t* park, i
             if (ln == 0) { hot->x_bits[pass & 1][wp] = bsum; hot->x_sum[pass & 1][wp] = ts; hot->x_flag[pass & 1][wp] = fl; }
         }
         FAB_TICK(4);
-        sync();   // B3: the partials are visible (and the tail ORs of the previous frame are ordered before its copy-out)
+        sync();   // B3: the partials are visible
         FAB_TICK(5);
         // every thread: partition order (maximum or 0) and size of the subframe; all inputs are block-uniform
         uint32_t bits_hi = 0, flag = 0;
@@ -2274,11 +2336,10 @@ FA_D bool enc_channel_full(const EncParams& P, EncCtx& X, const int32_t* park, i
     const int skip = t == 0 ? order : 0;
     const int ptype = cand == 0 ? 2 : 3;
     const int prec = cand == 0 ? 0 : prec1;
-    // ---- previous frame: copy to its slot.  This channel's header: the bit string k_enc_design prepared (every
-    //      thread fetches "its" word of it now and stores it behind B5); without one, thread 0 emits the fields into
-    //      hdr_tmp while threads 1..127 do the copying
+    // ---- this channel's header: the bit string k_enc_design prepared (every thread fetches "its" word of it now and
+    //      stores it behind B5); without one, thread 0 emits the fields into hdr_tmp
     const PlanHeader* ph = P.hdrs + ((size_t)(g - P.g_begin) * P.nch + c);
-    const uint32_t hn = P.hdrs != nullptr ? ldg32(cand ? &ph->nbits_lpc : &ph->nbits_fix) : 0u;     // (block-uniform)
+    const uint32_t hn = P.hdrs != nullptr ? (cand ? hot->pf_hdr[slot][c].x : hot->pf_hdr[slot][c].y) : 0u;     // (block-uniform)
     const bool pre = hn != 0;
     const uint32_t* hwords = cand ? ph->lpc : ph->fix;
     const uint32_t hs = (uint32_t)bitpos0 & 31u;
@@ -2288,7 +2349,6 @@ FA_D bool enc_channel_full(const EncParams& P, EncCtx& X, const int32_t* park, i
         const uint32_t b = ldg32(hwords + t), a = t > 0 ? ldg32(hwords + t - 1) : 0u;
         hval = hs ? funnel_r(b, a, hs) : b;
     }
-    if (retiring) retire_copyout(P, X, !pre);
     Pk pk;
     int hdr_words = 0;
     if (t == 0 && !pre) {
@@ -2337,9 +2397,8 @@ FA_D bool enc_channel_full(const EncParams& P, EncCtx& X, const int32_t* park, i
     }
     if (ln == 31) hot->scan[wp] = inc;
     FAB_TICK(7);
-    sync();   // B5: also orders the copy-out of the previous frame before the packing stores below
+    sync();   // B5
     FAB_TICK(8);
-    if (retiring) X.retired = true;
     uint32_t wbase = 0, total = 0;
 #pragma unroll
     for (int w = 0; w < kEncWarps; ++w) {
@@ -2723,6 +2782,23 @@ FA_D void enc_set_ticket(const EncParams& P, EncHot* hot, int slot, uint64_t g64
     hot->gq_bs[slot] = (int)(left < P.blocksize ? left : P.blocksize);
 }
 
+// Thread 0: the plans and the head of the prebuilt headers of the ticket in `slot` -> shared memory (cp.async: no register
+// is waited for; completion is collected before the next top-of-loop barrier).
+FA_D void enc_prefetch_plans(const EncParams& P, EncHot* hot, int slot) {
+    const uint32_t g = hot->gq[slot];
+    if (g < P.g_end) {
+        for (int c = 0; c < P.nch; ++c) {
+            const size_t r = (size_t)(g - P.g_begin) * P.nch + c;
+            const unsigned char* pp = (const unsigned char*)(P.plans + r);
+            cp_async16(&hot->pf_plan[slot][c][0], pp);
+            cp_async16(&hot->pf_plan[slot][c][1], pp + 16);
+            cp_async16(&hot->pf_plan[slot][c][2], pp + 32);
+            if (P.hdrs != nullptr) cp_async16(&hot->pf_hdr[slot][c], P.hdrs + r);
+        }
+    }
+    cp_async_commit();
+}
+
 // Where the samples of (stream, frame) unit g come from (short-frame and general paths; full frames read the
 // integers k_enc_analyze parked).
 FA_D FrameSrc enc_frame_src(const EncParams& P, uint32_t g, int f, int bs) {
@@ -2765,33 +2841,43 @@ FA_D void encode_frames_cta(const EncParams& P, unsigned char* smem_raw, uint32_
     uint64_t g_mine = (uint64_t)first + (uint64_t)blockIdx_x() * stride;      // (!FULLK)
     if (t == 0) {
         mbar_init(&hot->mbar, 1);
-        hot->prev_valid = 0;
-        if (FULLK) enc_fetch_ticket(P, hot, 0);
+        hot->prev_valid2[0] = hot->prev_valid2[1] = 0;
+        if (FULLK) { enc_fetch_ticket(P, hot, 0); enc_prefetch_plans(P, hot, 0); }
         else enc_set_ticket(P, hot, 0, g_mine);
     }
     hot->tail_val[0][t] = 0; hot->tail_val[1][t] = 0;
 
+    // Per iteration: [top barrier] start the TMA copy of this frame's samples -> copy the previous frame (packed in
+    // `out`) to its slot while that copy is in flight -> residuals, Rice parameters, packing -> [barrier] OR the
+    // trailing partial words of the packing sessions into the staged frame.
     for (int iter = 0;; ++iter) {
+        const int slot = iter & 1;
         // ---- work assignment: dynamic tickets (any order: every frame has its own output slot)
         FAB_TICK(10);
-        sync();   // also: every thread has finished packing the previous frame (all plain stores done)
+        if (FULLK && t == 0) cp_async_wait_all();      // this frame's plans (prefetched during the previous iteration)
+        sync();   // the previous frame is complete in `out` (packing + tail ORs); nobody reads the sample buffer any more
         FAB_TICK(0);
-        const uint32_t g = hot->gq[iter & 1];
-        const int f = hot->gq_f[iter & 1], bs = hot->gq_bs[iter & 1];
+        const uint32_t g = hot->gq[slot];
+        const int f = hot->gq_f[slot], bs = hot->gq_bs[slot];
+        const bool mine = g < total_frames && ((bs == kMaxBs) == FULLK);
         if (FULLK) {
-            if (t == 0) enc_fetch_ticket(P, hot, (iter + 1) & 1);   // for the next iteration
+            if (t == 0) {
+                if (mine) {
+                    fence_proxy_async();
+                    bulk_load(X.res, P.slots + (int64_t)(g - P.g_begin) * P.slot_bytes, (uint32_t)(kMaxBs * 4), &hot->mbar);
+                }
+                enc_fetch_ticket(P, hot, slot ^ 1);     // for the next iteration
+                enc_prefetch_plans(P, hot, slot ^ 1);
+            }
         } else {
             g_mine += (uint64_t)gridDim_x() * stride;
-            if (t == 0) enc_set_ticket(P, hot, (iter + 1) & 1, g_mine);
+            if (t == 0) enc_set_ticket(P, hot, slot ^ 1, g_mine);
         }
-        // trailing partial words of the previous frame's packing sessions
-        for (int c = 0; c < nch; ++c) {
-            uint32_t tv = hot->tail_val[c][t];
-            if (tv) { atom_or_shared(&X.out[ow(hot->tail_word[c][t])], tv); hot->tail_val[c][t] = 0; }
-        }
-        X.retired = false;
+        if (hot->prev_valid2[slot]) retire_copyout(P, X);
+        if (t == 0) hot->prev_valid2[slot ^ 1] = 0;    // (last read one top barrier ago)
+        X.retired = true;
         if (g >= total_frames) break;
-        if ((bs == kMaxBs) != FULLK) continue;      // the other kernel's frame (the pending frame, if any, stays pending)
+        if (!mine) continue;      // the other kernel's frame
 
         int bitpos = 0;
         for (int c = 0; c < nch; ++c) {
@@ -2801,28 +2887,26 @@ FA_D void encode_frames_cta(const EncParams& P, unsigned char* smem_raw, uint32_
                 // planar int32 samples parked by k_enc_analyze in this frame's slot (the compressed frame only
                 // replaces them when the frame is retired, one iteration from now)
                 const int32_t* park = (const int32_t*)(P.slots + (int64_t)(g - P.g_begin) * P.slot_bytes) + (int64_t)c * kMaxBs;
-                done = enc_channel_full<H>(P, X, park, c, f, g, bitpos, bend);
+                done = enc_channel_full<H>(P, X, park, c, f, g, bitpos, bend, slot);
             } else if (bs >= 64) {
-                // (the short path retires the previous frame on every return: its plans never have mode 0)
                 bend = enc_channel_short<H>(P, X, enc_frame_src(P, g, f, bs), c, f, g, bitpos);
                 done = bend >= 0;
-                X.retired = true;
             }
-            if (!done) {
-                bend = enc_channel_general(P, X, enc_frame_src(P, g, f, bs), c, f, g, bitpos);
-                X.retired = true;
-            }
+            if (!done) bend = enc_channel_general(P, X, enc_frame_src(P, g, f, bs), c, f, g, bitpos);
             bitpos = bend;
         }
-        // the frame now waits in `out`; it is retired during the next iteration (or the drain below).
-        // The writes below are ordered before their readers by the barrier at the top of the loop.
+        // the frame now waits in `out`; it is copied to its slot at the top of the next iteration
         if (t == 0) {
             if (bitpos & 31) X.out[ow(bitpos >> 5)] = 0;   // final partial word: nobody plain-stores it, tails are OR-ed in
-            hot->prev_valid = 1; hot->prev_g = g; hot->prev_nbytes = (bitpos + 7) >> 3;
+            hot->prev_valid2[slot ^ 1] = 1; hot->prev_g = g; hot->prev_nbytes = (bitpos + 7) >> 3;
+        }
+        sync();   // B6: every plain store of the packing sessions (and the word zeroed above) is in place
+        // trailing partial words of the packing sessions
+        for (int c = 0; c < nch; ++c) {
+            uint32_t tv = hot->tail_val[c][t];
+            if (tv) { atom_or_shared(&X.out[ow(hot->tail_word[c][t])], tv); hot->tail_val[c][t] = 0; }
         }
     }
-    // ---- drain: the last frame of this CTA (its tails were OR-ed in above)
-    retire_full(P, X);
 #if defined(FAB_PHASE_TIMING) && defined(__CUDACC__)
     if ((blockIdx.x == 7 || blockIdx.x == 300) && (t == 0 || t == 37 || t == 127 || t == 96))
         printf("cta %d t %d: top %lld | plan %lld tma %lld resid %lld est %lld B3 %lld hdr/copy %lld lens %lld B5 %lld pack %lld rest %lld\n",

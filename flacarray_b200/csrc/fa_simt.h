@@ -44,6 +44,7 @@ FA_D uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelsh
 FA_D uint32_t funnel_lc(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_lc(lo, hi, s); }
 // lower word of (hi:lo) >> (s & 31)
 FA_D uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_r(lo, hi, s); }
+FA_D uint32_t funnel_rc(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_rc(lo, hi, s); }   // s >= 32 -> hi
 FA_D void atom_or_shared(uint32_t* p, uint32_t v) { atomicOr(p, v); }
 FA_D void atom_add_shared64(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }
 FA_D void atom_or_shared_u32(uint32_t* p, uint32_t v) { atomicOr(p, v); }
@@ -99,6 +100,10 @@ FA_D void mbar_wait(unsigned long long* bar, uint32_t parity) {
                      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     } while (!ok);
 }
+// one thread: ask the L2 for `bytes` (a multiple of 16) from a 16-byte aligned global address; no destination, no wait
+FA_D void prefetch_l2_bulk(const void* gsrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
 FA_D uint32_t ldg32(const uint32_t* p) { return __ldg(p); }
 struct U4 { uint32_t x, y, z, w; };
 FA_D U4 ldg128(const void* p) {  // 16-byte aligned, read-only path
@@ -122,6 +127,8 @@ FA_D void st_global_u8x2(uint8_t* p, uint32_t hi, uint32_t lo) { p[0] = (uint8_t
 FA_D float fadd(float a, float b) { return __fadd_rn(a, b); }
 FA_D float fsub(float a, float b) { return __fsub_rn(a, b); }
 FA_D float fmul(float a, float b) { return __fmul_rn(a, b); }
+// trunc(a + b) of the exact sum, for |a + b| < 2^31: the round-towards-zero add never crosses an integer
+FA_D int32_t trunc_fadd(float a, float b) { return __float2int_rz(__fadd_rz(a, b)); }
 FA_D float fdiv(float a, float b) { return __fdiv_rn(a, b); }
 FA_D double dadd(double a, double b) { return __dadd_rn(a, b); }
 FA_D double dsub(double a, double b) { return __dsub_rn(a, b); }
@@ -244,6 +251,10 @@ inline uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {
     s &= 31;
     return s ? (lo >> s) | (hi << (32 - s)) : lo;
 }
+inline uint32_t funnel_rc(uint32_t lo, uint32_t hi, uint32_t s) {
+    if (s >= 32) return hi;
+    return s ? (lo >> s) | (hi << (32 - s)) : lo;
+}
 inline void atom_or_shared(uint32_t* p, uint32_t v) { __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
 inline void atom_add_shared64(unsigned long long* p, unsigned long long v) { __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 inline uint32_t atom_add_global(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
@@ -274,6 +285,7 @@ inline void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, unsigned
 inline void mbar_wait(unsigned long long* bar, uint32_t parity) {
     while ((__atomic_load_n(bar, __ATOMIC_ACQUIRE) & 1ull) == (unsigned long long)parity) std::this_thread::yield();
 }
+inline void prefetch_l2_bulk(const void*, uint32_t) {}
 inline uint32_t ldg32(const uint32_t* p) { return *p; }
 struct U4 { uint32_t x, y, z, w; };
 inline U4 ldg128(const void* p) { U4 r; memcpy(&r, p, 16); return r; }
@@ -305,6 +317,7 @@ inline void st_global_u8x2(uint8_t* p, uint32_t hi, uint32_t lo) { p[0] = (uint8
 inline float fadd(float a, float b) { return a + b; }
 inline float fsub(float a, float b) { return a - b; }
 inline float fmul(float a, float b) { return a * b; }
+inline int32_t trunc_fadd(float a, float b) { return (int32_t)((double)a + (double)b); }
 inline float fdiv(float a, float b) { return a / b; }
 inline double dadd(double a, double b) { return a + b; }
 inline double dsub(double a, double b) { return a - b; }

@@ -134,6 +134,78 @@ def _float_to_int(flatdata, n_stream, stream_size, quanta, fdt, idt, check_nan=F
     return to_host(out), to_host(off), to_host(gain)
 
 
+def stream_std_device(d, n_stream, stream_size):
+    """Population standard deviation of every stream of a CUDA tensor [n_stream * stream_size] (float32 /
+    float64), as a CUDA tensor of the same dtype: the device side of `precision` -> quanta (reference
+    utils.py:282-296, np.std(data, axis=-1)).  One read of the input, double-precision moments."""
+    dev = d.device
+    fdt = np.dtype(np.float32) if d.dtype == torch.float32 else np.dtype(np.float64)
+    with torch.cuda.device(dev):
+        ctx = _lib.context(dev)
+        out = torch.empty(n_stream, dtype=d.dtype, device=dev)
+        st = _stream(dev)
+        rc = _lib.lib().fab_stream_std(ctx.handle, _ptr(d), _FAB[fdt], n_stream, stream_size, _ptr(out), st)
+        if rc != 0:
+            _check(rc, ctx, st, "Standard deviation")
+    return out
+
+
+def stream_std(data):
+    """np.std(data, axis=-1) on the device.  CUDA tensors are reduced in place; host arrays are staged through
+    the device in chunks of whole streams (pinned double buffers), which beats a single-core host pass for anything
+    but small arrays.  Returns a numpy array with the leading shape of `data`."""
+    dt = np_dtype(data)
+    shape = tuple(data.shape)
+    stream_size = shape[-1]
+    lead = shape[:-1]
+    n_stream = 1 if len(lead) == 0 else int(np.prod(lead))
+    tdt = _NP2TORCH[dt]
+    if is_torch(data) and data.is_cuda:
+        d = data.reshape((-1,))
+        if not d.is_contiguous():
+            d = d.contiguous()
+        return to_host(stream_std_device(d, n_stream, stream_size)).reshape(lead)
+    dev = _device()
+    src = _as_host_tensor(data.numpy() if is_torch(data) else data).view(n_stream, stream_size)
+    ranges = _chunk_ranges(n_stream, stream_size * src.element_size())
+    if len(ranges) == 1:
+        d = src.to(dev, non_blocking=True)
+        return to_host(stream_std_device(d.view(-1), n_stream, stream_size)).reshape(lead)
+    with torch.cuda.device(dev):
+        cur = torch.cuda.current_stream(dev)
+        s_in, _ = _side_streams(dev)
+
+        def prep(feed, i):
+            a, b = ranges[i]
+            dc = torch.empty((b - a, stream_size), dtype=tdt, device=dev)
+            feed.copy(dc, src[a:b])
+            e = torch.cuda.Event()
+            e.record(s_in)
+            return dc, e
+
+        parts = []
+        for (a, b), (dc, ev) in zip(ranges, _Feeder(dev, s_in, prep, len(ranges))):
+            cur.wait_event(ev)
+            dc.record_stream(cur)
+            parts.append(stream_std_device(dc.view(-1), b - a, stream_size))
+            del dc
+        return to_host(torch.cat(parts)).reshape(lead)
+
+
+def quanta_from_std(rms, precision):
+    """rms / 10**precision, the reference's expression (utils.py:285-296) evaluated by numpy on the host so that the
+    quanta are bit-identical to what the reference derives from the same standard deviations (a scalar precision
+    keeps the storage type of the data, an array of precisions goes through float64; torch's division by a scalar
+    multiplies by the reciprocal and is 1 ulp off).  `rms`: numpy array or torch tensor (n_stream values cross the bus)."""
+    if is_torch(rms):
+        rms = to_host(rms)
+    try:
+        len(precision)
+    except TypeError:
+        return rms / 10**precision
+    return rms / 10 ** np.asarray(precision).reshape(rms.shape)
+
+
 def wrap_float32_to_int32(flatdata, n_stream, stream_size, quanta, check_nan=False):
     """pyx:113-161.  Returns (int32 flat, offsets float32[n], gains float32[n])."""
     return _float_to_int(flatdata, n_stream, stream_size, quanta, np.dtype(np.float32), np.dtype(np.int32), check_nan)
@@ -425,8 +497,12 @@ def _as_host_tensor(a):
     return torch.from_numpy(a)
 
 
-def _encode_host(flat, n_stream, stream_size, level, quanta, dt):
-    """numpy [n_stream * stream_size] -> (compressed u8 numpy, starts, nbytes, offsets, gains) (numpy)."""
+def _encode_host(flat, n_stream, stream_size, level, quanta, dt, precision=None):
+    """numpy [n_stream * stream_size] -> (compressed u8 numpy, starts, nbytes, offsets, gains) (numpy).
+
+    precision (scalar or one value per stream, float input only): the quanta of every chunk of streams are derived
+    on the device from the chunk's standard deviations right before it is encoded, so the host array crosses the
+    bus once."""
     dev = _device()
     tdt = _NP2TORCH[dt]
     src = _as_host_tensor(flat)
@@ -438,9 +514,20 @@ def _encode_host(flat, n_stream, stream_size, level, quanta, dt):
     q = None
     if quanta is not None:
         q = to_device(quanta, dev, tdt)
+    def chunk_quanta(dc, a, b):
+        if precision is None:
+            return None if q is None else q[a:b]
+        pr = precision
+        try:
+            len(precision)
+            pr = np.asarray(precision).reshape(-1)[a:b]
+        except TypeError:
+            pass
+        return to_device(np.asarray(quanta_from_std(stream_std_device(dc.view(-1), b - a, stream_size), pr)).astype(dt), dev, tdt)
+
     if len(ranges) == 1:
         d = src.to(dev, non_blocking=True)
-        comp, starts, nbytes, off, gain = encode_device(d.view(-1), n_stream, stream_size, level, q)
+        comp, starts, nbytes, off, gain = encode_device(d.view(-1), n_stream, stream_size, level, chunk_quanta(d, 0, n_stream))
         return (to_host(comp), to_host(starts), to_host(nbytes), None if off is None else to_host(off),
                 None if gain is None else to_host(gain))
     with torch.cuda.device(dev):
@@ -465,7 +552,7 @@ def _encode_host(flat, n_stream, stream_size, level, quanta, dt):
             cur.wait_event(ev)
             dc.record_stream(cur)
             out, starts, nbytes, tot, off, gain = _encode_device_raw(dc.view(-1), b - a, stream_size, level,
-                                                                     None if q is None else q[a:b])
+                                                                     chunk_quanta(dc, a, b))
             del dc                # input chunk can go back to the pool
             if host is None:
                 # capacity from the first chunk's ratio (+3 %); a wrong guess grows the buffer below
@@ -750,12 +837,13 @@ def decode_flac(compressed, starts, nbytes, stream_size, first_sample=-1, last_s
 # Fused entry points used by compress.py / decompress.py (no integer intermediate in host memory)
 # -------------------------------------------------------------------------------------------------
 
-def encode_flac_float(data, level, quanta):
+def encode_flac_float(data, level, quanta, precision=None):
     """float32/float64 [..., stream_size] -> (compressed, starts, nbytes, offsets, gains).
 
     Equivalent to utils.float_to_int (utils.c:160-328) followed by encode_flac, with the quantisation
     fused into the encoder's frame load.  `quanta`: None (derive from the data range) or an array with
-    one value per stream.
+    one value per stream.  `precision` (instead of quanta; scalar or one value per stream): quanta =
+    std(stream) / 10**precision (utils.py:282-296) with the standard deviation reduced on the device.
     """
     dt = np_dtype(data)
     shape = tuple(data.shape)
@@ -772,9 +860,12 @@ def encode_flac_float(data, level, quanta):
     if not on_dev:
         if is_torch(data):
             data = data.numpy()
-        comp, starts, nbytes, off, gain = _encode_host(data.reshape((-1,)), n_stream, stream_size, int(level), quanta, dt)
+        comp, starts, nbytes, off, gain = _encode_host(data.reshape((-1,)), n_stream, stream_size, int(level), quanta, dt,
+                                                       precision=precision)
         return comp, starts.reshape(lead), nbytes.reshape(lead), off, gain
     d = to_device(data.reshape((-1,)), dtype=_NP2TORCH[dt])
+    if precision is not None:
+        quanta = np.asarray(quanta_from_std(stream_std_device(d, n_stream, stream_size), precision)).astype(dt).reshape(-1)
     q = None if quanta is None else to_device(quanta, d.device, _NP2TORCH[dt])
     comp, starts, nbytes, off, gain = encode_device(d, n_stream, stream_size, int(level), q)
     return comp, starts.reshape(lead), nbytes.reshape(lead), off, gain

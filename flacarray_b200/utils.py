@@ -97,12 +97,12 @@ def compressed_dtype(n_channel, offsets, gains):
 
 
 def _std_last_axis(data):
-    """np.std(data, axis=-1, keepdims=True) (reference utils.py:284); torch inputs use torch.std."""
-    if is_torch(data):
-        import torch
+    """np.std(data, axis=-1, keepdims=True) (reference utils.py:284), reduced on the device
+    (libflacarray.stream_std -> fab_stream_std): one read of the data, double-precision moments.  numpy sums
+    float32 input pairwise in single precision, so the two differ by rounding only."""
+    from .libflacarray import stream_std
 
-        return torch.std(data, dim=-1, keepdim=True, unbiased=False).cpu().numpy()
-    return np.std(data, axis=-1, keepdims=True)
+    return np.asarray(stream_std(data))[..., None]
 
 
 def quanta_from_precision(data, precision, leading_shape):

@@ -140,6 +140,15 @@ int fab_decode(fab_ctx* ctx, const unsigned char* d_bytes, const int64_t* d_star
                void* d_out, const void* d_offsets, const void* d_gains, int64_t max_nbytes, int blocksize_hint,
                void* stream);
 
+/*
+ * Per-stream population standard deviation of float32 / float64 streams, in the input's type: the device side of
+ * `precision` -> quanta (replaces np.std(data, axis=-1) in utils.py:282-296).  One read of the input, moments
+ * accumulated in double precision; differs from numpy's pairwise single-precision sum by rounding only.
+ * d_std: [n_stream] of `dtype`.
+ */
+int fab_stream_std(fab_ctx* ctx, const void* d_input, int dtype, int64_t n_stream, int64_t stream_size, void* d_std,
+                   void* stream);
+
 /* utils.c:160-328 on device buffers (dtype FAB_F32 -> int32, FAB_F64 -> int64). */
 int fab_float_to_int(fab_ctx* ctx, const void* d_input, int dtype, int64_t n_stream, int64_t stream_size,
                      const void* d_quanta, void* d_output, void* d_offsets, void* d_gains, void* stream);

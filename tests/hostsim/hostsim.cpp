@@ -119,8 +119,13 @@ int hs_encode(const void* data, int dtype, int64_t n_stream, int64_t stream_size
     std::vector<uint16_t> ctab(4 * 256), s11(2 * 256);
     for (int i = 0; i < 4 * 256; ++i) ctab[(size_t)i] = crc()->crc16[i >> 8][i & 255];
     for (int i = 0; i < 256; ++i) { s11[(size_t)i] = crc()->shift_hi[11][i]; s11[(size_t)(256 + i)] = crc()->shift_lo[11][i]; }
+    std::vector<uint16_t> shd(5 * 2 * 256);
+    for (int i = 0; i < 5 * 2 * 256; ++i) {
+        const int d = i >> 9, lo = (i >> 8) & 1, b = i & 255;
+        shd[(size_t)i] = lo ? crc()->shift_lo[4 + d][b] : crc()->shift_hi[4 + d][b];
+    }
     fasim::launch((int)total_frames, 128, sizeof(CompactShared), [&](int b) {
-        compact_frame_cta(P, (uint32_t)b, ctab.data(), s11.data(), s11.data() + 256, (CompactShared*)fasim::smem());
+        compact_frame_cta(P, (uint32_t)b, ctab.data(), s11.data(), s11.data() + 256, shd.data(), (CompactShared*)fasim::smem());
     });
     fasim::launch(1, 1, 0, [&](int) {
         for (int64_t s = 0; s < n_stream; ++s)

@@ -74,6 +74,48 @@ def test_float_to_int_roundtrips(fa):
         assert np.allclose(fa.int_to_float(idata, off, gain), d32, rtol=0, atol=max(tol, 1e-5) * 10)
 
 
+def test_precision_quanta_on_device(fa):
+    """reference utils.py:282-296: quanta = np.std(data, axis=-1) / 10**precision.  The standard deviation is reduced on
+    the device (fab_stream_std, double-precision moments); numpy sums float32 pairwise in single precision, so the two
+    agree to rounding (tolerances below), and encoding with `precision` is byte-identical to encoding with the quanta
+    derived from the device's standard deviation -- in one shot, through the chunked host pipeline, and for a CUDA tensor."""
+    import torch
+    from flacarray_b200 import libflacarray as lf
+
+    rng = np.random.default_rng(20261018)
+    for dt, shape, rtol in ((np.float32, (6, 50000), 3e-6), (np.float64, (5, 70001), 1e-12), (np.float32, (2, 3, 1000), 3e-6)):
+        scale = 10.0 ** rng.integers(-3, 4, shape[:-1] + (1,))
+        data = (rng.normal(0, 1, shape) * scale + 100.0 * scale).astype(dt)
+        sd = lf.stream_std(data)
+        assert sd.dtype == dt and sd.shape == shape[:-1]
+        assert np.allclose(sd, np.std(data.astype(np.float64), axis=-1), rtol=rtol, atol=0)
+        assert np.allclose(sd, np.std(data, axis=-1), rtol=30 * rtol, atol=0)
+        sd_t = lf.stream_std(torch.from_numpy(data).cuda())
+        assert np.array_equal(sd_t, sd)
+        for prec in (4, rng.integers(2, 6, shape[:-1])):
+            q = np.asarray(lf.quanta_from_std(sd, prec)).astype(dt)
+            a = fa.array_compress(data, precision=prec)
+            b = fa.array_compress(data, quanta=q)
+            c = fa.array_compress(torch.from_numpy(data).cuda(), precision=prec)
+            for x, y, z in zip(a, b, c):
+                assert np.array_equal(x, y)
+                assert np.array_equal(x, z.cpu().numpy() if torch.is_tensor(z) else z)
+            idata, off, gain = fa.float_to_int(data, precision=prec)
+            idata2, off2, gain2 = fa.float_to_int(data, quanta=q)
+            assert np.array_equal(idata, idata2) and np.array_equal(off, off2) and np.array_equal(gain, gain2)
+    # a host array large enough for the chunked pipeline (chunks of whole streams, quanta per chunk on the device)
+    big = (rng.normal(0, 1, (64, 300000)) * np.linspace(0.5, 50, 64)[:, None]).astype(np.float32)
+    sd = lf.stream_std(big)
+    assert np.allclose(sd, np.std(big.astype(np.float64), axis=-1), rtol=3e-6, atol=0)
+    q = np.asarray(lf.quanta_from_std(sd, 5)).astype(np.float32)
+    a = fa.array_compress(big, precision=5)
+    b = fa.array_compress(big, quanta=q)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    out = fa.array_decompress(a[0], big.shape[-1], a[1], a[2], stream_offsets=a[3], stream_gains=a[4])
+    assert np.max(np.abs(out - big) / sd[:, None]) < 1e-5
+
+
 def test_helpers_all_dtypes(fa):
     """reference tests/array.py:26-146"""
     from flacarray_b200.demo import create_fake_data
