@@ -60,6 +60,10 @@ struct BitRdC {
     uint32_t wr;       // chunks issued so far
     uint32_t landed;   // chunks known to be complete in the ring
     int err;
+    // steady-state window (tile_next4): the big-endian ring words under the cursor and behind it, plus the byte offset of
+    // the latter inside the ring.  Only valid between brc_window_load and the next call of any other reader routine.
+    uint32_t cur, nxt, noff;
+    int wok;           // the window is valid
 };
 
 FA_D U4 u4_zero() { U4 z; z.x = z.y = z.z = z.w = 0; return z; }
@@ -106,6 +110,14 @@ FA_D uint32_t brc_peek(const BitRdC& br) {
     return funnel_l(w1, w0, br.pos & 31u);
 }
 
+// Load the two-word window at the cursor (the caller has ensured >= 64 bits).
+FA_D void brc_window_load(BitRdC& br) {
+    const uint32_t wi = br.pos >> 5;
+    br.cur = bswap32(br.ring[wi & (kRingWords - 1)]);
+    br.noff = ((wi + 1) & (kRingWords - 1)) * 4u;
+    br.nxt = bswap32(*(const uint32_t*)((const unsigned char*)br.ring + br.noff));
+}
+
 // Start reading at byte `start`.
 FA_D void brc_init(BitRdC& br, uint32_t* ring, const uint8_t* start, const uint8_t* end) {
     uintptr_t s = (uintptr_t)start;
@@ -117,6 +129,8 @@ FA_D void brc_init(BitRdC& br, uint32_t* ring, const uint8_t* start, const uint8
     br.wr = 0;
     br.landed = 0;
     br.err = 0;
+    br.cur = br.nxt = br.noff = 0;
+    br.wok = 0;
     brc_service(br);
 }
 
@@ -293,25 +307,45 @@ FA_D int32_t tile_next_sample(BitRdC& br, TileLane& L) {
     return (int32_t)((uint32_t)v << L.wasted);
 }
 
-// Four residual samples of one partition (k >= 0): the steady-state inner loop.  Codes of at most 32 bits are
-// taken straight from the window under the cursor; a longer one goes through the general routine.
+// Four residual samples of one partition (k >= 0): the steady-state inner loop.  The caller keeps the two-word window
+// (br.cur, br.nxt) valid across consecutive calls.  The four codes are decoded WITHOUT branches on the assumption that
+// each is at most 32 bits long: the 32 bits under the cursor come from the window with one funnel shift (no shared-memory
+// access on the dependent chain: the word behind the window is fetched, predicated, only when the cursor crosses a word
+// boundary), the position of the stop bit gives quotient, remainder shift and code length.  A code longer than 32 bits
+// (stop bit not inside the window's first 32 - k bits) sets the sign of `bad`; the group is then decoded again from
+// the saved cursor by the general routine -- rare: one code in ~10^4 on detector data.
 template <int ORD>
 FA_D void tile_next4(BitRdC& br, TileLane& L, int32_t* out4) {
     int32_t r[4];
     const int k = L.k;
-    brc_ensure(br, 4u * 32u + 32u);
+    brc_ensure(br, 4u * 32u + 64u);
+    const uint32_t pos0 = br.pos;
+    const uint32_t kmask = (1u << k) - 1u;
+    const int n0 = 32 + k;               // code length = n0 - f, f = index of the stop bit in the 32-bit view
+    int bad = 0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const uint32_t w = brc_peek(br);
-        const int z = clz32(w);
-        if (z + 1 + k <= 32) {
-            const uint32_t low = k ? ((w << (z + 1)) >> (32 - k)) : 0u;
-            br.pos += (uint32_t)(z + 1 + k);
-            r[q] = unzigzag32(((uint32_t)z << k) | low);
-        } else {
-            r[q] = brc_rice(br, k);
-            brc_ensure(br, 4u * 32u + 32u);
+        const uint32_t sh = br.pos & 31u;
+        const uint32_t w = funnel_l(br.nxt, br.cur, sh);
+        const int f = 31 - clz32(w);                     // -1 when w == 0
+        const int d = f - k;                             // remainder = (w >> d) & kmask; d < 0: the code is longer than 32 bits
+        bad |= d;
+        const uint32_t u = ((uint32_t)(31 - f) << k) | ((w >> (d & 31)) & kmask);
+        r[q] = unzigzag32(u);
+        const uint32_t n = (uint32_t)(n0 - f);
+        br.pos += n;
+        if (sh + n >= 32u) {             // (n <= 33 here, and a group with n > 32 is decoded again: at most one word is crossed)
+            br.cur = br.nxt;
+            br.noff = (br.noff + 4u) & (kRingWords * 4u - 1u);
+            br.nxt = bswap32(*(const uint32_t*)((const unsigned char*)br.ring + br.noff));
         }
+    }
+    if (bad < 0) {
+        br.pos = pos0;
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) r[q] = brc_rice(br, k);
+        brc_ensure(br, 64u);
+        brc_window_load(br);
     }
     L.left -= 4;
     int32_t s[4];
@@ -358,8 +392,10 @@ FA_D void tile_channel_pass(const TileParams& P, TileShared* ws, BitRdC& br, Til
             if (run && i < bs) {
                 bool fast = L.mode == 2 && L.raw_left == 0 && !L.need_params && L.left >= 4 && L.k >= 0 && i + 4 <= bs;
                 if (fast) {
+                    if (!br.wok) { brc_ensure(br, 64u); brc_window_load(br); br.wok = 1; }
                     tile_next4<ORD>(br, L, trow + s);
                 } else {
+                    br.wok = 0;
                     for (int q = 0; q < 4; ++q) {
                         int32_t v = 0;
                         if (run && i + q < bs) {
@@ -500,6 +536,7 @@ FA_D void tile_warp_body(const TileParams& P, int64_t item0, TileShared* ws) {
         brc_init(br, ws->ring + ln * kRingStride, fp + fh.hdr_bytes, end);
     } else {
         br.gp = br.gend = nullptr; br.ring = nullptr; br.pos = br.pos0 = 0; br.wr = 0; br.landed = 0; br.err = 0;
+        br.cur = br.nxt = br.noff = 0; br.wok = 0;
     }
     bool fail = false;      // stream problem -> walker
     bool punt = false;      // unsupported subframe -> general decoder

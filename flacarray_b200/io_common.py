@@ -102,10 +102,14 @@ def write_compressed(grp, leading_shape, global_leading_shape, stream_size, stre
     nbytes = _host(stream_nbytes).astype(np.int64).reshape(aux_local)
     offs = None if stream_offsets is None else _host(stream_offsets).reshape(aux_local)
     gains = None if stream_gains is None else _host(stream_gains).reshape(aux_local)
-    comp = _host(compressed).reshape(-1)
     if mpi_dist is None:
         mpi_dist = [(0, aux_global[0])]
     direct = _all_have_group(grp, mpi_comm)
+    # a rank that only ships its block to the writer keeps device-resident bytes on the device: a communicator that can
+    # move tensors (TorchComm over NCCL) sends them from there, instead of device -> host -> device -> wire
+    ship_dev = (not direct and rank != 0 and hasattr(compressed, "is_cuda") and compressed.is_cuda
+                and getattr(mpi_comm, "sends_tensors", False))
+    comp = compressed.reshape(-1) if ship_dev else _host(compressed).reshape(-1)
 
     dsets = None
     if rank == 0:

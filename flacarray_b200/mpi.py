@@ -70,11 +70,18 @@ class TorchComm:
     # a rank's multi-GB compressed block is never pickled.
     _BIG = 1 << 20
     _CHUNK = 256 << 20
+    sends_tensors = True    # torch tensors (host or device) inside a sent object arrive as numpy arrays
 
     def _split(self, obj, big):
         if isinstance(obj, np.ndarray) and obj.nbytes >= self._BIG:
             big.append(np.ascontiguousarray(obj))
             return ("__ndarray__", len(big) - 1, obj.dtype.str, obj.shape)
+        if torch is not None and isinstance(obj, torch.Tensor):
+            if obj.numel() * obj.element_size() < self._BIG:
+                return obj.detach().cpu().numpy()
+            # stays where it is (a CUDA tensor goes on the wire straight from device memory)
+            big.append(obj.detach().contiguous().reshape(-1).view(torch.uint8))
+            return ("__ndarray__", len(big) - 1, np.dtype(str(obj.dtype).replace("torch.", "")).str, tuple(obj.shape))
         if isinstance(obj, (tuple, list)):
             return type(obj)(self._split(o, big) for o in obj)
         return obj
@@ -89,12 +96,15 @@ class TorchComm:
     def send(self, obj, dest):
         big = []
         skel = self._split(obj, big)
-        dist.send_object_list([(skel, [b.nbytes for b in big])], dst=dest, group=self.group)
+        dist.send_object_list([(skel, [int(b.nbytes) if isinstance(b, np.ndarray) else int(b.numel()) for b in big])],
+                              dst=dest, group=self.group)
         for b in big:
-            flat = torch.from_numpy(b.reshape(-1).view(np.uint8))
+            flat = torch.from_numpy(b.reshape(-1).view(np.uint8)) if isinstance(b, np.ndarray) else b
             for o in range(0, flat.numel(), self._CHUNK):
                 piece = flat[o:o + self._CHUNK]
-                dist.send(piece.to(self.device) if self.device.type == "cuda" else piece, dst=dest, group=self.group)
+                if piece.device != self.device:
+                    piece = piece.to(self.device)
+                dist.send(piece, dst=dest, group=self.group)
 
     def recv(self, source):
         box = [None]

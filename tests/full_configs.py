@@ -208,6 +208,16 @@ def cfg5(scale):
     comm = TorchComm()
     rank, world = comm.rank, comm.size
     n_glob = max(world, int(10000 * scale)); L = 4000000
+    # the writer holds the whole compressed array (~0.5 x raw) in host memory next to one rank's block in flight
+    try:
+        with open("/proc/meminfo") as fh:
+            avail = [int(ln.split()[1]) * 1024 for ln in fh if ln.startswith("MemAvailable:")][0]
+        fit = int(avail / 3 / (0.5 * L * 4))
+        if fit < n_glob:
+            print(f"# cfg5: host memory ({avail / 1e9:.0f} GB available) limits the run to {fit} streams", file=sys.stderr, flush=True)
+            n_glob = max(world, fit)
+    except (OSError, IndexError):
+        pass
     a, b = _even_split(n_glob, world)[rank]
     x = bench.make_tod_torch(b - a, L, SEED + 1000 * rank, dev)
     torch.cuda.synchronize(); comm.barrier()
@@ -224,13 +234,17 @@ def cfg5(scale):
     gstarts = np.asarray(far.global_stream_starts).reshape(-1)
     lstarts = np.asarray(far.stream_starts).reshape(-1)
     proc = far.global_process_nbytes
-    ok = int(gstarts[0]) == int(sum(proc[:rank])) and bool(np.array_equal(gstarts - gstarts[0], lstarts))
-    ok = ok and far.global_nbytes == int(sum(proc)) and far.global_shape == (n_glob, L)
+    checks = {}
+    checks["global_starts"] = int(gstarts[0]) == int(sum(proc[:rank])) and bool(np.array_equal(gstarts - gstarts[0], lstarts))
+    checks["global_nbytes"] = int(far.global_nbytes) == int(sum(proc))
+    checks["global_shape"] = tuple(far.global_shape) == (n_glob, L)
+    ok = all(checks.values())
     # own streams: round trip error of a sample of streams
     rows = sample_rows(b - a, 4)
     back = far.to_array(keep=np.isin(np.arange(b - a), rows))
     err = float((back - x[rows]).abs().max())
-    ok = ok and err <= 0.5e-4 + 2e-6
+    checks["roundtrip_err"] = err <= 0.5e-4 + 2e-6
+    ok = ok and checks["roundtrip_err"]
     del back
     comm.barrier()
     # gather to the writer
@@ -241,12 +255,12 @@ def cfg5(scale):
     t_write = time.perf_counter() - tw0
     res = None
     if rank == 0:
-        # read back a window of every 97th stream, compare with (a) the oracle's decode of those streams from the bytes
+        # read back a window of every 97th (5th when scaled down) stream, compare with (a) the oracle's decode of those streams from the bytes
         # in the group and (b) the input of the streams rank 0 owns
-        keep = (np.arange(n_glob) % 97) == 0
+        keep = (np.arange(n_glob) % (97 if n_glob >= 970 else 5)) == 0
         sl = slice(L // 2 - 25000, L // 2 + 25000)
         tr0 = time.perf_counter()
-        part, idx = io_common.read_array(grp, keep=keep, stream_slice=sl, keep_indices=True)
+        part, idx = io_common.read_array(grp, keep=keep, stream_slice=sl, keep_indices=True, no_flatten=True)
         torch.cuda.synchronize()
         t_read = time.perf_counter() - tr0
         part = part.cpu().numpy() if torch.is_tensor(part) else np.asarray(part)
@@ -270,12 +284,13 @@ def cfg5(scale):
         res = dict(oracle_ok=ok_or, oracle_streams=len(pick), window=[int(keep.sum()), sl.stop - sl.start], read_s=t_read,
                    file_nbytes=int(comp.shape[0]) if hasattr(comp, "shape") else int(far.global_nbytes), ok_idx=ok_idx)
     oks = comm.allgather(bool(ok))
+    allchecks = comm.gather(checks, root=0)
     if rank != 0:
         return None
     raw = n_glob * L * 4
     return dict(cfg=5, workload=f"float32 TOD ({n_glob}, {L}) over {world} GPUs, quanta 1e-4: encode + all-gather + gather to rank 0 + "
                 f"HDF5-layout write (in-memory group) + keep/slice read-back", ok=all(oks) and res["oracle_ok"] and res["ok_idx"],
-                n_gpus=world, streams_per_gpu=b - a, ratio=far.global_nbytes / raw, raw_gb=raw / 1e9, enc_ms=t_enc,
+                rank_checks=allchecks, n_gpus=world, streams_per_gpu=b - a, ratio=far.global_nbytes / raw, raw_gb=raw / 1e9, enc_ms=t_enc,
                 enc_gbs_aggregate=raw / t_enc / 1e6, gather_write_s=t_write, gather_write_gbs=far.global_nbytes / t_write / 1e9,
                 max_err=err, **res)
 

@@ -25,6 +25,9 @@ def test_cfg5_two_ranks_nccl():
     lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
     assert lines, res.stdout[-2000:] + res.stderr[-2000:]
     r = json.loads(lines[-1])
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "cfg5_2gpu_scaled.json"), "w") as fh:
+        fh.write(lines[-1] + "\n")
     assert r["cfg"] == 5 and r["n_gpus"] == 2
     assert r["ok"] and r["oracle_ok"] and r["ok_idx"], r
     assert 0.3 < r["ratio"] < 0.7
