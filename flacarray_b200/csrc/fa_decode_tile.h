@@ -23,7 +23,8 @@
 namespace fa {
 
 constexpr int kTileOrd = 12;
-constexpr int kTileStride = 33;
+constexpr int kTileStride = 36;   // words per tile row: 16-byte aligned rows, and rows 9 x 16 bytes apart keep 16-byte accesses
+                                  // of 8 consecutive lanes (one row each, or one row together) on distinct banks
 #ifndef FAB_TILE_WARPS
 #define FAB_TILE_WARPS 4
 #endif
@@ -40,7 +41,7 @@ struct TileRow {          // per-lane output description, read by all lanes duri
 };
 
 struct TileShared {       // per warp
-    int32_t tile[32 * kTileStride];
+    alignas(16) int32_t tile[32 * kTileStride];
     TileRow row[32];
     uint32_t ring[32 * kRingStride];   // compressed bytes in flight: one ring of kRingChunks chunks per lane
 };
@@ -162,7 +163,7 @@ FA_D uint32_t brc_unary(BitRdC& br) {
         if (br.gp > br.gend + 4 + kRingChunks) { br.err = 1; return q; }  // ran off the end of the stream
     }
 }
-FA_D int32_t unzigzag32(uint32_t u) { return (int32_t)(u >> 1) ^ -(int32_t)(u & 1); }
+FA_D int32_t unzigzag32(uint32_t u) { return (int32_t)(u >> 1) ^ sext1(u); }
 // Rice code with parameter k (< 32): any length.
 FA_D int32_t brc_rice(BitRdC& br, int k) {
     brc_ensure(br, 64u);
@@ -342,8 +343,8 @@ FA_D void tile_next4(BitRdC& br, TileLane& L, int32_t* out4) {
     }
     if (bad < 0) {
         br.pos = pos0;
-#pragma unroll 1
-        for (int q = 0; q < 4; ++q) r[q] = brc_rice(br, k);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) r[q] = brc_rice(br, k);      // (unrolled: a rolled loop would index r[] and park it in local memory)
         brc_ensure(br, 64u);
         brc_window_load(br);
     }
@@ -351,10 +352,11 @@ FA_D void tile_next4(BitRdC& br, TileLane& L, int32_t* out4) {
     int32_t s[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
+        // history as seen by sample q: s[q-1], .., s[0], h[0], h[1], ...  The terms are added oldest first: the products with
+        // the old history do not wait for anything, and only the last multiply-add of sample q waits for sample q - 1
         int64_t sum = 0;
 #pragma unroll
-        for (int j = 0; j < ORD; ++j) {
-            // history as seen by sample q: s[q-1], .., s[0], h[0], h[1], ...
+        for (int j = ORD - 1; j >= 0; --j) {
             int32_t hv = (j < q) ? s[q - 1 - j] : L.h[j - q];
             sum += (int64_t)L.c[j] * (int64_t)hv;
         }
@@ -365,8 +367,9 @@ FA_D void tile_next4(BitRdC& br, TileLane& L, int32_t* out4) {
 #pragma unroll
     for (int q = 0; q < 4; ++q)
         if (3 - q < ORD) L.h[3 - q] = s[q];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) out4[q] = (int32_t)((uint32_t)s[q] << L.wasted);
+    U4 o;
+    o.x = (uint32_t)s[0] << L.wasted; o.y = (uint32_t)s[1] << L.wasted; o.z = (uint32_t)s[2] << L.wasted; o.w = (uint32_t)s[3] << L.wasted;
+    sts128(out4, o);      // (tile rows are 16-byte aligned, the group starts at a multiple of four samples)
 }
 
 struct TileParams {
@@ -431,8 +434,8 @@ FA_D void tile_channel_pass(const TileParams& P, TileShared* ws, BitRdC& br, Til
                 const int r = it * 4 + (ln >> 3);
                 const TileRow row = ws->row[r];
                 if (row.hi != 0) {
-                    const int32_t* tp = ws->tile + r * kTileStride + c4;
-                    const int32_t v0 = tp[0], v1 = tp[1], v2 = tp[2], v3 = tp[3];
+                    const U4 tv = lds128(ws->tile + r * kTileStride + c4);
+                    const int32_t v0 = (int32_t)tv.x, v1 = (int32_t)tv.y, v2 = (int32_t)tv.z, v3 = (int32_t)tv.w;
                     U4 q;
                     if (P.restore) {
                         float f0 = restore_f32(v0, row.off, row.coeff), f1 = restore_f32(v1, row.off, row.coeff);

@@ -44,6 +44,8 @@ FA_D uint32_t funnel_l(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelsh
 FA_D uint32_t funnel_lc(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_lc(lo, hi, s); }
 // lower word of (hi:lo) >> (s & 31)
 FA_D uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_r(lo, hi, s); }
+// 0 or -1 from bit 0 (one SGXT)
+FA_D int32_t sext1(uint32_t v) { int32_t r; asm("bfe.s32 %0, %1, 0, 1;" : "=r"(r) : "r"(v)); return r; }
 FA_D uint32_t funnel_rc(uint32_t lo, uint32_t hi, uint32_t s) { return __funnelshift_rc(lo, hi, s); }   // s >= 32 -> hi
 FA_D void atom_or_shared(uint32_t* p, uint32_t v) { atomicOr(p, v); }
 FA_D void atom_add_shared64(unsigned long long* p, unsigned long long v) { atomicAdd(p, v); }
@@ -251,6 +253,7 @@ inline uint32_t funnel_r(uint32_t lo, uint32_t hi, uint32_t s) {
     s &= 31;
     return s ? (lo >> s) | (hi << (32 - s)) : lo;
 }
+inline int32_t sext1(uint32_t v) { return -(int32_t)(v & 1u); }
 inline uint32_t funnel_rc(uint32_t lo, uint32_t hi, uint32_t s) {
     if (s >= 32) return hi;
     return s ? (lo >> s) | (hi << (32 - s)) : lo;
