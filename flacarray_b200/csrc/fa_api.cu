@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -85,21 +86,10 @@ __global__ void __launch_bounds__(kScanThreads) k_enc_scan(const EncParams P) {
 
 // frames of a batch from their slots to their final byte offsets, CRC-16 appended (CTAs stride over the frames)
 __global__ void __launch_bounds__(128) k_enc_compact(const EncParams P) {
-    __shared__ uint16_t crc_tab[4 * 256];
-    __shared__ uint16_t s11[2 * 256];     // multiply the state by x^(8 * 2048): tables of its high / low byte
-    __shared__ uint16_t shd[5 * 2 * 256]; // ... by x^(8 * 2^(4 + d)), d = 0 .. 4: [d][hi / lo][256]
     __shared__ CompactShared cs;
-    for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) crc_tab[i] = P.crc->crc16[i >> 8][i & 255];
-    for (int i = threadIdx.x; i < 2 * 256; i += blockDim.x)
-        s11[i] = i < 256 ? P.crc->shift_hi[11][i] : P.crc->shift_lo[11][i - 256];
-    for (int i = threadIdx.x; i < 5 * 2 * 256; i += blockDim.x) {
-        const int d = i >> 9, lo = (i >> 8) & 1, b = i & 255;
-        shd[i] = lo ? P.crc->shift_lo[4 + d][b] : P.crc->shift_hi[4 + d][b];
-    }
-    __syncthreads();
     const uint32_t n = P.g_end - P.g_begin;
     for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
-        compact_frame_cta(P, i, crc_tab, s11, s11 + 256, shd, &cs);
+        compact_frame_cta(P, i, &cs);
         __syncthreads();      // cs is reused by the next frame
     }
 }
@@ -368,15 +358,9 @@ __global__ void __launch_bounds__(kTileWarps * 32, FAB_DEC_CTAS) k_dec_tile(cons
 
 // frame CRC-16 of every (stream, frame) item: one warp per item, see crc_frame_warp
 __global__ void __launch_bounds__(128) k_dec_crc(const TileParams P) {
-    __shared__ uint16_t crc_tab[4 * 256];
-    __shared__ uint16_t s9[2 * 256];      // multiply the state by x^(8 * 512): tables of its high / low byte
-    for (int i = threadIdx.x; i < 4 * 256; i += blockDim.x) crc_tab[i] = P.D.crc->crc16[i >> 8][i & 255];
-    for (int i = threadIdx.x; i < 2 * 256; i += blockDim.x)
-        s9[i] = i < 256 ? P.D.crc->shift_hi[9][i] : P.D.crc->shift_lo[9][i - 256];
-    __syncthreads();
     int64_t idx = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (idx >= P.D.n_sel * P.nwin) return;
-    crc_frame_warp(P, idx, crc_tab, s9, s9 + 256);
+    crc_frame_warp(P, idx);
 }
 
 // int32 -> float32 for the sample ranges that were NOT written by the fused tile path (frames left to
@@ -446,8 +430,11 @@ struct fab_ctx {
     float* d_window[3] = {nullptr, nullptr, nullptr};  // [0] 1152, [1] 4096 (both zero-padded to 4096 floats), [2] 4096 in [quad][thread][4] order
     int* d_err = nullptr;
     int* h_err = nullptr;  // pinned
-    unsigned char* scratch = nullptr;
+    unsigned char* scratch = nullptr;      // grow-only block owned by the context ...
     size_t scratch_bytes = 0;
+    unsigned char* ws_user = nullptr;      // ... unless the caller supplied a workspace (fab_set_workspace)
+    size_t ws_user_bytes = 0;
+    cudaStream_t last_stream = nullptr;    // stream of the most recent call that used the scratch block
     int64_t launches = 0;
     std::string last_error = "";
     bool smem_configured = false;
@@ -501,10 +488,25 @@ static void prof_collect(fab_ctx* ctx) {
         }                                                                                     \
     } while (0)
 
-static int ctx_scratch(fab_ctx* ctx, size_t bytes, unsigned char** out) {
+static int ctx_scratch(fab_ctx* ctx, size_t bytes, unsigned char** out, cudaStream_t st) {
+    if (ctx->ws_user) {
+        // caller-supplied workspace (fab_set_workspace): never allocate behind the caller's back
+        if (bytes > ctx->ws_user_bytes) {
+            ctx->last_error = "workspace too small: " + std::to_string(bytes) + " bytes needed, " +
+                              std::to_string(ctx->ws_user_bytes) + " supplied (see fab_encode_workspace_bytes / fab_decode_workspace_bytes)";
+            return ERROR_ALLOC;
+        }
+        ctx->last_stream = st;
+        *out = ctx->ws_user;
+        return 0;
+    }
     if (bytes > ctx->scratch_bytes) {
         if (ctx->scratch) {
-            FAB_CUDA(ctx, cudaDeviceSynchronize());
+            // only this context's own work can still be reading the old block: the stream of its previous call and the
+            // helper streams (not the whole device -- other contexts and the caller's other streams keep running)
+            FAB_CUDA(ctx, cudaStreamSynchronize(ctx->last_stream));
+            FAB_CUDA(ctx, cudaStreamSynchronize(ctx->aux));
+            FAB_CUDA(ctx, cudaStreamSynchronize(ctx->aux2));
             cudaFree(ctx->scratch);
             ctx->scratch = nullptr;
             ctx->scratch_bytes = 0;
@@ -518,6 +520,7 @@ static int ctx_scratch(fab_ctx* ctx, size_t bytes, unsigned char** out) {
         }
         ctx->scratch_bytes = want;
     }
+    ctx->last_stream = st;
     *out = ctx->scratch;
     return 0;
 }
@@ -590,6 +593,26 @@ extern "C" void fab_destroy(fab_ctx* ctx) {
     delete ctx;
 }
 
+extern "C" int fab_set_workspace(fab_ctx* ctx, void* d_workspace, int64_t bytes) {
+    if (!ctx) return FAB_ERROR_CUDA;
+    if (d_workspace && (bytes <= 0 || ((uintptr_t)d_workspace & 255) != 0)) {
+        ctx->last_error = "fab_set_workspace: the block must be 256-byte aligned and not empty";
+        return ERROR_ALLOC;
+    }
+    // work queued by earlier calls may still use the block that is being replaced
+    FAB_CUDA(ctx, cudaStreamSynchronize(ctx->last_stream));
+    FAB_CUDA(ctx, cudaStreamSynchronize(ctx->aux));
+    FAB_CUDA(ctx, cudaStreamSynchronize(ctx->aux2));
+    ctx->ws_user = (unsigned char*)d_workspace;
+    ctx->ws_user_bytes = d_workspace ? (size_t)bytes : 0;
+    if (d_workspace && ctx->scratch) {
+        cudaFree(ctx->scratch);
+        ctx->scratch = nullptr;
+        ctx->scratch_bytes = 0;
+    }
+    return 0;
+}
+
 extern "C" const char* fab_last_error(const fab_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "no context"; }
 extern "C" int64_t fab_launch_count(const fab_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
@@ -629,13 +652,53 @@ extern "C" int64_t fab_encode_bound(int64_t n_stream, int64_t stream_size, int d
     return n_stream * (stream_header_bytes((int)nf) + nf * (16 + 2 + (int64_t)nch * (lp.blocksize * 4 + 8)));
 }
 
+// Workspace of one fab_encode call: [min/max partials of the quantise pre-pass] | byte prefixes | ends | work counters |
+// per-batch statistics, plans, frame sizes, slots.  Sized once up front so that the pre-pass (queued first on the same
+// stream) and the encoder never share bytes.
+struct EncWorkspace {
+    size_t pre, desc_b, ends_b, stats_b, plans_b, tick_b, fsize_b, slots_b, total;
+    int64_t total_frames, slot_bytes, batch, nbatch;
+    int nbuf;
+};
+static EncWorkspace enc_workspace(int64_t n_stream, int64_t stream_size, int dtype, const LevelPreset& lp) {
+    EncWorkspace W;
+    const int nch = dtype_channels(dtype);
+    const int64_t nf = (stream_size + lp.blocksize - 1) / lp.blocksize;
+    W.pre = 0;
+    if (dtype >= FAB_F32) {
+        int nchunk = (int)((stream_size + kMmChunk - 1) / kMmChunk);
+        W.pre = 2 * align256((size_t)n_stream * nchunk * (dtype == FAB_F32 ? 4 : 8));
+    }
+    W.desc_b = align256((size_t)(n_stream * nf) * 8);
+    W.ends_b = align256((size_t)n_stream * 8);
+    // the encoder kernels run over batches of (stream, frame) units so that the per-frame records and the
+    // slot buffers between them stay bounded (2 x 1 GB); one work counter per batch
+    W.total_frames = n_stream * nf;
+    W.slot_bytes = (int64_t)((16 + 2 + (int64_t)nch * (lp.blocksize * 4 + 8) + 15) & ~15ll);
+    W.batch = std::min<int64_t>(W.total_frames, std::max<int64_t>(1024, kEncBatchBytes / W.slot_bytes));
+    W.nbatch = (W.total_frames + W.batch - 1) / W.batch;
+    W.nbuf = W.nbatch > 1 ? 2 : 1;     // slot / frame-size buffers alternate between consecutive batches
+    W.stats_b = align256((size_t)W.batch * nch * sizeof(FrameStats));
+    W.plans_b = align256((size_t)W.batch * nch * sizeof(FramePlan)) + align256((size_t)W.batch * nch * sizeof(PlanHeader));
+    W.tick_b = align256((size_t)W.nbatch * 4 + 16);
+    W.fsize_b = align256((size_t)W.batch * 4);
+    W.slots_b = align256((size_t)W.batch * (size_t)W.slot_bytes);
+    W.total = W.pre + W.desc_b + W.ends_b + W.tick_b + W.stats_b + W.plans_b + W.nbuf * (W.fsize_b + W.slots_b) + 256;
+    return W;
+}
+
+extern "C" int64_t fab_encode_workspace_bytes(int64_t n_stream, int64_t stream_size, int dtype, uint32_t level) {
+    if (level > 8 || n_stream <= 0 || stream_size <= 0 || dtype < 0 || dtype > 3) return 0;
+    return (int64_t)enc_workspace(n_stream, stream_size, dtype, level_preset((int)level)).total;
+}
+
 template <typename T>
 static int launch_quant_params(fab_ctx* ctx, const T* d_in, int64_t n_stream, int64_t stream_size, const T* d_quanta,
                                T* d_off, T* d_gain, cudaStream_t st) {
     int nchunk = (int)((stream_size + kMmChunk - 1) / kMmChunk);
     unsigned char* scr;
     size_t need = 2 * align256((size_t)n_stream * nchunk * sizeof(T));
-    int rc = ctx_scratch(ctx, need, &scr);
+    int rc = ctx_scratch(ctx, need, &scr, st);
     if (rc) return rc;
     T* pmin = (T*)scr;
     T* pmax = (T*)(scr + align256((size_t)n_stream * nchunk * sizeof(T)));
@@ -674,29 +737,13 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
         return ERROR_ENCODE_INIT;
     }
 
-    // scratch: [min/max partials of the quantise pre-pass] | byte prefixes | ends | work counters | per-batch
-    // statistics, plans, frame sizes, slots.  Sized once up front
-    // so that the pre-pass (queued first on the same stream) and the encoder never share bytes.
-    size_t pre = 0;
-    if (dtype >= FAB_F32) {
-        int nchunk = (int)((stream_size + kMmChunk - 1) / kMmChunk);
-        pre = 2 * align256((size_t)n_stream * nchunk * (dtype == FAB_F32 ? 4 : 8));
-    }
-    size_t desc_b = align256((size_t)(n_stream * nf) * 8), ends_b = align256((size_t)n_stream * 8);
-    // the encoder kernels run over batches of (stream, frame) units so that the per-frame records and the
-    // slot buffers between them stay bounded (2 x 1 GB); one work counter per batch
-    const int64_t total_frames = n_stream * nf;
-    const int64_t slot_bytes = (int64_t)((16 + 2 + (int64_t)nch * (lp.blocksize * 4 + 8) + 15) & ~15ll);
-    const int64_t batch = std::min<int64_t>(total_frames, std::max<int64_t>(1024, kEncBatchBytes / slot_bytes));
-    const int64_t nbatch = (total_frames + batch - 1) / batch;
-    const int nbuf = nbatch > 1 ? 2 : 1;     // slot / frame-size buffers alternate between consecutive batches
-    size_t stats_b = align256((size_t)batch * nch * sizeof(FrameStats));
-    size_t plans_b = align256((size_t)batch * nch * sizeof(FramePlan)) + align256((size_t)batch * nch * sizeof(PlanHeader));
-    size_t tick_b = align256((size_t)nbatch * 4 + 16);
-    size_t fsize_b = align256((size_t)batch * 4);
-    size_t slots_b = align256((size_t)batch * (size_t)slot_bytes);
+    const EncWorkspace W = enc_workspace(n_stream, stream_size, dtype, lp);
+    const size_t pre = W.pre, desc_b = W.desc_b, ends_b = W.ends_b, stats_b = W.stats_b, plans_b = W.plans_b, tick_b = W.tick_b,
+                 fsize_b = W.fsize_b, slots_b = W.slots_b;
+    const int64_t total_frames = W.total_frames, slot_bytes = W.slot_bytes, batch = W.batch, nbatch = W.nbatch;
+    const int nbuf = W.nbuf;
     unsigned char* scr;
-    int rc = ctx_scratch(ctx, pre + desc_b + ends_b + tick_b + stats_b + plans_b + nbuf * (fsize_b + slots_b) + 256, &scr);
+    int rc = ctx_scratch(ctx, W.total, &scr, st);
     if (rc) return rc;
 
     prof_begin(ctx, 0, st);     // slot 0: every kernel of this call: min/max pre-pass, all encoder batches
@@ -845,6 +892,31 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
 // =================================================================================================
 // Decode
 // =================================================================================================
+// Workspace of one fab_decode call: stream metadata | frame offsets | stream flags | frame flags | one int64
+struct DecWorkspace { size_t meta_b, fo_b, flag_b, fflag_b, total; };
+static DecWorkspace dec_workspace(int64_t n_stream, int nframes_cap) {
+    DecWorkspace W;
+    W.meta_b = align256((size_t)n_stream * sizeof(StreamMeta));
+    W.fo_b = align256((size_t)n_stream * (size_t)(nframes_cap + 1) * 8);
+    W.flag_b = align256((size_t)n_stream * 4);
+    W.fflag_b = align256((size_t)n_stream * (size_t)nframes_cap);
+    W.total = W.meta_b + W.fo_b + W.flag_b + W.fflag_b + 256;
+    return W;
+}
+static int dec_frames_cap(int64_t stream_size, int blocksize_hint, int* cap) {
+    int bsh = blocksize_hint > 0 ? blocksize_hint : 4096;
+    if (bsh < 16) bsh = 16;
+    int64_t cap64 = (stream_size + bsh - 1) / bsh;
+    if (cap64 > (1 << 26)) return ERROR_ALLOC;
+    *cap = (int)cap64;
+    return 0;
+}
+extern "C" int64_t fab_decode_workspace_bytes(int64_t n_stream, int64_t stream_size, int blocksize_hint) {
+    int cap = 0;
+    if (n_stream <= 0 || stream_size <= 0 || dec_frames_cap(stream_size, blocksize_hint, &cap)) return 0;
+    return (int64_t)dec_workspace(n_stream, cap).total;
+}
+
 extern "C" int fab_decode(fab_ctx* ctx, const unsigned char* d_bytes, const int64_t* d_starts, const int64_t* d_nbytes,
                           int64_t n_stream, int64_t stream_size, int is_int64, int64_t first_sample, int64_t last_sample,
                           void* d_out, const void* d_offsets, const void* d_gains, int64_t max_nbytes,
@@ -863,18 +935,14 @@ extern "C" int fab_decode(fab_ctx* ctx, const unsigned char* d_bytes, const int6
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int nch = is_int64 ? 2 : 1;
-    int bsh = blocksize_hint > 0 ? blocksize_hint : 4096;
-    if (bsh < 16) bsh = 16;
-    int64_t cap64 = (stream_size + bsh - 1) / bsh;
-    if (cap64 > (1 << 26)) return ERROR_ALLOC;
-    const int nframes_cap = (int)cap64;
+    int nframes_cap = 0;
+    if (dec_frames_cap(stream_size, blocksize_hint, &nframes_cap)) return ERROR_ALLOC;
+    const int bsh = std::max(16, blocksize_hint > 0 ? blocksize_hint : 4096);
 
-    size_t meta_b = align256((size_t)n_stream * sizeof(StreamMeta));
-    size_t fo_b = align256((size_t)n_stream * (size_t)(nframes_cap + 1) * 8);
-    size_t flag_b = align256((size_t)n_stream * 4);
-    size_t fflag_b = align256((size_t)n_stream * (size_t)nframes_cap);
+    const DecWorkspace W = dec_workspace(n_stream, nframes_cap);
+    const size_t meta_b = W.meta_b, fo_b = W.fo_b, flag_b = W.flag_b, fflag_b = W.fflag_b;
     unsigned char* scr;
-    int rc = ctx_scratch(ctx, meta_b + fo_b + flag_b + fflag_b + 256, &scr);
+    int rc = ctx_scratch(ctx, W.total, &scr, st);
     if (rc) return rc;
     unsigned char* frame_flag = scr + meta_b + fo_b + flag_b;
 
@@ -978,7 +1046,7 @@ static int launch_stream_std(fab_ctx* ctx, const T* d_in, int64_t n_stream, int6
     int nchunk = (int)((stream_size + kMmChunk - 1) / kMmChunk);
     unsigned char* scr;
     const size_t part = align256((size_t)n_stream * nchunk * sizeof(double));
-    int rc = ctx_scratch(ctx, 2 * part, &scr);
+    int rc = ctx_scratch(ctx, 2 * part, &scr, st);
     if (rc) return rc;
     double* pmean = (double*)scr;
     double* pm2 = (double*)(scr + part);
@@ -1072,15 +1140,6 @@ extern "C" int fab_int_to_float(fab_ctx* ctx, const void* d_input, int dtype, in
 // Reference-compatible host-buffer entry points (flacarray.h:209-311)
 // =================================================================================================
 namespace {
-std::mutex g_mu;
-fab_ctx* g_ctx = nullptr;
-
-fab_ctx* default_ctx() {
-    if (!g_ctx) {
-        if (fab_create(&g_ctx) != 0) g_ctx = nullptr;
-    }
-    return g_ctx;
-}
 
 struct DevBuf {
     void* p = nullptr;
@@ -1151,7 +1210,61 @@ struct HostPipe {
     }
     void drain() { cudaStreamSynchronize(s_in); cudaStreamSynchronize(s_k); cudaStreamSynchronize(s_out); }
 };
-HostPipe g_pipe;
+
+// The reference's entry points are re-entrant (each call owns its libFLAC encoder / decoder objects).  Here a call
+// leases one of a few host slots -- a context (streams, scratch, size history) plus the pinned / device staging
+// buffers of the chunked pipeline -- so concurrent callers run side by side on separate CUDA streams instead of
+// queueing on one lock.  Slots are created on demand up to kHostSlots (FLACARRAY_B200_HOST_SLOTS, 1..16); callers
+// beyond that wait for a slot to come back.
+struct HostSlot {
+    fab_ctx* ctx = nullptr;
+    HostPipe pipe;
+    bool busy = false;
+};
+std::mutex g_slot_mu;
+std::condition_variable g_slot_cv;
+std::vector<HostSlot*> g_slots;
+int host_slot_limit() {
+    static const int lim = [] {
+        const char* e = getenv("FLACARRAY_B200_HOST_SLOTS");
+        int v = e ? atoi(e) : 4;
+        return v < 1 ? 1 : (v > 16 ? 16 : v);
+    }();
+    return lim;
+}
+class SlotLease {
+    HostSlot* s_ = nullptr;
+public:
+    SlotLease() {
+        std::unique_lock<std::mutex> lk(g_slot_mu);
+        for (;;) {
+            for (HostSlot* c : g_slots)
+                if (!c->busy) { s_ = c; break; }
+            if (s_) break;
+            if ((int)g_slots.size() < host_slot_limit()) {
+                HostSlot* c = new HostSlot();
+                if (fab_create(&c->ctx) != 0) { delete c; return; }     // no CUDA device: the caller reports FAB_ERROR_CUDA
+                g_slots.push_back(c);
+                s_ = c;
+                break;
+            }
+            g_slot_cv.wait(lk);
+        }
+        s_->busy = true;
+    }
+    ~SlotLease() {
+        if (!s_) return;
+        {
+            std::lock_guard<std::mutex> lk(g_slot_mu);
+            s_->busy = false;
+        }
+        g_slot_cv.notify_one();
+    }
+    SlotLease(const SlotLease&) = delete;
+    SlotLease& operator=(const SlotLease&) = delete;
+    fab_ctx* ctx() const { return s_ ? s_->ctx : nullptr; }
+    HostPipe& pipe() const { return s_->pipe; }
+};
 // measurement switch: FLACARRAY_B200_NO_PIPE=1 sends every call down the plain (unpipelined) path
 bool pipe_enabled() {
     static const bool off = [] { const char* e = getenv("FLACARRAY_B200_NO_PIPE"); return e && e[0] == '1'; }();
@@ -1196,9 +1309,8 @@ struct PipeClock {   // FLACARRAY_B200_PIPE_DEBUG=1: phase times of the pipeline
         }                                                  \
     } while (0)
 
-int host_encode_pipelined(fab_ctx* ctx, const void* data, int dtype, int64_t n_stream, int64_t stream_size, uint32_t level,
+int host_encode_pipelined(fab_ctx* ctx, HostPipe& hp, const void* data, int dtype, int64_t n_stream, int64_t stream_size, uint32_t level,
                           int64_t* n_bytes, int64_t* starts, unsigned char** bytes) {
-    HostPipe& hp = g_pipe;
     PipeClock clk;
     const size_t stream_b = (size_t)stream_size * (dtype == FAB_I64 ? 8 : 4);
     const int64_t per = std::max<int64_t>(1, (int64_t)(kPipeChunk / stream_b));
@@ -1288,10 +1400,9 @@ done:
     return ERROR_NONE;
 }
 
-int host_decode_pipelined(fab_ctx* ctx, const unsigned char* bytes, const int64_t* starts, const int64_t* nbytes,
+int host_decode_pipelined(fab_ctx* ctx, HostPipe& hp, const unsigned char* bytes, const int64_t* starts, const int64_t* nbytes,
                           int64_t n_stream, int64_t stream_size, int is_int64, int64_t first, int64_t last, int64_t n_decode,
                           void* data, bool* handled) {
-    HostPipe& hp = g_pipe;
     *handled = false;
     const size_t row_b = (size_t)n_decode * (is_int64 ? 8 : 4);
     const int64_t per = std::max<int64_t>(1, (int64_t)(kPipeChunk / row_b));
@@ -1383,12 +1494,12 @@ int host_encode(const void* data, int dtype, int64_t n_stream, int64_t stream_si
     if (stream_size == 0) return ERROR_ZERO_STREAMSIZE;
     *n_bytes = 0;
     *bytes = nullptr;
-    std::lock_guard<std::mutex> lock(g_mu);
-    fab_ctx* ctx = default_ctx();
+    SlotLease lease;
+    fab_ctx* ctx = lease.ctx();
     if (!ctx) return FAB_ERROR_CUDA;
     size_t in_b = (size_t)n_stream * stream_size * (dtype == FAB_I64 ? 8 : 4);
     if (in_b >= kPipeMin && n_stream >= 2 && pipe_enabled())
-        return host_encode_pipelined(ctx, data, dtype, n_stream, stream_size, level, n_bytes, starts, bytes);
+        return host_encode_pipelined(ctx, lease.pipe(), data, dtype, n_stream, stream_size, level, n_bytes, starts, bytes);
     int64_t bound = fab_encode_bound(n_stream, stream_size, dtype, level);
     DevBuf d_in, d_out, d_aux;
     if (!d_in.alloc(in_b) || !d_out.alloc((size_t)bound) || !d_aux.alloc((size_t)n_stream * 16 + 64)) {
@@ -1423,8 +1534,8 @@ int host_decode(const unsigned char* bytes, const int64_t* starts, const int64_t
         if (last > stream_size || first > stream_size - 1 || first >= last) return ERROR_DECODE_SAMPLE_RANGE;
         n_decode = last - first;
     }
-    std::lock_guard<std::mutex> lock(g_mu);
-    fab_ctx* ctx = default_ctx();
+    SlotLease lease;
+    fab_ctx* ctx = lease.ctx();
     if (!ctx) return FAB_ERROR_CUDA;
     // the selected windows may be scattered (keep mask): upload the covering byte range only
     int64_t lo = INT64_MAX, hi = 0, mx = 0;
@@ -1436,7 +1547,7 @@ int host_decode(const unsigned char* bytes, const int64_t* starts, const int64_t
     size_t out_b = (size_t)n_stream * n_decode * (is_int64 ? 8 : 4);
     if (out_b >= kPipeMin && n_stream >= 2 && pipe_enabled()) {
         bool handled = false;
-        int prc = host_decode_pipelined(ctx, bytes, starts, nbytes, n_stream, stream_size, is_int64, first, last, n_decode,
+        int prc = host_decode_pipelined(ctx, lease.pipe(), bytes, starts, nbytes, n_stream, stream_size, is_int64, first, last, n_decode,
                                         data, &handled);
         if (handled) return prc;
     }
@@ -1467,8 +1578,8 @@ int host_decode(const unsigned char* bytes, const int64_t* starts, const int64_t
 template <typename T, typename I>
 int host_float_to_int(const T* input, int64_t n_stream, int64_t stream_size, const T* quanta, I* output, T* offsets,
                       T* gains) {
-    std::lock_guard<std::mutex> lock(g_mu);
-    fab_ctx* ctx = default_ctx();
+    SlotLease lease;
+    fab_ctx* ctx = lease.ctx();
     if (!ctx) return FAB_ERROR_CUDA;
     size_t n = (size_t)n_stream * stream_size;
     DevBuf d_in, d_out, d_aux;
@@ -1496,8 +1607,8 @@ int host_float_to_int(const T* input, int64_t n_stream, int64_t stream_size, con
 
 template <typename I, typename T>
 void host_int_to_float(const I* input, int64_t n_stream, int64_t stream_size, const T* offsets, const T* gains, T* output) {
-    std::lock_guard<std::mutex> lock(g_mu);
-    fab_ctx* ctx = default_ctx();
+    SlotLease lease;
+    fab_ctx* ctx = lease.ctx();
     size_t n = (size_t)n_stream * stream_size;
     DevBuf d_in, d_out, d_aux;
     if (!ctx || !d_in.alloc(n * sizeof(I)) || !d_out.alloc(n * sizeof(T)) || !d_aux.alloc((size_t)n_stream * 2 * sizeof(T))) {

@@ -105,6 +105,64 @@ FA_D uint32_t crc16_word_alu(uint32_t c, uint32_t w) {
 FA_D uint32_t crc16_b(const uint16_t* T, uint32_t c, uint32_t byte) {
     return ((c << 8) & 0xFFFF) ^ T[((c >> 8) ^ byte) & 0xFF];
 }
+// ---- CRC-16 in the trinomial domain (the bulk passes: k_dec_crc, k_enc_compact) -----------------------------------
+// P = (t + 1) T with T = t^15 + t + 1.  Instead of the CRC state the bulk passes carry the residue R = M mod T of the
+// MESSAGE polynomial (lazily reduced: any 32-bit value congruent to it) and the XOR of all message words (its parity
+// is M mod (t + 1)); the CRC is formed once per frame by crct_finish.  Everything is shifts and XORs:
+//   * t^15 = t + 1, so a value v folds as (v & 0x7FFF) ^ h ^ (h << 1), h = v >> 15 (32 bits -> 18, 29 bits -> 15);
+//   * t^(2^k) mod T only has terms out of {t, t^2, t^4, t^8} for every k >= 3 (t^8, t^16 = t^2 + t, t^32 = t^4 + t^2, ...,
+//     period 15 in k), so advancing a residue over 2^j bytes is at most four shifts -- no tables, no shared memory.
+FA_D uint32_t crct_fold(uint32_t v) {
+    const uint32_t h = v >> 15;
+    return (v & 0x7FFFu) ^ h ^ (h << 1);
+}
+// multiply by the constant with terms t^1, t^2, t^4, t^8 selected by `m` (bits 1, 2, 4, 8 of m); a < 2^24
+template <uint32_t M>
+FA_D uint32_t crct_mulc(uint32_t a) {
+    uint32_t r = 0;
+    if (M & 2u) r ^= a << 1;
+    if (M & 4u) r ^= a << 2;
+    if (M & 16u) r ^= a << 4;
+    if (M & 256u) r ^= a << 8;
+    return r;
+}
+FA_D uint32_t crct_mulv(uint32_t a, uint32_t m) {     // the same with a run-time constant
+    return ((0u - ((m >> 1) & 1u)) & (a << 1)) ^ ((0u - ((m >> 2) & 1u)) & (a << 2)) ^ ((0u - ((m >> 4) & 1u)) & (a << 4)) ^
+           ((0u - ((m >> 8) & 1u)) & (a << 8));
+}
+// t^(8 * 2^j) mod T = t^(2^(j + 3)), j = 0..14 (then it repeats)
+FA_D uint32_t crct_pow2_const(int j) {
+    const uint32_t K[15] = {0x100u, 0x006u, 0x014u, 0x110u, 0x106u, 0x012u, 0x104u, 0x016u, 0x114u, 0x116u, 0x112u, 0x102u,
+                            0x002u, 0x004u, 0x010u};
+    return K[j % 15];
+}
+// residue after `r` is followed by n zero bytes; returns a value below 2^15
+FA_D uint32_t crct_shift_bytes(uint32_t r, uint64_t n) {
+    r = crct_fold(crct_fold(r));
+    for (int j = 0; n; ++j, n >>= 1)
+        if (n & 1) {
+            const uint32_t m = crct_pow2_const(j);
+            r = crct_fold(crct_mulv(r, m));
+        }
+    return r;
+}
+// residue of 16 message bytes (q = the four little-endian words as loaded); 32 bits, lazily reduced
+FA_D uint32_t crct_chunk(const U4& q) {
+    uint32_t r = bswap32(q.x);
+    r = crct_mulc<0x14u>(crct_fold(r)) ^ bswap32(q.y);       // * t^32, next word
+    r = crct_mulc<0x14u>(crct_fold(r)) ^ bswap32(q.z);
+    r = crct_mulc<0x14u>(crct_fold(r)) ^ bswap32(q.w);
+    return r;
+}
+FA_D uint32_t crct_byte(uint32_t r, uint32_t byte) { return crct_fold((r << 8) ^ byte); }   // r < 2^24
+// CRC-16 of the message from its residue mod T (any 32-bit representative) and the XOR of its words (any word size)
+FA_D uint32_t crct_finish(uint32_t r, uint32_t xor_words) {
+    const uint32_t m = crct_fold(crct_fold(r));                       // 15 bits
+    const uint32_t a = crct_fold(crct_mulc<0x6u>(m));                 // * t^16: the CRC is M t^16 mod P
+    const uint32_t q = (uint32_t)popc32(a ^ xor_words) & 1u;          // parity(a) != parity(M): add P's cofactor T
+    return a ^ ((0u - q) & 0x8003u);
+}
+
 // word steps of the CRC pass: table-free arithmetic (FAB_CRC_ALU words out of every 2) or shared-memory tables
 #ifndef FAB_CRC_ALU
 #define FAB_CRC_ALU 1

@@ -192,6 +192,7 @@ struct TileLane {
     int need_params;
     int32_t cval;
     int plen, esc, psize, part, nparts, left, k, rawbits;
+    int fl;         // residuals of the current partition open to the four-at-a-time path: `left` when k >= 0, else 0
     int32_t h[kTileOrd];
     int32_t c[kTileOrd];
 };
@@ -210,6 +211,7 @@ FA_D bool tile_subframe_begin(BitRdC& br, int bs, int bps, TileLane& L) {
     L.lpc = 0;
     L.shift = 0;
     L.left = 0;
+    L.fl = 0;
     L.part = -1;
     L.nparts = 0;
     L.k = 0;
@@ -270,17 +272,19 @@ FA_D bool tile_subframe_params(BitRdC& br, int bs, TileLane& L) {
     if (porder > 0 && L.psize < order) return false;
     L.part = -1;
     L.left = 0;
+    L.fl = 0;
     return !br.err;
 }
 
 FA_D void tile_open_partition(BitRdC& br, TileLane& L) {
     while (L.left == 0) {
         L.part++;
-        if (L.part >= L.nparts) { br.err = 1; L.left = 1 << 30; L.k = 0; return; }
+        if (L.part >= L.nparts) { br.err = 1; L.left = 1 << 30; L.k = 0; L.fl = 0; return; }
         L.left = L.psize - (L.part == 0 ? L.order : 0);
         int k = (int)brc_read(br, L.plen);
         if (k == L.esc) { L.k = -1; L.rawbits = (int)brc_read(br, 5); }
         else L.k = k;
+        L.fl = L.k >= 0 ? L.left : 0;
     }
 }
 
@@ -296,6 +300,7 @@ FA_D int32_t tile_next_sample(BitRdC& br, TileLane& L) {
     } else {
         if (L.left == 0) tile_open_partition(br, L);
         L.left--;
+        L.fl = L.fl > 0 ? L.fl - 1 : 0;
         int32_t r = (L.k >= 0) ? brc_rice(br, L.k) : brc_read_signed(br, L.rawbits);
         int64_t sum = 0;
 #pragma unroll
@@ -349,6 +354,7 @@ FA_D void tile_next4(BitRdC& br, TileLane& L, int32_t* out4) {
         brc_window_load(br);
     }
     L.left -= 4;
+    L.fl -= 4;
     int32_t s[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -393,7 +399,9 @@ FA_D void tile_channel_pass(const TileParams& P, TileShared* ws, BitRdC& br, Til
             int i = (int)base + s;
             if ((s & 4) == 0) brc_service(br);   // warp-uniform refill point of the compressed-byte rings (every 8 samples)
             if (run && i < bs) {
-                bool fast = L.mode == 2 && L.raw_left == 0 && !L.need_params && L.left >= 4 && L.k >= 0 && i + 4 <= bs;
+                // (fl >= 4 implies a predictive subframe past its warm-up and parameters, k >= 0, and -- partitions tile the
+                // block -- four more samples inside the block)
+                const bool fast = L.fl >= 4;
                 if (fast) {
                     if (!br.wok) { brc_ensure(br, 64u); brc_window_load(br); br.wok = 1; }
                     tile_next4<ORD>(br, L, trow + s);
@@ -544,7 +552,7 @@ FA_D void tile_warp_body(const TileParams& P, int64_t item0, TileShared* ws) {
     bool fail = false;      // stream problem -> walker
     bool punt = false;      // unsupported subframe -> general decoder
     TileLane L;
-    L.mode = 0; L.order = 0; L.raw_left = 0; L.need_params = 0; L.left = 0; L.k = 0; L.wasted = 0; L.shift = 0; L.cval = 0;
+    L.mode = 0; L.order = 0; L.raw_left = 0; L.need_params = 0; L.left = 0; L.fl = 0; L.k = 0; L.wasted = 0; L.shift = 0; L.cval = 0;
     for (int c = 0; c < nch; ++c) {
         if (active && !fail && !punt) {
             if (!tile_subframe_begin(br, bs, 32, L)) {
@@ -578,12 +586,11 @@ FA_D void tile_warp_body(const TileParams& P, int64_t item0, TileShared* ws) {
 // ------------------------------------------------------------------------------------------------------
 // Frame CRC-16 as its own frame-parallel pass (k_dec_crc): one warp per (stream, frame) item of the tile
 // decoder's index space.  Inside the tile decoder the CRC was 23 % of the instructions, sitting on the
-// serial per-lane chain and doubled by divergence; here every lane folds a contiguous slice of the frame
-// (slice-by-4 over aligned words, tables in shared memory), the slice CRCs are advanced to the frame end
-// with the shift tables and XOR-reduced.  A mismatch flags the stream for the sequential walker exactly
-// like a mismatch found by the fused check (tile_warp_body<true>).
+// serial per-lane chain and doubled by divergence; here the warp reads the frame in coalesced 512-byte rows
+// and works in the trinomial domain of fa_bits.h (shifts and XORs only: no tables, no shared memory).  A
+// mismatch flags the stream for the sequential walker exactly like a mismatch found by the general decoder.
 // ------------------------------------------------------------------------------------------------------
-FA_D void crc_frame_warp(const TileParams& P, int64_t idx, const uint16_t* T, const uint16_t* S9hi, const uint16_t* S9lo) {
+FA_D void crc_frame_warp(const TileParams& P, int64_t idx) {
     const DecParams& D = P.D;
     const int ln = lane();
     const int64_t k = idx / P.nwin;
@@ -604,45 +611,53 @@ FA_D void crc_frame_warp(const TileParams& P, int64_t idx, const uint16_t* T, co
     const uint8_t* fp = D.bytes + D.starts[k] + off;
     const int64_t nbody = len - 2;
     const uint32_t want = ((uint32_t)fp[len - 2] << 8) | fp[len - 1];
-    // The CRC is linear (zero initial state, no final XOR).  The frame is cut into `head` bytes up to a 16-byte
-    // boundary, n16 aligned 16-byte chunks and a `tail`; the chunks form rows of 32 that the warp loads with one
-    // coalesced 512-byte access each, RIGHT-aligned so that the last row is full.  Every lane keeps a Horner
-    // accumulator over its column (rows are 512 bytes apart: one table step), the 32 columns are then combined
-    // by a butterfly with power-of-two shifts, and the tail is appended.
+    // The frame is cut into `head` bytes up to a 16-byte boundary, n16 aligned 16-byte chunks and a `tail`; the chunks form
+    // rows of 32 that the warp loads with one coalesced 512-byte access each, RIGHT-aligned so that the last row is full.
+    // Every lane keeps a Horner accumulator over its column in the trinomial domain (fa_bits.h: rows are 512 bytes apart,
+    // * t^4096 is four shifts) plus the XOR of its words; the 32 columns are combined by a butterfly with power-of-two
+    // shifts, head and tail are added by lane 0, and crct_finish forms the CRC.
     int64_t head = (int64_t)((16 - ((uintptr_t)fp & 15)) & 15);
     if (head > nbody) head = nbody;
-    const int64_t n16 = (nbody - head) >> 4;
+    const int n16 = (int)((nbody - head) >> 4);
     const uint8_t* base = fp + head;
-    uint32_t c = 0;
-    if (n16 == 0) {
-        for (int64_t i = 0; i < nbody; ++i) c = crc16_b(T, c, fp[i]);
-        if (ln == 0 && c != want) atom_or_global(&D.stream_flag[k], 2);
-        return;
-    }
-    const int64_t rows = (n16 + 31) >> 5;
-    const int64_t first = (rows << 5) - n16;          // lanes below this have no chunk in row 0
-    for (int64_t r = 0; r < rows; ++r) {
-        const int64_t ci = (r << 5) + ln - first;
-        if (r > 0) c = (uint32_t)(S9hi[(c >> 8) & 0xFF] ^ S9lo[c & 0xFF]);       // 512 bytes further from the end
-        if (ci >= 0) {
-            uint32_t t = 0;
-            if (ci == 0) for (int64_t i = 0; i < head; ++i) t = crc16_b(T, t, fp[i]);   // the head runs into chunk 0
-            const U4 q = ldg128(base + (ci << 4));
-            t = FAB_CRC_STEP0(T, t, bswap32(q.x));
-            t = FAB_CRC_STEP1(T, t, bswap32(q.y));
-            t = FAB_CRC_STEP0(T, t, bswap32(q.z));
-            t = FAB_CRC_STEP1(T, t, bswap32(q.w));
-            c ^= t;
+    uint32_t c = 0, px = 0;
+    if (n16 > 0) {
+        const int rows = (n16 + 31) >> 5;
+        const int first = (rows << 5) - n16;          // lanes below this have no chunk in row 0
+        const U4* cp = (const U4*)base + (ln - first);
+        if (ln >= first) {
+            const U4 q = ldg128(cp);
+            c = crct_fold(crct_chunk(q));
+            px = q.x ^ q.y ^ q.z ^ q.w;
         }
+        for (int r = 1; r < rows; ++r) {
+            cp += 32;
+            const U4 q = ldg128(cp);
+            c = crct_fold(crct_mulc<0x116u>(c) ^ crct_chunk(q));      // (c < 2^18 -> * t^4096 < 2^26)
+            px ^= q.x ^ q.y ^ q.z ^ q.w;
+        }
+        c = crct_fold(crct_fold(c));
+        // lane l's column still has to move 16 * (31 - l) bytes: combine groups of 1, 2, 4, 8, 16 lanes
+        {
+            uint32_t u;
+            u = shfl_xor(c, 1);  if (ln & 1) c = crct_fold(crct_mulc<0x106u>(u)) ^ c;      // * t^128
+            u = shfl_xor(c, 2);  if (ln & 2) c = crct_fold(crct_mulc<0x012u>(u)) ^ c;      // * t^256
+            u = shfl_xor(c, 4);  if (ln & 4) c = crct_fold(crct_mulc<0x104u>(u)) ^ c;      // * t^512
+            u = shfl_xor(c, 8);  if (ln & 8) c = crct_fold(crct_mulc<0x016u>(u)) ^ c;      // * t^1024
+            u = shfl_xor(c, 16); if (ln & 16) c = crct_fold(crct_mulc<0x114u>(u)) ^ c;     // * t^2048
+        }
+        c = shfl(c, 31);
+        px = redux_xor(px);
     }
-    // lane l's column value still has to move 16 * (31 - l) bytes: combine groups of 1, 2, 4, 8, 16 lanes
-    for (int d = 0; d < 5; ++d) {
-        const uint32_t u = shfl_xor(c, 1 << d);
-        if ((ln >> d) & 1) c ^= crc16_shift_pow2(D.crc, u, 4 + d);
+    if (ln == 0) {
+        // the head sits n16 * 16 bytes in front of the end of the chunks
+        uint32_t h = 0;
+        for (int64_t i = 0; i < head; ++i) { h = crct_byte(h, fp[i]); px ^= fp[i]; }
+        if (head > 0 && n16 > 0) h = crct_shift_bytes(h, (uint64_t)n16 << 4);
+        c ^= h;
+        for (int64_t i = head + ((int64_t)n16 << 4); i < nbody; ++i) { c = crct_byte(c, fp[i]); px ^= fp[i]; }
+        if (crct_finish(c, px) != want) atom_or_global(&D.stream_flag[k], 2);
     }
-    c = shfl(c, 31);
-    for (int64_t i = head + (n16 << 4); i < nbody; ++i) c = crc16_b(T, c, fp[i]);
-    if (ln == 0 && c != want) atom_or_global(&D.stream_flag[k], 2);
 }
 
 }  // namespace fa

@@ -935,26 +935,24 @@ FA_D void scan_batch_cta(const EncParams& P, unsigned long long* sh_part /*[kSca
 // memory-bound, so the ~15 instructions per word ride along instead of sitting on k_encode's chain.
 // The CRC is linear (zero initial state, no final XOR): the body is cut into 16-byte chunks, rows of 128
 // chunks are loaded with one coalesced access each and RIGHT-aligned so that the last row is full; every
-// thread keeps a Horner accumulator over its column (rows are 2048 bytes apart: one step with the
-// shift tables S11), the 128 columns are combined by a butterfly of power-of-two shifts and the
+// thread keeps a Horner accumulator over its column in the trinomial domain of fa_bits.h (rows are 2048 bytes
+// apart: * t^16384 = two shifts; no tables), the 128 columns are combined by a butterfly of power-of-two shifts and the
 // (< 16) trailing bytes are appended.  The same registers feed the copy: the destination is cut into ALIGNED
 // 16-byte blocks, block k = the last `a` bytes of chunk k - 1 (from the left neighbour lane) and the first 16 - a
 // bytes of chunk k, a = destination address mod 16, assembled with funnel shifts (AW = a / 4 selects the words at
 // compile time) and written with one 16-byte store; the (< 16) bytes before the first and the (< 32) bytes
 // behind the last aligned block are stored bytewise.
-// T: [4][256] slice tables, S11hi / S11lo: state * x^(8 * 2048), SH: [5][2][256] = state * x^(8 * 2^(4 + d)), hi / lo byte.
-struct CompactShared { uint32_t wcrc[4]; };
+struct CompactShared { uint32_t wcrc[4], wpx[4]; };
 FA_D U4 u4_zero_enc() { U4 z; z.x = z.y = z.z = z.w = 0; return z; }
 
 template <int AW>
-FA_D uint32_t compact_rows(const uint32_t* src, uint8_t* dst_al, uint32_t a, uint32_t n16, const uint16_t* T,
-                           const uint16_t* S11hi, const uint16_t* S11lo) {
+FA_D uint32_t compact_rows(const uint32_t* src, uint8_t* dst_al, uint32_t a, uint32_t n16, uint32_t& px_out) {
     const int t = tid(), ln = lane();
     const uint32_t rows = (n16 + 127u) >> 7;
     const uint32_t first = (rows << 7) - n16;     // threads below this have no chunk in row 0
     const uint32_t sh = (a & 3u) ? 8u * (4u - (a & 3u)) : 32u;
     const int64_t kb0 = a ? 1 : 0;                // first destination block that lies inside the frame
-    uint32_t c = 0;
+    uint32_t c = 0, px = 0;
     int64_t ci = (int64_t)t - (int64_t)first;
     U4 q = u4_zero_enc(), pq = u4_zero_enc();
     if (ci >= 0) q = ldg128(src + (ci << 2));
@@ -967,7 +965,6 @@ FA_D uint32_t compact_rows(const uint32_t* src, uint8_t* dst_al, uint32_t a, uin
             qn = ldg128(src + (cn << 2));
             if (ln == 0) pn = ldg128(src + ((cn - 1) << 2));
         }
-        if (r > 0) c = (uint32_t)(S11hi[(c >> 8) & 0xFF] ^ S11lo[c & 0xFF]);
         // words 3 - AW .. 3 of the chunk on the left
         U4 p;
         p.w = shfl_up(q.w, 1);
@@ -976,12 +973,9 @@ FA_D uint32_t compact_rows(const uint32_t* src, uint8_t* dst_al, uint32_t a, uin
         p.x = AW >= 3 ? shfl_up(q.x, 1) : 0u;
         if (ln == 0) p = pq;
         if (ci >= 0) {
-            uint32_t x = 0;
-            x = FAB_CRC_STEP0(T, x, bswap32(q.x));
-            x = FAB_CRC_STEP1(T, x, bswap32(q.y));
-            x = FAB_CRC_STEP0(T, x, bswap32(q.z));
-            x = FAB_CRC_STEP1(T, x, bswap32(q.w));
-            c ^= x;
+            // rows are 2048 bytes apart: * t^16384 = * (t^8 + t) in the trinomial domain (c < 2^18 -> < 2^26)
+            c = crct_fold(crct_mulc<0x102u>(c) ^ crct_chunk(q));
+            px ^= q.x ^ q.y ^ q.z ^ q.w;
             if (ci >= kb0) {
                 const uint32_t W[8] = {p.x, p.y, p.z, p.w, q.x, q.y, q.z, q.w};
                 U4 o;
@@ -994,11 +988,11 @@ FA_D uint32_t compact_rows(const uint32_t* src, uint8_t* dst_al, uint32_t a, uin
         }
         q = qn; pq = pn; ci = cn;
     }
-    return c;
+    px_out = px;
+    return crct_fold(crct_fold(c));
 }
 
-FA_D void compact_frame_cta(const EncParams& P, uint32_t i, const uint16_t* T, const uint16_t* S11hi, const uint16_t* S11lo,
-                            const uint16_t* SH, CompactShared* cs) {
+FA_D void compact_frame_cta(const EncParams& P, uint32_t i, CompactShared* cs) {
     const uint32_t g = P.g_begin + i;
     const uint32_t len = P.fsize[i];              // body + the two CRC bytes
     const unsigned long long end = P.desc[g];
@@ -1014,19 +1008,24 @@ FA_D void compact_frame_cta(const EncParams& P, uint32_t i, const uint16_t* T, c
     const uint32_t a = (uint32_t)((uintptr_t)dst & 15u);
     uint8_t* dst_al = dst - a;
     const uint32_t n16 = body >> 4;
-    uint32_t c;
+    uint32_t c, px;
     switch (a >> 2) {
-        case 0: c = compact_rows<0>(src, dst_al, a, n16, T, S11hi, S11lo); break;
-        case 1: c = compact_rows<1>(src, dst_al, a, n16, T, S11hi, S11lo); break;
-        case 2: c = compact_rows<2>(src, dst_al, a, n16, T, S11hi, S11lo); break;
-        default: c = compact_rows<3>(src, dst_al, a, n16, T, S11hi, S11lo); break;
+        case 0: c = compact_rows<0>(src, dst_al, a, n16, px); break;
+        case 1: c = compact_rows<1>(src, dst_al, a, n16, px); break;
+        case 2: c = compact_rows<2>(src, dst_al, a, n16, px); break;
+        default: c = compact_rows<3>(src, dst_al, a, n16, px); break;
     }
     // thread t's column value still has to move 16 * (127 - t) bytes: lanes first (groups of 1 .. 16), then warps
-    for (int d = 0; d < 5; ++d) {
-        const uint32_t u = shfl_xor(c, 1 << d);
-        if ((ln >> d) & 1) c ^= (uint32_t)(SH[(2 * d) * 256 + ((u >> 8) & 0xFF)] ^ SH[(2 * d + 1) * 256 + (u & 0xFF)]);
+    {
+        uint32_t u;
+        u = shfl_xor(c, 1);  if (ln & 1) c = crct_fold(crct_mulc<0x106u>(u)) ^ c;      // * t^128
+        u = shfl_xor(c, 2);  if (ln & 2) c = crct_fold(crct_mulc<0x012u>(u)) ^ c;      // * t^256
+        u = shfl_xor(c, 4);  if (ln & 4) c = crct_fold(crct_mulc<0x104u>(u)) ^ c;      // * t^512
+        u = shfl_xor(c, 8);  if (ln & 8) c = crct_fold(crct_mulc<0x016u>(u)) ^ c;      // * t^1024
+        u = shfl_xor(c, 16); if (ln & 16) c = crct_fold(crct_mulc<0x114u>(u)) ^ c;     // * t^2048
     }
-    if (ln == 31) cs->wcrc[wp] = c;
+    px = redux_xor(px);
+    if (ln == 31) { cs->wcrc[wp] = c; cs->wpx[wp] = px; }
     // the bytes outside the aligned blocks: src [0, hb) in front, src [done, body) behind
     const uint32_t h = a ? 16u - a : 0u;
     const uint32_t hb = h < body ? h : body;
@@ -1038,9 +1037,13 @@ FA_D void compact_frame_cta(const EncParams& P, uint32_t i, const uint16_t* T, c
     }
     sync();
     if (t == 0) {
-        uint32_t v = 0;
-        for (int w = 0; w < 4; ++w) v = crc16_shift_pow2(P.crc, v, 9) ^ cs->wcrc[w];     // warps are 512 bytes apart
-        for (uint32_t k = n16 << 4; k < body; ++k) v = crc16_b(T, v, sb[k]);
+        uint32_t v = 0, x = 0;
+        for (int w = 0; w < 4; ++w) {                                  // warps are 512 bytes apart: * t^4096
+            v = crct_fold(crct_mulc<0x116u>(v)) ^ cs->wcrc[w];
+            x ^= cs->wpx[w];
+        }
+        for (uint32_t k = n16 << 4; k < body; ++k) { v = crct_byte(v, sb[k]); x ^= sb[k]; }
+        v = crct_finish(v, x);
         dst[body] = (uint8_t)(v >> 8);
         dst[body + 1] = (uint8_t)v;
     }

@@ -59,7 +59,9 @@ extern "C" {
  * (1) Reference-compatible host-buffer entry points
  *
  * Same signatures, ownership (`*bytes` is malloc()ed, the caller frees it) and return codes as the
- * reference.  Calls are serialised on one process-wide context.  Arrays of 64 MB or more move through
+ * reference.  Like the reference they are re-entrant: every call leases one of a few host slots (context +
+ * staging buffers, FLACARRAY_B200_HOST_SLOTS, default 4), so concurrent callers run side by side on their own
+ * CUDA streams; callers beyond the slot count wait for a slot.  Arrays of 64 MB or more move through
  * persistent pinned staging buffers in 128 MB chunks of whole streams (host copies on several threads,
  * H2D / kernels / D2H on three CUDA streams); FLACARRAY_B200_NO_PIPE=1 selects the plain
  * cudaMemcpy path, FLACARRAY_B200_PIPE_DEBUG=1 prints the phase times of the pipelined encode.
@@ -114,6 +116,20 @@ int64_t fab_launch_count(const fab_ctx* ctx);
 
 /* Upper bound of the compressed size (bytes) for n_stream streams of stream_size samples. */
 int64_t fab_encode_bound(int64_t n_stream, int64_t stream_size, int dtype, uint32_t level);
+
+/*
+ * Workspace.  fab_encode / fab_decode / fab_float_to_int / fab_stream_std keep their intermediates (per-frame
+ * statistics and plans, frame slots, frame-offset tables, min/max partials) in one device block.  By default the
+ * context owns a grow-only block; growing it waits for this context's own streams only.  A caller that wants no
+ * allocation inside the calls sizes the block with fab_*_workspace_bytes (0 = invalid arguments) and hands it
+ * over with fab_set_workspace (256-byte aligned device memory; NULL returns to the context-owned block).  With a
+ * caller-supplied workspace a call that needs more than was supplied fails with ERROR_ALLOC and says how much in
+ * fab_last_error -- it never allocates.  (The reference has no equivalent: libFLAC allocates per encoder object,
+ * compress.c:184-200.)
+ */
+int64_t fab_encode_workspace_bytes(int64_t n_stream, int64_t stream_size, int dtype, uint32_t level);
+int64_t fab_decode_workspace_bytes(int64_t n_stream, int64_t stream_size, int blocksize_hint);
+int fab_set_workspace(fab_ctx* ctx, void* d_workspace, int64_t bytes);
 
 /*
  * Encode (replaces compress.c:133-435 + the libFLAC encoder; for float input also utils.c:160-328

@@ -116,16 +116,8 @@ int hs_encode(const void* data, int dtype, int64_t n_stream, int64_t stream_size
         else encode_frames_cta<8, false>(P, fasim::smem(), 0, 1);
     });
     fasim::launch(1, kScanThreads, (kScanThreads / 32 + 1) * 8, [&](int) { scan_batch_cta(P, (unsigned long long*)fasim::smem()); });
-    std::vector<uint16_t> ctab(4 * 256), s11(2 * 256);
-    for (int i = 0; i < 4 * 256; ++i) ctab[(size_t)i] = crc()->crc16[i >> 8][i & 255];
-    for (int i = 0; i < 256; ++i) { s11[(size_t)i] = crc()->shift_hi[11][i]; s11[(size_t)(256 + i)] = crc()->shift_lo[11][i]; }
-    std::vector<uint16_t> shd(5 * 2 * 256);
-    for (int i = 0; i < 5 * 2 * 256; ++i) {
-        const int d = i >> 9, lo = (i >> 8) & 1, b = i & 255;
-        shd[(size_t)i] = lo ? crc()->shift_lo[4 + d][b] : crc()->shift_hi[4 + d][b];
-    }
     fasim::launch((int)total_frames, 128, sizeof(CompactShared), [&](int b) {
-        compact_frame_cta(P, (uint32_t)b, ctab.data(), s11.data(), s11.data() + 256, shd.data(), (CompactShared*)fasim::smem());
+        compact_frame_cta(P, (uint32_t)b, (CompactShared*)fasim::smem());
     });
     fasim::launch(1, 1, 0, [&](int) {
         for (int64_t s = 0; s < n_stream; ++s)
@@ -172,13 +164,11 @@ int hs_decode(const uint8_t* bytes, const long long* starts, const long long* nb
         TP.D = P; TP.j0 = first_decode / bsh; TP.nwin = nwin; TP.frame_flag = fflag.data();
         TP.restore = 0; TP.offsets = nullptr; TP.gains = nullptr;
         int64_t total = n_sel * nwin;
-        std::vector<uint16_t> tab(4 * 256);
-        for (int i = 0; i < 4 * 256; ++i) tab[(size_t)i] = crc()->crc16[i >> 8][i & 255];
         // the product launches the tile decoder without the fused CRC and checks it in k_dec_crc
         fasim::launch((int)((total + 31) / 32), 32, sizeof(TileShared) + 64, [&](int b) {
             tile_warp_body(TP, (int64_t)b * 32, (TileShared*)fasim::smem());
         });
-        fasim::launch((int)total, 32, 0, [&](int b) { crc_frame_warp(TP, (int64_t)b, tab.data(), crc()->shift_hi[9], crc()->shift_lo[9]); });
+        fasim::launch((int)total, 32, 0, [&](int b) { crc_frame_warp(TP, (int64_t)b); });
         int walked = 0, general = 0;
         fasim::launch(1, 1, 0, [&](int) {
             DecParams Q = P;
