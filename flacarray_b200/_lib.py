@@ -82,6 +82,12 @@ def lib():
         L.fab_launch_count.argtypes = [_vp]
         L.fab_encode_bound.restype = _i64
         L.fab_encode_bound.argtypes = [_i64, _i64, _i32, _u32]
+        L.fab_encode_workspace_bytes.restype = _i64
+        L.fab_encode_workspace_bytes.argtypes = [_i64, _i64, _i32, _u32]
+        L.fab_decode_workspace_bytes.restype = _i64
+        L.fab_decode_workspace_bytes.argtypes = [_i64, _i64, _i32]
+        L.fab_set_workspace.restype = _i32
+        L.fab_set_workspace.argtypes = [_vp, _vp, _i64]
         L.fab_encode.restype = _i32
         L.fab_encode.argtypes = [_vp, _vp, _i32, _i64, _i64, _u32, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]
         L.fab_decode.restype = _i32
@@ -106,6 +112,7 @@ EXPORTED = [
     "encode_i32", "encode_i32_threaded", "encode_i64", "encode_i64_threaded", "decode_i32", "decode_i64",
     "float32_to_int32", "float64_to_int64", "int64_to_float64", "int32_to_float32",
     "fab_create", "fab_destroy", "fab_last_error", "fab_launch_count", "fab_encode_bound", "fab_encode",
+    "fab_encode_workspace_bytes", "fab_decode_workspace_bytes", "fab_set_workspace",
     "fab_decode", "fab_stream_std", "fab_float_to_int", "fab_int_to_float", "fab_finish", "fab_profile", "fab_profile_ms",
 ]
 
@@ -132,6 +139,15 @@ class Context:
 
     def launches(self):
         return int(lib().fab_launch_count(self._h))
+
+    def set_workspace(self, tensor):
+        """Hand the context a caller-owned device block (uint8 tensor, 256-byte aligned; None = back to the
+        context-owned grow-only block).  With it no call allocates device memory: one that needs more fails."""
+        ptr, n = (None, 0) if tensor is None else (tensor.data_ptr(), tensor.numel() * tensor.element_size())
+        rc = lib().fab_set_workspace(self._h, ptr, n)
+        if rc != 0:
+            raise RuntimeError(f"fab_set_workspace failed (code {rc}): {self.last_error()}")
+        self._ws = tensor      # keep the block alive as long as the context uses it
 
     def profile(self, enable):
         lib().fab_profile(self._h, 1 if enable else 0)

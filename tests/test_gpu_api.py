@@ -363,3 +363,98 @@ def test_device_encode_capacity_guess_and_overflow_fallback(fa):
     assert sizes[0] == sizes[1] == sizes[4] and sizes[2] == sizes[3] > 3 * sizes[0]
     hist = lf._ratio_history()[(torch.cuda.current_device(), torch.int32, 5)]
     assert len(hist) == 4 and max(hist) > 0.9
+
+
+def test_caller_supplied_workspace(fa):
+    """fab_set_workspace: the calls use the caller's block and never allocate; a block that is too small is an
+    ERROR_ALLOC with the needed size in fab_last_error, not a hidden cudaMalloc (include/flacarray_b200.h)."""
+    import torch
+
+    from flacarray_b200 import _lib, libflacarray as lf
+
+    L = _lib.lib()
+    dev = torch.device("cuda", 0)
+    ctx = _lib.context(dev)
+    n_stream, n_samp = 24, 30000
+    rng = np.random.default_rng(5)
+    x = np.cumsum(rng.integers(-200, 201, (n_stream, n_samp)), axis=1).astype(np.int32)
+    need_e = L.fab_encode_workspace_bytes(n_stream, n_samp, 0, 5)
+    need_d = L.fab_decode_workspace_bytes(n_stream, n_samp, 4096)
+    assert need_e > 0 and need_d > 0
+    assert L.fab_encode_workspace_bytes(0, n_samp, 0, 5) == 0 and L.fab_encode_workspace_bytes(1, 1, 0, 9) == 0
+    ref = fa.array_compress(x, level=5)
+    try:
+        ws = torch.empty(max(need_e, need_d), dtype=torch.uint8, device=dev)
+        ctx.set_workspace(ws)
+        before = torch.cuda.memory_allocated(dev)
+        got = fa.array_compress(x, level=5)
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
+        y = fa.array_decompress(got[0], n_samp, got[1], got[2])
+        assert np.array_equal(y, x)
+        # too small: refused, with the size in the message
+        small = torch.empty(4096, dtype=torch.uint8, device=dev)
+        ctx.set_workspace(small)
+        with pytest.raises(Exception) as ei:
+            fa.array_compress(x, level=5)
+        assert "workspace too small" in str(ei.value) or "workspace too small" in ctx.last_error()
+        del before
+    finally:
+        ctx.set_workspace(None)
+    got = fa.array_compress(x, level=5)
+    assert np.array_equal(got[0], ref[0])
+
+
+def test_reference_signature_entry_points_are_reentrant(fa):
+    """Four host threads call encode_i32 / decode_i32 (host pointers, reference signatures) at once: each leases its
+    own host slot (context + staging buffers), results are identical to a serial call."""
+    import ctypes as C
+    import threading
+
+    from flacarray_b200 import _lib
+
+    L = _lib.lib()
+    rng = np.random.default_rng(77)
+    arrays = [np.cumsum(rng.integers(-500, 501, (16, 40000)), axis=1).astype(np.int32) for _ in range(4)]
+
+    def enc(a):
+        n_bytes = C.c_int64(0)
+        starts = np.zeros(a.shape[0], np.int64)
+        buf = C.POINTER(C.c_ubyte)()
+        rc = L.encode_i32(C.c_void_p(a.ctypes.data), C.c_int64(a.shape[0]), C.c_int64(a.shape[1]), C.c_uint32(5),
+                          C.byref(n_bytes), C.c_void_p(starts.ctypes.data), C.byref(buf))
+        assert rc == 0, rc
+        out = np.ctypeslib.as_array(buf, shape=(n_bytes.value,)).copy()
+        C.CDLL(None).free(buf)
+        return out, starts
+
+    def dec(b, starts, shape):
+        nb = np.diff(np.append(starts, b.size)).astype(np.int64)
+        out = np.zeros(shape, np.int32)
+        rc = L.decode_i32(C.c_void_p(b.ctypes.data), C.c_void_p(starts.ctypes.data), C.c_void_p(nb.ctypes.data),
+                          C.c_int64(shape[0]), C.c_int64(shape[1]), C.c_int64(-1), C.c_int64(-1), C.c_void_p(out.ctypes.data),
+                          C.c_bool(False))
+        assert rc == 0, rc
+        return out
+
+    L.encode_i32.restype = C.c_int
+    L.decode_i32.restype = C.c_int
+    serial = [enc(a) for a in arrays]
+    results = [None] * 4
+
+    def work(i):
+        try:
+            ok = True
+            for _ in range(4):
+                b, st = enc(arrays[i])
+                ok = ok and np.array_equal(b, serial[i][0]) and np.array_equal(st, serial[i][1])
+                ok = ok and np.array_equal(dec(b, st, arrays[i].shape), arrays[i])
+            results[i] = ok
+        except BaseException as e:  # noqa: BLE001
+            results[i] = e
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=180)
+    assert results == [True] * 4, results
