@@ -305,25 +305,13 @@ __global__ void __launch_bounds__(128) k_dec_meta(const DecParams P) {
 }
 
 constexpr int kSyncThreads = 256;
-constexpr int kSyncBytesPerThread = 64;
+constexpr int kSyncBytesPerThread = 64;      // grid sizing: bytes of a stream per thread and grid pass
 
+// frame-sync scan of the streams without a frame-size table: grid (x, stream), the warps of a stream's CTAs stride
+// over its 512-byte rows (sync_scan_warp)
 __global__ void __launch_bounds__(kSyncThreads) k_dec_sync(const DecParams P) {
     const int64_t k = blockIdx.y;
-    if (P.stream_flag[k] != 0 || P.meta[k].table_off >= 0) return;
-    const int64_t nb = P.nbytes[k];
-    const uint8_t* buf = P.bytes + P.starts[k];
-    for (int64_t c = blockIdx.x;; c += gridDim.x) {
-        const int64_t p0 = (c * kSyncThreads + threadIdx.x) * kSyncBytesPerThread;
-        if (c * kSyncThreads * kSyncBytesPerThread >= nb) return;
-        if (p0 >= nb) continue;
-        int64_t p1 = p0 + kSyncBytesPerThread < nb - 1 ? p0 + kSyncBytesPerThread : nb - 1;
-        uint32_t prev = buf[p0];
-        for (int64_t p = p0; p < p1; ++p) {
-            uint32_t cur = buf[p + 1];
-            if (prev == 0xFF && cur == 0xF8) sync_body(P, k, p);
-            prev = cur;
-        }
-    }
+    sync_scan_warp(P, k, (int64_t)blockIdx.x * (kSyncThreads / 32) + (threadIdx.x >> 5), (int64_t)gridDim.x * (kSyncThreads / 32));
 }
 
 constexpr int kDecThreads = 128;

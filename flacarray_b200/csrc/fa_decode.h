@@ -320,6 +320,53 @@ FA_D void sync_body(const DecParams& P, int64_t k, int64_t p) {
     if (prev != -1 && prev != p) atom_or_global(&P.stream_flag[k], 2);  // two candidates for one frame
 }
 
+// The scan itself, warp-cooperative: warp `w` of `nw` takes rows of 32 aligned 16-byte chunks of stream k (one
+// coalesced 512-byte load per row), every lane finds the positions of the byte pair FF F8 inside its chunk with
+// branch-free byte-parallel arithmetic (exact zero-byte masks of ~w and w ^ F8F8F8F8, the second shifted down one
+// byte through a funnel shift that pulls in the first byte of the next word / next lane's chunk) and hands the
+// candidates -- one per frame plus ~one false hit per 64 KB -- to sync_body.  ~3 instructions per byte.
+FA_D uint32_t zero_bytes(uint32_t v) {      // 0x80 in every byte of v that is zero (exact)
+    const uint32_t t = (v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+    return ~(t | v | 0x7F7F7F7Fu);
+}
+FA_D void sync_scan_warp(const DecParams& P, int64_t k, int64_t w, int64_t nw) {
+    if (P.stream_flag[k] != 0 || P.meta[k].table_off >= 0) return;
+    const int ln = lane();
+    const int64_t nb = P.nbytes[k];
+    const uint8_t* buf = P.bytes + P.starts[k];
+    const int64_t head = (int64_t)((uintptr_t)buf & 15);
+    const uint8_t* abase = buf - head;                    // (aligned chunks: the first / last one may hold a neighbour's bytes)
+    const int64_t n16 = (head + nb + 15) >> 4;
+    for (int64_t row = w; (row << 5) < n16; row += nw) {
+        const int64_t ci = (row << 5) + ln;
+        U4 q; q.x = q.y = q.z = q.w = 0;
+        if (ci < n16) q = ldg128(abase + (ci << 4));
+        uint32_t nxt = shfl_down(q.x, 1);                 // first word of the chunk behind this one
+        if (ln == 31) nxt = ci + 1 < n16 ? (uint32_t)abase[(ci + 1) << 4] : 0u;
+        const uint32_t f0 = zero_bytes(~q.x), f1 = zero_bytes(~q.y), f2 = zero_bytes(~q.z), f3 = zero_bytes(~q.w);
+        const uint32_t e0 = zero_bytes(q.x ^ 0xF8F8F8F8u), e1 = zero_bytes(q.y ^ 0xF8F8F8F8u),
+                       e2 = zero_bytes(q.z ^ 0xF8F8F8F8u), e3 = zero_bytes(q.w ^ 0xF8F8F8F8u);
+        const uint32_t e4 = zero_bytes((nxt & 0xFFu) ^ 0xF8u) & 0x80u;
+        // byte i is FF and byte i + 1 is F8 (little-endian words: the next byte sits 8 bits higher)
+        uint32_t c[4];
+        c[0] = f0 & funnel_r(e0, e1, 8);
+        c[1] = f1 & funnel_r(e1, e2, 8);
+        c[2] = f2 & funnel_r(e2, e3, 8);
+        c[3] = f3 & funnel_r(e3, e4, 8);
+        if ((c[0] | c[1] | c[2] | c[3]) != 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint32_t m = c[j];
+                while (m) {
+                    const int b = (31 - clz32(m)) >> 3;       // byte index inside the word
+                    m &= ~(0x80u << (8 * b));
+                    sync_body(P, k, (ci << 4) + 4 * j + b - head);
+                }
+            }
+        }
+    }
+}
+
 // ---- stage 3: one thread per (selected stream, frame overlapping the sample window) ---------------
 FA_D void frame_body(const DecParams& P, int64_t k, int64_t j) {
     if (P.stream_flag[k] != 0) return;

@@ -154,9 +154,9 @@ int hs_decode(const uint8_t* bytes, const long long* starts, const long long* nb
         // flagged frames -> walker on the flagged streams
         fasim::launch(1, 1, 0, [&](int) {
             for (int64_t k = 0; k < n_sel; ++k) meta_body(P, k);
-            for (int64_t k = 0; k < n_sel; ++k)
-                for (int64_t p = 0; p < nbytes[k]; ++p) sync_body(P, k, p);
         });
+        // the product's warp-cooperative scan (three warps striding over each stream's rows)
+        fasim::launch((int)n_sel * 3, 32, 0, [&](int b) { sync_scan_warp(P, (int64_t)(b / 3), (int64_t)(b % 3), 3); });
         int bsh = 4096;
         for (int64_t k = 0; k < n_sel; ++k) if (meta[(size_t)k].blocksize > 0) { bsh = meta[(size_t)k].blocksize; break; }
         int64_t nwin = (first_decode + n_decode - 1) / bsh - first_decode / bsh + 1;
