@@ -22,6 +22,7 @@
 #include "fa_decode.h"
 #include "fa_decode_tile.h"
 #include "fa_encode.h"
+#include "fa_encode_fixed.h"
 #include "fa_quant.h"
 
 using namespace fa;
@@ -70,6 +71,14 @@ __global__ void __launch_bounds__(kEncThreads) k_enc_analyze_short(const EncPara
     __shared__ AnShared sh;
     for (uint64_t g = (uint64_t)first + (uint64_t)blockIdx.x * stride; g < P.g_end; g += (uint64_t)gridDim.x * stride)
         analyze_frame_cta<H, false>(P, (uint32_t)g, &sh);
+}
+
+// levels 0..2: full blocksize-1152 frames, one warp each (fa_encode_fixed.h); what it declines keeps fsize == 0
+__global__ void __launch_bounds__(kFxWarps * 32, 7) k_enc_fixed(const EncParams P) {
+    __shared__ FxShared ws[kFxWarps];
+    const uint64_t g = (uint64_t)P.g_begin + (uint64_t)blockIdx.x * kFxWarps + (threadIdx.x >> 5);
+    if (g >= P.g_end) return;
+    fixed_frame_warp(P, (uint32_t)g, &ws[threadIdx.x >> 5]);
 }
 
 // predictor design: one thread per (frame, channel)
@@ -335,7 +344,7 @@ __global__ void __launch_bounds__(kDecThreads) k_dec_frames(const DecParams P, i
 
 // throughput path: one warp = 32 (stream, frame) items, see fa_decode_tile.h
 #ifndef FAB_DEC_CTAS
-#define FAB_DEC_CTAS 6
+#define FAB_DEC_CTAS 12
 #endif
 __global__ void __launch_bounds__(kTileWarps * 32, FAB_DEC_CTAS) k_dec_tile(const TileParams P) {
     __shared__ TileShared ws[kTileWarps];
@@ -799,6 +808,12 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
         // under the kernels of batch b + 1, which use the other slot / frame-size buffers; k_enc_analyze of batch
         // b + 2 parks samples in the slots batch b compacts from, so it waits for that compaction.
         if (bi >= 2) FAB_CUDA(ctx, cudaStreamWaitEvent(st, joins[bi & 1], 0));
+        if (lp.blocksize == kFxBs) {
+            // levels 0..2: the warp-per-frame encoder first; the kernels below then only see what it left (fsize == 0)
+            FAB_CUDA(ctx, cudaMemsetAsync(P.fsize, 0, (size_t)nfr * 4, st));
+            k_enc_fixed<<<(unsigned)((nfr + kFxWarps - 1) / kFxWarps), kFxWarps * 32, 0, st>>>(P);
+            ctx->launches++;
+        }
         // frames that are not full: every frame (blocksize 1152), or the last frame of each stream when the stream
         // length is not a multiple of the blocksize
         uint32_t first = P.g_begin, stride = 1;

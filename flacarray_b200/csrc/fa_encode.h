@@ -130,6 +130,11 @@ struct EncParams {
     uint32_t g_begin, g_end;   // (stream, frame) units covered by this batch of launches
 };
 
+// Levels 0..2 (blocksize 1152): fa_encode_fixed.h encodes full frames one warp each and publishes their size in fsize
+// (zeroed before); the kernels of this file skip those frames and take what that path declined.
+constexpr int kFxBs = 1152;
+FA_D bool fixed_done(const EncParams& P, uint32_t g) { return P.blocksize == kFxBs && P.fsize[g - P.g_begin] != 0u; }
+
 // Records exchanged between the three encoder kernels, one per (frame, channel):
 //   k_enc_analyze -> FrameStats -> k_enc_design -> FramePlan -> k_encode
 struct FrameStats {
@@ -1682,6 +1687,7 @@ FA_D void analyze_frame_cta(const EncParams& P, uint32_t g, AnShared* sh) {
     const int bs = (int)((P.stream_size - samp0) < P.blocksize ? (P.stream_size - samp0) : P.blocksize);
     FrameStats* st = P.stats + (size_t)(g - P.g_begin) * P.nch;
     if ((bs == kMaxBs) != FULL) return;
+    if (!FULL && fixed_done(P, g)) return;
     if (bs < 64) {
         if (tid() < P.nch) st[tid()].mode = 0;
         return;
@@ -1709,6 +1715,7 @@ FA_D void design_frame(const EncParams& P, int64_t i) {
     const int f = (int)(g % (uint32_t)P.nframes);
     const int64_t samp0 = (int64_t)f * P.blocksize;
     const int bs = (int)((P.stream_size - samp0) < P.blocksize ? (P.stream_size - samp0) : P.blocksize);
+    if (fixed_done(P, g)) return;
     const FrameStats& st = P.stats[i];
     FramePlan pl;
     memset(&pl, 0, sizeof(pl));
@@ -2862,7 +2869,7 @@ FA_D void encode_frames_cta(const EncParams& P, unsigned char* smem_raw, uint32_
         FAB_TICK(0);
         const uint32_t g = hot->gq[slot];
         const int f = hot->gq_f[slot], bs = hot->gq_bs[slot];
-        const bool mine = g < total_frames && ((bs == kMaxBs) == FULLK);
+        const bool mine = g < total_frames && ((bs == kMaxBs) == FULLK) && !(!FULLK && fixed_done(P, g));
         if (FULLK) {
             if (t == 0) {
                 if (mine) {

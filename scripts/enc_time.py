@@ -6,6 +6,7 @@ import bench
 from flacarray_b200 import _lib, libflacarray as lf
 dev = torch.device("cuda", 0)
 n_stream, n_samp = int(sys.argv[1]) if len(sys.argv) > 1 else 1000, 1000000
+level = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 data = bench.make_tod_torch(n_stream, n_samp, 1, dev)
 quanta = torch.full((n_stream,), 1e-4, dtype=torch.float32, device=dev)
 flat = data.reshape(-1)
@@ -15,7 +16,7 @@ for it in range(4):
     if it == 3: ctx.profile(True)
     e0.record()
     try:
-        comp, starts, nbytes, off, gain = lf.encode_device(flat, n_stream, n_samp, 5, quanta)
+        comp, starts, nbytes, off, gain = lf.encode_device(flat, n_stream, n_samp, level, quanta)
     except Exception as ex:
         print("err", ex)
     e1.record(); torch.cuda.synchronize()

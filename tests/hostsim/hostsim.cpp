@@ -10,6 +10,7 @@
 #include "../../flacarray_b200/csrc/fa_decode.h"
 #include "../../flacarray_b200/csrc/fa_decode_tile.h"
 #include "../../flacarray_b200/csrc/fa_encode.h"
+#include "../../flacarray_b200/csrc/fa_encode_fixed.h"
 
 namespace fasim {
 thread_local ThreadCtx tls;
@@ -93,6 +94,13 @@ int hs_encode(const void* data, int dtype, int64_t n_stream, int64_t stream_size
     unsigned long long base = 0;
     P.slots = (uint8_t*)(((uintptr_t)slots_w.data() + 15) & ~(uintptr_t)15); P.slot_bytes = slot_bytes;
     P.fsize = fsize.data(); P.base = &base;
+    if (lp.blocksize == kFxBs && getenv("HS_NO_FIXED") == nullptr) {
+        // levels 0..2: the warp-per-frame encoder first (the product's k_enc_fixed), the kernels below take the rest
+        fasim::launch((int)total_frames, 32, sizeof(FxShared) + 16, [&](int b) {
+            FxShared* ws = (FxShared*)(((uintptr_t)fasim::smem() + 15) & ~(uintptr_t)15);
+            fixed_frame_warp(P, (uint32_t)b, ws);
+        });
+    }
     fasim::launch(1, kEncThreads, sizeof(AnShared) + 16, [&](int) {
         AnShared* ash = (AnShared*)fasim::smem();
         if (lp.blocksize == kMaxBs) analyze_fill_window(P, ash);

@@ -20,7 +20,7 @@ def lib():
     so = os.path.join(_HERE, "libhostsim.so")
     srcs = [os.path.join(_HERE, "hostsim.cpp")] + [
         os.path.join(_HERE, "..", "..", "flacarray_b200", "csrc", f)
-        for f in ("fa_simt.h", "fa_bits.h", "fa_quant.h", "fa_decode.h", "fa_decode_tile.h", "fa_encode.h")]
+        for f in ("fa_simt.h", "fa_bits.h", "fa_quant.h", "fa_decode.h", "fa_decode_tile.h", "fa_encode.h", "fa_encode_fixed.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
         subprocess.run([cxx, "-O2", "-std=c++20", "-ffp-contract=off", "-fPIC", "-shared", "-pthread",
