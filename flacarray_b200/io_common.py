@@ -84,6 +84,31 @@ def _all_have_group(grp, comm):
     return all(int(f) == 1 for f in flags)
 
 
+def _h5_driver(grp):
+    """Driver name of the file behind an h5py group ("mpio", "sec2", ...); None for zarr / in-memory groups."""
+    f = getattr(grp, "file", None)
+    return getattr(f, "driver", None) if f is not None else None
+
+
+def _write_mode(grp, comm):
+    """How a distributed write proceeds: (direct, collective_create).
+
+    Every rank writing its own slices is only sound when the store allows uncoordinated writers (zarr, in-memory
+    groups) or coordinates them itself (h5py over the mpio driver, where dataset creation and attributes are
+    COLLECTIVE: every rank has to issue them, hdf5.py:247-268 of the reference does the same).  Serial h5py handles
+    on several ranks would have independent processes write one file: those go through the serial writer, with rank 0
+    the only one touching its handle."""
+    direct = _all_have_group(grp, comm)
+    if comm is None or not direct:
+        return direct, False
+    drivers = comm.allgather(_h5_driver(grp))
+    if all(d is None for d in drivers):
+        return True, False
+    if all(d == "mpio" for d in drivers):
+        return True, True
+    return False, False
+
+
 def _block_slices(dist_range, aux_shape):
     return (slice(dist_range[0], dist_range[1]),) + tuple(slice(0, int(x)) for x in aux_shape[1:])
 
@@ -104,7 +129,7 @@ def write_compressed(grp, leading_shape, global_leading_shape, stream_size, stre
     gains = None if stream_gains is None else _host(stream_gains).reshape(aux_local)
     if mpi_dist is None:
         mpi_dist = [(0, aux_global[0])]
-    direct = _all_have_group(grp, mpi_comm)
+    direct, collective_create = _write_mode(grp, mpi_comm)
     # a rank that only ships its block to the writer keeps device-resident bytes on the device: a communicator that can
     # move tensors (TorchComm over NCCL) sends them from there, instead of device -> host -> device -> wire
     ship_dev = (not direct and rank != 0 and hasattr(compressed, "is_cuda") and compressed.is_cuda
@@ -112,7 +137,7 @@ def write_compressed(grp, leading_shape, global_leading_shape, stream_size, stre
     comp = compressed.reshape(-1) if ship_dev else _host(compressed).reshape(-1)
 
     dsets = None
-    if rank == 0:
+    if rank == 0 or collective_create:
         if grp is None:
             raise RuntimeError("rank 0 needs the group handle")
         grp.attrs["flacarray_format_version"] = FORMAT_VERSION
