@@ -94,12 +94,26 @@ __global__ void __launch_bounds__(kScanThreads) k_enc_scan(const EncParams P) {
 }
 
 // frames of a batch from their slots to their final byte offsets, CRC-16 appended (CTAs stride over the frames)
-__global__ void __launch_bounds__(128) k_enc_compact(const EncParams P) {
+#ifndef FAB_COMPACT_MINB
+#define FAB_COMPACT_MINB 16     // (32 registers: 16 CTAs = 64 warps per SM hide the row loads; 12 and 8 CTAs measured slower)
+#endif
+__global__ void __launch_bounds__(128, FAB_COMPACT_MINB) k_enc_compact(const EncParams P) {
     __shared__ CompactShared cs;
     const uint32_t n = P.g_end - P.g_begin;
-    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
-        compact_frame_cta(P, i, &cs);
+    // (size and byte prefix of the CTA's next frame are loaded one frame ahead: the frame's first row would otherwise
+    // wait for two dependent trips to HBM)
+    uint32_t i = blockIdx.x;
+    uint32_t len = 0;
+    unsigned long long end = 0;
+    if (i < n) { len = P.fsize[i]; end = P.desc[P.g_begin + i]; }
+    while (i < n) {
+        const uint32_t inext = i + gridDim.x;
+        uint32_t len_n = 0;
+        unsigned long long end_n = 0;
+        if (inext < n) { len_n = P.fsize[inext]; end_n = P.desc[P.g_begin + inext]; }
+        compact_frame_cta(P, i, &cs, len, end);
         __syncthreads();      // cs is reused by the next frame
+        i = inext; len = len_n; end = end_n;
     }
 }
 
@@ -342,9 +356,16 @@ __global__ void __launch_bounds__(kDecThreads) k_dec_frames(const DecParams P, i
     frame_body(P, k, j);
 }
 
-// throughput path: one warp = 32 (stream, frame) items, see fa_decode_tile.h
+// throughput path: one warp = 32 (stream, frame) items, see fa_decode_tile.h.
+// 10 resident CTAs (20 warps) per SM at 96 registers: no spills in the sample loop.  Measured on cfg2-shaped decodes of
+// 350 / 600 / 1000 streams (k_dec_tile + k_dec_crc, ms; residency below the build's limit forced with unused shared
+// memory): 12 CTAs at 80 registers 1.58 / 2.59 / 3.74, 11: 1.55 / 2.63 / 3.82, 10 CTAs at 96 registers 1.33 / 2.34 / 3.41,
+// 9: 1.72 / 2.44 / 3.50, 8: 1.83 / 2.35 / 3.74, 13 CTAs at 72 registers 4.70 at 1000 streams (spills).  A work item is a
+// warp of 32 whole frames (~1 ms, a third of the kernel at cfg2), so the fill of the last wave shows in every column
+// (1340 CTAs on 1480 slots at 350 streams); a per-call choice of the residency from a wave model was tried and bought
+// nothing over the fixed 10.
 #ifndef FAB_DEC_CTAS
-#define FAB_DEC_CTAS 12
+#define FAB_DEC_CTAS 10
 #endif
 __global__ void __launch_bounds__(kTileWarps * 32, FAB_DEC_CTAS) k_dec_tile(const TileParams P) {
     __shared__ TileShared ws[kTileWarps];
@@ -424,6 +445,7 @@ struct fab_ctx {
     EncTables* d_tab = nullptr;
     int n_sm = 0;
     int enc_ctas_per_sm[2][2] = {{0, 0}, {0, 0}};   // [H == 12][nch - 1]
+    int compact_ctas_per_sm = 0;
     float* d_window[3] = {nullptr, nullptr, nullptr};  // [0] 1152, [1] 4096 (both zero-padded to 4096 floats), [2] 4096 in [quad][thread][4] order
     int* d_err = nullptr;
     int* h_err = nullptr;  // pinned
@@ -788,6 +810,7 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
             FAB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->enc_ctas_per_sm[0][c], k_encode<8>, kEncThreads, enc_smem_bytes(c + 1) + FAB_SMEM_PAD));
             FAB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->enc_ctas_per_sm[1][c], k_encode<12>, kEncThreads, enc_smem_bytes(c + 1)));
         }
+        FAB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->compact_ctas_per_sm, k_enc_compact, 128, 0));
         ctx->smem_configured = true;
     }
     P.stats = stats; P.plans = plans;
@@ -878,7 +901,12 @@ extern "C" int fab_encode(fab_ctx* ctx, const void* d_data, int dtype, int64_t n
         FAB_CUDA(ctx, cudaEventRecord(ctx->ev_fork, st));
         FAB_CUDA(ctx, cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
         k_enc_scan<<<1, kScanThreads, 0, ctx->aux>>>(P);      // (the running byte total is carried from scan to scan: all on aux)
-        k_enc_compact<<<(unsigned)std::min<int64_t>(nfr, (int64_t)ctx->n_sm * 16), 128, 0, ctx->aux>>>(P);
+        // (CTAs stride over the frames: exactly one resident wave, or the CTAs of a partial second wave run their whole
+        // share of the frames after everybody else has finished)
+#ifndef FAB_COMPACT_CTAS
+#define FAB_COMPACT_CTAS std::max(1, ctx->compact_ctas_per_sm)
+#endif
+        k_enc_compact<<<(unsigned)std::min<int64_t>(nfr, (int64_t)ctx->n_sm * (FAB_COMPACT_CTAS)), 128, 0, ctx->aux>>>(P);
         FAB_CUDA(ctx, cudaEventRecord(joins[bi & 1], ctx->aux));
         ctx->launches += 3;
     }

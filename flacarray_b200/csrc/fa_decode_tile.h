@@ -193,6 +193,14 @@ struct TileLane {
     int32_t cval;
     int plen, esc, psize, part, nparts, left, k, rawbits;
     int fl;         // residuals of the current partition open to the four-at-a-time path: `left` when k >= 0, else 0
+    // 32-bit prediction sums: exact whenever asum * (largest |sample| of the subframe) < 2^31.  `nar` is the lane's guess
+    // after the warm-up (the bound holds for samples up to the next power of two above the warm-up's largest magnitude;
+    // this library's encoder lowers the coefficient precision of narrow frames until asum * max|x| < 2^30, so the guess is
+    // always "yes" for them); mn / mx follow every decoded sample and the subframe is CHECKED at its end -- a subframe
+    // that breaks the bound after all goes to the general decoder, which keeps 64-bit sums.
+    int32_t mn, mx;
+    int asum;       // sum of |coefficient|
+    int nar;
     int32_t h[kTileOrd];
     int32_t c[kTileOrd];
 };
@@ -216,6 +224,7 @@ FA_D bool tile_subframe_begin(BitRdC& br, int bs, int bps, TileLane& L) {
     L.nparts = 0;
     L.k = 0;
     L.need_params = 0;
+    L.mn = 0; L.mx = 0; L.asum = 0; L.nar = 0;
 #pragma unroll
     for (int j = 0; j < kTileOrd; ++j) { L.h[j] = 0; L.c[j] = 0; }
     if (type == 0) {
@@ -260,6 +269,15 @@ FA_D bool tile_subframe_params(BitRdC& br, int bs, TileLane& L) {
         const int32_t fx[5][4] = {{0, 0, 0, 0}, {1, 0, 0, 0}, {2, -1, 0, 0}, {3, -3, 1, 0}, {4, -6, 4, -1}};
 #pragma unroll
         for (int j = 0; j < 4; ++j) L.c[j] = fx[order][j];
+    }
+    {
+        int a = 0;
+#pragma unroll
+        for (int j = 0; j < kTileOrd; ++j) a += L.c[j] < 0 ? -L.c[j] : L.c[j];        // < 12 * 2^14
+        L.asum = a;
+        const int64_t mw = (int64_t)L.mx > -(int64_t)L.mn ? (int64_t)L.mx : -(int64_t)L.mn;     // warm-up magnitude
+        const int bits = 64 - clz64((uint64_t)mw);                                    // mw < 2^bits
+        L.nar = (bits < 31 && ((uint64_t)a << bits) < (1ull << 31)) ? 1 : 0;
     }
     uint32_t method = brc_read(br, 2);
     if (method > 1) return false;
@@ -310,6 +328,8 @@ FA_D int32_t tile_next_sample(BitRdC& br, TileLane& L) {
 #pragma unroll
     for (int j = ORD - 1; j > 0; --j) L.h[j] = L.h[j - 1];
     if (ORD > 0) L.h[0] = v;
+    L.mn = v < L.mn ? v : L.mn;
+    L.mx = v > L.mx ? v : L.mx;
     return (int32_t)((uint32_t)v << L.wasted);
 }
 
@@ -320,8 +340,9 @@ FA_D int32_t tile_next_sample(BitRdC& br, TileLane& L) {
 // boundary), the position of the stop bit gives quotient, remainder shift and code length.  A code longer than 32 bits
 // (stop bit not inside the window's first 32 - k bits) sets the sign of `bad`; the group is then decoded again from
 // the saved cursor by the general routine -- rare: one code in ~10^4 on detector data.
+// narrow (warp-uniform): every lane of the warp guessed that 32-bit prediction sums are exact (TileLane::nar).
 template <int ORD>
-FA_D void tile_next4(BitRdC& br, TileLane& L, int32_t* out4) {
+FA_D void tile_next4(BitRdC& br, TileLane& L, int32_t* out4, const bool narrow) {
     int32_t r[4];
     const int k = L.k;
     brc_ensure(br, 4u * 32u + 64u);
@@ -356,17 +377,37 @@ FA_D void tile_next4(BitRdC& br, TileLane& L, int32_t* out4) {
     L.left -= 4;
     L.fl -= 4;
     int32_t s[4];
+    // history as seen by sample q: s[q-1], .., s[0], h[0], h[1], ...  The terms are added oldest first: the products with
+    // the old history do not wait for anything, and only the last multiply-add of sample q waits for sample q - 1
+    if (narrow) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        // history as seen by sample q: s[q-1], .., s[0], h[0], h[1], ...  The terms are added oldest first: the products with
-        // the old history do not wait for anything, and only the last multiply-add of sample q waits for sample q - 1
-        int64_t sum = 0;
+        for (int q = 0; q < 4; ++q) {
+            uint32_t sum = 0;
 #pragma unroll
-        for (int j = ORD - 1; j >= 0; --j) {
-            int32_t hv = (j < q) ? s[q - 1 - j] : L.h[j - q];
-            sum += (int64_t)L.c[j] * (int64_t)hv;
+            for (int j = ORD - 1; j >= 0; --j) {
+                int32_t hv = (j < q) ? s[q - 1 - j] : L.h[j - q];
+                sum += (uint32_t)L.c[j] * (uint32_t)hv;
+            }
+            s[q] = (int32_t)((uint32_t)r[q] + (uint32_t)((int32_t)sum >> L.shift));
         }
-        s[q] = (int32_t)((int64_t)r[q] + (sum >> L.shift));
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            int64_t sum = 0;
+#pragma unroll
+            for (int j = ORD - 1; j >= 0; --j) {
+                int32_t hv = (j < q) ? s[q - 1 - j] : L.h[j - q];
+                sum += (int64_t)L.c[j] * (int64_t)hv;
+            }
+            s[q] = (int32_t)((int64_t)r[q] + (sum >> L.shift));
+        }
+    }
+    {
+        const int32_t lo01 = s[0] < s[1] ? s[0] : s[1], hi01 = s[0] > s[1] ? s[0] : s[1];
+        const int32_t lo23 = s[2] < s[3] ? s[2] : s[3], hi23 = s[2] > s[3] ? s[2] : s[3];
+        const int32_t lo = lo01 < lo23 ? lo01 : lo23, hi = hi01 > hi23 ? hi01 : hi23;
+        L.mn = lo < L.mn ? lo : L.mn;
+        L.mx = hi > L.mx ? hi : L.mx;
     }
 #pragma unroll
     for (int j = ORD - 1; j >= 4; --j) L.h[j] = L.h[j - 4];
@@ -394,6 +435,9 @@ FA_D void tile_channel_pass(const TileParams& P, TileShared* ws, BitRdC& br, Til
     const int ln = lane();
     int32_t* trow = ws->tile + ln * kTileStride;
     for (uint32_t base = 0; base < bsmax; base += 32) {
+        // (once per 32 samples: a lane only makes its guess when it reads its subframe parameters, inside the first block;
+        // until every predictive lane has said "yes" the warp keeps the 64-bit loop)
+        const bool narrow = ballot(run && L.mode == 2 && (L.need_params != 0 || L.nar == 0)) == 0;
 #pragma unroll 1
         for (int s = 0; s < 32; s += 4) {
             int i = (int)base + s;
@@ -404,7 +448,7 @@ FA_D void tile_channel_pass(const TileParams& P, TileShared* ws, BitRdC& br, Til
                 const bool fast = L.fl >= 4;
                 if (fast) {
                     if (!br.wok) { brc_ensure(br, 64u); brc_window_load(br); br.wok = 1; }
-                    tile_next4<ORD>(br, L, trow + s);
+                    tile_next4<ORD>(br, L, trow + s, narrow);
                 } else {
                     br.wok = 0;
                     for (int q = 0; q < 4; ++q) {
@@ -469,6 +513,12 @@ FA_D void tile_channel_pass(const TileParams& P, TileShared* ws, BitRdC& br, Til
             }
         }
         syncwarp();
+    }
+    // the subframe's prediction sums were exact in 32 bits?  (checked whether or not the warp took the 32-bit loop: a lane
+    // only ever guesses "yes" wrongly when the signal outgrows its warm-up by more than a power of two)
+    if (run && L.mode == 2 && L.nar) {
+        const int64_t m = (int64_t)L.mx > -(int64_t)L.mn ? (int64_t)L.mx : -(int64_t)L.mn;
+        if ((int64_t)L.asum * m >= (1ll << 31)) { run = false; punt = true; }
     }
 }
 

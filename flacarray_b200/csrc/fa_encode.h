@@ -997,10 +997,8 @@ FA_D uint32_t compact_rows(const uint32_t* src, uint8_t* dst_al, uint32_t a, uin
     return crct_fold(crct_fold(c));
 }
 
-FA_D void compact_frame_cta(const EncParams& P, uint32_t i, CompactShared* cs) {
-    const uint32_t g = P.g_begin + i;
-    const uint32_t len = P.fsize[i];              // body + the two CRC bytes
-    const unsigned long long end = P.desc[g];
+// len = P.fsize[i] (body + the two CRC bytes), end = P.desc[P.g_begin + i] (inclusive byte prefix), loaded by the caller
+FA_D void compact_frame_cta(const EncParams& P, uint32_t i, CompactShared* cs, uint32_t len, unsigned long long end) {
     if ((long long)end > P.out_capacity) {
         if (tid() == 0) atom_or_global(P.err, kErrEncodeCollect);
         return;

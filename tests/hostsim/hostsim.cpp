@@ -125,7 +125,7 @@ int hs_encode(const void* data, int dtype, int64_t n_stream, int64_t stream_size
     });
     fasim::launch(1, kScanThreads, (kScanThreads / 32 + 1) * 8, [&](int) { scan_batch_cta(P, (unsigned long long*)fasim::smem()); });
     fasim::launch((int)total_frames, 128, sizeof(CompactShared), [&](int b) {
-        compact_frame_cta(P, (uint32_t)b, (CompactShared*)fasim::smem());
+        compact_frame_cta(P, (uint32_t)b, (CompactShared*)fasim::smem(), P.fsize[b], P.desc[P.g_begin + (uint32_t)b]);
     });
     fasim::launch(1, 1, 0, [&](int) {
         for (int64_t s = 0; s < n_stream; ++s)
