@@ -112,6 +112,33 @@ def test_decode_oracle_encoded(fa, oracle, level):
             assert np.array_equal(y, x[:, f:l]), name
 
 
+@pytest.mark.parametrize("level", [5, 8])
+@pytest.mark.parametrize("log2_amp", [14, 17, 20, 24, 30])
+def test_decode_32bit_prediction_guess_and_miss(fa, oracle, level, log2_amp):
+    """The tile decoder sums predictions in 32 bits when, after the warm-up, sum|coef| * (next power of two above the
+    warm-up magnitude) < 2^31, and checks the whole subframe at its end.  These signals are ~0 at every frame start and
+    grow to 2^log2_amp inside the frame: small amplitudes keep the 32-bit loop, large ones guess "exact", miss, and must
+    come back bit-exact through the general decoder (oracle-encoded: 15-bit coefficients, no narrow-frame guarantee)."""
+    rng = np.random.default_rng(1000 + log2_amp)
+    n = 3 * 4096 + 1500
+    i = np.arange(n)
+    env = np.sin(np.pi * (i % 4096) / 4096.0) ** 2          # 0 at the first samples of every 4096-sample frame
+    amp = float(2 ** log2_amp - 2 ** (log2_amp - 4))
+    rows = []
+    for k in range(40):                                      # more than one warp of frames
+        ph = rng.uniform(0, 2 * np.pi)
+        x = amp * env * np.sin(2 * np.pi * i / rng.uniform(37.0, 400.0) + ph) + rng.normal(0, 3.0, n)
+        rows.append(np.clip(np.rint(x), -2 ** 31, 2 ** 31 - 1))
+    x = np.array(rows).astype(np.int32)
+    c, s, nb = oracle.encode(x, level)
+    y = fa.array_decompress(c, n, s, nb)
+    assert np.array_equal(y, x)
+    # and the encoder's own streams of the same signals (narrow frames carry lowered precision, wide ones do not)
+    comp, starts, nbytes, _, _ = fa.array_compress(x, level=level)
+    assert np.array_equal(oracle.decode(comp, starts.reshape(-1), nbytes.reshape(-1), n), x)
+    assert np.array_equal(fa.array_decompress(comp, n, starts, nbytes), x)
+
+
 def test_decode_oracle_encoded_int64_all_stereo_modes(fa, oracle):
     from flacarray_b200.libflacarray import decode_flac
 

@@ -65,6 +65,27 @@ def test_decoder_bodies_on_own_and_foreign_streams(H, oracle):
                 assert np.array_equal(y, x[:, f:l]), name
 
 
+@pytest.mark.parametrize("log2_amp", [14, 20, 30])
+def test_tile_decoder_32bit_prediction_guess_and_miss(H, oracle, log2_amp):
+    """Signals that are ~0 at every frame start and grow to 2^log2_amp inside the frame: the warp-tile decoder guesses
+    "32-bit prediction sums are exact" from the warm-up; small amplitudes stay there, large ones fail the end-of-subframe
+    check and must come back bit-exact from the general decoder (no walker)."""
+    rng = np.random.default_rng(500 + log2_amp)
+    n = 2 * 4096 + 700
+    i = np.arange(n)
+    env = np.sin(np.pi * (i % 4096) / 4096.0) ** 2
+    amp = float(2 ** log2_amp - 2 ** (log2_amp - 4))
+    x = np.array([np.clip(np.rint(amp * env * np.sin(2 * np.pi * i / per + 0.3) + rng.normal(0, 3.0, n)), -2 ** 31, 2 ** 31 - 1)
+                  for per in (41.0, 113.0, 390.0)]).astype(np.int32)
+    for own, (comp, st, nb) in enumerate((oracle.encode(x, 5), H.encode(x, 5)[:3])):
+        y, info = H.decode(comp, st, nb, n, mode=2)       # info = streams walked + 1000 * frames left to the general decoder
+        assert np.array_equal(y, x) and info % 1000 == 0
+        if log2_amp == 14:
+            assert info == 0                              # the guess holds: nothing leaves the tile path
+        if log2_amp == 30 and not own:
+            assert info >= 1000                           # 15-bit coefficients x 2^30 samples: the check must fire
+
+
 def test_int64_bodies(H, oracle):
     rng = np.random.default_rng(23)
     a = rng.integers(-2 ** 63, 2 ** 63 - 1, (1, 5000), dtype=np.int64)
