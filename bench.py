@@ -40,9 +40,9 @@ METRIC = "encode+decode GB/s of raw samples (float32 TOD, quanta 1e-4, level 5)"
 
 
 def ncu_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r01_traffic.json)."""
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/r02_traffic.json)."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[kernel]
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))[kernel]
         return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
     except Exception:
         return None

@@ -907,17 +907,27 @@ FA_D void scan_batch_cta(const EncParams& P, unsigned long long* sh_part /*[kSca
     const uint32_t seg = (((n + kW - 1) / kW) + 31u) & ~31u;      // elements per warp, a multiple of 32
     const uint32_t lo = (uint32_t)wp * seg;
     unsigned long long run = 0;
-    for (uint32_t i = lo; i < lo + seg && i < n; i += 32) {
-        const uint32_t j = i + (uint32_t)ln;
-        uint32_t v = 0;
-        if (j < n) v = P.fsize[j] + (((P.g_begin + j) % (uint32_t)P.nframes) == 0 ? (uint32_t)P.hdr_bytes : 0u);
-        uint32_t inc = v;
-        for (int d = 1; d < 32; d <<= 1) {
-            uint32_t o = shfl_up(inc, d);
-            if (ln >= d) inc += o;
+    constexpr int kRows = 8;      // rows of 32 sizes loaded together: the scan itself is short, the trips to HBM are not
+    for (uint32_t i0 = lo; i0 < lo + seg && i0 < n; i0 += 32 * kRows) {
+        uint32_t v[kRows];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+            const uint32_t j = i0 + 32u * r + (uint32_t)ln;
+            v[r] = 0;
+            if (i0 + 32u * r < lo + seg && j < n)
+                v[r] = P.fsize[j] + (((P.g_begin + j) % (uint32_t)P.nframes) == 0 ? (uint32_t)P.hdr_bytes : 0u);
         }
-        if (j < n) P.desc[P.g_begin + j] = run + inc;
-        run += shfl(inc, 31);
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+            const uint32_t j = i0 + 32u * r + (uint32_t)ln;
+            uint32_t inc = v[r];
+            for (int d = 1; d < 32; d <<= 1) {
+                uint32_t o = shfl_up(inc, d);
+                if (ln >= d) inc += o;
+            }
+            if (i0 + 32u * r < lo + seg && j < n) P.desc[P.g_begin + j] = run + inc;
+            run += shfl(inc, 31);
+        }
     }
     if (ln == 0) sh_part[wp] = run;
     sync();
@@ -928,9 +938,18 @@ FA_D void scan_batch_cta(const EncParams& P, unsigned long long* sh_part /*[kSca
     }
     sync();
     const unsigned long long base = sh_part[wp];
-    for (uint32_t i = lo; i < lo + seg && i < n; i += 32) {
-        const uint32_t j = i + (uint32_t)ln;
-        if (j < n) P.desc[P.g_begin + j] += base;
+    for (uint32_t i0 = lo; i0 < lo + seg && i0 < n; i0 += 32 * kRows) {
+        unsigned long long d[kRows];
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+            const uint32_t j = i0 + 32u * r + (uint32_t)ln;
+            d[r] = (i0 + 32u * r < lo + seg && j < n) ? P.desc[P.g_begin + j] : 0ull;
+        }
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+            const uint32_t j = i0 + 32u * r + (uint32_t)ln;
+            if (i0 + 32u * r < lo + seg && j < n) P.desc[P.g_begin + j] = d[r] + base;
+        }
     }
     if (t == 0) *P.base = sh_part[kW];
 }
