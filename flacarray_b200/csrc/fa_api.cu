@@ -357,7 +357,8 @@ __global__ void __launch_bounds__(kDecThreads) k_dec_frames(const DecParams P, i
 }
 
 // throughput path: one warp = 32 (stream, frame) items, see fa_decode_tile.h.
-// 10 resident CTAs (20 warps) per SM at 96 registers: no spills in the sample loop.  Measured on cfg2-shaped decodes of
+// 20 resident one-warp CTAs per SM at 96 registers: no spills in the sample loop (21 would cap the kernel at 80).  The
+// figures below were taken with two-warp CTAs.  Measured on cfg2-shaped decodes of
 // 350 / 600 / 1000 streams (k_dec_tile + k_dec_crc, ms; residency below the build's limit forced with unused shared
 // memory): 12 CTAs at 80 registers 1.58 / 2.59 / 3.74, 11: 1.55 / 2.63 / 3.82, 10 CTAs at 96 registers 1.33 / 2.34 / 3.41,
 // 9: 1.72 / 2.44 / 3.50, 8: 1.83 / 2.35 / 3.74, 13 CTAs at 72 registers 4.70 at 1000 streams (spills).  A work item is a
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(kDecThreads) k_dec_frames(const DecParams P, i
 // (1340 CTAs on 1480 slots at 350 streams); a per-call choice of the residency from a wave model was tried and bought
 // nothing over the fixed 10.
 #ifndef FAB_DEC_CTAS
-#define FAB_DEC_CTAS 10
+#define FAB_DEC_CTAS (20 / FAB_TILE_WARPS)
 #endif
 __global__ void __launch_bounds__(kTileWarps * 32, FAB_DEC_CTAS) k_dec_tile(const TileParams P) {
     __shared__ TileShared ws[kTileWarps];

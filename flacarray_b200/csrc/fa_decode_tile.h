@@ -26,7 +26,7 @@ constexpr int kTileOrd = 12;
 constexpr int kTileStride = 36;   // words per tile row: 16-byte aligned rows, and rows 9 x 16 bytes apart keep 16-byte accesses
                                   // of 8 consecutive lanes (one row each, or one row together) on distinct banks
 #ifndef FAB_TILE_WARPS
-#define FAB_TILE_WARPS 2
+#define FAB_TILE_WARPS 1          // (CTAs of one warp retire item by item: 3.59 -> 3.53 ms against two-warp CTAs, 3.57 with four)
 #endif
 constexpr int kTileWarps = FAB_TILE_WARPS;  // warps per CTA
 
