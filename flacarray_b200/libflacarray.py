@@ -385,13 +385,31 @@ def _side_streams(dev):
     return _side[key]
 
 
+_NO_RAMP = os.environ.get("FLACARRAY_B200_NO_RAMP", "") == "1"      # measurement switch
+
+
 def _chunk_ranges(n_stream, bytes_per_stream):
+    """Whole-stream chunks of the host pipelines.  The copy-in of the first chunk and the kernels + copy-out of the last
+    one are the only parts nothing overlaps, so the pipeline starts and ends with a quarter- and a half-size chunk."""
     total = n_stream * bytes_per_stream
     if n_stream < 2 or total < _PIPE_MIN_BYTES:
         return [(0, n_stream)]
-    nchunk = min(n_stream, max(2, -(-total // _PIPE_CHUNK_BYTES)))
-    edges = [(n_stream * i) // nchunk for i in range(nchunk + 1)]
-    return [(edges[i], edges[i + 1]) for i in range(nchunk) if edges[i + 1] > edges[i]]
+    full = max(1, _PIPE_CHUNK_BYTES // max(bytes_per_stream, 1))
+    ramp = [max(1, full // 4), max(1, full // 2)]
+    if not _NO_RAMP and full >= 4 and n_stream >= 2 * sum(ramp) + full:
+        mid = n_stream - 2 * sum(ramp)
+        nmid = max(1, -(-mid // full))
+        sizes = ramp + [(mid * (i + 1)) // nmid - (mid * i) // nmid for i in range(nmid)] + ramp[::-1]
+    else:
+        nchunk = min(n_stream, max(2, -(-total // _PIPE_CHUNK_BYTES)))
+        sizes = [(n_stream * (i + 1)) // nchunk - (n_stream * i) // nchunk for i in range(nchunk)]
+    out, a = [], 0
+    for n in sizes:
+        if n > 0:
+            out.append((a, a + n))
+            a += n
+    assert a == n_stream
+    return out
 
 
 _STAGE_MIN_BYTES = 1 << 20        # pageable pieces below this go straight to cudaMemcpy

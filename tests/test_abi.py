@@ -115,3 +115,20 @@ def test_keep_select_matches_reference_loop():
     assert keep_select(None, starts, nbytes) == (starts, nbytes, None)
     with pytest.raises(RuntimeError):
         keep_select(keep[0], starts, nbytes)
+
+
+def test_host_pipeline_chunks_cover_every_stream_once():
+    """Host-buffer pipelines cut the array into whole-stream chunks: every stream exactly once, in order, with a short
+    first and last chunk (the only copy-in / copy-out nothing overlaps) when the array is long enough."""
+    from flacarray_b200 import libflacarray as lf
+
+    for n_stream, bps in [(1, 10), (2, 1 << 30), (7, 50 << 20), (1000, 4_000_000), (4096, 16_000_000), (50, 4_000_000),
+                          (100, 1000), (3, 100_000_000), (12345, 40_000)]:
+        r = lf._chunk_ranges(n_stream, bps)
+        assert r[0][0] == 0 and r[-1][1] == n_stream
+        assert all(a < b for a, b in r) and all(r[i][1] == r[i + 1][0] for i in range(len(r) - 1))
+        if n_stream * bps < lf._PIPE_MIN_BYTES:
+            assert len(r) == 1
+    sizes = [b - a for a, b in lf._chunk_ranges(1000, 4_000_000)]
+    assert sizes[0] < sizes[1] < sizes[2] and sizes[-1] < sizes[-2] < sizes[-3]
+    assert max(sizes) * 4_000_000 <= lf._PIPE_CHUNK_BYTES * 1.05
