@@ -171,13 +171,15 @@ struct Plan {
     int32_t qlp[kMaxOrd];
 };
 
+constexpr int kStagePitch = kEncThreads + 1;
 struct AnShared {              // k_enc_analyze: per-warp partials of the block reductions
     uint32_t w_or[kEncWarps];
     int32_t w_mn[kEncWarps], w_mx[kEncWarps];
     uint32_t w_bad[kEncWarps];
     unsigned long long w_fe[kEncWarps][5];
     double w_ac[kEncWarps][kMaxOrd + 1];
-    int32_t stage[kEncThreads * kSpt];   // full frames: the channel's int32 samples, [quad][thread][4]; afterwards every
+    int32_t stage[8 * kStagePitch * 4];  // full frames: the channel's int32 samples, [quad][thread][4], quad rows kStagePitch
+                                         // 16-byte units apart (odd: a warp may store eight quads of one thread at once); afterwards every
                                          // warp's own quads hold its per-lane autocorrelation partials
     float wqt[kEncThreads * kSpt];       // the window in the same [quad][thread][4] order (filled once per CTA)
 };
@@ -1360,38 +1362,50 @@ FA_D void analyze_stage(const FrameSrc& S, int c, int t, int32_t* park_frame, in
 #pragma unroll
         for (int q = 0; q < kSpt / 4; ++q) {
             const int o = (q * kEncThreads + t) << 2;
-            sts128(stage + o, ld128(park_frame + c * kMaxBs + o));
+            sts128(stage + ((q * kStagePitch + t) << 2), ld128(park_frame + c * kMaxBs + o));
         }
         return;
     }
     if (S.dtype == kI32 || S.dtype == kF32) {
-        const uint32_t* p = (const uint32_t*)S.base + t * kSpt;
         const bool gain_pos = S.gain32 > 0.0f;
-        U4 v[kSpt / 4];
         if (S.vec) {
+            // coalesced: the warp reads its 32 threads' 4 KB of input as eight rows of 512 contiguous bytes; lane L of warp
+            // w holds, in row k, quad L & 7 of thread 32 w + 4 k + (L >> 3).  Quantising is elementwise, so every lane
+            // converts what it loaded and stores it where its owner expects it (8 lanes = the 8 quads of one thread:
+            // 64-byte runs in the parked copy, distinct banks in the staged one thanks to the odd row pitch).
+            const int wq = t >> 5, L = t & 31;
+            const uint32_t* p = (const uint32_t*)S.base + wq * (32 * kSpt);
+            U4 v[kSpt / 4];
 #pragma unroll
-            for (int q = 0; q < kSpt / 4; ++q) v[q] = ldg128(p + 4 * q);
+            for (int k = 0; k < kSpt / 4; ++k) v[k] = ldg128(p + ((k * 32 + L) << 2));
+#pragma unroll
+            for (int k = 0; k < kSpt / 4; ++k) {
+                U4 w = v[k];
+                if (S.dtype == kF32) {
+                    w.x = (uint32_t)quant_f32_fast(u2f(w.x), S.off32, S.gain32, gain_pos);
+                    w.y = (uint32_t)quant_f32_fast(u2f(w.y), S.off32, S.gain32, gain_pos);
+                    w.z = (uint32_t)quant_f32_fast(u2f(w.z), S.off32, S.gain32, gain_pos);
+                    w.w = (uint32_t)quant_f32_fast(u2f(w.w), S.off32, S.gain32, gain_pos);
+                }
+                const int T = wq * 32 + 4 * k + (L >> 3), q = L & 7;
+                sts128(park_frame + ((q * kEncThreads + T) << 2), w);
+                sts128(stage + ((q * kStagePitch + T) << 2), w);
+            }
         } else {
+            const uint32_t* p = (const uint32_t*)S.base + t * kSpt;
 #pragma unroll 1
-            for (int q = 0; q < kSpt / 4; ++q) {      // (rolled: keeps ptxas from predicating 32 scalar loads into the aligned path)
+            for (int q = 0; q < kSpt / 4; ++q) {      // (unaligned input: scalar loads, rolled)
                 U4 w;
                 w.x = ldg32(p + 4 * q); w.y = ldg32(p + 4 * q + 1); w.z = ldg32(p + 4 * q + 2); w.w = ldg32(p + 4 * q + 3);
-#pragma unroll
-                for (int k = 0; k < kSpt / 4; ++k) if (k == q) v[k] = w;
+                if (S.dtype == kF32) {
+                    w.x = (uint32_t)quant_f32_fast(u2f(w.x), S.off32, S.gain32, gain_pos);
+                    w.y = (uint32_t)quant_f32_fast(u2f(w.y), S.off32, S.gain32, gain_pos);
+                    w.z = (uint32_t)quant_f32_fast(u2f(w.z), S.off32, S.gain32, gain_pos);
+                    w.w = (uint32_t)quant_f32_fast(u2f(w.w), S.off32, S.gain32, gain_pos);
+                }
+                sts128(park_frame + ((q * kEncThreads + t) << 2), w);
+                sts128(stage + ((q * kStagePitch + t) << 2), w);
             }
-        }
-#pragma unroll
-        for (int q = 0; q < kSpt / 4; ++q) {
-            U4 w = v[q];
-            if (S.dtype == kF32) {
-                w.x = (uint32_t)quant_f32_fast(u2f(w.x), S.off32, S.gain32, gain_pos);
-                w.y = (uint32_t)quant_f32_fast(u2f(w.y), S.off32, S.gain32, gain_pos);
-                w.z = (uint32_t)quant_f32_fast(u2f(w.z), S.off32, S.gain32, gain_pos);
-                w.w = (uint32_t)quant_f32_fast(u2f(w.w), S.off32, S.gain32, gain_pos);
-            }
-            const int o = (q * kEncThreads + t) << 2;
-            sts128(park_frame + o, w);
-            sts128(stage + o, w);
         }
     } else {
         const unsigned long long* p = (const unsigned long long*)S.base + t * kSpt;
@@ -1420,7 +1434,7 @@ FA_D void analyze_stage(const FrameSrc& S, int c, int t, int32_t* park_frame, in
             const int o = (q * kEncThreads + t) << 2;
             sts128(park_frame + o, lo);
             sts128(park_frame + kMaxBs + o, hi);
-            sts128(stage + o, lo);
+            sts128(stage + ((q * kStagePitch + t) << 2), lo);
         }
     }
 }
@@ -1447,7 +1461,7 @@ FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const FrameSrc&
     if (t != 0) {
 #pragma unroll
         for (int qq = 0; qq < H / 4; ++qq) {
-            const U4 v = lds128(stage + (((8 - H / 4 + qq) * kEncThreads + (t - 1)) << 2));
+            const U4 v = lds128(stage + (((8 - H / 4 + qq) * kStagePitch + (t - 1)) << 2));
             hx[4 * qq] = (int32_t)v.x; hx[4 * qq + 1] = (int32_t)v.y; hx[4 * qq + 2] = (int32_t)v.z; hx[4 * qq + 3] = (int32_t)v.w;
         }
         if (do_lpc) {
@@ -1485,7 +1499,7 @@ FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const FrameSrc&
         int32_t x[B];
 #pragma unroll
         for (int qq = 0; qq < B / 4; ++qq) {
-            const U4 v = lds128(stage + (((it * (B / 4) + qq) * kEncThreads + t) << 2));
+            const U4 v = lds128(stage + (((it * (B / 4) + qq) * kStagePitch + t) << 2));
             x[4 * qq] = (int32_t)v.x; x[4 * qq + 1] = (int32_t)v.y; x[4 * qq + 2] = (int32_t)v.z; x[4 * qq + 3] = (int32_t)v.w;
         }
         const bool head = it == 0 && t == 0;     // the frame's first four samples stay out of the fixed-predictor sums
@@ -1539,7 +1553,7 @@ FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const FrameSrc&
             int32_t x[B2];
 #pragma unroll
             for (int qq = 0; qq < B2 / 4; ++qq) {
-                const U4 v = lds128(stage + (((it * (B2 / 4) + qq) * kEncThreads + t) << 2));
+                const U4 v = lds128(stage + (((it * (B2 / 4) + qq) * kStagePitch + t) << 2));
                 x[4 * qq] = (int32_t)v.x; x[4 * qq + 1] = (int32_t)v.y; x[4 * qq + 2] = (int32_t)v.z; x[4 * qq + 3] = (int32_t)v.w;
             }
             double cw[B2];      // windowed samples of this trip
@@ -1580,14 +1594,14 @@ FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const FrameSrc&
             syncwarp();
 #pragma unroll
             for (int l = 0; l <= H; ++l)
-                ((double*)(stage + (((l >> 1) * kEncThreads + 32 * wp) << 2) + (l & 1) * 64))[(ln + l) & 31] = ac[l];
+                ((double*)(stage + (((l >> 1) * kStagePitch + 32 * wp) << 2) + (l & 1) * 64))[(ln + l) & 31] = ac[l];
             syncwarp();
             // NP lanes per lag, each sums a contiguous third (half) of the 32 columns; the parts meet in the first one
             constexpr int NP = (H + 1) * 3 <= 32 ? 3 : 2;
             const int l = ln / NP, part = ln - l * NP;
             double acc = 0.0;
             if (l <= H) {
-                const double* r = (const double*)(stage + (((l >> 1) * kEncThreads + 32 * wp) << 2) + (l & 1) * 64);
+                const double* r = (const double*)(stage + (((l >> 1) * kStagePitch + 32 * wp) << 2) + (l & 1) * 64);
                 const int c0 = (part * 32) / NP, c1 = ((part + 1) * 32) / NP;
                 for (int i = c0; i < c1; ++i) acc = dadd(acc, r[(i + l) & 31]);
             }
