@@ -1460,6 +1460,40 @@ FA_D void analyze_fill_window(const EncParams& P, AnShared* sh) {      // once p
     for (int i = tid(); i < kEncThreads * kSpt / 4; i += kEncThreads) sts128(sh->wqt + 4 * i, ldg128(P.window_qt + 4 * i));
 }
 
+// One trip of the autocorrelation pass: B2 staged samples of thread t -> windowed doubles `cur`, every product with the
+// lags 0..H (history beyond the trip start comes from `prev`, the previous trip in natural order) -> ac.
+template <int H, int B2>
+FA_D void analyze_ac_trip(const int32_t* stage, const float* wqt, int it, int t, bool flat, double* cur, const double* prev,
+                          double* ac) {
+    int32_t x[B2];
+#pragma unroll
+    for (int qq = 0; qq < B2 / 4; ++qq) {
+        const U4 v = lds128(stage + (((it * (B2 / 4) + qq) * kStagePitch + t) << 2));
+        x[4 * qq] = (int32_t)v.x; x[4 * qq + 1] = (int32_t)v.y; x[4 * qq + 2] = (int32_t)v.z; x[4 * qq + 3] = (int32_t)v.w;
+    }
+    if (flat) {
+#pragma unroll
+        for (int j = 0; j < B2; ++j) cur[j] = (double)(float)x[j];
+    } else {
+#pragma unroll
+        for (int qq = 0; qq < B2 / 4; ++qq) {
+            const U4 w4 = lds128(wqt + (((it * (B2 / 4) + qq) * kEncThreads + t) << 2));
+            cur[4 * qq] = (double)fmul((float)x[4 * qq], u2f(w4.x));
+            cur[4 * qq + 1] = (double)fmul((float)x[4 * qq + 1], u2f(w4.y));
+            cur[4 * qq + 2] = (double)fmul((float)x[4 * qq + 2], u2f(w4.z));
+            cur[4 * qq + 3] = (double)fmul((float)x[4 * qq + 3], u2f(w4.w));
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < B2; ++j) {
+#pragma unroll
+        for (int l = 0; l <= H; ++l) {
+            const double other = l <= j ? cur[j - l] : prev[B2 + j - l];
+            ac[l] = dfma(cur[j], other, ac[l]);
+        }
+    }
+}
+
 template <int H>
 FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const FrameSrc& S, int c, FrameStats* st,
                                int32_t* park_frame) {
@@ -1565,6 +1599,20 @@ FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const FrameSrc&
 #define FAB_AN_B2 8
 #endif
         constexpr int B2 = FAB_AN_B2;
+#ifndef FAB_AN_NO_PINGPONG
+        if constexpr (H == B2) {
+            // the history of a trip is exactly the trip before it: two trips per turn, each writing the array the other
+            // one reads as its history -- no register moves between trips (they were 2 of ~54 instructions per sample)
+            double pa[B2], pb[B2];
+#pragma unroll
+            for (int j = 0; j < B2; ++j) pa[j] = hw[B2 - 1 - j];
+#pragma unroll 1
+            for (int it = 0; it < kSpt / B2; it += 2) {
+                analyze_ac_trip<H, B2>(stage, sh->wqt, it, t, flat, pb, pa, ac);
+                analyze_ac_trip<H, B2>(stage, sh->wqt, it + 1, t, flat, pa, pb, ac);
+            }
+        } else
+#endif
 #pragma unroll 1
         for (int it = 0; it < kSpt / B2; ++it) {
             int32_t x[B2];
@@ -1620,7 +1668,10 @@ FA_D void analyze_channel_full(const EncParams& P, AnShared* sh, const FrameSrc&
             if (l <= H) {
                 const double* r = (const double*)(stage + (((l >> 1) * kStagePitch + 32 * wp) << 2) + (l & 1) * 64);
                 const int c0 = (part * 32) / NP, c1 = ((part + 1) * 32) / NP;
-                for (int i = c0; i < c1; ++i) acc = dadd(acc, r[(i + l) & 31]);
+                constexpr int kMin = 32 / NP;        // every part has kMin or kMin + 1 columns
+#pragma unroll
+                for (int k = 0; k < kMin; ++k) acc = dadd(acc, r[(c0 + k + l) & 31]);
+                if (c1 - c0 > kMin) acc = dadd(acc, r[(c0 + kMin + l) & 31]);
             }
             const double a1 = shfl_down_d(acc, 1), a2 = shfl_down_d(acc, 2);
             if (part == 0 && l <= H) sh->w_ac[wp][l] = NP == 3 ? dadd(dadd(acc, a1), a2) : dadd(acc, a1);
